@@ -1,0 +1,215 @@
+"""CPU: pin the oracle (oracle/elbo_oracle.py, oracle/gp_posterior.py) against
+(a) the reference's MATLAB known-answer fixtures and (b) outputs of the unmodified
+reference (tests/golden/ref_*.npz, produced by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from golden_util import REF_CASES, VAR_CASES, eps_for, load_case, load_npz, relerr, relmax
+from oracle import elbo_oracle as eo
+from oracle import gp_posterior as gpp
+
+TOL = 1e-9  # oracle vs unmodified reference, fp64 both sides (direct vs log-sum-exp evaluation)
+
+
+# ---------------------------------------------------------------- MATLAB known answers
+def _matlab_problem():
+    m = load_npz("matlab_vbmc")
+    D = K = 2
+    posts = gpp.posteriors(m["X"], m["y"], m["hyp"])
+    gp = eo.make_gp(m["X"], posts)
+    vp = eo.OracleVP.create(D, K, m["mu"], 1e-3 * np.ones(K), np.ones(D), np.ones(K) / K, np.ones(K) / K)
+    return m, gp, vp
+
+
+def test_matlab_gp_log_joint():
+    # pyvbmc/testing/vbmc/test_variational_optimization.py:120-162
+    m, gp, vp = _matlab_problem()
+    G, dG, varG, dvarG, var_ss, I_sk, J_sjk = eo.gp_log_joint(vp, gp, False, True, True, True, True)
+    assert np.isclose(G, m["G"])
+    assert dG is None and dvarG is None
+    assert np.isclose(varG, m["varG"])
+    assert np.isclose(var_ss, m["var_ss"])
+    assert I_sk.shape == (8, 2) and J_sjk.shape == (8, 2, 2)
+    G, dG, varG, dvarG, var_ss = eo.gp_log_joint(vp, gp, True, True, True, False, False)
+    assert np.allclose(dG, m["dG"])
+    assert np.isclose(G, m["G"])
+    assert varG is None
+
+
+def test_matlab_neg_elcbo():
+    # test_variational_optimization.py:165-211
+    m, gp, vp = _matlab_problem()
+    theta = eo.get_parameters(vp)
+    F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk = eo.neg_elcbo(
+        theta, gp, vp, 0.0, 0, False, True, None, 0.0, True
+    )
+    assert np.isclose(F, m["F"]) and dF is None and dH is None
+    assert np.isclose(G, m["G"]) and np.isclose(H, m["H"])
+    assert np.isclose(varF, m["varG"]) and np.isclose(varG, m["varG"]) and varH == 0.0
+    F, dF, G, H, varF = eo.neg_elcbo(theta, gp, vp, 0.0, 0, True, False, None, 0.0, False)
+    assert np.allclose(dF, m["dF"])
+
+
+def test_matlab_vp_bound_loss():
+    # test_variational_optimization.py:214-241
+    m, gp, vp = _matlab_problem()
+    options = {"tol_con_loss": 0.01, "tol_weight": 1e-2, "weight_penalty": 0.1, "tol_length": 1e-6}
+    theta = eo.get_parameters(vp)
+    bnd = eo.get_bounds(vp, m["X"], options, 2)
+    L, dL = eo.vp_bound_loss(vp, theta, bnd)
+    assert L == 0.0 and np.all(dL == 0.0)
+    theta[-1] = 1.0
+    L, dL = eo.vp_bound_loss(vp, theta, bnd, tol_con=0.01)
+    assert np.isclose(L, m["bound_L"])
+    assert np.isclose(dL[-1], m["bound_dL_last"])
+    assert np.all(dL[:-1] == 0.0)
+
+
+def test_soft_bound_loss_closed_form():
+    # test_variational_optimization.py:37-60
+    D = 3
+    slb, sub = np.full(D, -10.0), np.full(D, 10.0)
+    assert eo.soft_bound_loss(np.zeros(D), slb, sub) == 0.0
+    x = np.zeros(D)
+    x[0], x[1] = 15.0, -20.0
+    L, dL = eo.soft_bound_loss(x, slb, sub, compute_grad=True)
+    assert np.isclose(L, 156250.0)
+    assert np.isclose(dL[0], 12500.0) and np.isclose(dL[1], -25000.0) and np.allclose(dL[2:], 0.0)
+
+
+def test_matlab_get_bounds():
+    # pyvbmc/testing/variational_posterior/test_variational_posterior.py:761-791
+    m = load_npz("matlab_bounds")
+    vp = eo.OracleVP.create(2, 2, m["mu"], 1e-3 * np.ones(2), np.ones(2), np.ones(2) / 2, np.ones(2) / 2)
+    options = {"tol_con_loss": 0.01, "tol_weight": 1e-2, "weight_penalty": 0.1, "tol_length": 1e-6}
+    bnd = eo.get_bounds(vp, m["X"], options)
+    assert np.allclose(bnd["lb"], m["lb"]) and np.allclose(bnd["ub"], m["ub"])
+    assert bnd["tol_con"] == 0.01 and bnd["weight_threshold"] == 0.125 and bnd["weight_penalty"] == 0.1
+
+
+def test_matlab_entropy():
+    # test_entlb_vbmc.py:101-119 (exact) and test_entmc_vbmc.py:140-171 (1 %: RNG streams differ)
+    m = load_npz("matlab_entropy")
+    D, K, Ns = int(m["D"]), int(m["K"]), int(m["Ns"])
+    vp = eo.OracleVP.create(D, K, m["mu"], m["sigma"], m["lambd"], m["w"], m["eta"])
+    Hl, dHl = eo.entlb(vp, (True,) * 4, int(m["jacobian_flag"]))
+    assert np.isclose(Hl, m["Hl"]) and np.allclose(dHl, m["dHl"])
+    eps = eps_for(42, K, eo.even_ns(Ns), D)
+    H, dH = eo.entmc(vp, eps, (True,) * 4, int(m["jacobian_flag"]))
+    assert np.isclose(H, m["H"], rtol=0.01)
+    assert np.allclose(dH, m["dH"], rtol=0.01, atol=0.01)
+
+
+# ---------------------------------------------------------------- closed forms (test_entmc_vbmc.py:11-115)
+def test_entropy_single_gaussian_closed_form():
+    D, K = 3, 1
+    vp = eo.OracleVP.create(D, K, np.ones((D, K)), np.ones(K), np.ones(D), np.ones(K), np.ones(K))
+    H_exact = 0.5 * D * (1 + np.log(2 * np.pi))
+    dH_exact = np.concatenate([np.zeros(D), [D], np.ones(D), [H_exact - 1]])
+    H, dH = eo.entmc(vp, eps_for(0, K, 100000, D), (True,) * 4, False)
+    assert np.isclose(H, H_exact, rtol=0.01, atol=0.01)
+    assert np.allclose(dH, dH_exact, rtol=0.01, atol=0.01)
+    Hl, dHl = eo.entlb(vp, (True,) * 4, False)
+    assert np.isclose(Hl, H_exact)
+
+
+def test_entropy_grad_flag_shapes():
+    # test_entmc_vbmc.py:174-183, test_entlb_vbmc.py:122-131
+    D, K = 4, 3
+    vp = eo.OracleVP.create(D, K, np.zeros((D, K)), 1e-3 * np.ones(K), np.ones(D), np.ones(K) / K, np.ones(K) / K)
+    eps = eps_for(0, K, 10, D)
+    assert eo.entmc(vp, eps, (False,) * 4)[1].shape == (0,)
+    assert eo.entmc(vp, eps, (False, False, False, True))[1].shape == (K,)
+    assert eo.entlb(vp, (False,) * 4)[1].shape == (0,)
+    assert eo.entlb(vp, (False, False, False, True))[1].shape == (K,)
+
+
+# ---------------------------------------------------------------- unmodified reference outputs
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_ref_neg_elcbo_mc(stem):
+    c = load_case(stem)
+    g = c.g
+    vp = c.vp()
+    eps = eps_for(0, c.K, c.Ns_K, c.D)
+    F, dF, G, H, varF = eo.neg_elcbo(g["theta"], c.gp, vp, 0.0, c.Ns_K, True, False, c.theta_bnd, eps_half=eps)
+    assert relerr(F, g["mc_F"]) < TOL and relerr(G, g["mc_G"]) < TOL and relerr(H, g["mc_H"]) < TOL
+    assert relmax(dF, g["mc_dF"]) < TOL
+    assert varF == 0
+    # side effects on vp (variational_optimization.py:1080-1085)
+    for a, b in [(vp.mu, "post_mu"), (vp.sigma, "post_sigma"), (vp.lambd, "post_lambd"), (vp.w, "post_w"), (vp.eta, "post_eta")]:
+        assert np.allclose(a, g[b], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_ref_neg_elcbo_lb(stem):
+    c = load_case(stem)
+    g = c.g
+    F, dF, G, H, varF = eo.neg_elcbo(g["theta2"], c.gp, c.vp(), 0.0, 0, True, False, c.theta_bnd)
+    assert relerr(F, g["lb_F"]) < TOL and relerr(G, g["lb_G"]) < TOL and relerr(H, g["lb_H"]) < TOL
+    assert relmax(dF, g["lb_dF"]) < TOL
+    F, dF, *_ = eo.neg_elcbo(g["theta2"], c.gp, c.vp(), 0.0, 0, False, False, c.theta_bnd)
+    assert dF is None and relerr(F, g["lbv_F"]) < TOL
+
+
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_ref_standalone(stem):
+    c = load_case(stem)
+    g = c.g
+    vp = c.sa_vp()
+    G, dG, varG, dvarG, var_ss = eo.gp_log_joint(vp, c.gp, c.opt, True, True, False)
+    assert relerr(G, g["gp_G"]) < TOL and relmax(dG, g["gp_dG"]) < TOL and varG is None and dvarG is None
+    if c.S > 1:
+        G, dG, *_ = eo.gp_log_joint(vp, c.gp, c.opt, False, True, False)
+        assert G.shape == (c.S,) and dG.shape == g["gp_dG_noavg"].shape
+        assert relmax(G, g["gp_G_noavg"]) < TOL and relmax(dG, g["gp_dG_noavg"]) < TOL
+    H, dH = eo.entmc(vp, eps_for(g["ent_seed"], c.K, c.Ns_K, c.D), c.opt, True)
+    assert relerr(H, g["ent_H"]) < TOL and relmax(dH, g["ent_dH"]) < TOL
+    H, dH = eo.entmc(vp, eps_for(g["entnj_seed"], c.K, c.Ns_K, c.D), (True,) * 4, False)
+    assert relerr(H, g["entnj_H"]) < TOL and relmax(dH, g["entnj_dH"]) < TOL
+    H, dH = eo.entmc(vp, eps_for(g["entnj_seed"], c.K, c.Ns_K, c.D), (False, False, False, True), True)
+    assert relerr(H, g["entw_H"]) < TOL and relmax(dH, g["entw_dH"]) < TOL
+    H, dH = eo.entlb(vp, c.opt, True)
+    assert relerr(H, g["elb_H"]) < TOL and relmax(dH, g["elb_dH"]) < TOL
+    H, dH = eo.entlb(vp, (True,) * 4, False)
+    assert relerr(H, g["elbnj_H"]) < TOL and relmax(dH, g["elbnj_dH"]) < TOL
+
+
+@pytest.mark.parametrize("stem", VAR_CASES)
+def test_ref_variance_path(stem):
+    c = load_case(stem)
+    g = c.g
+    eps = eps_for(g["var_seed"], c.K, c.Ns_K, c.D)
+    r = eo.neg_elcbo(g["theta2"], c.gp, c.vp(), 0.0, c.Ns_K, False, True, None, 0.0, True, eps_half=eps)
+    F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk = r
+    assert dF is None and dH is None and varH == 0
+    assert relerr(F, g["var_F"]) < TOL and relerr(G, g["var_G"]) < TOL and relerr(H, g["var_H"]) < TOL
+    # the variance is a cancellation (prior - explained); 1e-8 relative is the fp64 noise floor here
+    assert relerr(varF, g["var_varF"]) < 1e-8 and relerr(varG, g["var_varG"]) < 1e-8
+    if c.S > 1:
+        assert relerr(varG_ss, g["var_varG_ss"]) < 1e-8
+    else:
+        assert varG_ss == 0 and g["var_varG_ss"] == 0
+    assert relmax(I_sk, g["var_I_sk"]) < TOL
+    assert relmax(J_sjk, g["var_J_sjk"]) < 1e-8
+    G, dG, varG, dvarG, var_ss = eo.gp_log_joint(c.sa_vp(), c.gp, False, True, True, True)
+    assert relerr(G, g["gpv_G"]) < TOL and relerr(varG, g["gpv_varG"]) < 1e-8 and relerr(var_ss, g["gpv_var_ss"]) < 1e-8 or c.S == 1
+
+
+def test_ref_entropy_edge_cases():
+    g = load_npz("ref_entropy_edge")
+    for i, (D, K, Ns) in enumerate(g["specs"]):
+        vp = eo.OracleVP.create(D, K, g[f"mu{i}"], g[f"sigma{i}"], g[f"lambd{i}"], g[f"w{i}"], g[f"eta{i}"])
+        H, dH = eo.entmc(vp, eps_for(100 + i, K, eo.even_ns(Ns), D), (True,) * 4, True)
+        assert relerr(H, g[f"H{i}"]) < TOL and relmax(dH, g[f"dH{i}"]) < TOL
+        Hl, dHl = eo.entlb(vp, (True,) * 4, True)
+        assert relerr(Hl, g[f"Hl{i}"]) < TOL and relmax(dHl, g[f"dHl{i}"]) < TOL
+
+
+def test_errors():
+    c = load_case("c1")
+    with pytest.raises(ValueError):
+        eo.neg_elcbo(c.g["theta2"], c.gp, c.vp(), 0.0, 0, True, False, None, 0.0, True)
+    with pytest.raises(NotImplementedError):
+        eo.neg_elcbo(c.g["theta2"], c.gp, c.vp(), 1.0, 0, True, None, None)
+    with pytest.raises(NotImplementedError):
+        eo.gp_log_joint(c.vp(), c.gp, True, True, True, True)
