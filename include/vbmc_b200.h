@@ -1,0 +1,185 @@
+/* vbmc_b200.h -- C ABI of the B200-native PyVBMC ELBO inner loop.
+ *
+ * The reference (acerbilab/pyvbmc) has no FFI: its hot path is reached through
+ * module-level Python functions.  Each entry point below replaces one of them
+ * (citations are reference file:line) and is what a ctypes binding on the
+ * reference side would call (INTEGRATION.md shows the stub):
+ *
+ *   vbmc_entmc        <- entmc_vbmc          pyvbmc/entropy/entmc_vbmc.py:6-134
+ *   vbmc_entlb        <- entlb_vbmc          pyvbmc/entropy/entlb_vbmc.py:6-180
+ *   vbmc_gp_pack      <- the gpyreg posterior fields read at
+ *                                            pyvbmc/vbmc/variational_optimization.py:1311,1367-1398
+ *   vbmc_gplogjoint   <- _gp_log_joint       pyvbmc/vbmc/variational_optimization.py:1238-1606
+ *   vbmc_set_bounds   <- theta_bnd dict      pyvbmc/variational_posterior/variational_posterior.py:140-239
+ *   vbmc_negelcbo     <- _neg_elcbo          pyvbmc/vbmc/variational_optimization.py:991-1235
+ *                        (incl. _vp_bound_loss :503-606, _soft_bound_loss :609-657,
+ *                         weight penalty :1212-1229)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is host memory, fp64, C-contiguous,
+ *     unless a parameter name ends in _dev (device pointer) -- those entry points are
+ *     the split-phase / device-resident variants used for multi-GPU sharding and for
+ *     kernel-only timing;
+ *   - mu is COMPONENT-MAJOR: mu[k*D + d]  (== vp.mu.ravel(order="F"), the theta layout);
+ *   - gradients come back in the reference's theta order [mu (D*K) | sigma (K) |
+ *     lambda (D) | w (K)], only the groups whose grad_flags[i] != 0;
+ *   - return value 0 = success, otherwise a VBMC_ERR_* code; vbmc_last_error() gives
+ *     the message.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with VBMC_ERR_CUDA.
+ *   - all work of one call is enqueued on the context's stream and the call returns
+ *     after the results have landed in the host buffers (the *_async variants return
+ *     after enqueueing).
+ */
+#ifndef VBMC_B200_H
+#define VBMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBMC_B200_ABI_VERSION 1
+
+enum {
+    VBMC_OK = 0,
+    VBMC_ERR_CUDA = 1,        /* CUDA runtime error / no device */
+    VBMC_ERR_ARG = 2,         /* invalid argument */
+    VBMC_ERR_UNSUPPORTED = 3, /* maps to NotImplementedError on the Python side */
+    VBMC_ERR_STATE = 4        /* e.g. GP not packed */
+};
+
+/* GP mean function (variational_optimization.py:1328-1330,1383-1392) */
+enum { VBMC_MEAN_ZERO = 0, VBMC_MEAN_CONST = 1, VBMC_MEAN_NEGQUAD = 2 };
+
+/* arithmetic of the Monte-Carlo entropy kernel */
+enum {
+    VBMC_PREC_F32 = 0, /* fp32 compute, fp64 accumulation (default) */
+    VBMC_PREC_F64 = 1  /* all fp64 */
+};
+
+/* source of the standard-normal draws of entmc */
+enum {
+    VBMC_RNG_EPS = 0,   /* caller supplies eps[K][Ns/2][D] (parity mode; entmc_vbmc.py:64-68) */
+    VBMC_RNG_PHILOX = 1 /* device counter-based Philox4x32-10 + Box-Muller keyed (seed, j, i, d) */
+};
+
+typedef struct vbmc_ctx vbmc_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int vbmc_abi_version(void);
+const char *vbmc_last_error(void);
+/* number of visible CUDA devices (0 if none / driver missing); never fails */
+int vbmc_device_count(void);
+int vbmc_ctx_create(int device, vbmc_ctx **out);
+void vbmc_ctx_destroy(vbmc_ctx *ctx);
+/* stream all kernels/copies of this context are enqueued on (a cudaStream_t) */
+void *vbmc_ctx_stream(vbmc_ctx *ctx);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t vbmc_ctx_launch_count(vbmc_ctx *ctx);
+
+/* ---- variational posterior parameters -------------------------------------------
+ * All compute entry points take the mixture as it stands AFTER
+ * VariationalPosterior.set_parameters (variational_posterior.py:680-759):            */
+typedef struct vbmc_vp {
+    int D, K;
+    const double *mu;    /* [K*D] component-major */
+    const double *sigma; /* [K] */
+    const double *lambd; /* [D] */
+    const double *w;     /* [K] */
+    const double *eta;   /* [K] (softmax pre-activations; used by the w Jacobian) */
+} vbmc_vp;
+
+/* ---- entropy --------------------------------------------------------------------- */
+/* entmc_vbmc(vp, Ns, grad_flags, jacobian_flag) -> (H, dH).  Ns = draws per component,
+ * rounded up to even (entmc_vbmc.py:61).  rng_mode VBMC_RNG_EPS: eps = [K][Ns_even/2][D]
+ * host doubles, mirrored antithetically on the device.  VBMC_RNG_PHILOX: eps ignored,
+ * (seed, offset) key the draws.  dH has room for D*K+K+D+K doubles.                     */
+int vbmc_entmc(vbmc_ctx *ctx, const vbmc_vp *vp, int64_t Ns, const int grad_flags[4],
+               int jacobian_flag, int rng_mode, const double *eps, uint64_t seed,
+               uint64_t offset, int precision, double *H, double *dH);
+
+/* entlb_vbmc(vp, grad_flags, jacobian_flag) -> (H, dH) */
+int vbmc_entlb(vbmc_ctx *ctx, const vbmc_vp *vp, const int grad_flags[4], int jacobian_flag,
+               double *H, double *dH);
+
+/* debugging / test hook: the eps[K][Ns_even/2][D] that VBMC_RNG_PHILOX uses */
+int vbmc_philox_normals(vbmc_ctx *ctx, int D, int K, int64_t Ns, uint64_t seed,
+                        uint64_t offset, double *eps_out);
+
+/* ---- GP surrogate ---------------------------------------------------------------- */
+/* Upload a trained GP: X[N][D]; hyp[S][H] in gpyreg order [ln ell (D), ln sf, noise
+ * (noise_N), m0, xm (D), ln omega (D)] with cov_N = D+1; alpha[S][N]; L[S][N][N] (may be
+ * NULL if the variance path is never used), L_chol[S], sn2_eff[S] = 1/sW[0]^2.           */
+int vbmc_gp_pack(vbmc_ctx *ctx, int D, int N, int S, const double *X, const double *hyp,
+                 int H, const double *alpha, const double *L, const int *L_chol,
+                 const double *sn2_eff, int mean_kind, int cov_N, int noise_N);
+
+/* _gp_log_joint(vp, gp, grad_flags, avg_flag, jacobian_flag, compute_var, separate_K).
+ * Outputs (any may be NULL when not wanted):
+ *   G      [1] if avg_flag and S>1 (or S==1), else [S]
+ *   dG     [P] (averaged) or [P][S] (avg_flag == 0), P from grad_flags
+ *   varG   [1] or [S] (compute_var != 0),  var_ss [1]
+ *   I_sk   [S][K], J_sjk [S][K][K] (separate_K)                                          */
+int vbmc_gplogjoint(vbmc_ctx *ctx, const vbmc_vp *vp, const int grad_flags[4], int avg_flag,
+                    int jacobian_flag, int compute_var, int separate_K, double *G, double *dG,
+                    double *varG, double *var_ss, double *I_sk, double *J_sjk);
+
+/* ---- negative ELCBO -------------------------------------------------------------- */
+/* Soft bounds (theta_bnd of VariationalPosterior.get_bounds).  n = length of lb/ub =
+ * [mu (D*K) if optimize_mu | ln-scale (D*K) | eta (K) if optimize_weights].  Pass n = 0
+ * to clear (theta_bnd=None).                                                             */
+int vbmc_set_bounds(vbmc_ctx *ctx, int n, const double *lb, const double *ub, double tol_con,
+                    double weight_threshold, double weight_penalty);
+
+typedef struct vbmc_elcbo_in {
+    vbmc_vp vp;          /* state after vp.set_parameters(theta) and the eta shift (:1080-1085) */
+    int optimize[4];     /* vp.optimize_{mu,sigma,lambd,weights} */
+    /* inputs of _vp_bound_loss taken from theta itself (:536-555); ignored without bounds */
+    const double *ln_sigma_b; /* [K] theta's ln sigma block, or log(vp.sigma)  */
+    const double *ln_lambd_b; /* [D] theta's ln lambda block, or log(vp.lambd) */
+    const double *eta_b;      /* [K] theta[-K:] (unshifted), NULL if !optimize_weights */
+    int64_t Ns;          /* draws per component; 0 -> entlb (:1163-1168) */
+    int compute_grad;
+    int compute_var;     /* 0/1 */
+    int separate_K;
+    int use_bounds;      /* theta_bnd is not None */
+    int rng_mode;
+    const double *eps;
+    uint64_t seed, offset;
+    int precision;
+} vbmc_elcbo_in;
+
+typedef struct vbmc_elcbo_out {
+    double F, G, H, varF, varG_ss;
+    double *dF;    /* [P] or NULL */
+    double *dH;    /* [P] or NULL */
+    double *I_sk;  /* [S][K] or NULL */
+    double *J_sjk; /* [S][K][K] or NULL */
+} vbmc_elcbo_out;
+
+int vbmc_negelcbo(vbmc_ctx *ctx, const vbmc_elcbo_in *in, vbmc_elcbo_out *out);
+
+/* ---- split-phase, device-resident variants ----------------------------------------
+ * One evaluation = partials (this rank's shard of draws and hyper-samples, raw sums
+ * BEFORE the sigma/lambda/softmax Jacobians, already scaled by the GLOBAL 1/Ns and 1/S)
+ * -> [all-reduce SUM of raw_dev over ranks, e.g. NCCL] -> finalize (identical on every
+ * rank).  raw_dev holds vbmc_raw_len(D, K) doubles.  Results stay on the device in
+ * out_dev: [F, G, H, varF, varG_ss, 0, 0, 0, dF (P)...].  Nothing is synchronised.       */
+size_t vbmc_raw_len(int D, int K);
+size_t vbmc_out_len(int D, int K);
+int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
+int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
+int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
+int vbmc_stream_synchronize(vbmc_ctx *ctx);
+/* Kernel timing for bench.py's roofline: when enabled, every entmc launch is bracketed by
+ * CUDA events on the context stream (and synchronised -- measurement mode only);
+ * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */
+int vbmc_set_kernel_timing(vbmc_ctx *ctx, int on);
+int vbmc_entmc_kernel_ms(vbmc_ctx *ctx, double *avg_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBMC_B200_H */

@@ -1,0 +1,399 @@
+"""Device context: owns one packed GP plus the evaluation workspace on one B200.
+
+Thin object wrapper over the C ABI (``include/vbmc_b200.h``).  NumPy fp64 in, NumPy
+fp64 / Python floats out -- the ownership contract of the reference's functions
+(SURVEY 8b): inputs are never kept, outputs are fresh host arrays, device buffers
+never hang off ``vp`` / ``gp`` objects (those get pickled with dill by the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _capi
+from .config import config
+
+_F64 = np.float64
+
+
+def _arr(a, shape=None):
+    out = np.ascontiguousarray(a, dtype=_F64)
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_capi.c_double_p) if a is not None else None
+
+
+def _flags(grad_flags):
+    if np.isscalar(grad_flags):
+        grad_flags = (bool(grad_flags),) * 4
+    g = tuple(bool(x) for x in grad_flags)
+    if len(g) != 4:
+        raise ValueError("grad_flags must be a bool or a 4-tuple")
+    return g
+
+
+def packed_len(D, K, g):
+    return (D * K if g[0] else 0) + (K if g[1] else 0) + (D if g[2] else 0) + (K if g[3] else 0)
+
+
+class _VPView:
+    """Flattened fp64 view of a (duck-typed) VariationalPosterior in the C layout."""
+
+    def __init__(self, vp):
+        self.D, self.K = int(vp.D), int(vp.K)
+        D, K = self.D, self.K
+        # vp.mu is (D, K); the C side wants component-major == ravel(order="F")
+        self.mu = np.ascontiguousarray(np.asarray(vp.mu, dtype=_F64).reshape(D, K).T).reshape(-1)
+        self.sigma = _arr(vp.sigma, (K,))
+        self.lambd = _arr(vp.lambd, (D,))
+        self.w = _arr(vp.w, (K,))
+        self.eta = _arr(vp.eta, (K,))
+        self.c = _capi.VP(D, K, _ptr(self.mu), _ptr(self.sigma), _ptr(self.lambd), _ptr(self.w), _ptr(self.eta))
+
+
+def gp_mean_kind(gp) -> int:
+    """variational_optimization.py:1328-1330,1383 -- decided there with isinstance on gpyreg classes."""
+    kind = getattr(gp, "mean_kind", None)
+    if kind is None:
+        kind = type(gp.mean).__name__
+    table = {
+        "negquad": _capi.MEAN_NEGQUAD,
+        "NegativeQuadratic": _capi.MEAN_NEGQUAD,
+        "const": _capi.MEAN_CONST,
+        "ConstantMean": _capi.MEAN_CONST,
+        "zero": _capi.MEAN_ZERO,
+        "ZeroMean": _capi.MEAN_ZERO,
+    }
+    if kind not in table:
+        raise NotImplementedError(f"GP mean function {kind!r} is not supported on the log-joint path")
+    return table[kind]
+
+
+def gp_counts(gp, D):
+    """(cov_N, noise_N) as read at variational_optimization.py:1367-1369."""
+    if hasattr(gp, "covariance"):
+        cov_N = int(gp.covariance.hyperparameter_count(D))
+    else:
+        cov_N = int(gp.cov_N)
+    if hasattr(gp, "noise"):
+        noise_N = int(gp.noise.hyperparameter_count())
+    else:
+        noise_N = int(gp.noise_N)
+    return cov_N, noise_N
+
+
+class Context:
+    def __init__(self, device: int = None):
+        lib = _capi.load()
+        if lib.vbmc_device_count() <= 0:
+            raise RuntimeError(
+                "pyvbmc_b200: no CUDA device visible -- this package has no CPU fallback "
+                "(use the reference NumPy path instead)"
+            )
+        self._lib = lib
+        self.device = config.device if device is None else int(device)
+        h = C.c_void_p()
+        _capi.check(lib.vbmc_ctx_create(self.device, C.byref(h)))
+        self._h = h
+        self._gp_token = None
+        self._gp_has_L = False
+        self._bnd_cache = None
+        self.S = 0
+        self.N = 0
+        self.D = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vbmc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ bookkeeping
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vbmc_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.vbmc_ctx_stream(self._h) or 0)
+
+    def synchronize(self):
+        _capi.check(self._lib.vbmc_stream_synchronize(self._h))
+
+    def set_kernel_timing(self, on: bool):
+        _capi.check(self._lib.vbmc_set_kernel_timing(self._h, int(bool(on))))
+
+    def entmc_kernel_ms(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        _capi.check(self._lib.vbmc_entmc_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # ------------------------------------------------------------------ GP
+    @staticmethod
+    def gp_token(gp, need_L: bool):
+        posts = gp.posteriors
+        return (id(gp), len(posts), tuple((id(p.hyp), id(p.alpha), id(p.L)) for p in posts), bool(need_L))
+
+    def pack_gp(self, gp, need_L: bool = False):
+        """Upload the GP fields read by ``_gp_log_joint`` (variational_optimization.py:1311,1367-1398)."""
+        X = _arr(gp.X)
+        N, D = X.shape
+        posts = gp.posteriors
+        S = len(posts)
+        cov_N, noise_N = gp_counts(gp, D)
+        hyp = np.stack([_arr(p.hyp).reshape(-1) for p in posts])
+        alpha = np.stack([_arr(p.alpha).reshape(-1) for p in posts])
+        if alpha.shape != (S, N):
+            raise ValueError("gp.posteriors[s].alpha must have N entries")
+        L_chol = np.array([int(bool(p.L_chol)) for p in posts], dtype=np.int32)
+        sn2 = np.array([1.0 / float(np.asarray(p.sW).reshape(-1)[0]) ** 2 for p in posts], dtype=_F64)
+        L = None
+        if need_L:
+            L = np.stack([_arr(p.L).reshape(N, N) for p in posts])
+        _capi.check(
+            self._lib.vbmc_gp_pack(
+                self._h, D, N, S, _ptr(X), _ptr(hyp), hyp.shape[1], _ptr(alpha), _ptr(L),
+                L_chol.ctypes.data_as(_capi.c_int_p), _ptr(sn2), gp_mean_kind(gp), cov_N, noise_N,
+            )
+        )
+        self.S, self.N, self.D = S, N, D
+        self._gp_has_L = bool(need_L)
+
+    # ------------------------------------------------------------------ bounds
+    def set_bounds(self, theta_bnd):
+        """Upload ``theta_bnd`` (variational_posterior.py:225-239) unless unchanged."""
+        if theta_bnd is None:
+            return False
+        lb = _arr(theta_bnd["lb"]).reshape(-1)
+        ub = _arr(theta_bnd["ub"]).reshape(-1)
+        tol = float(theta_bnd["tol_con"])
+        thr = float(theta_bnd.get("weight_threshold", 0.0))
+        pen = float(theta_bnd.get("weight_penalty", 0.0))
+        c = self._bnd_cache
+        if (
+            c is not None
+            and c[2:] == (tol, thr, pen)
+            and c[0].shape == lb.shape
+            and np.array_equal(c[0], lb)
+            and np.array_equal(c[1], ub)
+        ):
+            return True
+        _capi.check(self._lib.vbmc_set_bounds(self._h, lb.size, _ptr(lb), _ptr(ub), tol, thr, pen))
+        self._bnd_cache = (lb.copy(), ub.copy(), tol, thr, pen)
+        return True
+
+    # ------------------------------------------------------------------ entropy
+    def entmc(self, vp, Ns, grad_flags=(True,) * 4, jacobian_flag=True, eps=None, seed=0, offset=0, precision=None):
+        g = _flags(grad_flags)
+        v = _VPView(vp)
+        Ns_even = int(np.ceil(Ns / 2)) * 2  # entmc_vbmc.py:61 (Ns may arrive as a float)
+        if Ns_even <= 0:
+            raise ValueError("Ns must be > 0")
+        prec = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
+        if eps is not None:
+            eps = _arr(eps)
+            if eps.size != v.K * (Ns_even // 2) * v.D:
+                raise ValueError("eps must have shape (K, Ns/2, D)")
+            mode = _capi.RNG_EPS
+        else:
+            mode = _capi.RNG_PHILOX
+        H = C.c_double()
+        dH = np.empty(packed_len(v.D, v.K, (True,) * 4), dtype=_F64)
+        gf = (C.c_int * 4)(*[int(x) for x in g])
+        _capi.check(
+            self._lib.vbmc_entmc(
+                self._h, C.byref(v.c), Ns_even, gf, int(bool(jacobian_flag)), mode, _ptr(eps), int(seed), int(offset),
+                prec, C.byref(H), _ptr(dH),
+            )
+        )
+        return float(H.value), dH[: packed_len(v.D, v.K, g)].copy()
+
+    def entlb(self, vp, grad_flags=(True,) * 4, jacobian_flag=True):
+        g = _flags(grad_flags)
+        v = _VPView(vp)
+        H = C.c_double()
+        dH = np.empty(packed_len(v.D, v.K, (True,) * 4), dtype=_F64)
+        gf = (C.c_int * 4)(*[int(x) for x in g])
+        _capi.check(self._lib.vbmc_entlb(self._h, C.byref(v.c), gf, int(bool(jacobian_flag)), C.byref(H), _ptr(dH)))
+        return float(H.value), dH[: packed_len(v.D, v.K, g)].copy()
+
+    def philox_normals(self, D, K, Ns, seed=0, offset=0):
+        Ns_even = int(np.ceil(Ns / 2)) * 2
+        out = np.empty((K, Ns_even // 2, D), dtype=_F64)
+        _capi.check(self._lib.vbmc_philox_normals(self._h, D, K, Ns_even, int(seed), int(offset), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ log joint
+    def gplogjoint(self, vp, grad_flags, avg_flag=True, jacobian_flag=True, compute_var=False, separate_K=False):
+        """Raw outputs of ``vbmc_gplogjoint``: dict(G, dG, varG, var_ss, I_sk, J_sjk)."""
+        g = _flags(grad_flags)
+        v = _VPView(vp)
+        S, K, D = self.S, v.K, v.D
+        jac = bool(jacobian_flag)
+        g_eff = (g[0], g[1] and jac, g[2] and jac, g[3] and jac)
+        P = packed_len(D, K, g_eff)
+        per_s = S > 1 and not avg_flag
+        G = np.zeros(S if per_s else 1, dtype=_F64)
+        dG = np.zeros((P, S) if per_s else (P,), dtype=_F64)
+        varG = np.zeros(S if per_s else 1, dtype=_F64)
+        var_ss = np.zeros(1, dtype=_F64)
+        I_sk = np.zeros((S, K), dtype=_F64) if separate_K else None
+        J_sjk = np.zeros((S, K, K), dtype=_F64) if (separate_K and compute_var) else None
+        gf = (C.c_int * 4)(*[int(x) for x in g])
+        _capi.check(
+            self._lib.vbmc_gplogjoint(
+                self._h, C.byref(v.c), gf, int(bool(avg_flag)), int(jac), int(compute_var), int(bool(separate_K)),
+                _ptr(G), _ptr(dG) if P else None, _ptr(varG), _ptr(var_ss), _ptr(I_sk), _ptr(J_sjk),
+            )
+        )
+        return dict(G=G, dG=dG if any(g) else None, varG=varG, var_ss=float(var_ss[0]), I_sk=I_sk, J_sjk=J_sjk,
+                    per_s=per_s)
+
+    # ------------------------------------------------------------------ negative ELCBO
+    def _elcbo_in(self, vp, optimize, ln_sigma_b, ln_lambd_b, eta_b, Ns, compute_grad, compute_var, separate_K,
+                  use_bounds, eps, seed, offset, precision):
+        v = _VPView(vp)
+        keep = [v]
+        inp = _capi.ElcboIn()
+        inp.vp = v.c
+        inp.optimize = (C.c_int * 4)(*[int(bool(o)) for o in optimize])
+        for name, a, n in (("ln_sigma_b", ln_sigma_b, v.K), ("ln_lambd_b", ln_lambd_b, v.D), ("eta_b", eta_b, v.K)):
+            if a is not None:
+                a = _arr(a, (n,))
+                keep.append(a)
+                setattr(inp, name, _ptr(a))
+        Ns_even = int(np.ceil(Ns / 2)) * 2 if Ns > 0 else 0
+        inp.Ns = Ns_even
+        inp.compute_grad = int(bool(compute_grad))
+        inp.compute_var = int(bool(compute_var))
+        inp.separate_K = int(bool(separate_K))
+        inp.use_bounds = int(bool(use_bounds))
+        if eps is not None and Ns_even > 0:
+            eps = _arr(eps)
+            if eps.size != v.K * (Ns_even // 2) * v.D:
+                raise ValueError("eps must have shape (K, Ns/2, D)")
+            keep.append(eps)
+            inp.rng_mode = _capi.RNG_EPS
+            inp.eps = _ptr(eps)
+        else:
+            inp.rng_mode = _capi.RNG_PHILOX
+        inp.seed = int(seed)
+        inp.offset = int(offset)
+        inp.precision = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
+        return inp, v, keep
+
+    def negelcbo(self, vp, optimize, Ns, compute_grad, compute_var=False, separate_K=False, use_bounds=False,
+                 ln_sigma_b=None, ln_lambd_b=None, eta_b=None, eps=None, seed=0, offset=0, precision=None):
+        inp, v, keep = self._elcbo_in(vp, optimize, ln_sigma_b, ln_lambd_b, eta_b, Ns, compute_grad, compute_var,
+                                      separate_K, use_bounds, eps, seed, offset, precision)
+        D, K, S = v.D, v.K, self.S
+        g = tuple(bool(o) for o in optimize) if compute_grad else (False,) * 4
+        P = packed_len(D, K, g)
+        out = _capi.ElcboOut()
+        dF = np.empty(max(P, 1), dtype=_F64)
+        dH = np.empty(max(P, 1), dtype=_F64)
+        out.dF, out.dH = _ptr(dF), _ptr(dH)
+        I_sk = J_sjk = None
+        if separate_K:
+            I_sk = np.zeros((S, K), dtype=_F64)
+            out.I_sk = _ptr(I_sk)
+            if compute_var:
+                J_sjk = np.zeros((S, K, K), dtype=_F64)
+                out.J_sjk = _ptr(J_sjk)
+        _capi.check(self._lib.vbmc_negelcbo(self._h, C.byref(inp), C.byref(out)))
+        del keep
+        return dict(
+            F=float(out.F), G=float(out.G), H=float(out.H), varF=float(out.varF), varG_ss=float(out.varG_ss),
+            dF=dF[:P].copy() if compute_grad else None, dH=dH[:P].copy() if compute_grad else None,
+            I_sk=I_sk, J_sjk=J_sjk,
+        )
+
+    # split-phase API (multi-GPU / kernel-only timing); device pointers are plain ints
+    def upload(self, vp, optimize, Ns, compute_grad=True, use_bounds=False, ln_sigma_b=None, ln_lambd_b=None,
+               eta_b=None, eps=None, seed=0, offset=0, precision=None):
+        inp, v, keep = self._elcbo_in(vp, optimize, ln_sigma_b, ln_lambd_b, eta_b, Ns, compute_grad, False, False,
+                                      use_bounds, eps, seed, offset, precision)
+        _capi.check(self._lib.vbmc_negelcbo_upload(self._h, C.byref(inp)))
+        # the upload is asynchronous w.r.t. pageable eps memory only until the copy is enqueued;
+        # pinned staging is owned by the library, so nothing needs to outlive this call.
+        self.synchronize() if eps is not None else None
+        return v.D, v.K
+
+    def partials_async(self, rank, world, raw_dev_ptr):
+        _capi.check(self._lib.vbmc_negelcbo_partials_async(self._h, int(rank), int(world), C.c_void_p(raw_dev_ptr)))
+
+    def finalize_async(self, raw_dev_ptr, out_dev_ptr):
+        _capi.check(self._lib.vbmc_negelcbo_finalize_async(self._h, C.c_void_p(raw_dev_ptr), C.c_void_p(out_dev_ptr)))
+
+    def raw_len(self, D, K):
+        return int(self._lib.vbmc_raw_len(D, K))
+
+    def out_len(self, D, K):
+        return int(self._lib.vbmc_out_len(D, K))
+
+
+# ---------------------------------------------------------------------- per-process caches
+_entropy_ctx = {}
+_gp_ctx = OrderedDict()
+_GP_CTX_MAX = 4
+
+
+def entropy_context(device=None) -> Context:
+    """Context for the GP-free entry points (entmc / entlb)."""
+    dev = config.device if device is None else int(device)
+    if dev not in _entropy_ctx:
+        _entropy_ctx[dev] = Context(dev)
+    return _entropy_ctx[dev]
+
+
+def context_for_gp(gp, need_L=False, device=None) -> Context:
+    """Context holding ``gp`` on the device (packed once per trained GP, small LRU).
+
+    Keyed by the identity of the posterior arrays: ``gp.update`` / ``gp.fit`` create new
+    posterior records, which invalidates the entry.  Nothing is attached to ``gp`` itself.
+    """
+    dev = config.device if device is None else int(device)
+    tok = (dev,) + Context.gp_token(gp, False)
+    hit = _gp_ctx.get(tok)
+    if hit is not None:
+        ctx, ref = hit
+        alive = ref is None or ref() is gp
+        if alive:
+            _gp_ctx.move_to_end(tok)
+            if need_L and not ctx._gp_has_L:
+                ctx.pack_gp(gp, need_L=True)
+            return ctx
+        del _gp_ctx[tok]
+    ctx = Context(dev)
+    ctx.pack_gp(gp, need_L=need_L)
+    try:
+        ref = weakref.ref(gp)
+    except TypeError:
+        ref = None
+    _gp_ctx[tok] = (ctx, ref)
+    while len(_gp_ctx) > _GP_CTX_MAX:
+        _, (old, _r) = _gp_ctx.popitem(last=False)
+        old.close()
+    return ctx
+
+
+def clear_caches():
+    for ctx, _ in _gp_ctx.values():
+        ctx.close()
+    _gp_ctx.clear()
+    for ctx in _entropy_ctx.values():
+        ctx.close()
+    _entropy_ctx.clear()

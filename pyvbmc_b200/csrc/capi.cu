@@ -1,0 +1,581 @@
+// capi.cu -- extern "C" entry points declared in include/vbmc_b200.h: context, GP pack and the
+// orchestration of one evaluation  upload -> partials -> [all-reduce] -> finalize -> download.
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vbmc {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+int ensure(double **p, size_t *cap, size_t need) {
+    if (need <= *cap && *p) return VBMC_OK;
+    if (*p) VBMC_CUDA_CHECK(cudaFree(*p));
+    *p = nullptr;
+    size_t n = need + need / 4 + 64;
+    VBMC_CUDA_CHECK(cudaMalloc((void **)p, n * sizeof(double)));
+    *cap = n;
+    return VBMC_OK;
+}
+
+int ensure_pinned(double **d, double **h, size_t *cap, size_t need) {
+    if (need <= *cap && *d && *h) return VBMC_OK;
+    if (*d) VBMC_CUDA_CHECK(cudaFree(*d));
+    if (*h) VBMC_CUDA_CHECK(cudaFreeHost(*h));
+    *d = *h = nullptr;
+    size_t n = need + need / 4 + 64;
+    VBMC_CUDA_CHECK(cudaMalloc((void **)d, n * sizeof(double)));
+    VBMC_CUDA_CHECK(cudaMallocHost((void **)h, n * sizeof(double)));
+    *cap = n;
+    return VBMC_OK;
+}
+
+namespace {
+
+struct Bind {
+    explicit Bind(Ctx *c) { cudaSetDevice(c->device); }
+};
+
+int check_vp(const vbmc_vp *vp) {
+    VBMC_REQUIRE(vp && vp->mu && vp->sigma && vp->lambd && vp->w && vp->eta, VBMC_ERR_ARG, "vp: null field");
+    VBMC_REQUIRE(vp->D >= 1 && vp->K >= 1, VBMC_ERR_ARG, "vp: D and K must be >= 1");
+    VBMC_REQUIRE(vp->D <= kMaxD, VBMC_ERR_UNSUPPORTED, "D > 32 is not supported by the CUDA path");
+    return VBMC_OK;
+}
+
+int64_t even_ns(int64_t Ns) { return ((Ns + 1) / 2) * 2; }
+
+int packed_len(int D, int K, const int g[4]) {
+    return (g[0] ? D * K : 0) + (g[1] ? K : 0) + (g[2] ? D : 0) + (g[3] ? K : 0);
+}
+
+// internal description of one evaluation
+struct Spec {
+    vbmc_vp vp;
+    int grad[4];
+    int jacobian = 1;
+    int optimize[4] = {1, 1, 1, 1};
+    const double *ln_sigma_b = nullptr, *ln_lambd_b = nullptr, *eta_b = nullptr;
+    int64_t Ns = 0;
+    bool have_ent = true, have_gp = true;
+    bool use_bounds = false;
+    int rng_mode = VBMC_RNG_EPS;
+    const double *eps = nullptr;
+    uint64_t seed = 0, offset = 0;
+    int precision = VBMC_PREC_F32;
+};
+
+struct Staged {
+    Spec s;
+    int D = 0, DP = 0, K = 0;
+    EvalFlags f{};
+    EntmcPlan plan{};
+    bool planned = false;
+};
+
+// per-context staged state (kept outside Ctx to keep common.cuh light)
+struct CtxEx {
+    Ctx c;
+    Staged st;
+    std::vector<double> host_tmp;
+};
+
+CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
+
+int stage(CtxEx *x, const Spec &s) {
+    Ctx *c = &x->c;
+    VBMC_TRY(check_vp(&s.vp));
+    const int D = s.vp.D, K = s.vp.K, DP = pad_dim(D);
+    if (s.have_gp) {
+        VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "no GP packed (call vbmc_gp_pack first)");
+        VBMC_REQUIRE(c->gD == D, VBMC_ERR_ARG, "vp.D does not match the packed GP");
+    }
+    ParamLayout lay{D, DP, K};
+    RawLayout rl{D, K};
+    VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total()));
+    double *h = c->h_in;
+    memcpy(h + lay.mu(), s.vp.mu, sizeof(double) * K * D);
+    memcpy(h + lay.sigma(), s.vp.sigma, sizeof(double) * K);
+    memcpy(h + lay.lambd(), s.vp.lambd, sizeof(double) * D);
+    memcpy(h + lay.w(), s.vp.w, sizeof(double) * K);
+    memcpy(h + lay.eta(), s.vp.eta, sizeof(double) * K);
+    for (int k = 0; k < K; ++k) h[lay.lnsig_b() + k] = s.ln_sigma_b ? s.ln_sigma_b[k] : log(s.vp.sigma[k]);
+    for (int d = 0; d < D; ++d) h[lay.lnlam_b() + d] = s.ln_lambd_b ? s.ln_lambd_b[d] : log(s.vp.lambd[d]);
+    for (int k = 0; k < K; ++k) h[lay.eta_b() + k] = s.eta_b ? s.eta_b[k] : s.vp.eta[k];
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * lay.total(), cudaMemcpyHostToDevice, c->stream));
+
+    if (s.use_bounds) {
+        const int n_expect = (s.optimize[0] ? K * D : 0) + K * D + (s.optimize[3] ? K : 0);
+        VBMC_REQUIRE(c->n_bnd == n_expect, VBMC_ERR_ARG, "soft bounds: lb/ub length does not match [mu|ln-scale|eta]");
+    }
+    VBMC_TRY(ensure(&c->d_raw, &c->raw_cap, (size_t)rl.total()));
+    VBMC_TRY(ensure_pinned(&c->d_out, &c->h_out, &c->out_cap, vbmc_out_len(D, K)));
+    if (s.have_gp) {
+        VBMC_TRY(ensure(&c->d_gppart, &c->gppart_cap, (size_t)c->S * K * gppart_stride(DP)));
+        VBMC_TRY(ensure(&c->d_gps, &c->gps_cap, (size_t)c->S * (1 + rl.block())));
+    }
+    if (s.have_ent && s.Ns > 0 && s.rng_mode == VBMC_RNG_EPS) {
+        VBMC_REQUIRE(s.eps != nullptr, VBMC_ERR_ARG, "entmc: eps required in VBMC_RNG_EPS mode");
+        const size_t n = (size_t)K * (size_t)(even_ns(s.Ns) / 2) * (size_t)D;
+        VBMC_TRY(ensure(&c->d_eps, &c->eps_cap, n));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_eps, s.eps, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    Staged &st = x->st;
+    st.s = s;
+    st.D = D, st.DP = DP, st.K = K;
+    EvalFlags &f = st.f;
+    for (int i = 0; i < 4; ++i) f.grad[i] = s.grad[i], f.optimize[i] = s.optimize[i];
+    f.jacobian = s.jacobian;
+    f.use_ent_mc = s.Ns > 0;
+    f.have_ent = s.have_ent, f.have_gp = s.have_gp;
+    f.use_bounds = s.use_bounds;
+    f.avg = 1;
+    st.planned = false;
+    c->staged = true;
+    return VBMC_OK;
+}
+
+int partials(CtxEx *x, int rank, int world, double *raw_dev) {
+    Ctx *c = &x->c;
+    Staged &st = x->st;
+    VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged (call vbmc_negelcbo_upload first)");
+    VBMC_REQUIRE(world >= 1 && rank >= 0 && rank < world, VBMC_ERR_ARG, "bad rank/world");
+    const Spec &s = st.s;
+    const int D = st.D, DP = st.DP, K = st.K;
+    const bool anyg = s.grad[0] || s.grad[1] || s.grad[2] || s.grad[3];
+    RawLayout rl{D, K};
+    EvalFlags f = st.f;
+    const EntmcPlan *planp = nullptr;
+    int64_t Ns_glob = 0;
+    if (s.have_ent) {
+        if (s.Ns > 0) {
+            Ns_glob = even_ns(s.Ns);
+            const int64_t half_glob = Ns_glob / 2;
+            const int64_t p0 = half_glob * rank / world, p1 = half_glob * (rank + 1) / world;
+            VBMC_TRY(entmc_plan(c, D, K, p1 - p0, s.grad[3] != 0, s.precision, &st.plan));
+            st.plan.pair0 = p0;
+            st.plan.half_glob = half_glob;
+            VBMC_TRY(ensure(&c->d_entpart, &c->entpart_cap, (size_t)K * st.plan.slabs * entpart_stride(DP, K)));
+            VBMC_TRY(entmc_launch(c, c->d_in, D, K, st.plan, anyg, s.grad[3] != 0, s.precision, s.rng_mode, c->d_eps,
+                                  s.seed, s.offset, c->d_entpart));
+            planp = &st.plan;
+        } else if (rank == 0) {
+            VBMC_TRY(entlb_launch(c, c->d_in, D, K, s.grad, raw_dev + rl.ent(), raw_dev));
+        } else {
+            f.have_ent = 0;
+        }
+    }
+    if (s.have_gp) VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart));
+    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev));
+    return VBMC_OK;
+}
+
+int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
+    Ctx *c = &x->c;
+    Staged &st = x->st;
+    VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged");
+    return finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev);
+}
+
+// run everything on one GPU and bring `n` leading doubles of out back to the host
+int run_single(CtxEx *x, const Spec &s, size_t n_out) {
+    Ctx *c = &x->c;
+    VBMC_TRY(stage(x, s));
+    VBMC_TRY(partials(x, 0, 1, c->d_raw));
+    VBMC_TRY(finalize(x, c->d_raw, c->d_out));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->h_out, c->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return VBMC_OK;
+}
+
+}  // namespace
+}  // namespace vbmc
+
+using namespace vbmc;
+
+extern "C" {
+
+int vbmc_abi_version(void) { return VBMC_B200_ABI_VERSION; }
+const char *vbmc_last_error(void) { return g_err.c_str(); }
+
+int vbmc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int vbmc_ctx_create(int device, vbmc_ctx **out) {
+    VBMC_REQUIRE(out != nullptr, VBMC_ERR_ARG, "ctx_create: null out");
+    *out = nullptr;
+    int n = 0;
+    VBMC_CUDA_CHECK(cudaGetDeviceCount(&n));
+    VBMC_REQUIRE(n > 0, VBMC_ERR_CUDA, "no CUDA device visible (vbmc_b200 has no CPU fallback)");
+    VBMC_REQUIRE(device >= 0 && device < n, VBMC_ERR_ARG, "ctx_create: bad device index");
+    VBMC_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VBMC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    VBMC_REQUIRE(prop.major >= 10, VBMC_ERR_CUDA, "vbmc_b200 kernels are built for sm_100a (B200) only");
+    CtxEx *x = new CtxEx();
+    x->c.device = device;
+    x->c.sm_count = prop.multiProcessorCount;
+    VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
+    VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev0));
+    VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev1));
+    *out = reinterpret_cast<vbmc_ctx *>(x);
+    return VBMC_OK;
+}
+
+void vbmc_ctx_destroy(vbmc_ctx *p) {
+    if (!p) return;
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in,
+                     c->d_entpart, c->d_gppart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+    for (double *d : dev)
+        if (d) cudaFree(d);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete x;
+}
+
+void *vbmc_ctx_stream(vbmc_ctx *p) { return p ? (void *)ex(p)->c.stream : nullptr; }
+int64_t vbmc_ctx_launch_count(vbmc_ctx *p) { return p ? ex(p)->c.launches : 0; }
+
+int vbmc_gp_pack(vbmc_ctx *p, int D, int N, int S, const double *X, const double *hyp, int H, const double *alpha,
+                 const double *L, const int *L_chol, const double *sn2_eff, int mean_kind, int cov_N, int noise_N) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "gp_pack: null ctx");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_REQUIRE(X && hyp && alpha, VBMC_ERR_ARG, "gp_pack: null array");
+    VBMC_REQUIRE(D >= 1 && N >= 1 && S >= 1, VBMC_ERR_ARG, "gp_pack: bad sizes");
+    VBMC_REQUIRE(D <= kMaxD, VBMC_ERR_UNSUPPORTED, "D > 32 is not supported by the CUDA path");
+    VBMC_REQUIRE(cov_N == D + 1, VBMC_ERR_UNSUPPORTED, "gp_pack: only the SE-ARD covariance (D+1 hyper-parameters) is supported");
+    VBMC_REQUIRE(mean_kind == VBMC_MEAN_ZERO || mean_kind == VBMC_MEAN_CONST || mean_kind == VBMC_MEAN_NEGQUAD,
+                 VBMC_ERR_UNSUPPORTED, "gp_pack: unsupported mean function");
+    const int base = cov_N + noise_N;
+    const int need_H = base + (mean_kind == VBMC_MEAN_ZERO ? 0 : (mean_kind == VBMC_MEAN_CONST ? 1 : 1 + 2 * D));
+    VBMC_REQUIRE(H >= need_H, VBMC_ERR_ARG, "gp_pack: hyp rows are too short for this mean function");
+    const int DP = pad_dim(D), hs = hyp_stride(DP);
+
+    cudaStreamSynchronize(c->stream);
+    double *old[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L, c->d_Linv};
+    for (double *d : old)
+        if (d) cudaFree(d);
+    c->d_Xt = c->d_alpha = c->d_hyp = c->d_L = c->d_Linv = nullptr;
+    c->has_gp = false;
+
+    std::vector<double> Xt((size_t)DP * N, 0.0), hp((size_t)S * hs, 0.0);
+    for (int n = 0; n < N; ++n)
+        for (int d = 0; d < D; ++d) Xt[(size_t)d * N + n] = X[(size_t)n * D + d];
+    for (int s = 0; s < S; ++s) {
+        const double *h = hyp + (size_t)s * H;
+        double *o = hp.data() + (size_t)s * hs;
+        double sum_lnell = 0.0;
+        for (int d = 0; d < D; ++d) {
+            o[d] = exp(h[d]);
+            sum_lnell += h[d];
+            o[DP + d] = 0.0;
+            o[2 * DP + d] = 0.0;
+        }
+        for (int d = D; d < DP; ++d) o[d] = 1.0;
+        o[3 * DP + 0] = 2.0 * h[D];
+        o[3 * DP + 1] = sum_lnell;
+        o[3 * DP + 2] = mean_kind == VBMC_MEAN_ZERO ? 0.0 : h[base];
+        o[3 * DP + 3] = sn2_eff ? sn2_eff[s] : 1.0;
+        o[3 * DP + 4] = L_chol ? (double)(L_chol[s] != 0) : 1.0;
+        if (mean_kind == VBMC_MEAN_NEGQUAD)
+            for (int d = 0; d < D; ++d) {
+                o[DP + d] = h[base + 1 + d];
+                const double om = exp(h[base + 1 + D + d]);
+                o[2 * DP + d] = 1.0 / (om * om);
+            }
+    }
+    VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_Xt, Xt.size() * sizeof(double)));
+    VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_alpha, (size_t)S * N * sizeof(double)));
+    VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_hyp, hp.size() * sizeof(double)));
+    VBMC_CUDA_CHECK(cudaMemcpy(c->d_Xt, Xt.data(), Xt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    VBMC_CUDA_CHECK(cudaMemcpy(c->d_alpha, alpha, (size_t)S * N * sizeof(double), cudaMemcpyHostToDevice));
+    VBMC_CUDA_CHECK(cudaMemcpy(c->d_hyp, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->has_L = false;
+    if (L) {
+        VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_L, (size_t)S * N * N * sizeof(double)));
+        VBMC_CUDA_CHECK(cudaMemcpy(c->d_L, L, (size_t)S * N * N * sizeof(double), cudaMemcpyHostToDevice));
+        c->has_L = true;
+    }
+    c->gD = D, c->gDP = DP, c->N = N, c->S = S, c->mean_kind = mean_kind;
+    c->has_gp = true;
+    c->staged = false;
+    return VBMC_OK;
+}
+
+int vbmc_set_bounds(vbmc_ctx *p, int n, const double *lb, const double *ub, double tol_con, double weight_threshold,
+                    double weight_penalty) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "set_bounds: null ctx");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_REQUIRE(n >= 0, VBMC_ERR_ARG, "set_bounds: negative length");
+    c->n_bnd = 0;
+    if (n == 0) return VBMC_OK;
+    VBMC_REQUIRE(lb && ub, VBMC_ERR_ARG, "set_bounds: null array");
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if ((size_t)n > c->bnd_cap) {
+        if (c->d_lb) cudaFree(c->d_lb);
+        if (c->d_ub) cudaFree(c->d_ub);
+        c->d_lb = c->d_ub = nullptr;
+        VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_lb, (size_t)n * sizeof(double)));
+        VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_ub, (size_t)n * sizeof(double)));
+        c->bnd_cap = n;
+    }
+    VBMC_CUDA_CHECK(cudaMemcpy(c->d_lb, lb, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    VBMC_CUDA_CHECK(cudaMemcpy(c->d_ub, ub, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    c->n_bnd = n;
+    c->tol_con = tol_con, c->w_thr = weight_threshold, c->w_pen = weight_penalty;
+    return VBMC_OK;
+}
+
+int vbmc_entmc(vbmc_ctx *p, const vbmc_vp *vp, int64_t Ns, const int grad_flags[4], int jacobian_flag, int rng_mode,
+               const double *eps, uint64_t seed, uint64_t offset, int precision, double *H, double *dH) {
+    VBMC_REQUIRE(p && vp && grad_flags && H, VBMC_ERR_ARG, "entmc: null argument");
+    VBMC_REQUIRE(Ns > 0, VBMC_ERR_ARG, "entmc: Ns must be > 0");
+    CtxEx *x = ex(p);
+    Bind b(&x->c);
+    Spec s;
+    s.vp = *vp;
+    for (int i = 0; i < 4; ++i) s.grad[i] = grad_flags[i] != 0;
+    s.jacobian = jacobian_flag != 0;
+    s.Ns = Ns;
+    s.have_gp = false;
+    s.rng_mode = rng_mode, s.eps = eps, s.seed = seed, s.offset = offset, s.precision = precision;
+    const int P = packed_len(vp->D, vp->K, s.grad);
+    const size_t Pfull = RawLayout{vp->D, vp->K}.block();
+    VBMC_TRY(run_single(x, s, kOutHead + 2 * Pfull));
+    const double *o = x->c.h_out;
+    *H = o[2];
+    if (dH)
+        for (int i = 0; i < P; ++i) dH[i] = o[kOutHead + Pfull + i];
+    return VBMC_OK;
+}
+
+int vbmc_entlb(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int jacobian_flag, double *H, double *dH) {
+    VBMC_REQUIRE(p && vp && grad_flags && H, VBMC_ERR_ARG, "entlb: null argument");
+    CtxEx *x = ex(p);
+    Bind b(&x->c);
+    Spec s;
+    s.vp = *vp;
+    for (int i = 0; i < 4; ++i) s.grad[i] = grad_flags[i] != 0;
+    s.jacobian = jacobian_flag != 0;
+    s.Ns = 0;
+    s.have_gp = false;
+    const int P = packed_len(vp->D, vp->K, s.grad);
+    const size_t Pfull = RawLayout{vp->D, vp->K}.block();
+    VBMC_TRY(run_single(x, s, kOutHead + 2 * Pfull));
+    const double *o = x->c.h_out;
+    *H = o[2];
+    if (dH)
+        for (int i = 0; i < P; ++i) dH[i] = o[kOutHead + Pfull + i];
+    return VBMC_OK;
+}
+
+int vbmc_philox_normals(vbmc_ctx *p, int D, int K, int64_t Ns, uint64_t seed, uint64_t offset, double *eps_out) {
+    VBMC_REQUIRE(p && eps_out, VBMC_ERR_ARG, "philox_normals: null argument");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    const int64_t half = even_ns(Ns) / 2;
+    const size_t n = (size_t)K * half * D;
+    VBMC_TRY(ensure(&c->d_eps, &c->eps_cap, n));
+    VBMC_TRY(philox_normals_launch(c, D, K, half, seed, offset, c->d_eps));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(eps_out, c->d_eps, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return VBMC_OK;
+}
+
+int vbmc_gplogjoint(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int avg_flag, int jacobian_flag,
+                    int compute_var, int separate_K, double *G, double *dG, double *varG, double *var_ss,
+                    double *I_sk, double *J_sjk) {
+    VBMC_REQUIRE(p && vp && grad_flags, VBMC_ERR_ARG, "gplogjoint: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    Spec s;
+    s.vp = *vp;
+    // the reference appends the sigma/lambda/w blocks only under jacobian_flag (:1529-1546)
+    s.grad[0] = grad_flags[0] != 0;
+    for (int i = 1; i < 4; ++i) s.grad[i] = (grad_flags[i] != 0) && (jacobian_flag != 0);
+    s.jacobian = jacobian_flag != 0;
+    s.have_ent = false;
+    const bool anyg = grad_flags[0] || grad_flags[1] || grad_flags[2] || grad_flags[3];
+    VBMC_REQUIRE(!(compute_var && anyg), VBMC_ERR_UNSUPPORTED,
+                 "gradient of the log-joint variance is not available (reference raises at :1302-1307)");
+    VBMC_REQUIRE(compute_var == 0 || compute_var == 1, VBMC_ERR_UNSUPPORTED,
+                 "diagonal variance approximation is not implemented (reference raises at :1467-1471)");
+    const int D = vp->D, K = vp->K;
+    const int P = packed_len(D, K, s.grad);
+    const size_t Pfull = RawLayout{D, K}.block();
+    VBMC_TRY(run_single(x, s, kOutHead + 3 * Pfull));
+    const int S = c->S;
+    const double *o = c->h_out;
+    const bool per_s = !(avg_flag && S > 1) && S > 1;
+    std::vector<double> gps;
+    if (per_s || separate_K || compute_var) {
+        gps.resize((size_t)S * (1 + Pfull));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(gps.data(), c->d_gps, gps.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    if (!per_s) {
+        if (G) *G = o[1];
+        if (dG)
+            for (int i = 0; i < P; ++i) dG[i] = o[kOutHead + 2 * Pfull + i];
+    } else {
+        // per-sample Jacobians on the device, then [S][1+P] -> G[S], dG[P][S]
+        x->st.f.avg = 0;
+        double *d_out_s = nullptr;
+        size_t cap = 0;
+        VBMC_TRY(ensure(&c->d_var, &c->var_cap, (size_t)S * (1 + Pfull)));
+        d_out_s = c->d_var;
+        (void)cap;
+        VBMC_TRY(gps_finalize_launch(c, c->d_in, D, K, x->st.f, d_out_s));
+        std::vector<double> hs((size_t)S * (1 + Pfull));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(hs.data(), d_out_s, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int si = 0; si < S; ++si) {
+            if (G) G[si] = hs[(size_t)si * (1 + Pfull)];
+            if (dG)
+                for (int i = 0; i < P; ++i) dG[(size_t)i * S + si] = hs[(size_t)si * (1 + Pfull) + 1 + i];
+        }
+    }
+    if (separate_K && I_sk) {
+        RawLayout rl{D, K};
+        for (int si = 0; si < S; ++si)
+            for (int k = 0; k < K; ++k) I_sk[(size_t)si * K + k] = gps[(size_t)si * (1 + Pfull) + 1 + rl.o_w() + k];
+    }
+    if (compute_var) {
+        (void)varG, (void)var_ss, (void)J_sjk;
+        set_error("gp_log_joint: variance path not built yet");
+        return VBMC_ERR_UNSUPPORTED;
+    }
+    return VBMC_OK;
+}
+
+static int spec_from_in(const vbmc_elcbo_in *in, Spec *s) {
+    VBMC_REQUIRE(in, VBMC_ERR_ARG, "negelcbo: null input");
+    VBMC_REQUIRE(!(in->separate_K && in->compute_grad), VBMC_ERR_ARG,
+                 "gradient and per-component results requested together (reference raises ValueError at :1114-1118)");
+    s->vp = in->vp;
+    for (int i = 0; i < 4; ++i) {
+        s->optimize[i] = in->optimize[i] != 0;
+        s->grad[i] = in->compute_grad ? s->optimize[i] : 0;
+    }
+    s->jacobian = 1;
+    s->ln_sigma_b = in->ln_sigma_b, s->ln_lambd_b = in->ln_lambd_b, s->eta_b = in->eta_b;
+    s->Ns = in->Ns;
+    s->use_bounds = in->use_bounds != 0;
+    s->rng_mode = in->rng_mode, s->eps = in->eps, s->seed = in->seed, s->offset = in->offset;
+    s->precision = in->precision;
+    return VBMC_OK;
+}
+
+int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
+    VBMC_REQUIRE(p && in && out, VBMC_ERR_ARG, "negelcbo: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    Spec s;
+    VBMC_TRY(spec_from_in(in, &s));
+    if (in->compute_var) {
+        set_error("neg_elcbo: variance path not built yet");
+        return VBMC_ERR_UNSUPPORTED;
+    }
+    const int D = in->vp.D, K = in->vp.K;
+    const int P = packed_len(D, K, s.grad);
+    const size_t Pfull = RawLayout{D, K}.block();
+    VBMC_TRY(run_single(x, s, kOutHead + (in->compute_grad ? 2 * Pfull : 0)));
+    const double *o = c->h_out;
+    if (o[7] != 0.0 && s.precision == VBMC_PREC_F32 && s.Ns > 0) {
+        // fp32 density ratios overflowed (or a weight underflowed): redo the entropy in fp64 on the GPU
+        s.precision = VBMC_PREC_F64;
+        VBMC_TRY(run_single(x, s, kOutHead + (in->compute_grad ? 2 * Pfull : 0)));
+        o = c->h_out;
+    }
+    out->F = o[0], out->G = o[1], out->H = o[2], out->varF = 0.0, out->varG_ss = 0.0;
+    if (in->compute_grad) {
+        if (out->dF)
+            for (int i = 0; i < P; ++i) out->dF[i] = o[kOutHead + i];
+        if (out->dH)
+            for (int i = 0; i < P; ++i) out->dH[i] = o[kOutHead + Pfull + i];
+    }
+    if (in->separate_K && out->I_sk) {
+        RawLayout rl{D, K};
+        std::vector<double> gps((size_t)c->S * (1 + Pfull));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(gps.data(), c->d_gps, gps.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int si = 0; si < c->S; ++si)
+            for (int k = 0; k < K; ++k) out->I_sk[(size_t)si * K + k] = gps[(size_t)si * (1 + Pfull) + 1 + rl.o_w() + k];
+    }
+    return VBMC_OK;
+}
+
+size_t vbmc_raw_len(int D, int K) { return (size_t)RawLayout{D, K}.total(); }
+size_t vbmc_out_len(int D, int K) { return (size_t)kOutHead + 3 * (size_t)RawLayout{D, K}.block() + (size_t)K * D; }
+
+int vbmc_negelcbo_upload(vbmc_ctx *p, const vbmc_elcbo_in *in) {
+    VBMC_REQUIRE(p && in, VBMC_ERR_ARG, "negelcbo_upload: null argument");
+    CtxEx *x = ex(p);
+    Bind b(&x->c);
+    Spec s;
+    VBMC_TRY(spec_from_in(in, &s));
+    VBMC_REQUIRE(!in->compute_var, VBMC_ERR_UNSUPPORTED, "split-phase evaluation does not cover the variance path");
+    return stage(x, s);
+}
+
+int vbmc_negelcbo_partials_async(vbmc_ctx *p, int rank, int world, double *raw_dev) {
+    VBMC_REQUIRE(p && raw_dev, VBMC_ERR_ARG, "partials: null argument");
+    CtxEx *x = ex(p);
+    Bind b(&x->c);
+    return partials(x, rank, world, raw_dev);
+}
+
+int vbmc_negelcbo_finalize_async(vbmc_ctx *p, const double *raw_dev, double *out_dev) {
+    VBMC_REQUIRE(p && raw_dev && out_dev, VBMC_ERR_ARG, "finalize: null argument");
+    CtxEx *x = ex(p);
+    Bind b(&x->c);
+    return finalize(x, raw_dev, out_dev);
+}
+
+int vbmc_stream_synchronize(vbmc_ctx *p) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
+    Bind b(&ex(p)->c);
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(ex(p)->c.stream));
+    return VBMC_OK;
+}
+
+int vbmc_entmc_kernel_ms(vbmc_ctx *p, double *avg_ms, int64_t *launches) {
+    VBMC_REQUIRE(p && avg_ms && launches, VBMC_ERR_ARG, "null argument");
+    Ctx *c = &ex(p)->c;
+    *launches = c->entmc_ms_n;
+    *avg_ms = c->entmc_ms_n ? c->entmc_ms_sum / (double)c->entmc_ms_n : 0.0;
+    c->entmc_ms_sum = 0, c->entmc_ms_n = 0;
+    return VBMC_OK;
+}
+
+int vbmc_set_kernel_timing(vbmc_ctx *p, int on) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
+    Ctx *c = &ex(p)->c;
+    c->time_entmc = on != 0;
+    c->entmc_ms_sum = 0, c->entmc_ms_n = 0;
+    return VBMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// common.cuh -- shared declarations of the vbmc_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/vbmc_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "vbmc_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace vbmc {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const std::string &msg);
+#define VBMC_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::vbmc::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +  \
+                              __FILE__ + ":" + std::to_string(__LINE__) + ")");            \
+            return VBMC_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+#define VBMC_REQUIRE(cond, code, msg)   \
+    do {                                \
+        if (!(cond)) {                  \
+            ::vbmc::set_error(msg);     \
+            return code;                \
+        }                               \
+    } while (0)
+#define VBMC_TRY(expr)              \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != VBMC_OK) return _rc; \
+    } while (0)
+
+// ----------------------------------------------------------------------------- layout
+// D is padded to a multiple of 4 (DP) so that per-dimension tables are float4/double2
+// addressable and register arrays have a compile-time size.
+static inline int pad_dim(int D) {
+    const int opts[] = {4, 8, 12, 16, 20, 24, 28, 32};
+    for (int o : opts)
+        if (D <= o) return o;
+    return -1;
+}
+constexpr int kMaxD = 32;
+
+// processed hyper-parameter record per GP sample s (doubles), see ctx.cu:pack_hyp
+//   [0..DP)        ell_d
+//   [DP..2DP)      xm_d          (negquad mean)
+//   [2DP..3DP)     1/omega_d^2   (negquad mean)
+//   [3DP+0]        ln sf^2
+//   [3DP+1]        sum_d ln ell_d
+//   [3DP+2]        m0
+//   [3DP+3]        sn2_eff
+//   [3DP+4]        L_chol (0/1)
+static inline int hyp_stride(int DP) { return 3 * DP + 8; }
+
+// device parameter block (doubles): what the kernels read for one evaluation
+struct ParamLayout {
+    int D, DP, K;
+    __host__ __device__ int mu() const { return 0; }                  // [K][D] component-major
+    __host__ __device__ int sigma() const { return K * D; }           // [K]
+    __host__ __device__ int lambd() const { return K * D + K; }       // [D]
+    __host__ __device__ int w() const { return K * D + K + D; }       // [K]
+    __host__ __device__ int eta() const { return K * D + 2 * K + D; } // [K]
+    __host__ __device__ int lnsig_b() const { return K * D + 3 * K + D; }     // [K]
+    __host__ __device__ int lnlam_b() const { return K * D + 4 * K + D; }     // [D]
+    __host__ __device__ int eta_b() const { return K * D + 4 * K + 2 * D; }   // [K]
+    __host__ __device__ int total() const { return K * D + 5 * K + 2 * D; }
+};
+
+// raw (pre-Jacobian) vector exchanged between ranks:  [H, G, flag, 0 | ent block | gp block]
+// each block = [gmu (K*D) | gsig (K) | glam (D) | gw (K)]
+struct RawLayout {
+    int D, K;
+    __host__ __device__ int block() const { return K * D + 2 * K + D; }
+    __host__ __device__ int ent() const { return 4; }
+    __host__ __device__ int gp() const { return 4 + block(); }
+    __host__ __device__ int total() const { return 4 + 2 * block(); }
+    __host__ __device__ int o_mu() const { return 0; }
+    __host__ __device__ int o_sig() const { return K * D; }
+    __host__ __device__ int o_lam() const { return K * D + K; }
+    __host__ __device__ int o_w() const { return K * D + K + D; }
+};
+
+// out vector:  [F, G, H, varF, varG_ss, Lbound, Lpen, nonfinite | dF (Pfull) | dH (Pfull) | dG (Pfull)]
+constexpr int kOutHead = 8;
+
+// entmc per-CTA partial record (doubles): [hacc | A (DP) | Be (DP) | racc (K)]
+static inline int entpart_stride(int DP, int K) { return 1 + 2 * DP + K; }
+// gplj per-(s,k) record (doubles): [U | M (DP) | Q2 (DP)]
+static inline int gppart_stride(int DP) { return 1 + 2 * DP; }
+
+struct EvalFlags {
+    int grad[4];       // which gradient groups are wanted
+    int jacobian;      // apply log / softmax Jacobians
+    int use_ent_mc;    // 1: entmc partials present, 0: entlb raw already in place
+    int have_ent, have_gp;
+    int use_bounds;
+    int optimize[4];
+    int avg;
+};
+
+// ----------------------------------------------------------------------------- context
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // GP pack
+    bool has_gp = false, has_L = false;
+    int gD = 0, gDP = 0, N = 0, S = 0, mean_kind = VBMC_MEAN_NEGQUAD;
+    double *d_Xt = nullptr;    // [DP][N] transposed, padded rows are zero
+    double *d_alpha = nullptr; // [S][N]
+    double *d_hyp = nullptr;   // [S][hyp_stride]
+    double *d_L = nullptr;     // [S][N][N]
+    double *d_Linv = nullptr;  // lazily built for the variance path
+
+    // bounds
+    int n_bnd = 0;
+    double *d_lb = nullptr, *d_ub = nullptr;
+    size_t bnd_cap = 0;
+    double tol_con = 0, w_thr = 0, w_pen = 0;
+
+    // per-evaluation buffers (grown on demand)
+    double *d_in = nullptr, *h_in = nullptr;
+    size_t in_cap = 0;
+    double *d_entpart = nullptr;
+    size_t entpart_cap = 0;
+    double *d_gppart = nullptr;
+    size_t gppart_cap = 0;
+    double *d_gps = nullptr; // [S][1 + block] per-sample raw log-joint terms
+    size_t gps_cap = 0;
+    double *d_raw = nullptr;
+    size_t raw_cap = 0;
+    double *d_out = nullptr, *h_out = nullptr;
+    size_t out_cap = 0;
+    double *d_eps = nullptr;
+    size_t eps_cap = 0;
+    double *d_lbws = nullptr; // entlb workspace
+    size_t lbws_cap = 0;
+    double *d_var = nullptr;  // variance-path workspace
+    size_t var_cap = 0;
+
+    // state of the evaluation uploaded by vbmc_negelcbo_upload
+    bool staged = false;
+    int D = 0, DP = 0, K = 0;
+    vbmc_elcbo_in cur{};
+    int ent_grid_slabs = 0;
+
+    // entmc kernel timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool time_entmc = false;
+    double entmc_ms_sum = 0;
+    int64_t entmc_ms_n = 0;
+};
+
+int ensure(double **p, size_t *cap, size_t need);
+int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
+
+// ----------------------------------------------------------------------------- launchers
+// entmc.cu
+struct EntmcPlan {
+    int threads, slabs, pairs_per_thread;
+    int64_t half;      // pairs per component handled by THIS rank
+    int64_t pair0;     // first pair index (global) of this rank's range
+    int64_t half_glob; // pairs per component over all ranks (Ns/2)
+    size_t smem;
+};
+int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int precision, EntmcPlan *plan);
+int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &plan, bool anygrad,
+                 bool wgrad, int precision, int rng_mode, const double *d_eps, uint64_t seed,
+                 uint64_t offset, double *d_part);
+int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
+
+// gplj.cu
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part);
+int gpvar_launch(Ctx *c, const double *d_params, int K, double *d_J /*[S][K][K]*/);
+
+// entlb.cu
+int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4], double *d_raw_ent /*H at [0], block*/,
+                 double *d_H);
+
+// finalize.cu
+int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw);
+int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
+                    double *d_out);
+int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s);
+
+// ----------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum, result valid in every thread; scratch must hold 32 doubles
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < nw; ++i) r += scratch[i];  // fixed order: deterministic
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = scratch[0];
+    for (int i = 1; i < nw; ++i) r = fmax(r, scratch[i]);
+    return r;
+}
+#endif
+
+}  // namespace vbmc

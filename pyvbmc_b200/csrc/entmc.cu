@@ -1,0 +1,385 @@
+// entmc.cu -- Monte-Carlo mixture entropy and its reparameterisation gradient.
+//
+// Replaces the NumPy loop of pyvbmc/entropy/entmc_vbmc.py:64-112 (reference).
+//
+// Work decomposition
+//   grid = (slabs, K); CTA (slab, j) owns a contiguous range of ANTITHETIC PAIRS of
+//   component j.  One thread evaluates one pair (+eps, -eps) at a time: the pair shares the
+//   noise registers e_d = sigma_j*eps_d and every shared-memory load of the component table.
+//
+// Arithmetic (scaled coordinates y = x / lambda, so that lambda drops out of the distances)
+//   Delta_kd = (mu_dj - mu_dk) / lambda_d                      (fp64 -> T, exact for k == j)
+//   t(+-)_kd = Delta_kd +- e_d                                  = (x_d - mu_dk) / lambda_d
+//   s_k      = D log2(sigma_j/sigma_k) - h_k |t_k|^2 + h_j |e|^2,   h_k = log2(e) / (2 sigma_k^2)
+//            = log2( N_k(x) / N_j(x) )      -> the own component is the log-sum-exp reference
+//              point: u_j = 1, every other u_k = 2^s_k is a density RATIO under x ~ N_j, whose
+//              mean is 1 (overflow needs a 2^127-sigma event; checked downstream via isfinite).
+//   q_rel    = sum_k w_k u_k ,  log q(x) = ln N_j(x) + ln q_rel
+//   l_d      = sum_k (w_k u_k / sigma_k^2) t_kd      ( = lambda_d * lsum_d / N_j(x),  :93-95 )
+//   per pair:  hacc += log q(x+) + log q(x-)
+//              A_d  += l+_d/q+ + l-_d/q-                  (-> d/dmu_j,            :98)
+//              Be_d += e_d (l+_d/q+ - l-_d/q-)            (-> d/dsigma_j, d/dlambda :102-108)
+//              racc_k += u+_k/q+ + u-_k/q-                (-> d/dw_k,             :112)
+//   Per-thread running sums live in shared memory columns (no bank conflicts, no atomics);
+//   each CTA writes ONE record [hacc | A | Be | racc] of fp64 partial sums, reduced in fixed
+//   order by reduce_kernel (finalize.cu) => bitwise run-to-run determinism.
+//
+// T = float : fp32 compute, fp64 accumulation across threads (default, ~6D+10 FP32-pipe
+//             instructions per (pair, k)).   T = double: everything fp64 (validation mode).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace vbmc {
+
+namespace {
+
+template <typename T>
+struct M;
+template <>
+struct M<float> {
+    static __device__ __forceinline__ float ex2(float x) {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ double lg2(float x) { return (double)log2f(x); }
+};
+template <>
+struct M<double> {
+    static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double lg2(double x) { return log2(x); }
+};
+
+template <typename T>
+struct alignas(16) KConst {
+    T ck, h, w, wis2;
+};
+
+template <typename T, int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128)
+entmc_kernel(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
+             int R, const double *__restrict__ eps, uint64_t seed, uint64_t offset, double *__restrict__ part,
+             int part_stride) {
+    constexpr bool kKeepT = sizeof(T) == 4;  // fp32: keep t(+-) in registers; fp64: recompute
+    const int D = lay.D, K = lay.K;
+    const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sDl = reinterpret_cast<T *>(smem_raw);                        // [K][DP]
+    KConst<T> *sKc = reinterpret_cast<KConst<T> *>(sDl + K * DP);    // [K]
+    T *sAcc = reinterpret_cast<T *>(sKc + K);                        // accA [DP][nt], accB [DP][nt]
+    T *sU = sAcc + (ANYGRAD ? 2 * DP * nt : 0);                      // Up [K][nt], Um [K][nt], racc [K][nt]
+    double *scratch = reinterpret_cast<double *>(sU + (WGRAD ? 3 * K * nt : 0));  // [32] (16B aligned by sizes)
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double sig_j = sigma[j];
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    // ---- component tables ---------------------------------------------------------------
+    for (int i = tid; i < K * DP; i += nt) {
+        const int k = i / DP, d = i - k * DP;
+        sDl[i] = (d < D) ? (T)((mu[j * D + d] - mu[k * D + d]) / lambd[d]) : (T)0;
+    }
+    for (int k = tid; k < K; k += nt) {
+        const double sk = sigma[k];
+        KConst<T> c;
+        c.ck = (T)(D * (log2(sig_j) - log2(sk)));
+        c.h = (T)(kHalfLog2e / (sk * sk));
+        c.w = (T)w[k];
+        c.wis2 = (T)(w[k] / (sk * sk));
+        sKc[k] = c;
+    }
+    if (ANYGRAD)
+        for (int i = tid; i < 2 * DP * nt; i += nt) sAcc[i] = (T)0;
+    if (WGRAD)
+        for (int i = tid; i < K * nt; i += nt) sU[2 * K * nt + i] = (T)0;
+    __syncthreads();
+
+    T *accA = sAcc + tid, *accB = sAcc + DP * nt + tid;
+    T *Up = sU + tid, *Um = sU + K * nt + tid, *racc = sU + 2 * K * nt + tid;
+    const T hj = (T)(kHalfLog2e / (sig_j * sig_j));
+    const double is2j = 1.0 / (sig_j * sig_j);
+    const T sj = (T)sig_j;
+    double hacc = 0.0;
+
+    const int64_t slab_base = (int64_t)slab * nt * R;
+    for (int r = 0; r < R; ++r) {
+        const int64_t p = slab_base + (int64_t)r * nt + tid;  // local pair index
+        if (p >= half) break;                                  // no barriers inside the loop
+        const int64_t gpair = pair0 + p;
+
+        T e[DP];
+        if (PHILOX) {
+            float z[DP];
+            philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)gpair, D, z);
+#pragma unroll
+            for (int d = 0; d < DP; ++d) e[d] = sj * (T)z[d];
+        } else {
+            const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) e[d] = (d < D) ? sj * (T)__ldg(ep + d) : (T)0;
+        }
+        T e2a = 0, e2b = 0;
+#pragma unroll
+        for (int d = 0; d < DP; d += 2) {
+            e2a = fma(e[d], e[d], e2a);
+            e2b = fma(e[d + 1], e[d + 1], e2b);
+        }
+        const T e2 = e2a + e2b;
+        const T base = hj * e2;
+
+        T lp[ANYGRAD ? DP : 1], lm[ANYGRAD ? DP : 1];
+        if (ANYGRAD) {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) lp[d] = lm[d] = (T)0;
+        }
+        T qp = 0, qm = 0;
+
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const KConst<T> c = sKc[k];
+            const T *dl = sDl + k * DP;
+            T tp[kKeepT ? DP : 1], tm[kKeepT ? DP : 1];
+            T a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+            for (int d = 0; d < DP; d += 2) {
+                const T x0 = dl[d] + e[d], y0 = dl[d] - e[d];
+                const T x1 = dl[d + 1] + e[d + 1], y1 = dl[d + 1] - e[d + 1];
+                if (kKeepT) {
+                    tp[d] = x0, tm[d] = y0, tp[d + 1] = x1, tm[d + 1] = y1;
+                }
+                a0 = fma(x0, x0, a0), b0 = fma(y0, y0, b0);
+                a1 = fma(x1, x1, a1), b1 = fma(y1, y1, b1);
+            }
+            const T cb = c.ck + base;
+            const T up = M<T>::ex2(fma(-c.h, a0 + a1, cb));
+            const T um = M<T>::ex2(fma(-c.h, b0 + b1, cb));
+            if (WGRAD) {
+                Up[k * nt] = up;
+                Um[k * nt] = um;
+            }
+            qp = fma(c.w, up, qp);
+            qm = fma(c.w, um, qm);
+            if (ANYGRAD) {
+                const T gp = c.wis2 * up, gm = c.wis2 * um;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) {
+                    const T x = kKeepT ? tp[d] : dl[d] + e[d];
+                    const T y = kKeepT ? tm[d] : dl[d] - e[d];
+                    lp[d] = fma(gp, x, lp[d]);
+                    lm[d] = fma(gm, y, lm[d]);
+                }
+            }
+        }
+
+        // log q(x+) + log q(x-)  without the per-component constant (added by reduce_kernel)
+        hacc += 0.69314718055994530942 * (M<T>::lg2(qp) + M<T>::lg2(qm)) - (double)e2 * is2j;
+        if (ANYGRAD) {
+            const T iqp = M<T>::rcp(qp), iqm = M<T>::rcp(qm);
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                const T a = lp[d] * iqp, b = lm[d] * iqm;
+                accA[d * nt] += a + b;
+                accB[d * nt] += e[d] * (a - b);
+            }
+            if (WGRAD) {
+                for (int k = 0; k < K; ++k) racc[k * nt] += fma(Up[k * nt], iqp, Um[k * nt] * iqm);
+            }
+        }
+    }
+
+    // ---- CTA record: fixed-order fp64 reduction over the thread columns ------------------
+    double *rec = part + ((size_t)j * gridDim.x + slab) * (size_t)part_stride;
+    const double hs = block_sum(hacc, scratch);
+    if (tid == 0) rec[0] = hs;
+    if (ANYGRAD) {
+        __syncthreads();
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        const int rows = 2 * DP + (WGRAD ? K : 0);
+        for (int row = wid; row < rows; row += nw) {
+            const T *src = (row < 2 * DP) ? (sAcc + row * nt) : (sU + 2 * K * nt + (row - 2 * DP) * nt);
+            double v = 0.0;
+            for (int c = lane; c < nt; c += 32) v += (double)src[c];
+            v = warp_sum(v);
+            if (lane == 0) rec[1 + row] = v;
+        }
+    }
+}
+
+template <typename T>
+size_t entmc_smem(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    size_t b = (size_t)K * DP * sizeof(T) + (size_t)K * sizeof(KConst<T>);
+    if (anygrad) b += (size_t)2 * DP * nt * sizeof(T);
+    if (wgrad) b += (size_t)3 * K * nt * sizeof(T);
+    b = (b + 15) & ~(size_t)15;
+    return b + 32 * sizeof(double);
+}
+
+template <typename T, int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, const double *d_eps,
+                uint64_t seed, uint64_t offset, double *d_part) {
+    auto kern = entmc_kernel<T, DP, WGRAD, ANYGRAD, PHILOX>;
+    VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    dim3 grid(plan.slabs, lay.K);
+    if (c->time_entmc) VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
+                                                       plan.pairs_per_thread, d_eps, seed, offset, d_part,
+                                                       entpart_stride(DP, lay.K));
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    if (c->time_entmc) {
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+        VBMC_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        VBMC_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->entmc_ms_sum += ms;
+        c->entmc_ms_n++;
+    }
+    return VBMC_OK;
+}
+
+template <typename T, int DP>
+int launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool wgrad,
+              bool philox, const double *d_eps, uint64_t seed, uint64_t offset, double *d_part) {
+#define VBMC_GO(W, A, P) return launch_inst<T, DP, W, A, P>(c, d_params, lay, plan, d_eps, seed, offset, d_part)
+    if (wgrad) {
+        if (philox) VBMC_GO(true, true, true);
+        VBMC_GO(true, true, false);
+    }
+    if (anygrad) {
+        if (philox) VBMC_GO(false, true, true);
+        VBMC_GO(false, true, false);
+    }
+    if (philox) VBMC_GO(false, false, true);
+    VBMC_GO(false, false, false);
+#undef VBMC_GO
+}
+
+template <typename T>
+int launch_t(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool wgrad,
+             bool philox, const double *d_eps, uint64_t seed, uint64_t offset, double *d_part) {
+    switch (lay.DP) {
+#define VBMC_CASE(N) \
+    case N:          \
+        return launch_dp<T, N>(c, d_params, lay, plan, anygrad, wgrad, philox, d_eps, seed, offset, d_part)
+        VBMC_CASE(4);
+        VBMC_CASE(8);
+        VBMC_CASE(12);
+        VBMC_CASE(16);
+        VBMC_CASE(20);
+        VBMC_CASE(24);
+        VBMC_CASE(28);
+        VBMC_CASE(32);
+#undef VBMC_CASE
+    }
+    set_error("entmc: unsupported padded dimension");
+    return VBMC_ERR_UNSUPPORTED;
+}
+
+template <int DP>
+__global__ void philox_dump_kernel(int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)K * half) return;
+    const int j = (int)(i / half);
+    const int64_t p = i - (int64_t)j * half;
+    float z[DP];
+    philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)p, D, z);
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+        if (d < D) out[(size_t)i * D + d] = (double)z[d];
+}
+
+}  // namespace
+
+// Choose threads / pairs-per-thread so that the grid is a whole number of waves of the
+// resident-CTA capacity whenever possible (148 SMs x CTAs that fit by shared memory).
+int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int precision, EntmcPlan *plan) {
+    const int DP = pad_dim(D);
+    VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "entmc: D > 32 is not supported");
+    VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
+    const size_t smem_cap = 227 * 1024;
+    int nt = 128;
+    auto smem_of = [&](int t) {
+        return precision == VBMC_PREC_F64 ? entmc_smem<double>(DP, K, t, wgrad, true)
+                                          : entmc_smem<float>(DP, K, t, wgrad, true);
+    };
+    while (nt > 32 && smem_of(nt) > smem_cap) nt >>= 1;
+    VBMC_REQUIRE(smem_of(nt) <= smem_cap, VBMC_ERR_UNSUPPORTED, "entmc: K too large for shared memory");
+    const size_t smem = smem_of(nt);
+    int per_sm = (int)(smem_cap / (smem + 1024));
+    const int reg_limit = precision == VBMC_PREC_F64 ? (nt >= 128 ? 2 : 4) : (nt >= 128 ? 3 : 6);
+    if (per_sm > reg_limit) per_sm = reg_limit;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t slots = (int64_t)c->sm_count * per_sm;
+
+    // candidate R: cost ~ waves * (R + overhead); overhead ~ table set-up + record reduction
+    int bestR = 1;
+    double best = 1e300;
+    const double overhead = 0.35;
+    for (int R = 1; R <= 64; ++R) {
+        const int64_t slabs = (half_local + (int64_t)nt * R - 1) / ((int64_t)nt * R);
+        const int64_t ctas = slabs * K;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (R + overhead);
+        if (cost < best - 1e-9) best = cost, bestR = R;
+        if (slabs <= 1) break;
+    }
+    plan->threads = nt;
+    plan->pairs_per_thread = bestR;
+    plan->slabs = (int)((half_local + (int64_t)nt * bestR - 1) / ((int64_t)nt * bestR));
+    if (plan->slabs < 1) plan->slabs = 1;
+    plan->half = half_local;
+    plan->pair0 = 0;
+    plan->half_glob = half_local;
+    plan->smem = smem;
+    return VBMC_OK;
+}
+
+int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &plan, bool anygrad, bool wgrad,
+                 int precision, int rng_mode, const double *d_eps, uint64_t seed, uint64_t offset, double *d_part) {
+    ParamLayout lay{D, pad_dim(D), K};
+    const bool philox = rng_mode == VBMC_RNG_PHILOX;
+    VBMC_REQUIRE(philox || d_eps != nullptr, VBMC_ERR_ARG, "entmc: eps required in VBMC_RNG_EPS mode");
+    VBMC_REQUIRE(plan.half_glob < ((int64_t)1 << 32), VBMC_ERR_UNSUPPORTED, "entmc: more than 2^32 pairs per component");
+    // smem of the plan was sized for anygrad; recompute for the actual instantiation
+    EntmcPlan p = plan;
+    p.smem = precision == VBMC_PREC_F64 ? entmc_smem<double>(lay.DP, K, plan.threads, wgrad, anygrad)
+                                        : entmc_smem<float>(lay.DP, K, plan.threads, wgrad, anygrad);
+    if (precision == VBMC_PREC_F64)
+        return launch_t<double>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
+    return launch_t<float>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
+}
+
+int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps) {
+    const int DP = pad_dim(D);
+    VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "philox: D > 32 is not supported");
+    const int64_t n = (int64_t)K * half;
+    if (n == 0) return VBMC_OK;
+    const int nt = 128;
+    const unsigned grid = (unsigned)((n + nt - 1) / nt);
+    switch (DP) {
+#define VBMC_CASE(N)                                                                               \
+    case N:                                                                                        \
+        philox_dump_kernel<N><<<grid, nt, 0, c->stream>>>(D, K, half, seed, offset, d_eps);        \
+        break
+        VBMC_CASE(4);
+        VBMC_CASE(8);
+        VBMC_CASE(12);
+        VBMC_CASE(16);
+        VBMC_CASE(20);
+        VBMC_CASE(24);
+        VBMC_CASE(28);
+        VBMC_CASE(32);
+#undef VBMC_CASE
+    }
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+}  // namespace vbmc

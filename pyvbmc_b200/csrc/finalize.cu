@@ -1,0 +1,469 @@
+// finalize.cu -- fixed-order reduction of the kernel partials into the RAW vector, and the
+// final assembly (Jacobians, soft-bound loss, weight penalty) of F and dF.
+//
+//   reduce_kernel   : entmc CTA records + gplj (s,k) records  ->  raw = [H, G, .. | ent | gp]
+//                     (raw = pre-Jacobian sums, already scaled by the GLOBAL 1/Ns and 1/S, so a
+//                      SUM all-reduce over ranks yields the single-GPU value)
+//   finalize_kernel : raw -> out = [F, G, H, .., | dF | dH | dG]
+//                     log/softmax Jacobians  entmc_vbmc.py:114-130, variational_optimization.py:1522-1548
+//                     soft bounds            variational_optimization.py:503-657 (incl. the row-major
+//                                            reshape of the column-major ln-scale block at :584-586)
+//                     weight penalty         variational_optimization.py:1212-1229
+// Both are single-CTA kernels: O(S K D) work, fp64, deterministic summation order.
+#include "common.cuh"
+
+namespace vbmc {
+namespace {
+
+constexpr double kLog2Pi = 1.8378770664093454836;
+
+struct ReduceArgs {
+    ParamLayout lay;
+    RawLayout rl;
+    EvalFlags f;
+    // entmc
+    const double *entpart;
+    int slabs, ent_stride;
+    double Ns_glob;     // draws per component over all ranks
+    double draws_local; // draws per component on this rank
+    // gp
+    const double *gppart;
+    const double *hyp;
+    int hs, s_begin, s_step, S, S_glob;
+    int mean_kind;
+    double *gps;  // [S][1 + block]
+    double *raw;
+};
+
+__global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ prm, ReduceArgs a) {
+    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double scratch[32];
+    const double *mu = prm + a.lay.mu(), *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(),
+                 *w = prm + a.lay.w();
+    double *raw = a.raw;
+    const RawLayout rl = a.rl;
+
+    // raw[0] (H) is written by the entlb kernels when the deterministic entropy is used
+    if (tid < 4 && !(tid == 0 && a.f.have_ent && !a.f.use_ent_mc)) raw[tid] = 0.0;
+    if (!a.f.have_ent)
+        for (int e = tid; e < rl.block(); e += nt) raw[rl.ent() + e] = 0.0;
+    if (!a.f.have_gp)
+        for (int e = tid; e < rl.block(); e += nt) raw[rl.gp() + e] = 0.0;
+    __syncthreads();
+
+    // ------------------------------------------------------------------ Monte-Carlo entropy
+    if (a.f.have_ent && a.f.use_ent_mc) {
+        const double inv_ns = 1.0 / a.Ns_glob;
+        const int st = a.ent_stride;
+        double *ent = raw + rl.ent();
+        double sumlnl = 0.0;
+        for (int d = 0; d < D; ++d) sumlnl += log(lambd[d]);
+        // H and the direct part of d/dw_j
+        double hpart = 0.0;
+        for (int j = tid; j < K; j += nt) {
+            double hs = 0.0;
+            for (int s = 0; s < a.slabs; ++s) hs += a.entpart[((size_t)j * a.slabs + s) * st];
+            const double lnC = -0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]);
+            hs += a.draws_local * lnC;  // sum_i log q(x_ji) over this rank's draws
+            hpart -= w[j] * hs * inv_ns;
+            ent[rl.o_w() + j] = -hs * inv_ns;  // entmc_vbmc.py:111
+        }
+        hpart = block_sum(hpart, scratch);
+        if (tid == 0) raw[0] = hpart;  // entmc_vbmc.py:80
+        if (a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3]) {
+            // d/dmu_j  (:98)
+            for (int e = tid; e < K * D; e += nt) {
+                const int j = e / D, d = e - j * D;
+                double v = 0.0;
+                for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + 1 + d];
+                ent[rl.o_mu() + e] = w[j] * v * inv_ns / lambd[d];
+            }
+            // d/dsigma_j  (:102-103)
+            for (int j = tid; j < K; j += nt) {
+                double v = 0.0;
+                for (int d = 0; d < D; ++d)
+                    for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + 1 + DP + d];
+                ent[rl.o_sig() + j] = w[j] * v * inv_ns / sigma[j];
+            }
+            // d/dlambda_d  (:106-108)
+            for (int d = tid; d < D; d += nt) {
+                double v = 0.0;
+                for (int j = 0; j < K; ++j) {
+                    double u = 0.0;
+                    for (int s = 0; s < a.slabs; ++s) u += a.entpart[((size_t)j * a.slabs + s) * st + 1 + DP + d];
+                    v += w[j] * u;
+                }
+                ent[rl.o_lam() + d] = v * inv_ns / lambd[d];
+            }
+            __syncthreads();
+            // d/dw_k  cross term  -sum_j w_j E_j[N_k / q]  (:112)
+            if (a.f.grad[3]) {
+                for (int k = tid; k < K; k += nt) {
+                    double v = 0.0;
+                    for (int j = 0; j < K; ++j) {
+                        double u = 0.0;
+                        for (int s = 0; s < a.slabs; ++s)
+                            u += a.entpart[((size_t)j * a.slabs + s) * st + 1 + 2 * DP + k];
+                        v += w[j] * u;
+                    }
+                    ent[rl.o_w() + k] -= v * inv_ns;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ GP expected log joint
+    if (a.f.have_gp) {
+        const int gst = 1 + 2 * DP;
+        const int blk = rl.block();
+        const bool quad = a.mean_kind == VBMC_MEAN_NEGQUAD, zero = a.mean_kind == VBMC_MEAN_ZERO;
+        const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+        for (int s = a.s_begin; s < a.S; s += a.s_step) {
+            const double *h = a.hyp + (size_t)s * a.hs;
+            const double *ell = h, *xm = h + DP, *iom2 = h + 2 * DP;
+            const double m0 = zero ? 0.0 : h[3 * DP + 2];
+            double *gs = a.gps + (size_t)s * (1 + blk);
+            const double *rec_s = a.gppart + (size_t)s * K * gst;
+            // I_sk -> the w block (variational_optimization.py:1407-1428,1464-1465)
+            double gpart = 0.0;
+            for (int k = tid; k < K; k += nt) {
+                double I = rec_s[(size_t)k * gst] + m0;
+                if (quad) {
+                    const double s2 = sigma[k] * sigma[k];
+                    double nu = 0.0;
+                    for (int d = 0; d < D; ++d) {
+                        const double m = mu[k * D + d];
+                        nu += iom2[d] * (m * m + s2 * lambd[d] * lambd[d] - 2.0 * m * xm[d] + xm[d] * xm[d]);
+                    }
+                    I -= 0.5 * nu;
+                }
+                gs[1 + rl.o_w() + k] = I;
+                gpart += w[k] * I;
+            }
+            gpart = block_sum(gpart, scratch);
+            if (tid == 0) gs[0] = gpart;  // G_s (:1425)
+            if (anyg) {
+                // d/dmu (:1430-1436)
+                for (int e = tid; e < K * D; e += nt) {
+                    const int k = e / D, d = e - k * D;
+                    const double sl = sigma[k] * lambd[d];
+                    const double tau = sqrt(sl * sl + ell[d] * ell[d]);
+                    double g = -rec_s[(size_t)k * gst + 1 + d] / tau;
+                    if (quad) g -= iom2[d] * (mu[e] - xm[d]);
+                    gs[1 + rl.o_mu() + e] = w[k] * g;
+                }
+                // d/dsigma (:1438-1450)
+                for (int k = tid; k < K; k += nt) {
+                    const double U = rec_s[(size_t)k * gst];
+                    double acc = 0.0, accq = 0.0;
+                    for (int d = 0; d < D; ++d) {
+                        const double sl = sigma[k] * lambd[d];
+                        const double t2 = sl * sl + ell[d] * ell[d];
+                        acc += lambd[d] * lambd[d] / t2 * (rec_s[(size_t)k * gst + 1 + DP + d] - U);
+                        accq += lambd[d] * lambd[d] * iom2[d];
+                    }
+                    double g = sigma[k] * acc;
+                    if (quad) g -= sigma[k] * accq;
+                    gs[1 + rl.o_sig() + k] = w[k] * g;
+                }
+                // d/dlambda (:1452-1462)
+                for (int d = tid; d < D; d += nt) {
+                    double acc = 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        const double s2 = sigma[k] * sigma[k];
+                        const double t2 = s2 * lambd[d] * lambd[d] + ell[d] * ell[d];
+                        double g = s2 / t2 * lambd[d] * (rec_s[(size_t)k * gst + 1 + DP + d] - rec_s[(size_t)k * gst]);
+                        if (quad) g -= s2 * lambd[d] * iom2[d];
+                        acc += w[k] * g;
+                    }
+                    gs[1 + rl.o_lam() + d] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        // average over hyper-samples (:1578-1596); this rank contributes its own s / S_glob
+        const double inv_S = 1.0 / (double)a.S_glob;
+        for (int e = tid; e < blk + 1; e += nt) {
+            if (e > 0 && !anyg) break;
+            double v = 0.0;
+            for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * (1 + blk) + e];
+            v *= inv_S;
+            if (e == 0)
+                raw[1] = v;
+            else
+                raw[rl.gp() + e - 1] = v;
+        }
+    }
+}
+
+// Apply the reparameterisation Jacobians to one raw block and scatter it into theta order.
+// es = sum exp(eta), dot = sum exp(eta_k) gw_k.  Returns the packed length via *P (thread 0 view).
+__device__ __forceinline__ void pack_block(const double *__restrict__ blk, const RawLayout rl, const double *prm,
+                                           const ParamLayout lay, const int grad[4], int jac, double es, double dot,
+                                           double sign, double *__restrict__ dst, bool accumulate) {
+    const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
+    int off = 0;
+    if (grad[0]) {
+        for (int e = tid; e < K * D; e += nt) {
+            const double v = sign * blk[rl.o_mu() + e];
+            dst[off + e] = accumulate ? dst[off + e] + v : v;
+        }
+        off += K * D;
+    }
+    if (grad[1]) {
+        for (int k = tid; k < K; k += nt) {
+            double v = sign * blk[rl.o_sig() + k];
+            if (jac) v *= prm[lay.sigma() + k];
+            dst[off + k] = accumulate ? dst[off + k] + v : v;
+        }
+        off += K;
+    }
+    if (grad[2]) {
+        for (int d = tid; d < D; d += nt) {
+            double v = sign * blk[rl.o_lam() + d];
+            if (jac) v *= prm[lay.lambd() + d];
+            dst[off + d] = accumulate ? dst[off + d] + v : v;
+        }
+        off += D;
+    }
+    if (grad[3]) {
+        for (int k = tid; k < K; k += nt) {
+            double v = blk[rl.o_w() + k];
+            if (jac) {
+                const double ek = exp(prm[lay.eta() + k]);
+                v = ek / es * v - ek / (es * es) * dot;  // row k of J_w @ g   (entmc_vbmc.py:122-130)
+            }
+            v *= sign;
+            dst[off + k] = accumulate ? dst[off + k] + v : v;
+        }
+    }
+}
+
+struct FinalArgs {
+    ParamLayout lay;
+    RawLayout rl;
+    EvalFlags f;
+    const double *raw;
+    const double *lb, *ub;
+    int n_bnd;
+    double tol_con, w_thr, w_pen;
+    double *out;
+    int Pfull;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
+    const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double scratch[32];
+    const RawLayout rl = a.rl;
+    const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
+    double *out = a.out;
+    double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull, *tmp = dG + a.Pfull;  // tmp: [K*D]
+    const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+
+    // softmax pieces
+    double es = 0.0, dote = 0.0, dotg = 0.0;
+    if (anyg && a.f.grad[3] && a.f.jacobian) {
+        for (int k = tid; k < K; k += nt) {
+            const double ek = exp(eta[k]);
+            es += ek;
+            dote += ek * a.raw[rl.ent() + rl.o_w() + k];
+            dotg += ek * a.raw[rl.gp() + rl.o_w() + k];
+        }
+        es = block_sum(es, scratch);
+        dote = block_sum(dote, scratch);
+        dotg = block_sum(dotg, scratch);
+    }
+    if (anyg) {
+        pack_block(a.raw + rl.ent(), rl, prm, a.lay, a.f.grad, a.f.jacobian, es, dote, 1.0, dH, false);
+        pack_block(a.raw + rl.gp(), rl, prm, a.lay, a.f.grad, a.f.jacobian, es, dotg, 1.0, dG, false);
+        __syncthreads();
+        int P = 0;
+        if (a.f.grad[0]) P += K * D;
+        if (a.f.grad[1]) P += K;
+        if (a.f.grad[2]) P += D;
+        if (a.f.grad[3]) P += K;
+        for (int e = tid; e < P; e += nt) dF[e] = -dG[e] - dH[e];  // variational_optimization.py:1171-1173
+    }
+    __syncthreads();
+
+    // ---- soft bounds on [mu | ln sigma_k + ln lambda_d | eta]  (:503-657) -----------------
+    double Lb = 0.0, Lp = 0.0;
+    if (a.f.use_bounds && a.n_bnd > 0) {
+        const double *lnsig = prm + a.lay.lnsig_b(), *lnlam = prm + a.lay.lnlam_b(), *etab = prm + a.lay.eta_b();
+        const double *mu = prm + a.lay.mu();
+        const int n_mu = a.f.optimize[0] ? K * D : 0;
+        const int n_sc = K * D;
+        const int n_eta = a.f.optimize[3] ? K : 0;
+        // offsets of the groups in the packed gradient (grad == optimize when compute_grad)
+        int o_sig = n_mu, o_lam = o_sig + (a.f.optimize[1] ? K : 0), o_eta = o_lam + (a.f.optimize[2] ? D : 0);
+        for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) {
+            double x;
+            if (e < n_mu)
+                x = mu[e];
+            else if (e < n_mu + n_sc) {
+                const int i = e - n_mu, k = i / D, d = i - k * D;  // column-major (D,K) ravel (:557-562)
+                x = lnlam[d] + lnsig[k];
+            } else
+                x = etab[e - n_mu - n_sc];
+            const double lo = a.lb[e], hi = a.ub[e];
+            const double ell = (hi - lo) * a.tol_con;
+            double viol = 0.0;
+            if (x < lo)
+                viol = x - lo;
+            else if (x > hi)
+                viol = x - hi;
+            double dy = 0.0;
+            if (viol != 0.0) {
+                const double r = viol / ell;
+                Lb += 0.5 * r * r;
+                dy = viol / (ell * ell);
+            }
+            if (anyg) {
+                if (e < n_mu)
+                    dF[e] += dy;
+                else if (e < n_mu + n_sc)
+                    tmp[e - n_mu] = dy;
+                else
+                    dF[o_eta + (e - n_mu - n_sc)] += dy;
+            }
+        }
+        Lb = block_sum(Lb, scratch);
+        __syncthreads();
+        if (anyg) {
+            // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[a][b] = tmp[a*K + b]
+            if (a.f.optimize[1])
+                for (int b = tid; b < K; b += nt) {
+                    double v = 0.0;
+                    for (int r = 0; r < D; ++r) v += tmp[r * K + b];
+                    dF[o_sig + b] += v;
+                }
+            if (a.f.optimize[2])
+                for (int r = tid; r < D; r += nt) {
+                    double v = 0.0;
+                    for (int b = 0; b < K; ++b) v += tmp[r * K + b];
+                    dF[o_lam + r] += v;
+                }
+        }
+        // ---- weight penalty (:1212-1229) ---------------------------------------------------
+        if (a.f.optimize[3]) {
+            double es2 = 0.0, dot = 0.0;
+            for (int k = tid; k < K; k += nt) {
+                const double wk = w[k];
+                Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;
+                const double ek = exp(eta[k]);
+                es2 += ek;
+                dot += ek * (wk < a.w_thr ? a.w_pen : 0.0);
+            }
+            Lp = block_sum(Lp, scratch);
+            es2 = block_sum(es2, scratch);
+            dot = block_sum(dot, scratch);
+            __syncthreads();
+            if (anyg)
+                for (int k = tid; k < K; k += nt) {
+                    const double ek = exp(eta[k]);
+                    const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
+                    dF[o_eta + k] += ek / es2 * g - ek / (es2 * es2) * dot;
+                }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double H = a.raw[0], G = a.raw[1];
+        const double F = -G - H + Lb + Lp;
+        out[0] = F;
+        out[1] = G;
+        out[2] = H;
+        out[3] = 0.0;
+        out[4] = 0.0;
+        out[5] = Lb;
+        out[6] = Lp;
+        out[7] = isfinite(F) ? 0.0 : 1.0;
+    }
+}
+
+// per-hyper-sample Jacobians for avg_flag == 0: CTA s -> out_s[s] = [G_s | dG_s (P)]
+__global__ void __launch_bounds__(256)
+gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout rl, EvalFlags f,
+                    const double *__restrict__ gps, double *__restrict__ out_s, int Pfull) {
+    const int K = lay.K, s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double scratch[32];
+    const double *blk = gps + (size_t)s * (1 + rl.block()) + 1;
+    double *dst = out_s + (size_t)s * (1 + Pfull);
+    double es = 0.0, dot = 0.0;
+    if (f.grad[3] && f.jacobian) {
+        for (int k = tid; k < K; k += nt) {
+            const double ek = exp(prm[lay.eta() + k]);
+            es += ek;
+            dot += ek * blk[rl.o_w() + k];
+        }
+        es = block_sum(es, scratch);
+        dot = block_sum(dot, scratch);
+    }
+    if (tid == 0) dst[0] = blk[-1];
+    pack_block(blk, rl, prm, lay, f.grad, f.jacobian, es, dot, 1.0, dst + 1, false);
+}
+
+}  // namespace
+
+int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw) {
+    ReduceArgs a{};
+    const int DP = pad_dim(D);
+    a.lay = ParamLayout{D, DP, K};
+    a.rl = RawLayout{D, K};
+    a.f = f;
+    a.entpart = c->d_entpart;
+    if (plan) {
+        a.slabs = plan->slabs;
+        a.ent_stride = entpart_stride(DP, K);
+        a.Ns_glob = (double)Ns_glob;
+        a.draws_local = 2.0 * (double)plan->half;
+    }
+    a.gppart = c->d_gppart;
+    a.hyp = c->d_hyp;
+    a.hs = hyp_stride(DP);
+    a.s_begin = s_begin;
+    a.s_step = s_step;
+    a.S = c->S;
+    a.S_glob = S_glob;
+    a.mean_kind = c->mean_kind;
+    a.gps = c->d_gps;
+    a.raw = d_raw;
+    reduce_kernel<<<1, 256, 0, c->stream>>>(d_params, a);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
+                    double *d_out) {
+    FinalArgs a{};
+    a.lay = ParamLayout{D, pad_dim(D), K};
+    a.rl = RawLayout{D, K};
+    a.f = f;
+    a.raw = d_raw;
+    a.lb = c->d_lb;
+    a.ub = c->d_ub;
+    a.n_bnd = c->n_bnd;
+    a.tol_con = c->tol_con;
+    a.w_thr = c->w_thr;
+    a.w_pen = c->w_pen;
+    a.out = d_out;
+    a.Pfull = a.rl.block();
+    finalize_kernel<<<1, 256, 0, c->stream>>>(d_params, a);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s) {
+    ParamLayout lay{D, pad_dim(D), K};
+    RawLayout rl{D, K};
+    gps_finalize_kernel<<<c->S, 256, 0, c->stream>>>(d_params, lay, rl, f, c->d_gps, d_out_s, rl.block());
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+}  // namespace vbmc

@@ -1,0 +1,146 @@
+// gplj.cu -- GP-surrogate expected log joint (Bayesian quadrature) per hyper-sample and component.
+//
+// Replaces the S x K Python loop of pyvbmc/vbmc/variational_optimization.py:1374-1465 (reference).
+// All fp64: z . alpha is ill-conditioned on real GPs (sigma_f^2 ~ 1e4, sigma_n^2 ~ 1e-5).
+//
+// One CTA per (component k, hyper-sample s); threads stride over the N training points
+// (X is stored TRANSPOSED [D][N] by vbmc_gp_pack so that lanes read consecutive doubles).
+//   tau_kd   = sqrt(sigma_k^2 lambda_d^2 + ell_d^2)                                   (:1401)
+//   delta_dn = (mu_dk - X_nd) / tau_kd ,  z_n = exp(lnnf_k - 1/2 sum_d delta_dn^2)    (:1402-1406)
+//   U   = sum_n alpha_n z_n                      -> I_k = U + m0 + nu_k               (:1407-1424)
+//   M_d = sum_n alpha_n z_n delta_dn             -> d/dmu      = -w_k M_d / tau_kd    (:1430-1436)
+//   Q_d = sum_n alpha_n z_n delta_dn^2           -> d/dsigma, d/dlambda via (Q_d - U) (:1438-1462)
+// The (s,k) record [U | M | Q] is turned into G_s and raw gradients by reduce_kernel.
+#include "common.cuh"
+
+namespace vbmc {
+namespace {
+
+template <int DP, bool GRAD>
+__global__ void __launch_bounds__(128)
+gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__restrict__ Xt,
+            const double *__restrict__ alpha, const double *__restrict__ hyp, int hs, int N, int s_begin,
+            int s_step, double *__restrict__ part, double *__restrict__ Zout) {
+    const int D = lay.D, K = lay.K;
+    const int k = blockIdx.x, s = s_begin + blockIdx.y * s_step;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double s_itau[DP], s_mu[DP], s_red[4][1 + 2 * DP], s_lnnf;
+
+    const double *h = hyp + (size_t)s * hs;
+    if (tid < DP) {
+        double it = 0.0, m = 0.0;
+        if (tid < D) {
+            const double sg = prm[lay.sigma() + k], lm = prm[lay.lambd() + tid], el = h[tid];
+            it = 1.0 / sqrt(sg * sg * lm * lm + el * el);
+            m = prm[lay.mu() + k * D + tid];
+        }
+        s_itau[tid] = it;
+        s_mu[tid] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc += log(s_itau[d]);  // -sum ln tau
+        s_lnnf = h[3 * DP + 0] + h[3 * DP + 1] + acc;       // ln sf^2 + sum ln ell - sum ln tau
+    }
+    __syncthreads();
+    const double lnnf = s_lnnf;
+    const double *al = alpha + (size_t)s * N;
+
+    double U = 0.0, Mv[GRAD ? DP : 1], Qv[GRAD ? DP : 1];
+    if constexpr (GRAD) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) Mv[d] = Qv[d] = 0.0;
+    }
+    for (int n = tid; n < N; n += nt) {
+        double dl[DP];
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; d += 2) {
+            dl[d] = (d < D) ? (s_mu[d] - Xt[(size_t)d * N + n]) * s_itau[d] : 0.0;
+            dl[d + 1] = (d + 1 < D) ? (s_mu[d + 1] - Xt[(size_t)(d + 1) * N + n]) * s_itau[d + 1] : 0.0;
+            a0 = fma(dl[d], dl[d], a0);
+            a1 = fma(dl[d + 1], dl[d + 1], a1);
+        }
+        const double z = exp(lnnf - 0.5 * (a0 + a1));
+        if (Zout) Zout[((size_t)s * K + k) * N + n] = z;
+        const double za = z * al[n];
+        U += za;
+        if constexpr (GRAD) {
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                const double t = za * dl[d];
+                Mv[d] += t;
+                Qv[d] = fma(t, dl[d], Qv[d]);
+            }
+        }
+    }
+
+    // block reduction in fixed order (warp shuffle, then <= 4 warps serially)
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    U = warp_sum(U);
+    if (lane == 0) s_red[wid][0] = U;
+    if constexpr (GRAD) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            const double m = warp_sum(Mv[d]), q = warp_sum(Qv[d]);
+            if (lane == 0) s_red[wid][1 + d] = m, s_red[wid][1 + DP + d] = q;
+        }
+    }
+    __syncthreads();
+    double *rec = part + ((size_t)s * K + k) * (1 + 2 * DP);
+    const int rows = GRAD ? 1 + 2 * DP : 1;
+    for (int r = tid; r < rows; r += nt) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += s_red[w][r];
+        rec[r] = v;
+    }
+}
+
+}  // namespace
+
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part) {
+    VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "gp_log_joint: no GP packed (call vbmc_gp_pack first)");
+    const int D = c->gD, DP = c->gDP;
+    ParamLayout lay{D, DP, K};
+    const int S_local = (c->S - s_begin + s_step - 1) / s_step;
+    if (S_local <= 0) return VBMC_OK;
+    dim3 grid(K, S_local);
+    const int nt = c->N >= 96 ? 128 : (c->N >= 48 ? 64 : 32);
+    const int hs = hyp_stride(DP);
+    double *Zout = nullptr;
+#define VBMC_CASE(NDP)                                                                                          \
+    case NDP:                                                                                                   \
+        if (anygrad)                                                                                            \
+            gplj_kernel<NDP, true><<<grid, nt, 0, c->stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, \
+                                                               c->N, s_begin, s_step, d_part, Zout);            \
+        else                                                                                                    \
+            gplj_kernel<NDP, false><<<grid, nt, 0, c->stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp,   \
+                                                                hs, c->N, s_begin, s_step, d_part, Zout);       \
+        break
+    switch (DP) {
+        VBMC_CASE(4);
+        VBMC_CASE(8);
+        VBMC_CASE(12);
+        VBMC_CASE(16);
+        VBMC_CASE(20);
+        VBMC_CASE(24);
+        VBMC_CASE(28);
+        VBMC_CASE(32);
+        default:
+            set_error("gp_log_joint: unsupported dimension");
+            return VBMC_ERR_UNSUPPORTED;
+    }
+#undef VBMC_CASE
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int gpvar_launch(Ctx *c, const double *d_params, int K, double *d_J) {
+    (void)c, (void)d_params, (void)K, (void)d_J;
+    set_error("gp_log_joint: variance path not built yet");
+    return VBMC_ERR_UNSUPPORTED;
+}
+
+}  // namespace vbmc

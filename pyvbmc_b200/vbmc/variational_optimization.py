@@ -1,0 +1,197 @@
+"""B200 replacements for the objective part of
+``pyvbmc/vbmc/variational_optimization.py``: ``_neg_elcbo`` (:991-1235), ``_gp_log_joint``
+(:1238-1606), ``_vp_bound_loss`` (:503-606) and ``_soft_bound_loss`` (:609-657).
+
+Signatures, return tuples, exception types and the side effects on ``vp`` follow the
+reference; the arithmetic runs in the CUDA library behind ``include/vbmc_b200.h``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..config import config
+from ..context import context_for_gp
+from ..entropy.entmc_vbmc import draw_eps_numpy, draw_seed
+
+
+def _as_flags(grad_flags):
+    if np.isscalar(grad_flags):
+        return (bool(grad_flags),) * 4  # :1296-1300
+    return tuple(bool(g) for g in grad_flags)
+
+
+def _gp_log_joint(vp, gp, grad_flags, avg_flag=True, jacobian_flag=True, compute_var=False, separate_K=False):
+    """Expected variational log joint via the GP surrogate.
+
+    Returns ``(G, dG, varG, dvarG, var_ss)`` or, with ``separate_K``,
+    ``(G, dG, varG, dvarG, var_ss, I_sk, J_sjk)`` exactly like the reference (scalars
+    unwrapped when there is a single hyper-parameter sample, ``dG=None`` without flags,
+    ``varG=None`` unless requested, ``dvarG`` always ``None``)."""
+    g = _as_flags(grad_flags)
+    compute_vargrad = compute_var and any(g)
+    if compute_vargrad and compute_var != 2:
+        raise NotImplementedError(
+            "Computation of gradient of log joint variance is currently "
+            "available only for diagonal approximation of the variance."
+        )  # :1302-1307
+    if compute_var == 2:
+        raise NotImplementedError("Diagonal approximation of GP log-joint variance not implemented.")  # :1467-1471
+    ctx = context_for_gp(gp, need_L=bool(compute_var))
+    r = ctx.gplogjoint(vp, g, avg_flag, jacobian_flag, int(bool(compute_var)), separate_K)
+    S = ctx.S
+    G, dG = r["G"], r["dG"]
+    varG = r["varG"] if compute_var else None
+    var_ss = r["var_ss"] if (compute_var and S > 1 and avg_flag) else 0
+    if not r["per_s"]:
+        G = float(G[0])  # averaged (:1594) or S == 1 (:1598-1602)
+        if varG is not None:
+            varG = float(varG[0]) if (S > 1 and avg_flag) else (varG if S > 1 else varG[:1])
+    if separate_K:
+        return G, dG, varG, None, var_ss, r["I_sk"], r["J_sjk"]
+    return G, dG, varG, None, var_ss
+
+
+def _soft_bound_loss(x, slb, sub, tol_con=1e-3, compute_grad=False):
+    """Quadratic penalty outside ``[slb, sub]`` (:609-657).  O(len(x)) host arithmetic on the
+    caller's vectors; inside ``_neg_elcbo`` the same loss is evaluated by the CUDA finalize
+    kernel, this stand-alone form exists for API parity with the reference's tests."""
+    x = np.asarray(x, dtype=float)
+    slb = np.asarray(slb, dtype=float)
+    sub = np.asarray(sub, dtype=float)
+    ell = (sub - slb) * tol_con
+    y = 0.0
+    dy = np.zeros(x.shape)
+    for idx, edge in ((x < slb, slb), (x > sub, sub)):
+        if np.any(idx):
+            y += 0.5 * np.sum(((x[idx] - edge[idx]) / ell[idx]) ** 2)
+            if compute_grad:
+                dy[idx] = (x[idx] - edge[idx]) / ell[idx] ** 2
+    if compute_grad:
+        return y, dy
+    return y
+
+
+def _bound_inputs(vp, theta):
+    """The pieces of theta that ``_vp_bound_loss`` reads (:536-555)."""
+    D, K = vp.D, vp.K
+    pos = D * K if vp.optimize_mu else 0
+    if vp.optimize_sigma:
+        ln_sigma = theta[pos : pos + K]
+        pos += K
+    else:
+        ln_sigma = np.log(np.ravel(vp.sigma))
+    if vp.optimize_lambd:
+        ln_lambd = theta[pos : pos + D]
+    else:
+        ln_lambd = np.log(np.ravel(vp.lambd))
+    eta = theta[-K:] if vp.optimize_weights else None
+    return ln_sigma, ln_lambd, eta
+
+
+def _vp_bound_loss(vp, theta, theta_bnd, tol_con=1e-3, compute_grad=True):
+    """Soft-bound loss on ``[mu | ln sigma_k + ln lambda_d | eta]`` (:503-606), including the
+    reference's row-major reshape of the ln-scale gradient block (:584-586)."""
+    D, K = vp.D, vp.K
+    theta = np.asarray(theta, dtype=float)
+    ln_sigma, ln_lambd, eta = _bound_inputs(vp, theta)
+    mu = theta[: D * K] if vp.optimize_mu else np.asarray(vp.mu).ravel(order="F")
+    ln_scale = np.reshape(ln_lambd, (-1, 1)) + np.reshape(ln_sigma, (1, -1))
+    ext = []
+    if vp.optimize_mu:
+        ext.append(mu.ravel())
+    ext.append(ln_scale.ravel(order="F"))
+    if vp.optimize_weights:
+        ext.append(np.ravel(eta))
+    ext = np.concatenate(ext)
+    lb, ub = np.ravel(theta_bnd["lb"]), np.ravel(theta_bnd["ub"])
+    if not compute_grad:
+        return _soft_bound_loss(ext, lb, ub, tol_con)
+    L, dL = _soft_bound_loss(ext, lb, ub, tol_con, compute_grad=True)
+    parts = []
+    pos = 0
+    if vp.optimize_mu:
+        parts.append(dL[: D * K])
+        pos = D * K
+    dls = np.reshape(dL[pos : pos + D * K], (D, K))
+    if vp.optimize_sigma:
+        parts.append(np.sum(dls, axis=0))
+    if vp.optimize_lambd:
+        parts.append(np.sum(dls, axis=1))
+    if vp.optimize_weights:
+        parts.append(dL[-K:])
+    return L, np.concatenate(parts)
+
+
+def _neg_elcbo(
+    theta,
+    gp,
+    vp,
+    beta=0.0,
+    Ns=0,
+    compute_grad=True,
+    compute_var=None,
+    theta_bnd=None,
+    _entropy_alpha=0.0,
+    separate_K=False,
+    *,
+    eps=None,
+    seed=None,
+):
+    """Negative evidence lower confidence bound and its gradient.
+
+    Drop-in for the reference function: returns ``(F, dF, G, H, varF)`` or the 11-tuple
+    ``(F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk)`` with ``separate_K``.
+    ``vp`` is mutated exactly like the reference does (``set_parameters(theta)`` and the
+    shifted ``eta``, :1080-1085).  Keyword-only extensions: ``eps`` (explicit draws,
+    shape ``(K, Ns/2, D)``) and ``seed`` (explicit Philox seed)."""
+    if not np.isfinite(beta):
+        beta = 0
+    if compute_var is None:
+        compute_var = beta != 0
+    if compute_grad and beta != 0 and compute_var != 2:
+        raise NotImplementedError("Computation of the gradient of ELBO with full variance not supported")  # :1066-1070
+    if separate_K and compute_grad:
+        raise ValueError(
+            "Computing the gradient of variational parameters and requesting per-component results at the same time."
+        )  # :1114-1118
+    if compute_var == 2:
+        raise NotImplementedError("Diagonal approximation of GP log-joint variance not implemented.")
+
+    theta = np.asarray(theta, dtype=float)
+    K, D = vp.K, vp.D
+    vp.set_parameters(theta)  # :1080
+    if vp.optimize_weights:
+        vp.eta = theta[-K:].copy()
+        vp.eta -= np.amax(vp.eta)
+        vp.eta = np.reshape(vp.eta, (1, -1))  # :1082-1085
+
+    optimize = (vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights)
+    ctx = context_for_gp(gp, need_L=bool(compute_var))
+    use_bounds = ctx.set_bounds(theta_bnd)
+    ln_sigma_b = ln_lambd_b = eta_b = None
+    if use_bounds:
+        ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
+
+    Ns_even = int(np.ceil(Ns / 2)) * 2 if Ns > 0 else 0
+    if Ns_even > 0 and eps is None and seed is None:
+        if config.rng_mode == "numpy":
+            eps = draw_eps_numpy(K, Ns_even, D)
+        else:
+            seed = draw_seed()
+
+    r = ctx.negelcbo(
+        vp, optimize, Ns_even, compute_grad, bool(compute_var), separate_K, use_bounds,
+        ln_sigma_b, ln_lambd_b, eta_b, eps=eps, seed=seed or 0,
+    )
+    F, G, H = r["F"], r["G"], r["H"]
+    dF = r["dF"] if compute_grad else None
+    dH = r["dH"] if compute_grad else None
+    varH = 0  # :1179
+    varG = r["varF"] if compute_var else 0
+    varG_ss = r["varG_ss"] if compute_var else 0
+    varF = varG + varH if compute_var else 0
+    if beta != 0:  # dead in practice: elcbo_beta is hard-wired to 0 (:743); value-only branch
+        F += beta * np.sqrt(varF)
+    if separate_K:
+        return F, dF, G, H, varF, dH, varG_ss, varG, varH, r["I_sk"], r["J_sjk"]
+    return F, dF, G, H, varF

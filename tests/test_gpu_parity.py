@@ -1,0 +1,245 @@
+"""GPU parity: the CUDA path (through the C ABI, via the reference-shaped Python functions of
+``pyvbmc_b200``) against the committed golden vectors of the unmodified reference and against
+the fp64 oracle on identical inputs (theta, GP arrays, eps).
+
+Tolerances (BASELINE.json north_star): |F - F_ref| / |F_ref| <= 1e-5 and
+max|dF - dF_ref| / max|dF_ref| <= 1e-4 for the default fp32-compute/fp64-accumulate entropy
+kernel; the all-fp64 kernel and the fp64 log-joint / lower-bound kernels are held to 1e-9.
+"""
+import numpy as np
+import pytest
+
+from golden_util import REF_CASES, eps_for, load_case, load_npz, relerr, relmax
+from oracle import elbo_oracle as eo
+from oracle import gp_posterior as gpp
+from oracle import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32_VAL, TOL_F32_GRAD = 1e-5, 1e-4
+TOL_F64 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def pv():
+    import pyvbmc_b200
+
+    return pyvbmc_b200
+
+
+def make_vp(pv, D, K, mu, sigma, lambd, w, eta, opt=(True,) * 4):
+    state = np.random.get_state()
+    vp = pv.VariationalPosterior(D, K)
+    np.random.set_state(state)
+    vp.mu = np.array(mu, dtype=float).reshape(D, K)
+    vp.sigma = np.array(sigma, dtype=float).reshape(1, K)
+    vp.lambd = np.array(lambd, dtype=float).reshape(D, 1)
+    vp.w = np.array(w, dtype=float).reshape(1, K)
+    vp.eta = np.array(eta, dtype=float).reshape(1, K)
+    vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights = [bool(o) for o in opt]
+    return vp
+
+
+def case_vp(pv, c, which="vp"):
+    g = c.g
+    p = "vp_" if which == "vp" else "sa_"
+    return make_vp(pv, c.D, c.K, g[p + "mu"], g[p + "sigma"], g[p + "lambd"], g[p + "w"], g[p + "eta"], c.opt)
+
+
+# ------------------------------------------------------------------ entropy kernels
+@pytest.mark.parametrize("stem", REF_CASES)
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_entmc_golden(pv, stem, prec):
+    c = load_case(stem)
+    g = c.g
+    ctx = pv.entropy_context()
+    tv, tg = (TOL_F32_VAL, TOL_F32_GRAD) if prec == "f32" else (TOL_F64, TOL_F64)
+    vp = case_vp(pv, c, "sa")
+    for key, seed, flags, jac in [
+        ("ent", g["ent_seed"], c.opt, True),
+        ("entnj", g["entnj_seed"], (True,) * 4, False),
+        ("entw", g["entnj_seed"], (False, False, False, True), True),
+    ]:
+        eps = eps_for(seed, c.K, c.Ns_K, c.D)
+        H, dH = ctx.entmc(vp, c.Ns_K, flags, jac, eps=eps, precision=prec)
+        assert dH.shape == g[key + "_dH"].shape
+        assert relerr(H, g[key + "_H"]) < tv, (key, H, g[key + "_H"])
+        assert relmax(dH, g[key + "_dH"]) < tg, key
+
+
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_entlb_golden(pv, stem):
+    c = load_case(stem)
+    g = c.g
+    vp = case_vp(pv, c, "sa")
+    H, dH = pv.entlb_vbmc(vp, c.opt, True)
+    assert relerr(H, g["elb_H"]) < TOL_F64 and relmax(dH, g["elb_dH"]) < TOL_F64
+    H, dH = pv.entlb_vbmc(vp, (True,) * 4, False)
+    assert relerr(H, g["elbnj_H"]) < TOL_F64 and relmax(dH, g["elbnj_dH"]) < TOL_F64
+
+
+def test_entropy_edge_cases(pv):
+    g = load_npz("ref_entropy_edge")
+    for i, (D, K, Ns) in enumerate(g["specs"]):
+        vp = make_vp(pv, D, K, g[f"mu{i}"], g[f"sigma{i}"], g[f"lambd{i}"], g[f"w{i}"], g[f"eta{i}"])
+        eps = eps_for(100 + i, K, eo.even_ns(Ns), D)
+        for prec, tv, tg in (("f32", TOL_F32_VAL, TOL_F32_GRAD), ("f64", TOL_F64, TOL_F64)):
+            H, dH = pv.entropy_context().entmc(vp, Ns, (True,) * 4, True, eps=eps, precision=prec)
+            assert relerr(H, g[f"H{i}"]) < tv and relmax(dH, g[f"dH{i}"]) < tg, (i, prec)
+        Hl, dHl = pv.entlb_vbmc(vp)
+        assert relerr(Hl, g[f"Hl{i}"]) < TOL_F64 and relmax(dHl, g[f"dHl{i}"]) < TOL_F64
+
+
+def test_entropy_grad_flag_shapes(pv):
+    # pyvbmc/testing/entropy/test_entmc_vbmc.py:174-183, test_entlb_vbmc.py:122-131
+    D, K = 4, 3
+    vp = pv.VariationalPosterior(D, K)
+    _, dH = pv.entmc_vbmc(vp, Ns=1e3, grad_flags=(False,) * 4)
+    assert dH.shape == (0,)
+    _, dH = pv.entmc_vbmc(vp, Ns=1e3, grad_flags=(False, False, False, True))
+    assert dH.shape == (K,)
+    _, dH = pv.entlb_vbmc(vp, grad_flags=(False,) * 4)
+    assert dH.shape == (0,)
+    _, dH = pv.entlb_vbmc(vp, grad_flags=(False, False, False, True))
+    assert dH.shape == (K,)
+
+
+def test_matlab_entropy(pv):
+    # test_entlb_vbmc.py:101-119 (exact), test_entmc_vbmc.py:140-171 (1 %)
+    m = load_npz("matlab_entropy")
+    D, K, Ns = int(m["D"]), int(m["K"]), int(m["Ns"])
+    vp = make_vp(pv, D, K, m["mu"], m["sigma"], m["lambd"], m["w"], m["eta"])
+    Hl, dHl = pv.entlb_vbmc(vp, jacobian_flag=int(m["jacobian_flag"]))
+    assert np.isclose(Hl, m["Hl"]) and np.allclose(dHl, m["dHl"])
+    np.random.seed(42)
+    H, dH = pv.entmc_vbmc(vp, Ns, grad_flags=(True,) * 4, jacobian_flag=int(m["jacobian_flag"]))
+    assert np.isclose(H, m["H"], rtol=0.01)
+    assert np.allclose(dH, m["dH"], rtol=0.01, atol=0.01)
+
+
+def test_entmc_single_gaussian_closed_form(pv):
+    # test_entmc_vbmc.py:52-69
+    D, K = 3, 1
+    vp = make_vp(pv, D, K, np.ones((D, K)), np.ones(K), np.ones(D), np.ones(K), np.ones(K))
+    H_exact = 0.5 * D * (1 + np.log(2 * np.pi))
+    dH_exact = np.concatenate([np.zeros(D), [D], np.ones(D), [H_exact - 1]])
+    np.random.seed(1)
+    H, dH = pv.entmc_vbmc(vp, 1e5, jacobian_flag=False)
+    assert np.isclose(H, H_exact, rtol=0.01, atol=0.01)
+    assert np.allclose(dH, dH_exact, rtol=0.01, atol=0.01)
+
+
+def test_philox_mode_matches_oracle_on_dumped_draws(pv):
+    """Production RNG: the kernel's Philox draws, dumped through vbmc_philox_normals and fed to
+    the oracle, must reproduce the kernel's result; draws must look standard normal."""
+    c = load_case("c2")
+    vp = case_vp(pv, c, "sa")
+    ctx = pv.entropy_context()
+    Ns = 200
+    eps = ctx.philox_normals(c.D, c.K, Ns, seed=1234, offset=7)
+    assert eps.shape == (c.K, Ns // 2, c.D)
+    assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1) < 0.02
+    H, dH = ctx.entmc(vp, Ns, (True,) * 4, True, eps=None, seed=1234, offset=7)
+    Ho, dHo = eo.entmc(c.sa_vp(), eps, (True,) * 4, True)
+    assert relerr(H, Ho) < TOL_F32_VAL and relmax(dH, dHo) < TOL_F32_GRAD
+    H2, dH2 = ctx.entmc(vp, Ns, (True,) * 4, True, eps=None, seed=1234, offset=7)
+    assert H2 == H and np.array_equal(dH, dH2)  # bitwise run-to-run determinism
+    H3, _ = ctx.entmc(vp, Ns, (True,) * 4, True, eps=None, seed=1235, offset=7)
+    assert H3 != H
+    big = ctx.philox_normals(8, 4, 200000, seed=5)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1) < 5e-3
+    assert abs(np.mean(big**4) - 3.0) < 0.05
+
+
+# ------------------------------------------------------------------ GP log joint
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_gplogjoint_golden(pv, stem):
+    c = load_case(stem)
+    g = c.g
+    vp = case_vp(pv, c, "sa")
+    G, dG, varG, dvarG, var_ss = pv._gp_log_joint(vp, c.gp, c.opt, True, True, False)
+    assert relerr(G, g["gp_G"]) < TOL_F64 and relmax(dG, g["gp_dG"]) < TOL_F64
+    assert varG is None and dvarG is None and var_ss == 0
+    if c.S > 1:
+        G, dG, *_ = pv._gp_log_joint(vp, c.gp, c.opt, False, True, False)
+        assert G.shape == (c.S,) and dG.shape == g["gp_dG_noavg"].shape
+        assert relmax(G, g["gp_G_noavg"]) < TOL_F64 and relmax(dG, g["gp_dG_noavg"]) < TOL_F64
+    G, dG, *_ = pv._gp_log_joint(vp, c.gp, False, True, True, False)
+    assert dG is None and relerr(G, g["gp_G"]) < TOL_F64
+
+
+def test_matlab_gp_log_joint_and_neg_elcbo(pv):
+    # pyvbmc/testing/vbmc/test_variational_optimization.py:120-211 (gradient / value parts)
+    m = load_npz("matlab_vbmc")
+    D = K = 2
+    posts = gpp.posteriors(m["X"], m["y"], m["hyp"])
+    gp = eo.make_gp(m["X"], posts)
+    vp = make_vp(pv, D, K, m["mu"], 1e-3 * np.ones(K), np.ones(D), np.ones(K) / K, np.ones(K) / K)
+    G, dG, varG, dvarG, var_ss = pv._gp_log_joint(vp, gp, True, True, True, False, False)
+    assert np.allclose(dG, m["dG"]) and np.isclose(G, m["G"])
+    theta = vp.get_parameters()
+    F, dF, G, H, varF = pv._neg_elcbo(theta, gp, vp, 0.0, 0, True, False, None, 0.0, False)
+    assert np.isclose(F, m["F"]) and np.isclose(G, m["G"]) and np.isclose(H, m["H"])
+    assert np.allclose(dF, m["dF"])
+
+
+# ------------------------------------------------------------------ negative ELCBO
+@pytest.mark.parametrize("stem", REF_CASES)
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_negelcbo_mc_golden(pv, stem, prec):
+    c = load_case(stem)
+    g = c.g
+    pv.config.precision = prec
+    try:
+        vp = case_vp(pv, c)
+        eps = eps_for(0, c.K, c.Ns_K, c.D)
+        F, dF, G, H, varF = pv._neg_elcbo(g["theta"], c.gp, vp, 0.0, c.Ns_K, True, False, c.theta_bnd, eps=eps)
+    finally:
+        pv.config.precision = "f32"
+    tv, tg = (TOL_F32_VAL, TOL_F32_GRAD) if prec == "f32" else (TOL_F64, TOL_F64)
+    assert relerr(F, g["mc_F"]) < tv and relerr(G, g["mc_G"]) < TOL_F64 and relerr(H, g["mc_H"]) < tv
+    assert dF.shape == g["mc_dF"].shape and relmax(dF, g["mc_dF"]) < tg
+    assert varF == 0
+    for a, b in [(vp.mu, "post_mu"), (vp.sigma, "post_sigma"), (vp.lambd, "post_lambd"), (vp.w, "post_w"), (vp.eta, "post_eta")]:
+        assert np.asarray(a).shape == g[b].shape and np.allclose(a, g[b], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("stem", REF_CASES)
+def test_negelcbo_lb_golden(pv, stem):
+    c = load_case(stem)
+    g = c.g
+    F, dF, G, H, varF = pv._neg_elcbo(g["theta2"], c.gp, case_vp(pv, c), 0.0, 0, True, False, c.theta_bnd)
+    assert relerr(F, g["lb_F"]) < TOL_F64 and relerr(G, g["lb_G"]) < TOL_F64 and relerr(H, g["lb_H"]) < TOL_F64
+    assert relmax(dF, g["lb_dF"]) < TOL_F64
+    F, dF, *_ = pv._neg_elcbo(g["theta2"], c.gp, case_vp(pv, c), 0.0, 0, False, False, c.theta_bnd)
+    assert dF is None and relerr(F, g["lbv_F"]) < TOL_F64
+
+
+def test_negelcbo_errors(pv):
+    c = load_case("c1")
+    with pytest.raises(ValueError):
+        pv._neg_elcbo(c.g["theta2"], c.gp, case_vp(pv, c), 0.0, 0, True, False, None, 0.0, True)
+    with pytest.raises(NotImplementedError):
+        pv._neg_elcbo(c.g["theta2"], c.gp, case_vp(pv, c), 1.0, 0, True, None, None)
+    with pytest.raises(NotImplementedError):
+        pv._gp_log_joint(case_vp(pv, c), c.gp, True, True, True, True)
+
+
+# ------------------------------------------------------------------ full-size workloads vs the oracle
+@pytest.mark.parametrize("name", ["C2", "C4", "C3"])
+def test_full_size_against_oracle(pv, name):
+    """BASELINE.json configs at their full draw counts: CUDA vs oracle on the same eps."""
+    pr = syn.make_problem(name)
+    eps = syn.draw_eps(pr.K, pr.Ns_K, pr.D, seed=0)
+    Fo, dFo, Go, Ho, _ = eo.neg_elcbo(pr.theta, pr.gp, pr.vp.copy(), 0.0, pr.Ns_K, True, False, pr.theta_bnd, eps_half=eps)
+    vp = make_vp(pv, pr.D, pr.K, pr.vp.mu, pr.vp.sigma, pr.vp.lambd, pr.vp.w, pr.vp.eta)
+    F, dF, G, H, _ = pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd, eps=eps)
+    assert relerr(F, Fo) < TOL_F32_VAL and relerr(H, Ho) < TOL_F32_VAL and relerr(G, Go) < TOL_F64
+    assert relmax(dF, dFo) < TOL_F32_GRAD
+    # per-block gradient parity (per-element relative error is ill-posed)
+    D, K = pr.D, pr.K
+    for lo, hi in [(0, D * K), (D * K, D * K + K), (D * K + K, D * K + K + D), (D * K + K + D, D * K + 2 * K + D)]:
+        assert relmax(dF[lo:hi], dFo[lo:hi]) < TOL_F32_GRAD
+    # bitwise determinism of the whole evaluation
+    F2, dF2, *_ = pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd, eps=eps)
+    assert F2 == F and np.array_equal(dF, dF2)
