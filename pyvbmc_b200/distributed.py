@@ -1,0 +1,102 @@
+"""Multi-GPU evaluation of the negative ELCBO: one process per GPU (torchrun), the entropy
+draws and the GP hyper-samples sharded over ranks, ONE all-reduce of the raw vector.
+
+Sharding: for every mixture component, rank r owns the antithetic pairs
+``[r*half/W, (r+1)*half/W)`` (a pair never straddles ranks); hyper-sample ``s`` belongs to rank
+``s mod W``.  Each rank's kernels emit the raw (pre-Jacobian) sums already scaled by the GLOBAL
+``1/Ns`` and ``1/S``; a SUM all-reduce of ``2 + 2P`` doubles (< 20 KB) yields the single-GPU
+value on every rank, and every rank then runs the identical finalize kernel (Jacobians, soft
+bounds, penalty), so theta updates stay replicated with no broadcast.  Philox draws are keyed
+by the global (component, pair) index => the result does not depend on the number of ranks
+beyond fp64 summation order.
+
+``torch`` is used for the device tensors and ``torch.distributed`` (NCCL over NVLink/NVSwitch;
+gloo in CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pair_range(half_glob: int, rank: int, world: int):
+    """Antithetic pairs of each component owned by ``rank`` (mirrors capi.cu:partials)."""
+    return half_glob * rank // world, half_glob * (rank + 1) // world
+
+
+def sample_indices(S: int, rank: int, world: int):
+    """GP hyper-samples owned by ``rank``."""
+    return list(range(rank, S, world))
+
+
+def raw_layout(D: int, K: int):
+    """Offsets inside the raw vector (mirrors RawLayout in csrc/common.cuh)."""
+    block = K * D + 2 * K + D
+    return {"H": 0, "G": 1, "ent": 4, "gp": 4 + block, "block": block, "total": 4 + 2 * block}
+
+
+class ShardedNegElcbo:
+    """``_neg_elcbo(theta, gp, vp, 0, Ns, True, False, theta_bnd)`` evaluated by all ranks.
+
+    Every rank must call :meth:`__call__` with the same ``theta``; every rank gets the same
+    ``(F, dF, G, H, varF)``.
+    """
+
+    def __init__(self, gp, device=None, group=None, seed=0):
+        import torch
+        import torch.distributed as dist
+
+        from .context import Context
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.ctx = Context(self.device)
+        self.ctx.pack_gp(gp)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+        self.seed = int(seed)
+        self.step = 0
+        self._raw = self._out = None
+        self._host = None
+
+    def _buffers(self, D, K):
+        torch = self.torch
+        n_raw, n_out = self.ctx.raw_len(D, K), self.ctx.out_len(D, K)
+        if self._raw is None or self._raw.numel() != n_raw:
+            dev = torch.device("cuda", self.device)
+            self._raw = torch.zeros(n_raw, dtype=torch.float64, device=dev)
+            self._out = torch.zeros(n_out, dtype=torch.float64, device=dev)
+            self._host = torch.zeros(n_out, dtype=torch.float64).pin_memory()
+        return self._raw, self._out, self._host
+
+    def enqueue(self, D, K):
+        """partials -> all-reduce -> finalize on the context stream (no host sync)."""
+        raw, out, _ = self._buffers(D, K)
+        self.ctx.partials_async(self.rank, self.world, raw.data_ptr())
+        if self.world > 1:
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.ctx.finalize_async(raw.data_ptr(), out.data_ptr())
+        return out
+
+    def __call__(self, theta, vp, Ns, theta_bnd=None, eps=None):
+        from .vbmc.variational_optimization import _bound_inputs
+
+        torch = self.torch
+        theta = np.asarray(theta, dtype=float)
+        K, D = vp.K, vp.D
+        vp.set_parameters(theta)
+        if vp.optimize_weights:
+            vp.eta = (theta[-K:] - np.amax(theta[-K:])).reshape(1, -1)
+        optimize = (vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights)
+        use_bounds = self.ctx.set_bounds(theta_bnd)
+        b = _bound_inputs(vp, theta) if use_bounds else (None, None, None)
+        self.step += 1
+        self.ctx.upload(vp, optimize, Ns, True, use_bounds, b[0], b[1], b[2], eps=eps, seed=self.seed, offset=self.step)
+        out = self.enqueue(D, K)
+        P = sum(n for n, o in zip((D * K, K, D, K), optimize) if o)
+        with torch.cuda.stream(self.stream):
+            self._host[: 8 + P].copy_(out[: 8 + P], non_blocking=True)
+        self.stream.synchronize()
+        h = self._host.numpy()
+        return float(h[0]), h[8 : 8 + P].copy(), float(h[1]), float(h[2]), 0
