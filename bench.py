@@ -343,6 +343,9 @@ def run_b200(args):
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
+    torch.cuda.synchronize()
+    ev.close()
+    pv.clear_caches()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

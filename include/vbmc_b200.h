@@ -170,9 +170,14 @@ int vbmc_negelcbo(vbmc_ctx *ctx, const vbmc_elcbo_in *in, vbmc_elcbo_out *out);
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
+/* NOTE: with world == 1 the cross-component assembly of raw_dev is deferred into the finalize
+ * launch (one kernel less); raw_dev is only complete after partials when world > 1.          */
 int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
 int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
 int vbmc_stream_synchronize(vbmc_ctx *ctx);
+/* copy n doubles from device memory to the host through the context's pinned staging buffer,
+ * ordered after everything enqueued on the context stream (synchronises)                     */
+int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst_host);
 /* Kernel timing for bench.py's roofline: when enabled, every entmc launch is bracketed by
  * CUDA events on the context stream (and synchronised -- measurement mode only);
  * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */

@@ -7,7 +7,9 @@ never hang off ``vp`` / ``gp`` objects (those get pickled with dill by the refer
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
+import sys
 import weakref
 from collections import OrderedDict
 
@@ -89,6 +91,18 @@ def gp_counts(gp, D):
     return cov_N, noise_N
 
 
+_live = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():  # runs before interpreter finalisation: contexts are released in order
+    for ctx in list(_live):
+        try:
+            ctx.close()
+        except Exception:
+            pass
+
+
 class Context:
     def __init__(self, device: int = None):
         lib = _capi.load()
@@ -102,6 +116,7 @@ class Context:
         h = C.c_void_p()
         _capi.check(lib.vbmc_ctx_create(self.device, C.byref(h)))
         self._h = h
+        _live.add(self)
         self._gp_token = None
         self._gp_has_L = False
         self._bnd_cache = None
@@ -115,10 +130,21 @@ class Context:
             self._h = None
 
     def __del__(self):  # pragma: no cover
+        # never touch the CUDA runtime while the interpreter is being torn down (other libraries
+        # sharing the primary context may already have released it): leak at exit instead
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
             pass
+
+    def read_device(self, dev_ptr: int, n: int) -> np.ndarray:
+        """Copy ``n`` doubles from a device pointer to a fresh host array, ordered after the
+        work enqueued on this context's stream (synchronises)."""
+        out = np.empty(int(n), dtype=_F64)
+        _capi.check(self._lib.vbmc_read_device(self._h, C.c_void_p(int(dev_ptr)), int(n), _ptr(out)))
+        return out
 
     # ------------------------------------------------------------------ bookkeeping
     @property

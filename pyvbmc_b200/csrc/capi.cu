@@ -76,6 +76,8 @@ struct Staged {
     EvalFlags f{};
     EntmcPlan plan{};
     bool planned = false;
+    bool assemble_pending = false;  // world == 1: the raw vector is assembled inside the finalize launch
+    EvalFlags f_partials{};
 };
 
 // per-context staged state (kept outside Ctx to keep common.cuh light)
@@ -152,6 +154,16 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     EvalFlags f = st.f;
     const EntmcPlan *planp = nullptr;
     int64_t Ns_glob = 0;
+    // the fp64 log-joint kernel runs beside the fp32 entropy kernel on a side stream
+    const bool fork = s.have_gp && s.have_ent && s.Ns > 0;
+    if (s.have_gp) {
+        if (fork) {
+            VBMC_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+            VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        }
+        VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart, fork ? c->stream2 : c->stream));
+        if (fork) VBMC_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+    }
     if (s.have_ent) {
         if (s.Ns > 0) {
             Ns_glob = even_ns(s.Ns);
@@ -170,8 +182,10 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
             f.have_ent = 0;
         }
     }
-    if (s.have_gp) VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart));
-    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev));
+    if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    st.f_partials = f;
+    st.assemble_pending = (world == 1);
+    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, !st.assemble_pending));
     return VBMC_OK;
 }
 
@@ -179,7 +193,9 @@ int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
     Ctx *c = &x->c;
     Staged &st = x->st;
     VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged");
-    return finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev);
+    const bool fuse = st.assemble_pending;
+    st.assemble_pending = false;
+    return finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev, fuse);
 }
 
 // run everything on one GPU and bring `n` leading doubles of out back to the host
@@ -227,6 +243,9 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     x->c.device = device;
     x->c.sm_count = prop.multiProcessorCount;
     VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
+    VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream2, cudaStreamNonBlocking));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_fork, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_join, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev0));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev1));
     *out = reinterpret_cast<vbmc_ctx *>(x);
@@ -239,7 +258,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     Ctx *c = &x->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in,
+    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_crec,
                      c->d_entpart, c->d_gppart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
@@ -247,6 +266,9 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete x;
 }
@@ -552,6 +574,20 @@ int vbmc_negelcbo_finalize_async(vbmc_ctx *p, const double *raw_dev, double *out
     CtxEx *x = ex(p);
     Bind b(&x->c);
     return finalize(x, raw_dev, out_dev);
+}
+
+int vbmc_read_device(vbmc_ctx *p, const double *src_dev, size_t n, double *dst_host) {
+    VBMC_REQUIRE(p && src_dev && dst_host, VBMC_ERR_ARG, "read_device: null argument");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    if (!c->h_out) VBMC_TRY(ensure_pinned(&c->d_out, &c->h_out, &c->out_cap, 4096));
+    for (size_t off = 0; off < n; off += c->out_cap) {  // staged through the pinned buffer in chunks
+        const size_t m = n - off < c->out_cap ? n - off : c->out_cap;
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(c->h_out, src_dev + off, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        memcpy(dst_host + off, c->h_out, m * sizeof(double));
+    }
+    return VBMC_OK;
 }
 
 int vbmc_stream_synchronize(vbmc_ctx *p) {

@@ -112,6 +112,8 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: gplj overlaps entmc
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
 
     // GP pack
@@ -138,6 +140,12 @@ struct Ctx {
     size_t gppart_cap = 0;
     double *d_gps = nullptr; // [S][1 + block] per-sample raw log-joint terms
     size_t gps_cap = 0;
+    double *d_crec = nullptr; // [K][entpart_stride] per-component entropy records
+    size_t crec_cap = 0;
+    // arguments of the last reduce stage (for the fused assemble+finalize launch)
+    bool red_args_valid = false;
+    int red_plan_slabs = 0, red_s_begin = 0, red_s_step = 1, red_S_glob = 1;
+    double red_Ns_glob = 0, red_draws_local = 0;
     double *d_raw = nullptr;
     size_t raw_cap = 0;
     double *d_out = nullptr, *h_out = nullptr;
@@ -181,7 +189,8 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
 int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
 
 // gplj.cu
-int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part);
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
+                cudaStream_t stream);
 int gpvar_launch(Ctx *c, const double *d_params, int K, double *d_J /*[S][K][K]*/);
 
 // entlb.cu
@@ -190,9 +199,9 @@ int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4]
 
 // finalize.cu
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw);
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool assemble);
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
-                    double *d_out);
+                    double *d_out, bool assemble_first);
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s);
 
 // ----------------------------------------------------------------------------- device helpers

@@ -26,6 +26,7 @@ struct ReduceArgs {
     int slabs, ent_stride;
     double Ns_glob;     // draws per component over all ranks
     double draws_local; // draws per component on this rank
+    double *crec;       // [K][ent_stride] per-component records
     // gp
     const double *gppart;
     const double *hyp;
@@ -35,154 +36,161 @@ struct ReduceArgs {
     double *raw;
 };
 
-__global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ prm, ReduceArgs a) {
+// Stage 1 (many CTAs): CTA j < K sums the slab records of mixture component j in slab order;
+// CTA K + i turns the (s_i, k) log-joint records into G_s and the raw per-sample gradients.
+__global__ void __launch_bounds__(128) reduce_kernel(const double *__restrict__ prm, ReduceArgs a) {
     const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[32];
     const double *mu = prm + a.lay.mu(), *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(),
                  *w = prm + a.lay.w();
-    double *raw = a.raw;
     const RawLayout rl = a.rl;
+    const bool ent_on = a.f.have_ent && a.f.use_ent_mc;
+    const int n_ent = ent_on ? K : 0;
 
-    // raw[0] (H) is written by the entlb kernels when the deterministic entropy is used
-    if (tid < 4 && !(tid == 0 && a.f.have_ent && !a.f.use_ent_mc)) raw[tid] = 0.0;
+    if ((int)blockIdx.x < n_ent) {
+        // ---------------------------------------------------------- Monte-Carlo entropy, component j
+        const int j = blockIdx.x, st = a.ent_stride;
+        for (int t = tid; t < st; t += nt) {
+            double v = 0.0;
+            for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + t];
+            if (t == 0) {
+                double sumlnl = 0.0;
+                for (int d = 0; d < D; ++d) sumlnl += log(lambd[d]);
+                // + (draws of this rank) * log( nconst / sigma_j^D )   (entmc_vbmc.py:53-56,77)
+                v += a.draws_local * (-0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]));
+            }
+            a.crec[(size_t)j * st + t] = v;
+        }
+        return;
+    }
+    if (!a.f.have_gp) return;
+    // -------------------------------------------------------------- GP expected log joint, sample s
+    const int s = a.s_begin + ((int)blockIdx.x - n_ent) * a.s_step;
+    if (s >= a.S) return;
+    const int gst = 1 + 2 * DP;
+    const int blk = rl.block();
+    const bool quad = a.mean_kind == VBMC_MEAN_NEGQUAD, zero = a.mean_kind == VBMC_MEAN_ZERO;
+    const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+    const double *h = a.hyp + (size_t)s * a.hs;
+    const double *ell = h, *xm = h + DP, *iom2 = h + 2 * DP;
+    const double m0 = zero ? 0.0 : h[3 * DP + 2];
+    double *gs = a.gps + (size_t)s * (1 + blk);
+    const double *rec_s = a.gppart + (size_t)s * K * gst;
+    // I_sk -> the w block (variational_optimization.py:1407-1428,1464-1465)
+    double gpart = 0.0;
+    for (int k = tid; k < K; k += nt) {
+        double I = rec_s[(size_t)k * gst] + m0;
+        if (quad) {
+            const double s2 = sigma[k] * sigma[k];
+            double nu = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double m = mu[k * D + d];
+                nu += iom2[d] * (m * m + s2 * lambd[d] * lambd[d] - 2.0 * m * xm[d] + xm[d] * xm[d]);
+            }
+            I -= 0.5 * nu;
+        }
+        gs[1 + rl.o_w() + k] = I;
+        gpart += w[k] * I;
+    }
+    gpart = block_sum(gpart, scratch);
+    if (tid == 0) gs[0] = gpart;  // G_s (:1425)
+    if (!anyg) return;
+    // d/dmu (:1430-1436)
+    for (int e = tid; e < K * D; e += nt) {
+        const int k = e / D, d = e - k * D;
+        const double sl = sigma[k] * lambd[d];
+        const double tau = sqrt(sl * sl + ell[d] * ell[d]);
+        double g = -rec_s[(size_t)k * gst + 1 + d] / tau;
+        if (quad) g -= iom2[d] * (mu[e] - xm[d]);
+        gs[1 + rl.o_mu() + e] = w[k] * g;
+    }
+    // d/dsigma (:1438-1450)
+    for (int k = tid; k < K; k += nt) {
+        const double U = rec_s[(size_t)k * gst];
+        double acc = 0.0, accq = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double sl = sigma[k] * lambd[d];
+            const double t2 = sl * sl + ell[d] * ell[d];
+            acc += lambd[d] * lambd[d] / t2 * (rec_s[(size_t)k * gst + 1 + DP + d] - U);
+            accq += lambd[d] * lambd[d] * iom2[d];
+        }
+        double g = sigma[k] * acc;
+        if (quad) g -= sigma[k] * accq;
+        gs[1 + rl.o_sig() + k] = w[k] * g;
+    }
+    // d/dlambda (:1452-1462): warp per dimension, lanes over components, fixed-order shuffle tree
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        for (int d = wid; d < D; d += nw) {
+            double acc = 0.0;
+            for (int k = lane; k < K; k += 32) {
+                const double s2 = sigma[k] * sigma[k];
+                const double t2 = s2 * lambd[d] * lambd[d] + ell[d] * ell[d];
+                double g = s2 / t2 * lambd[d] * (rec_s[(size_t)k * gst + 1 + DP + d] - rec_s[(size_t)k * gst]);
+                if (quad) g -= s2 * lambd[d] * iom2[d];
+                acc += w[k] * g;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) gs[1 + rl.o_lam() + d] = acc;
+        }
+    }
+}
+
+// Stage 2, part A (device function, whole CTA): per-component / per-sample records -> raw vector.
+__device__ void assemble_raw(const double *__restrict__ prm, const ReduceArgs &a, double *scratch) {
+    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
+    const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
+    const RawLayout rl = a.rl;
+    double *raw = a.raw;
+    const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+    const bool ent_mc = a.f.have_ent && a.f.use_ent_mc;
+    const bool ent_lb = a.f.have_ent && !a.f.use_ent_mc;  // entlb kernels already wrote raw[0] and the block
+
+    if (tid >= 1 && tid < 4) raw[tid] = 0.0;
+    if (tid == 0 && !ent_lb) raw[0] = 0.0;
     if (!a.f.have_ent)
         for (int e = tid; e < rl.block(); e += nt) raw[rl.ent() + e] = 0.0;
     if (!a.f.have_gp)
         for (int e = tid; e < rl.block(); e += nt) raw[rl.gp() + e] = 0.0;
-    __syncthreads();
 
-    // ------------------------------------------------------------------ Monte-Carlo entropy
-    if (a.f.have_ent && a.f.use_ent_mc) {
+    if (ent_mc) {
         const double inv_ns = 1.0 / a.Ns_glob;
         const int st = a.ent_stride;
         double *ent = raw + rl.ent();
-        double sumlnl = 0.0;
-        for (int d = 0; d < D; ++d) sumlnl += log(lambd[d]);
-        // H and the direct part of d/dw_j
         double hpart = 0.0;
-        for (int j = tid; j < K; j += nt) {
-            double hs = 0.0;
-            for (int s = 0; s < a.slabs; ++s) hs += a.entpart[((size_t)j * a.slabs + s) * st];
-            const double lnC = -0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]);
-            hs += a.draws_local * lnC;  // sum_i log q(x_ji) over this rank's draws
-            hpart -= w[j] * hs * inv_ns;
-            ent[rl.o_w() + j] = -hs * inv_ns;  // entmc_vbmc.py:111
-        }
+        for (int j = tid; j < K; j += nt) hpart -= w[j] * a.crec[(size_t)j * st] * inv_ns;  // entmc_vbmc.py:80
         hpart = block_sum(hpart, scratch);
-        if (tid == 0) raw[0] = hpart;  // entmc_vbmc.py:80
-        if (a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3]) {
-            // d/dmu_j  (:98)
-            for (int e = tid; e < K * D; e += nt) {
-                const int j = e / D, d = e - j * D;
-                double v = 0.0;
-                for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + 1 + d];
-                ent[rl.o_mu() + e] = w[j] * v * inv_ns / lambd[d];
-            }
-            // d/dsigma_j  (:102-103)
-            for (int j = tid; j < K; j += nt) {
-                double v = 0.0;
-                for (int d = 0; d < D; ++d)
-                    for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + 1 + DP + d];
-                ent[rl.o_sig() + j] = w[j] * v * inv_ns / sigma[j];
-            }
-            // d/dlambda_d  (:106-108)
-            for (int d = tid; d < D; d += nt) {
-                double v = 0.0;
-                for (int j = 0; j < K; ++j) {
+        if (tid == 0) raw[0] = hpart;
+        if (anyg) {
+            for (int e = tid; e < rl.block(); e += nt) {
+                double v;
+                if (e < rl.o_sig()) {  // d/dmu_j (:98)
+                    const int j = e / D, d = e - j * D;
+                    v = w[j] * a.crec[(size_t)j * st + 1 + d] * inv_ns / lambd[d];
+                } else if (e < rl.o_lam()) {  // d/dsigma_j (:102-103)
+                    const int j = e - rl.o_sig();
                     double u = 0.0;
-                    for (int s = 0; s < a.slabs; ++s) u += a.entpart[((size_t)j * a.slabs + s) * st + 1 + DP + d];
-                    v += w[j] * u;
+                    for (int d = 0; d < D; ++d) u += a.crec[(size_t)j * st + 1 + DP + d];
+                    v = w[j] * u * inv_ns / sigma[j];
+                } else if (e < rl.o_w()) {  // d/dlambda_d (:106-108)
+                    const int d = e - rl.o_lam();
+                    double u = 0.0;
+                    for (int j = 0; j < K; ++j) u += w[j] * a.crec[(size_t)j * st + 1 + DP + d];
+                    v = u * inv_ns / lambd[d];
+                } else {  // d/dw_k (:111-112)
+                    const int k = e - rl.o_w();
+                    double u = 0.0;
+                    if (a.f.grad[3])
+                        for (int j = 0; j < K; ++j) u += w[j] * a.crec[(size_t)j * st + 1 + 2 * DP + k];
+                    v = -(a.crec[(size_t)k * st] + u) * inv_ns;
                 }
-                ent[rl.o_lam() + d] = v * inv_ns / lambd[d];
-            }
-            __syncthreads();
-            // d/dw_k  cross term  -sum_j w_j E_j[N_k / q]  (:112)
-            if (a.f.grad[3]) {
-                for (int k = tid; k < K; k += nt) {
-                    double v = 0.0;
-                    for (int j = 0; j < K; ++j) {
-                        double u = 0.0;
-                        for (int s = 0; s < a.slabs; ++s)
-                            u += a.entpart[((size_t)j * a.slabs + s) * st + 1 + 2 * DP + k];
-                        v += w[j] * u;
-                    }
-                    ent[rl.o_w() + k] -= v * inv_ns;
-                }
+                ent[e] = v;
             }
         }
     }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ GP expected log joint
     if (a.f.have_gp) {
-        const int gst = 1 + 2 * DP;
-        const int blk = rl.block();
-        const bool quad = a.mean_kind == VBMC_MEAN_NEGQUAD, zero = a.mean_kind == VBMC_MEAN_ZERO;
-        const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
-        for (int s = a.s_begin; s < a.S; s += a.s_step) {
-            const double *h = a.hyp + (size_t)s * a.hs;
-            const double *ell = h, *xm = h + DP, *iom2 = h + 2 * DP;
-            const double m0 = zero ? 0.0 : h[3 * DP + 2];
-            double *gs = a.gps + (size_t)s * (1 + blk);
-            const double *rec_s = a.gppart + (size_t)s * K * gst;
-            // I_sk -> the w block (variational_optimization.py:1407-1428,1464-1465)
-            double gpart = 0.0;
-            for (int k = tid; k < K; k += nt) {
-                double I = rec_s[(size_t)k * gst] + m0;
-                if (quad) {
-                    const double s2 = sigma[k] * sigma[k];
-                    double nu = 0.0;
-                    for (int d = 0; d < D; ++d) {
-                        const double m = mu[k * D + d];
-                        nu += iom2[d] * (m * m + s2 * lambd[d] * lambd[d] - 2.0 * m * xm[d] + xm[d] * xm[d]);
-                    }
-                    I -= 0.5 * nu;
-                }
-                gs[1 + rl.o_w() + k] = I;
-                gpart += w[k] * I;
-            }
-            gpart = block_sum(gpart, scratch);
-            if (tid == 0) gs[0] = gpart;  // G_s (:1425)
-            if (anyg) {
-                // d/dmu (:1430-1436)
-                for (int e = tid; e < K * D; e += nt) {
-                    const int k = e / D, d = e - k * D;
-                    const double sl = sigma[k] * lambd[d];
-                    const double tau = sqrt(sl * sl + ell[d] * ell[d]);
-                    double g = -rec_s[(size_t)k * gst + 1 + d] / tau;
-                    if (quad) g -= iom2[d] * (mu[e] - xm[d]);
-                    gs[1 + rl.o_mu() + e] = w[k] * g;
-                }
-                // d/dsigma (:1438-1450)
-                for (int k = tid; k < K; k += nt) {
-                    const double U = rec_s[(size_t)k * gst];
-                    double acc = 0.0, accq = 0.0;
-                    for (int d = 0; d < D; ++d) {
-                        const double sl = sigma[k] * lambd[d];
-                        const double t2 = sl * sl + ell[d] * ell[d];
-                        acc += lambd[d] * lambd[d] / t2 * (rec_s[(size_t)k * gst + 1 + DP + d] - U);
-                        accq += lambd[d] * lambd[d] * iom2[d];
-                    }
-                    double g = sigma[k] * acc;
-                    if (quad) g -= sigma[k] * accq;
-                    gs[1 + rl.o_sig() + k] = w[k] * g;
-                }
-                // d/dlambda (:1452-1462)
-                for (int d = tid; d < D; d += nt) {
-                    double acc = 0.0;
-                    for (int k = 0; k < K; ++k) {
-                        const double s2 = sigma[k] * sigma[k];
-                        const double t2 = s2 * lambd[d] * lambd[d] + ell[d] * ell[d];
-                        double g = s2 / t2 * lambd[d] * (rec_s[(size_t)k * gst + 1 + DP + d] - rec_s[(size_t)k * gst]);
-                        if (quad) g -= s2 * lambd[d] * iom2[d];
-                        acc += w[k] * g;
-                    }
-                    gs[1 + rl.o_lam() + d] = acc;
-                }
-            }
-            __syncthreads();
-        }
         // average over hyper-samples (:1578-1596); this rank contributes its own s / S_glob
+        const int blk = rl.block();
         const double inv_S = 1.0 / (double)a.S_glob;
         for (int e = tid; e < blk + 1; e += nt) {
             if (e > 0 && !anyg) break;
@@ -195,6 +203,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ 
                 raw[rl.gp() + e - 1] = v;
         }
     }
+    __syncthreads();
 }
 
 // Apply the reparameterisation Jacobians to one raw block and scatter it into theta order.
@@ -244,6 +253,8 @@ struct FinalArgs {
     ParamLayout lay;
     RawLayout rl;
     EvalFlags f;
+    int do_assemble, do_finalize;
+    ReduceArgs red;  // used when do_assemble
     const double *raw;
     const double *lb, *ub;
     int n_bnd;
@@ -252,9 +263,13 @@ struct FinalArgs {
     int Pfull;
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
+// Stage 2 (single CTA, 1024 threads): [assemble raw] and/or [finalize].  On one GPU both run in one
+// launch; with several ranks the all-reduce of raw sits between an assemble-only and a finalize-only launch.
+__global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[32];
+    if (a.do_assemble) assemble_raw(prm, a.red, scratch);
+    if (!a.do_finalize) return;
     const RawLayout rl = a.rl;
     const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
     double *out = a.out;
@@ -406,17 +421,18 @@ gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout r
 
 }  // namespace
 
-int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw) {
+static ReduceArgs make_reduce_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *plan, int64_t Ns_glob,
+                                   int s_begin, int s_step, int S_glob, double *d_raw) {
     ReduceArgs a{};
     const int DP = pad_dim(D);
     a.lay = ParamLayout{D, DP, K};
     a.rl = RawLayout{D, K};
     a.f = f;
     a.entpart = c->d_entpart;
+    a.crec = c->d_crec;
+    a.ent_stride = entpart_stride(DP, K);
     if (plan) {
         a.slabs = plan->slabs;
-        a.ent_stride = entpart_stride(DP, K);
         a.Ns_glob = (double)Ns_glob;
         a.draws_local = 2.0 * (double)plan->half;
     }
@@ -430,18 +446,53 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
     a.mean_kind = c->mean_kind;
     a.gps = c->d_gps;
     a.raw = d_raw;
-    reduce_kernel<<<1, 256, 0, c->stream>>>(d_params, a);
-    VBMC_CUDA_CHECK(cudaGetLastError());
-    c->launches++;
+    return a;
+}
+
+// records -> (optionally) raw vector.  With assemble == false the caller fuses the assembly into
+// finalize_launch (single-GPU fast path: one launch less).
+int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool assemble) {
+    const int DP = pad_dim(D);
+    const bool ent_on = f.have_ent && f.use_ent_mc;
+    if (ent_on) VBMC_TRY(ensure(&c->d_crec, &c->crec_cap, (size_t)K * entpart_stride(DP, K)));
+    ReduceArgs a = make_reduce_args(c, D, K, f, plan, Ns_glob, s_begin, s_step, S_glob, d_raw);
+    c->red_args_valid = true;
+    c->red_plan_slabs = a.slabs, c->red_Ns_glob = a.Ns_glob, c->red_draws_local = a.draws_local;
+    c->red_s_begin = s_begin, c->red_s_step = s_step, c->red_S_glob = S_glob;
+    const int S_local = f.have_gp ? (c->S - s_begin + s_step - 1) / s_step : 0;
+    const int grid = (ent_on ? K : 0) + (S_local > 0 ? S_local : 0);
+    if (grid > 0) {
+        reduce_kernel<<<grid, 128, 0, c->stream>>>(d_params, a);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
+    }
+    if (assemble) {
+        FinalArgs fa{};
+        fa.lay = a.lay, fa.rl = a.rl, fa.f = f;
+        fa.do_assemble = 1, fa.do_finalize = 0;
+        fa.red = a;
+        finalize_kernel<<<1, 1024, 0, c->stream>>>(d_params, fa);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
+    }
     return VBMC_OK;
 }
 
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
-                    double *d_out) {
+                    double *d_out, bool assemble_first) {
     FinalArgs a{};
     a.lay = ParamLayout{D, pad_dim(D), K};
     a.rl = RawLayout{D, K};
     a.f = f;
+    a.do_assemble = assemble_first ? 1 : 0;
+    a.do_finalize = 1;
+    if (assemble_first) {
+        VBMC_REQUIRE(c->red_args_valid, VBMC_ERR_STATE, "finalize: no reduce stage to assemble from");
+        a.red = make_reduce_args(c, D, K, f, nullptr, 0, c->red_s_begin, c->red_s_step, c->red_S_glob,
+                                 const_cast<double *>(d_raw));
+        a.red.slabs = c->red_plan_slabs, a.red.Ns_glob = c->red_Ns_glob, a.red.draws_local = c->red_draws_local;
+    }
     a.raw = d_raw;
     a.lb = c->d_lb;
     a.ub = c->d_ub;
@@ -451,7 +502,7 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.w_pen = c->w_pen;
     a.out = d_out;
     a.Pfull = a.rl.block();
-    finalize_kernel<<<1, 256, 0, c->stream>>>(d_params, a);
+    finalize_kernel<<<1, 1024, 0, c->stream>>>(d_params, a);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

@@ -38,10 +38,11 @@ gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__res
         s_mu[tid] = m;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
         double acc = 0.0;
-        for (int d = 0; d < D; ++d) acc += log(s_itau[d]);  // -sum ln tau
-        s_lnnf = h[3 * DP + 0] + h[3 * DP + 1] + acc;       // ln sf^2 + sum ln ell - sum ln tau
+        for (int d = tid; d < D; d += 32) acc += log(s_itau[d]);  // -sum ln tau
+        acc = warp_sum(acc);
+        if (tid == 0) s_lnnf = h[3 * DP + 0] + h[3 * DP + 1] + acc;  // ln sf^2 + sum ln ell - sum ln tau
     }
     __syncthreads();
     const double lnnf = s_lnnf;
@@ -53,25 +54,27 @@ gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__res
         for (int d = 0; d < DP; ++d) Mv[d] = Qv[d] = 0.0;
     }
     for (int n = tid; n < N; n += nt) {
-        double dl[DP];
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int d = 0; d < DP; d += 2) {
-            dl[d] = (d < D) ? (s_mu[d] - Xt[(size_t)d * N + n]) * s_itau[d] : 0.0;
-            dl[d + 1] = (d + 1 < D) ? (s_mu[d + 1] - Xt[(size_t)(d + 1) * N + n]) * s_itau[d + 1] : 0.0;
-            a0 = fma(dl[d], dl[d], a0);
-            a1 = fma(dl[d + 1], dl[d + 1], a1);
+            // padded rows of Xt are zero and s_mu / s_itau are zero there: no guards needed
+            const double t0 = (s_mu[d] - Xt[(size_t)d * N + n]) * s_itau[d];
+            const double t1 = (s_mu[d + 1] - Xt[(size_t)(d + 1) * N + n]) * s_itau[d + 1];
+            a0 = fma(t0, t0, a0);
+            a1 = fma(t1, t1, a1);
         }
         const double z = exp(lnnf - 0.5 * (a0 + a1));
         if (Zout) Zout[((size_t)s * K + k) * N + n] = z;
         const double za = z * al[n];
         U += za;
         if constexpr (GRAD) {
+            // delta is recomputed (2 flops) instead of kept: 40 fewer live registers -> 2x the CTAs per SM
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
-                const double t = za * dl[d];
+                const double dl = (s_mu[d] - Xt[(size_t)d * N + n]) * s_itau[d];
+                const double t = za * dl;
                 Mv[d] += t;
-                Qv[d] = fma(t, dl[d], Qv[d]);
+                Qv[d] = fma(t, dl, Qv[d]);
             }
         }
     }
@@ -99,7 +102,8 @@ gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__res
 
 }  // namespace
 
-int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part) {
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
+                cudaStream_t stream) {
     VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "gp_log_joint: no GP packed (call vbmc_gp_pack first)");
     const int D = c->gD, DP = c->gDP;
     ParamLayout lay{D, DP, K};
@@ -112,10 +116,10 @@ int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, 
 #define VBMC_CASE(NDP)                                                                                          \
     case NDP:                                                                                                   \
         if (anygrad)                                                                                            \
-            gplj_kernel<NDP, true><<<grid, nt, 0, c->stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, \
+            gplj_kernel<NDP, true><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, \
                                                                c->N, s_begin, s_step, d_part, Zout);            \
         else                                                                                                    \
-            gplj_kernel<NDP, false><<<grid, nt, 0, c->stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp,   \
+            gplj_kernel<NDP, false><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp,   \
                                                                 hs, c->N, s_begin, s_step, d_part, Zout);       \
         break
     switch (DP) {

@@ -57,7 +57,6 @@ class ShardedNegElcbo:
         self.seed = int(seed)
         self.step = 0
         self._raw = self._out = None
-        self._host = None
 
     def _buffers(self, D, K):
         torch = self.torch
@@ -66,12 +65,11 @@ class ShardedNegElcbo:
             dev = torch.device("cuda", self.device)
             self._raw = torch.zeros(n_raw, dtype=torch.float64, device=dev)
             self._out = torch.zeros(n_out, dtype=torch.float64, device=dev)
-            self._host = torch.zeros(n_out, dtype=torch.float64).pin_memory()
-        return self._raw, self._out, self._host
+        return self._raw, self._out
 
     def enqueue(self, D, K):
         """partials -> all-reduce -> finalize on the context stream (no host sync)."""
-        raw, out, _ = self._buffers(D, K)
+        raw, out = self._buffers(D, K)
         self.ctx.partials_async(self.rank, self.world, raw.data_ptr())
         if self.world > 1:
             with self.torch.cuda.stream(self.stream):
@@ -82,7 +80,6 @@ class ShardedNegElcbo:
     def __call__(self, theta, vp, Ns, theta_bnd=None, eps=None):
         from .vbmc.variational_optimization import _bound_inputs
 
-        torch = self.torch
         theta = np.asarray(theta, dtype=float)
         K, D = vp.K, vp.D
         vp.set_parameters(theta)
@@ -95,8 +92,9 @@ class ShardedNegElcbo:
         self.ctx.upload(vp, optimize, Ns, True, use_bounds, b[0], b[1], b[2], eps=eps, seed=self.seed, offset=self.step)
         out = self.enqueue(D, K)
         P = sum(n for n, o in zip((D * K, K, D, K), optimize) if o)
-        with torch.cuda.stream(self.stream):
-            self._host[: 8 + P].copy_(out[: 8 + P], non_blocking=True)
-        self.stream.synchronize()
-        h = self._host.numpy()
+        h = self.ctx.read_device(out.data_ptr(), 8 + P)  # D2H through the library's pinned buffer
         return float(h[0]), h[8 : 8 + P].copy(), float(h[1]), float(h[2]), 0
+
+    def close(self):
+        self.ctx.synchronize()
+        self.ctx.close()
