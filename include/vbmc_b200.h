@@ -183,7 +183,8 @@ int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst
  * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */
 int vbmc_set_kernel_timing(vbmc_ctx *ctx, int on);
 int vbmc_entmc_kernel_ms(vbmc_ctx *ctx, double *avg_ms, int64_t *launches);
-/* measurement only: best-of-5 FMA issue peak of this device in TFLOP/s (fp64 != 0 -> DFMA) */
+/* measurement only: best-of-5 FMA issue peak of this device in TFLOP/s
+ * (fp64: 0 -> FFMA, 1 -> DFMA, 2 -> packed FFMA2)                                         */
 int vbmc_fma_peak(vbmc_ctx *ctx, int fp64, double *tflops);
 
 #ifdef __cplusplus

@@ -167,10 +167,11 @@ class Context:
         _capi.check(self._lib.vbmc_entmc_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
-    def fma_peak(self, fp64=False) -> float:
-        """Measured FMA issue peak of this device in TFLOP/s (bench.py's compute denominator)."""
+    def fma_peak(self, kind=0) -> float:
+        """Measured FMA issue peak of this device in TFLOP/s (bench.py's compute denominator);
+        kind 0 = FFMA, 1 = DFMA, 2 = packed FFMA2."""
         tf = C.c_double()
-        _capi.check(self._lib.vbmc_fma_peak(self._h, int(bool(fp64)), C.byref(tf)))
+        _capi.check(self._lib.vbmc_fma_peak(self._h, int(kind), C.byref(tf)))
         return float(tf.value)
 
     # ------------------------------------------------------------------ GP

@@ -211,6 +211,203 @@ entmc_kernel(const double *__restrict__ prm, ParamLayout lay, int64_t half, int6
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 production kernel: same mathematics as entmc_kernel<float,...>, but
+//   * all per-dimension arithmetic is issued as packed f32x2 instructions (sm_100 FADD2 / FFMA2,
+//     two adjacent dimensions per instruction): 6*DP/2 packed ops per (pair, component) instead of
+//     6*DP scalar ones -- the kernel is bound by instruction issue / fixed-latency stalls at
+//     2 CTAs per SM, so halving the instruction count is what moves it towards the FMA-pipe roof;
+//   * the per-thread gradient sums A_d, Be_d stay in registers across the thread's pairs and are
+//     spilled to shared-memory columns once, right before the CTA record is reduced.
+template <int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128, 2)
+entmc_kernel_f32x2(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
+                   int R, const double *__restrict__ eps, uint64_t seed, uint64_t offset,
+                   double *__restrict__ part, int part_stride) {
+    constexpr int H = DP / 2;  // packed pairs of dimensions
+    const int D = lay.D, K = lay.K;
+    const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sDl = reinterpret_cast<float *>(smem_raw);                        // [K][DP]
+    KConst<float> *sKc = reinterpret_cast<KConst<float> *>(sDl + K * DP);    // [K]
+    float *sU = reinterpret_cast<float *>(sKc + K);  // Up [K][nt], Um [K][nt], racc [K][nt]  (WGRAD)
+    // without WGRAD the region only serves as the [2*DP][nt] spill area of the record reduction
+    const int u_floats = WGRAD ? 3 * K * nt : (ANYGRAD ? 2 * DP * nt : 0);
+    double *scratch = reinterpret_cast<double *>(sU + ((u_floats + 3) & ~3));
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double sig_j = sigma[j];
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    for (int i = tid; i < K * DP; i += nt) {
+        const int k = i / DP, d = i - k * DP;
+        sDl[i] = (d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) / lambd[d]) : 0.0f;
+    }
+    for (int k = tid; k < K; k += nt) {
+        const double sk = sigma[k];
+        KConst<float> c;
+        c.ck = (float)(D * (log2(sig_j) - log2(sk)));
+        c.h = (float)(kHalfLog2e / (sk * sk));
+        c.w = (float)w[k];
+        c.wis2 = (float)(w[k] / (sk * sk));
+        sKc[k] = c;
+    }
+    if (WGRAD)
+        for (int i = tid; i < K * nt; i += nt) sU[2 * K * nt + i] = 0.0f;
+    __syncthreads();
+
+    float *Up = sU + tid, *Um = sU + K * nt + tid, *racc = sU + 2 * K * nt + tid;
+    const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+    const double is2j = 1.0 / (sig_j * sig_j);
+    const float sj = (float)sig_j;
+    double hacc = 0.0;
+    float2 accA[ANYGRAD ? H : 1], accB[ANYGRAD ? H : 1];
+    if constexpr (ANYGRAD) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+    }
+
+    const int64_t slab_base = (int64_t)slab * nt * R;
+    for (int r = 0; r < R; ++r) {
+        const int64_t p = slab_base + (int64_t)r * nt + tid;  // local pair index
+        if (p >= half) break;                                  // no barriers inside the loop
+        const int64_t gpair = pair0 + p;
+
+        float2 e2[H], ne2[H];
+        {
+            float z[DP];
+            if (PHILOX) {
+                philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)gpair, D, z);
+            } else {
+                const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = (d < D) ? (float)__ldg(ep + d) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                e2[i] = make_float2(sj * z[2 * i], sj * z[2 * i + 1]);
+                ne2[i] = make_float2(-e2[i].x, -e2[i].y);
+            }
+        }
+        float2 ee = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < H; ++i) ee = __ffma2_rn(e2[i], e2[i], ee);
+        const float e2sum = ee.x + ee.y;
+        const float base = hj * e2sum;
+
+        float2 lp[ANYGRAD ? H : 1], lm[ANYGRAD ? H : 1];
+        if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) lp[i] = lm[i] = make_float2(0.f, 0.f);
+        }
+        float qp = 0.f, qm = 0.f;
+
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const KConst<float> c = sKc[k];
+            const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
+            float2 tp[H], tm[H];
+            float2 ap0 = make_float2(0.f, 0.f), ap1 = ap0, am0 = ap0, am1 = ap0;
+#pragma unroll
+            for (int i = 0; i < H; i += 2) {
+                const float2 d0 = dl2[i], d1 = dl2[i + 1];  // one LDS.128
+                tp[i] = __fadd2_rn(d0, e2[i]);
+                tm[i] = __fadd2_rn(d0, ne2[i]);
+                tp[i + 1] = __fadd2_rn(d1, e2[i + 1]);
+                tm[i + 1] = __fadd2_rn(d1, ne2[i + 1]);
+                ap0 = __ffma2_rn(tp[i], tp[i], ap0);
+                am0 = __ffma2_rn(tm[i], tm[i], am0);
+                ap1 = __ffma2_rn(tp[i + 1], tp[i + 1], ap1);
+                am1 = __ffma2_rn(tm[i + 1], tm[i + 1], am1);
+            }
+            const float2 ap = __fadd2_rn(ap0, ap1), am = __fadd2_rn(am0, am1);
+            const float cb = c.ck + base;
+            const float up = M<float>::ex2(fmaf(-c.h, ap.x + ap.y, cb));
+            const float um = M<float>::ex2(fmaf(-c.h, am.x + am.y, cb));
+            if (WGRAD) {
+                Up[k * nt] = up;
+                Um[k * nt] = um;
+            }
+            qp = fmaf(c.w, up, qp);
+            qm = fmaf(c.w, um, qm);
+            if constexpr (ANYGRAD) {
+                const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
+                    lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
+                }
+            }
+        }
+
+        hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)e2sum * is2j;
+        if constexpr (ANYGRAD) {
+            const float iqp = __frcp_rn(qp), iqm = __frcp_rn(qm);
+            const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm), nim2 = make_float2(-iqm, -iqm);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const float2 a = __fmul2_rn(lp[i], ip2);
+                accA[i] = __fadd2_rn(accA[i], __ffma2_rn(lm[i], im2, a));      // l+/q+ + l-/q-
+                accB[i] = __ffma2_rn(e2[i], __ffma2_rn(lm[i], nim2, a), accB[i]);  // e (l+/q+ - l-/q-)
+            }
+            if (WGRAD) {
+                for (int k = 0; k < K; ++k) racc[k * nt] += fmaf(Up[k * nt], iqp, Um[k * nt] * iqm);
+            }
+        }
+    }
+
+    // ---- CTA record: fixed-order fp64 reduction over the thread columns ------------------
+    double *rec = part + ((size_t)j * gridDim.x + slab) * (size_t)part_stride;
+    const double hs = block_sum(hacc, scratch);
+    if (tid == 0) rec[0] = hs;
+    if constexpr (ANYGRAD) {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        __syncthreads();
+        if (WGRAD) {
+            for (int row = wid; row < K; row += nw) {
+                const float *src = sU + 2 * K * nt + row * nt;
+                double v = 0.0;
+                for (int c = lane; c < nt; c += 32) v += (double)src[c];
+                v = warp_sum(v);
+                if (lane == 0) rec[1 + 2 * DP + row] = v;
+            }
+            __syncthreads();
+        }
+        // spill the register sums into columns [2*DP][nt] (the Up/Um scratch is free now)
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            sU[(2 * i) * nt + tid] = accA[i].x;
+            sU[(2 * i + 1) * nt + tid] = accA[i].y;
+            sU[(DP + 2 * i) * nt + tid] = accB[i].x;
+            sU[(DP + 2 * i + 1) * nt + tid] = accB[i].y;
+        }
+        __syncthreads();
+        for (int row = wid; row < 2 * DP; row += nw) {
+            const float *src = sU + row * nt;
+            double v = 0.0;
+            for (int c = lane; c < nt; c += 32) v += (double)src[c];
+            v = warp_sum(v);
+            if (lane == 0) rec[1 + row] = v;
+        }
+    }
+}
+
+static size_t entmc_smem_f32x2(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    size_t fl = (size_t)K * DP;
+    size_t b = fl * sizeof(float) + (size_t)K * sizeof(KConst<float>);
+    size_t u = wgrad ? (size_t)3 * K * nt : (anygrad ? (size_t)2 * DP * nt : 0);
+    if (wgrad && u < (size_t)2 * DP * nt) u = (size_t)2 * DP * nt;
+    u = (u + 3) & ~(size_t)3;
+    b += u * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    return b + 32 * sizeof(double);
+}
+
 template <typename T>
 size_t entmc_smem(int DP, int K, int nt, bool wgrad, bool anygrad) {
     size_t b = (size_t)K * DP * sizeof(T) + (size_t)K * sizeof(KConst<T>);
@@ -223,13 +420,21 @@ size_t entmc_smem(int DP, int K, int nt, bool wgrad, bool anygrad) {
 template <typename T, int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
 int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, const double *d_eps,
                 uint64_t seed, uint64_t offset, double *d_part) {
-    auto kern = entmc_kernel<T, DP, WGRAD, ANYGRAD, PHILOX>;
-    VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     dim3 grid(plan.slabs, lay.K);
     if (c->time_entmc) VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
-    kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
-                                                       plan.pairs_per_thread, d_eps, seed, offset, d_part,
-                                                       entpart_stride(DP, lay.K));
+    if constexpr (sizeof(T) == 4) {
+        auto kern = entmc_kernel_f32x2<DP, WGRAD, ANYGRAD, PHILOX>;
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
+                                                           plan.pairs_per_thread, d_eps, seed, offset, d_part,
+                                                           entpart_stride(DP, lay.K));
+    } else {
+        auto kern = entmc_kernel<T, DP, WGRAD, ANYGRAD, PHILOX>;
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
+                                                           plan.pairs_per_thread, d_eps, seed, offset, d_part,
+                                                           entpart_stride(DP, lay.K));
+    }
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     if (c->time_entmc) {
@@ -306,13 +511,13 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     int nt = 128;
     auto smem_of = [&](int t) {
         return precision == VBMC_PREC_F64 ? entmc_smem<double>(DP, K, t, wgrad, true)
-                                          : entmc_smem<float>(DP, K, t, wgrad, true);
+                                          : entmc_smem_f32x2(DP, K, t, wgrad, true);
     };
     while (nt > 32 && smem_of(nt) > smem_cap) nt >>= 1;
     VBMC_REQUIRE(smem_of(nt) <= smem_cap, VBMC_ERR_UNSUPPORTED, "entmc: K too large for shared memory");
     const size_t smem = smem_of(nt);
     int per_sm = (int)(smem_cap / (smem + 1024));
-    const int reg_limit = precision == VBMC_PREC_F64 ? (nt >= 128 ? 2 : 4) : (nt >= 128 ? 3 : 6);
+    const int reg_limit = nt >= 128 ? 2 : 4;  // both kernels sit near 200-255 registers per thread
     if (per_sm > reg_limit) per_sm = reg_limit;
     if (per_sm < 1) per_sm = 1;
     const int64_t slots = (int64_t)c->sm_count * per_sm;
@@ -349,7 +554,7 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
     // smem of the plan was sized for anygrad; recompute for the actual instantiation
     EntmcPlan p = plan;
     p.smem = precision == VBMC_PREC_F64 ? entmc_smem<double>(lay.DP, K, plan.threads, wgrad, anygrad)
-                                        : entmc_smem<float>(lay.DP, K, plan.threads, wgrad, anygrad);
+                                        : entmc_smem_f32x2(lay.DP, K, plan.threads, wgrad, anygrad);
     if (precision == VBMC_PREC_F64)
         return launch_t<double>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
     return launch_t<float>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);

@@ -50,17 +50,26 @@ __global__ void __launch_bounds__(128) reduce_kernel(const double *__restrict__ 
     if ((int)blockIdx.x < n_ent) {
         // ---------------------------------------------------------- Monte-Carlo entropy, component j
         const int j = blockIdx.x, st = a.ent_stride;
+        // last warp: sum_d ln lambda_d (lanes over d) while the others stream the slab records
+        if (tid >= nt - 32) {
+            double sl = 0.0;
+            for (int d = tid - (nt - 32); d < D; d += 32) sl += log(lambd[d]);
+            sl = warp_sum(sl);
+            if (tid == nt - 32) scratch[0] = sl;
+        }
+        double v0 = 0.0;
         for (int t = tid; t < st; t += nt) {
             double v = 0.0;
+#pragma unroll 4
             for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + t];
-            if (t == 0) {
-                double sumlnl = 0.0;
-                for (int d = 0; d < D; ++d) sumlnl += log(lambd[d]);
-                // + (draws of this rank) * log( nconst / sigma_j^D )   (entmc_vbmc.py:53-56,77)
-                v += a.draws_local * (-0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]));
-            }
-            a.crec[(size_t)j * st + t] = v;
+            if (t == 0)
+                v0 = v;
+            else
+                a.crec[(size_t)j * st + t] = v;
         }
+        __syncthreads();
+        // + (draws of this rank) * log( nconst / sigma_j^D )   (entmc_vbmc.py:53-56,77)
+        if (tid == 0) a.crec[(size_t)j * st] = v0 + a.draws_local * (-0.5 * D * kLog2Pi - scratch[0] - D * log(sigma[j]));
         return;
     }
     if (!a.f.have_gp) return;
@@ -162,29 +171,31 @@ __device__ void assemble_raw(const double *__restrict__ prm, const ReduceArgs &a
         hpart = block_sum(hpart, scratch);
         if (tid == 0) raw[0] = hpart;
         if (anyg) {
-            for (int e = tid; e < rl.block(); e += nt) {
-                double v;
-                if (e < rl.o_sig()) {  // d/dmu_j (:98)
-                    const int j = e / D, d = e - j * D;
-                    v = w[j] * a.crec[(size_t)j * st + 1 + d] * inv_ns / lambd[d];
-                } else if (e < rl.o_lam()) {  // d/dsigma_j (:102-103)
-                    const int j = e - rl.o_sig();
-                    double u = 0.0;
-                    for (int d = 0; d < D; ++d) u += a.crec[(size_t)j * st + 1 + DP + d];
-                    v = w[j] * u * inv_ns / sigma[j];
-                } else if (e < rl.o_w()) {  // d/dlambda_d (:106-108)
-                    const int d = e - rl.o_lam();
-                    double u = 0.0;
-                    for (int j = 0; j < K; ++j) u += w[j] * a.crec[(size_t)j * st + 1 + DP + d];
-                    v = u * inv_ns / lambd[d];
-                } else {  // d/dw_k (:111-112)
-                    const int k = e - rl.o_w();
-                    double u = 0.0;
+            // d/dmu_j (:98): element-wise
+            for (int e = tid; e < K * D; e += nt) {
+                const int j = e / D, d = e - j * D;
+                ent[rl.o_mu() + e] = w[j] * a.crec[(size_t)j * st + 1 + d] * inv_ns / lambd[d];
+            }
+            // cross sums: one WARP per output entry, lanes over the summed index, butterfly tree
+            const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+            for (int idx = wid; idx < 2 * K + D; idx += nw) {
+                double u = 0.0;
+                if (idx < K) {  // d/dsigma_j (:102-103): sum over dimensions
+                    for (int d = lane; d < D; d += 32) u += a.crec[(size_t)idx * st + 1 + DP + d];
+                    u = warp_sum(u);
+                    if (lane == 0) ent[rl.o_sig() + idx] = w[idx] * u * inv_ns / sigma[idx];
+                } else if (idx < K + D) {  // d/dlambda_d (:106-108): sum over components
+                    const int d = idx - K;
+                    for (int j = lane; j < K; j += 32) u += w[j] * a.crec[(size_t)j * st + 1 + DP + d];
+                    u = warp_sum(u);
+                    if (lane == 0) ent[rl.o_lam() + d] = u * inv_ns / lambd[d];
+                } else {  // d/dw_k (:111-112): direct term + sum over components
+                    const int k = idx - K - D;
                     if (a.f.grad[3])
-                        for (int j = 0; j < K; ++j) u += w[j] * a.crec[(size_t)j * st + 1 + 2 * DP + k];
-                    v = -(a.crec[(size_t)k * st] + u) * inv_ns;
+                        for (int j = lane; j < K; j += 32) u += w[j] * a.crec[(size_t)j * st + 1 + 2 * DP + k];
+                    u = warp_sum(u);
+                    if (lane == 0) ent[rl.o_w() + k] = -(a.crec[(size_t)k * st] + u) * inv_ns;
                 }
-                ent[e] = v;
             }
         }
     }
@@ -195,6 +206,7 @@ __device__ void assemble_raw(const double *__restrict__ prm, const ReduceArgs &a
         for (int e = tid; e < blk + 1; e += nt) {
             if (e > 0 && !anyg) break;
             double v = 0.0;
+#pragma unroll 4
             for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * (1 + blk) + e];
             v *= inv_S;
             if (e == 0)
