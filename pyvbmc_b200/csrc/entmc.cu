@@ -397,6 +397,219 @@ entmc_kernel_f32x2(const double *__restrict__ prm, ParamLayout lay, int64_t half
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 production kernel, "dimension-split": TWO ADJACENT LANES evaluate one antithetic pair, lane
+// h in {0,1} holding dims [h*DP/2, (h+1)*DP/2).  Same instruction count per pair as the one-thread
+// version (the per-dimension work splits evenly; only the scalar tail is duplicated), but half the
+// registers (~110) and half the per-thread shared-memory columns, so 4 CTAs x 128 threads fit per
+// SM instead of 2: the kernel is bound by fixed-latency stalls of the dependent FADD2->FFMA2 chains,
+// and twice the resident warps is what hides them (ncu: issue-active 43 % -> see profiles/).
+//   per (pair, k) and lane:  DP/4 FADD2 x2 (t+, t-), DP/4 FFMA2 x2 (|t|^2), 2 SHFL (combine the two
+//   half-sums), 2 MUFU.EX2, DP/4 FFMA2 x2 (l+, l-).
+template <int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128, 4)
+entmc_kernel_f32x2_ds(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0,
+                      int64_t half_glob, int R, const double *__restrict__ eps, uint64_t seed, uint64_t offset,
+                      double *__restrict__ part, int part_stride) {
+    constexpr int DH = DP / 2;            // dims per lane
+    constexpr int H2 = DH / 2;            // packed float2 per lane
+    constexpr int DHP = (DH + 3) & ~3;    // table row length per half (float4 addressable)
+    constexpr int NQ = DHP / 4;
+    const int D = lay.D, K = lay.K;
+    const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int h = tid & 1, pt = tid >> 1, npt = nt >> 1;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sDl = reinterpret_cast<float *>(smem_raw);                             // [K][2][DHP]
+    KConst<float> *sKc = reinterpret_cast<KConst<float> *>(sDl + K * 2 * DHP);    // [K]
+    float *sU = reinterpret_cast<float *>(sKc + K);  // U [K][nt], racc [K][nt] (WGRAD); later the [2*DP][npt] spill
+    const int u_floats = WGRAD ? max(2 * K * nt, DP * nt) : (ANYGRAD ? DP * nt : 0);
+    double *scratch = reinterpret_cast<double *>(sU + ((u_floats + 3) & ~3));
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double sig_j = sigma[j];
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    for (int i = tid; i < K * 2 * DHP; i += nt) {
+        const int k = i / (2 * DHP), r = i - k * 2 * DHP, hh = r / DHP, c = r - hh * DHP;
+        const int d = hh * DH + c;
+        sDl[i] = (c < DH && d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) / lambd[d]) : 0.0f;
+    }
+    for (int k = tid; k < K; k += nt) {
+        const double sk = sigma[k];
+        KConst<float> c;
+        c.ck = (float)(D * (log2(sig_j) - log2(sk)));
+        c.h = (float)(kHalfLog2e / (sk * sk));
+        c.w = (float)w[k];
+        c.wis2 = (float)(w[k] / (sk * sk));
+        sKc[k] = c;
+    }
+    if (WGRAD)
+        for (int i = tid; i < K * nt; i += nt) sU[K * nt + i] = 0.0f;
+    __syncthreads();
+
+    float *Ucol = sU + tid, *racc = sU + K * nt + tid;
+    const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+    const double is2j = 1.0 / (sig_j * sig_j);
+    const float sj = (float)sig_j;
+    double hacc = 0.0;
+    float2 accA[ANYGRAD ? H2 : 1], accB[ANYGRAD ? H2 : 1];
+    if constexpr (ANYGRAD) {
+#pragma unroll
+        for (int i = 0; i < H2; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+    }
+
+    const int64_t slab_base = (int64_t)slab * npt * R;
+    for (int r = 0; r < R; ++r) {
+        const int64_t p = slab_base + (int64_t)r * npt + pt;  // local pair index (same for both lanes)
+        const bool live = p < half;                            // whole warps keep running: shuffles below
+        if (!__any_sync(0xffffffffu, live)) break;
+        const int64_t gpair = pair0 + (live ? p : 0);
+
+        float2 e2[H2], ne2[H2];
+        {
+            float z[DH];
+            if (PHILOX) {
+                philox_normals_half<DH>(seed, offset, (uint32_t)j, (uint64_t)gpair, h, D, z);
+            } else {
+                const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D + h * DH;
+#pragma unroll
+                for (int i = 0; i < DH; ++i) z[i] = (h * DH + i < D) ? (float)__ldg(ep + i) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < H2; ++i) {
+                e2[i] = make_float2(sj * z[2 * i], sj * z[2 * i + 1]);
+                ne2[i] = make_float2(-e2[i].x, -e2[i].y);
+            }
+        }
+        float2 ee = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < H2; ++i) ee = __ffma2_rn(e2[i], e2[i], ee);
+        float e2sum = ee.x + ee.y;
+        e2sum += __shfl_xor_sync(0xffffffffu, e2sum, 1);
+        const float base = hj * e2sum;
+
+        float2 lp[ANYGRAD ? H2 : 1], lm[ANYGRAD ? H2 : 1];
+        if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < H2; ++i) lp[i] = lm[i] = make_float2(0.f, 0.f);
+        }
+        float qp = 0.f, qm = 0.f;
+
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const KConst<float> c = sKc[k];
+            const float4 *row = reinterpret_cast<const float4 *>(sDl + (k * 2 + h) * DHP);
+            float2 tp[H2], tm[H2];
+            float2 ap0 = make_float2(0.f, 0.f), ap1 = ap0, am0 = ap0, am1 = ap0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 v = row[q];
+                if (2 * q < H2) {
+                    const float2 d0 = make_float2(v.x, v.y);
+                    tp[2 * q] = __fadd2_rn(d0, e2[2 * q]);
+                    tm[2 * q] = __fadd2_rn(d0, ne2[2 * q]);
+                    ap0 = __ffma2_rn(tp[2 * q], tp[2 * q], ap0);
+                    am0 = __ffma2_rn(tm[2 * q], tm[2 * q], am0);
+                }
+                if (2 * q + 1 < H2) {
+                    const float2 d1 = make_float2(v.z, v.w);
+                    tp[2 * q + 1] = __fadd2_rn(d1, e2[2 * q + 1]);
+                    tm[2 * q + 1] = __fadd2_rn(d1, ne2[2 * q + 1]);
+                    ap1 = __ffma2_rn(tp[2 * q + 1], tp[2 * q + 1], ap1);
+                    am1 = __ffma2_rn(tm[2 * q + 1], tm[2 * q + 1], am1);
+                }
+            }
+            const float2 ap = __fadd2_rn(ap0, ap1), am = __fadd2_rn(am0, am1);
+            float pa = ap.x + ap.y, pm = am.x + am.y;
+            pa += __shfl_xor_sync(0xffffffffu, pa, 1);  // |t+|^2 over all dims (commutative: both lanes agree bitwise)
+            pm += __shfl_xor_sync(0xffffffffu, pm, 1);
+            const float cb = c.ck + base;
+            const float up = M<float>::ex2(fmaf(-c.h, pa, cb));
+            const float um = M<float>::ex2(fmaf(-c.h, pm, cb));
+            if (WGRAD) Ucol[k * nt] = h ? um : up;  // lane 0 keeps u+, lane 1 keeps u-
+            qp = fmaf(c.w, up, qp);
+            qm = fmaf(c.w, um, qm);
+            if constexpr (ANYGRAD) {
+                const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                for (int i = 0; i < H2; ++i) {
+                    lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
+                    lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
+                }
+            }
+        }
+
+        if (live && h == 0)
+            hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)e2sum * is2j;
+        if constexpr (ANYGRAD) {
+            const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
+            const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm), nim2 = make_float2(-iqm, -iqm);
+#pragma unroll
+            for (int i = 0; i < H2; ++i) {
+                const float2 a = __fmul2_rn(lp[i], ip2);
+                accA[i] = __fadd2_rn(accA[i], __ffma2_rn(lm[i], im2, a));          // l+/q+ + l-/q-
+                accB[i] = __ffma2_rn(e2[i], __ffma2_rn(lm[i], nim2, a), accB[i]);  // e (l+/q+ - l-/q-)
+            }
+            if (WGRAD) {
+                const float iq = h ? iqm : iqp;
+                for (int k = 0; k < K; ++k) racc[k * nt] = fmaf(Ucol[k * nt], iq, racc[k * nt]);
+            }
+        }
+    }
+
+    // ---- CTA record: fixed-order fp64 reduction over the thread columns ------------------
+    double *rec = part + ((size_t)j * gridDim.x + slab) * (size_t)part_stride;
+    const double hs = block_sum(hacc, scratch);
+    if (tid == 0) rec[0] = hs;
+    if constexpr (ANYGRAD) {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        __syncthreads();
+        if (WGRAD) {
+            for (int row = wid; row < K; row += nw) {
+                const float *src = sU + K * nt + row * nt;
+                double v = 0.0;
+                for (int c = lane; c < nt; c += 32) v += (double)src[c];
+                v = warp_sum(v);
+                if (lane == 0) rec[1 + 2 * DP + row] = v;
+            }
+            __syncthreads();
+        }
+        // spill the register sums into [2*DP][npt] columns (the U scratch is free now)
+#pragma unroll
+        for (int i = 0; i < H2; ++i) {
+            const int d = h * DH + 2 * i;
+            sU[(d)*npt + pt] = accA[i].x;
+            sU[(d + 1) * npt + pt] = accA[i].y;
+            sU[(DP + d) * npt + pt] = accB[i].x;
+            sU[(DP + d + 1) * npt + pt] = accB[i].y;
+        }
+        __syncthreads();
+        for (int row = wid; row < 2 * DP; row += nw) {
+            const float *src = sU + row * npt;
+            double v = 0.0;
+            for (int c = lane; c < npt; c += 32) v += (double)src[c];
+            v = warp_sum(v);
+            if (lane == 0) rec[1 + row] = v;
+        }
+    }
+}
+
+static size_t entmc_smem_ds(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    const int DHP = ((DP / 2) + 3) & ~3;
+    size_t b = (size_t)K * 2 * DHP * sizeof(float) + (size_t)K * sizeof(KConst<float>);
+    size_t u = wgrad ? (size_t)2 * K * nt : 0;
+    if (anygrad && u < (size_t)DP * nt) u = (size_t)DP * nt;
+    u = (u + 3) & ~(size_t)3;
+    b += u * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    return b + 32 * sizeof(double);
+}
+
 static size_t entmc_smem_f32x2(int DP, int K, int nt, bool wgrad, bool anygrad) {
     size_t fl = (size_t)K * DP;
     size_t b = fl * sizeof(float) + (size_t)K * sizeof(KConst<float>);
@@ -423,7 +636,7 @@ int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan
     dim3 grid(plan.slabs, lay.K);
     if (c->time_entmc) VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
     if constexpr (sizeof(T) == 4) {
-        auto kern = entmc_kernel_f32x2<DP, WGRAD, ANYGRAD, PHILOX>;
+        auto kern = entmc_kernel_f32x2_ds<DP, WGRAD, ANYGRAD, PHILOX>;
         VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
         kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
                                                            plan.pairs_per_thread, d_eps, seed, offset, d_part,
@@ -511,23 +724,27 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     int nt = 128;
     auto smem_of = [&](int t) {
         return precision == VBMC_PREC_F64 ? entmc_smem<double>(DP, K, t, wgrad, true)
-                                          : entmc_smem_f32x2(DP, K, t, wgrad, true);
+                                          : entmc_smem_ds(DP, K, t, wgrad, true);
     };
     while (nt > 32 && smem_of(nt) > smem_cap) nt >>= 1;
     VBMC_REQUIRE(smem_of(nt) <= smem_cap, VBMC_ERR_UNSUPPORTED, "entmc: K too large for shared memory");
     const size_t smem = smem_of(nt);
     int per_sm = (int)(smem_cap / (smem + 1024));
-    const int reg_limit = nt >= 128 ? 2 : 4;  // both kernels sit near 200-255 registers per thread
+    // registers: the fp64 kernel sits near 255/thread (2 CTAs of 128), the dimension-split fp32 kernel
+    // is built with __launch_bounds__(128, 4)
+    const int reg_limit = (precision == VBMC_PREC_F64 ? 2 : 4) * (128 / nt);
     if (per_sm > reg_limit) per_sm = reg_limit;
     if (per_sm < 1) per_sm = 1;
     const int64_t slots = (int64_t)c->sm_count * per_sm;
+    // pairs evaluated per CTA sweep: one per thread (fp64) or one per two lanes (fp32, dimension-split)
+    const int ppi = precision == VBMC_PREC_F64 ? nt : nt / 2;
 
     // candidate R: cost ~ waves * (R + overhead); overhead ~ table set-up + record reduction
     int bestR = 1;
     double best = 1e300;
     const double overhead = 0.35;
     for (int R = 1; R <= 64; ++R) {
-        const int64_t slabs = (half_local + (int64_t)nt * R - 1) / ((int64_t)nt * R);
+        const int64_t slabs = (half_local + (int64_t)ppi * R - 1) / ((int64_t)ppi * R);
         const int64_t ctas = slabs * K;
         const int64_t waves = (ctas + slots - 1) / slots;
         const double cost = (double)waves * (R + overhead);
@@ -536,7 +753,7 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     }
     plan->threads = nt;
     plan->pairs_per_thread = bestR;
-    plan->slabs = (int)((half_local + (int64_t)nt * bestR - 1) / ((int64_t)nt * bestR));
+    plan->slabs = (int)((half_local + (int64_t)ppi * bestR - 1) / ((int64_t)ppi * bestR));
     if (plan->slabs < 1) plan->slabs = 1;
     plan->half = half_local;
     plan->pair0 = 0;
@@ -554,7 +771,7 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
     // smem of the plan was sized for anygrad; recompute for the actual instantiation
     EntmcPlan p = plan;
     p.smem = precision == VBMC_PREC_F64 ? entmc_smem<double>(lay.DP, K, plan.threads, wgrad, anygrad)
-                                        : entmc_smem_f32x2(lay.DP, K, plan.threads, wgrad, anygrad);
+                                        : entmc_smem_ds(lay.DP, K, plan.threads, wgrad, anygrad);
     if (precision == VBMC_PREC_F64)
         return launch_t<double>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
     return launch_t<float>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);

@@ -33,22 +33,39 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &z0, fl
     z1 = r * s;
 }
 
+// The D (padded: DP) dimensions of a draw are generated in two halves of DH = DP/2 dimensions:
+// half h in {0,1} owns dims [h*DH, h*DH + DH) and takes its normals from the Philox blocks
+// (pair, j | b << 20 | h << 28), b = 0 .. ceil(DH/4)-1.  The split mirrors the fp32 entropy kernel,
+// where two adjacent lanes evaluate one antithetic pair, each lane holding one half of the dims.
+template <int DH>
+__device__ __forceinline__ void philox_normals_half(uint64_t seed, uint64_t offset, uint32_t j, uint64_t pair,
+                                                    int h, int D, float (&z)[DH]) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    constexpr int NB = (DH + 3) / 4;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint4 ctr = make_uint4((uint32_t)pair, j | ((uint32_t)b << 20) | ((uint32_t)h << 28), (uint32_t)offset,
+                                     (uint32_t)(offset >> 32) ^ (uint32_t)(pair >> 32));
+        const uint4 x = philox4x32_10(ctr, key);
+        float n[4];
+        box_muller(x.x, x.y, n[0], n[1]);
+        box_muller(x.z, x.w, n[2], n[3]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (4 * b + t < DH) z[4 * b + t] = (h * DH + 4 * b + t < D) ? n[t] : 0.0f;
+    }
+}
+
 // z[0..D) ~ N(0,1) for (component j, antithetic pair `pair`); z[d >= D] = 0
 template <int DP>
 __device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t offset, uint32_t j, uint64_t pair, int D,
                                                float (&z)[DP]) {
-    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    constexpr int DH = DP / 2;
+    float a[DH], b[DH];
+    philox_normals_half<DH>(seed, offset, j, pair, 0, D, a);
+    philox_normals_half<DH>(seed, offset, j, pair, 1, D, b);
 #pragma unroll
-    for (int b = 0; b < DP / 4; ++b) {
-        const uint4 ctr = make_uint4((uint32_t)pair, j | ((uint32_t)b << 24), (uint32_t)offset,
-                                     (uint32_t)(offset >> 32) ^ (uint32_t)(pair >> 32));
-        const uint4 x = philox4x32_10(ctr, key);
-        box_muller(x.x, x.y, z[4 * b + 0], z[4 * b + 1]);
-        box_muller(x.z, x.w, z[4 * b + 2], z[4 * b + 3]);
-    }
-#pragma unroll
-    for (int d = 0; d < DP; ++d)
-        if (d >= D) z[d] = 0.0f;
+    for (int i = 0; i < DH; ++i) z[i] = a[i], z[DH + i] = b[i];
 }
 
 }  // namespace vbmc
