@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points declared in include/vbmc_b200.h: context, GP pack and the
 // orchestration of one evaluation  upload -> partials -> [all-reduce] -> finalize -> download.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -242,6 +243,8 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     CtxEx *x = new CtxEx();
     x->c.device = device;
     x->c.sm_count = prop.multiProcessorCount;
+    if (const char *v = getenv("VBMC_ENTMC_VARIANT")) x->c.entmc_variant = atoi(v);
+    if (const char *g = getenv("VBMC_ENTMC_GUARD")) x->c.entmc_guard = (float)atof(g);
     VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
     VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream2, cudaStreamNonBlocking));
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_fork, cudaEventDisableTiming));

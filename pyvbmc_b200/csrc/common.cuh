@@ -163,6 +163,10 @@ struct Ctx {
     vbmc_elcbo_in cur{};
     int ent_grid_slabs = 0;
 
+    // fp32 entropy kernel selection (VBMC_ENTMC_VARIANT / VBMC_ENTMC_GUARD environment overrides)
+    int entmc_variant = 0;
+    float entmc_guard = 128.0f;
+
     // entmc kernel timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool time_entmc = false;
@@ -175,7 +179,9 @@ int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
 // ----------------------------------------------------------------------------- launchers
 // entmc.cu
+enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3 };
 struct EntmcPlan {
+    int variant;
     int threads, slabs, pairs_per_thread;
     int64_t half;      // pairs per component handled by THIS rank
     int64_t pair0;     // first pair index (global) of this rank's range

@@ -599,6 +599,247 @@ entmc_kernel_f32x2_ds(const double *__restrict__ prm, ParamLayout lay, int64_t h
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 production kernel, "expanded" form.  One thread per antithetic pair.  Per (pair, component):
+//   B      = sum_d Delta_kd e_d                                  (DP/2 FFMA2)
+//   |t+-|^2 = A_k + E +- 2B,   A_k = |Delta_k|^2 (table), E = |e|^2 (per pair)
+//   s+-    = (ck - h_k A_k) + (h_j - h_k) E -+ 2 h_k B           (3 FFMA, constants folded per k)
+//   l+-    = sum_k g+-_k Delta_k  +- e sum_k g+-_k                (DP/2 FFMA2 each; the e-term once per pair)
+// i.e. 1.5 DP packed FMAs per (pair, k) instead of the 3 DP of the direct form, and no t+- registers
+// live across the exponential.  The expansion cancels when a draw lands close to ANOTHER component's
+// centre relative to |Delta|: the absolute error of s is ~ h_k (A_k + E) 2^-24.  The set-up therefore
+// flags every k with h_k (A_k + E_max) > kGuard and those components take the DIRECT path
+// (t = Delta +- e, |t|^2 summed term by term, l += g t) inside the same loop; the flag is uniform over
+// the CTA (one mixture component j per CTA), so the branch never diverges.  k == j has Delta = 0, A = 0:
+// its distance is E exactly in both forms.
+struct alignas(8) KFast {
+    float ck2, h2, hd, w, wis2, flag;  // ck - h A | 2 h | h_j - h | w_k | w_k / sigma_k^2 | 1 => direct path
+    float ck, h;                       // direct-path constants
+};
+
+template <int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128, 2)
+entmc_kernel_fast(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
+                  int R, const double *__restrict__ eps, uint64_t seed, uint64_t offset, double *__restrict__ part,
+                  int part_stride, float guard) {
+    constexpr int H = DP / 2;  // packed pairs of dimensions
+    const int D = lay.D, K = lay.K;
+    const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sDl = reinterpret_cast<float *>(smem_raw);              // [K][DP]
+    KFast *sKc = reinterpret_cast<KFast *>(sDl + K * DP);          // [K]
+    float *sU = reinterpret_cast<float *>(sKc + K);  // Up [K][nt], Um [K][nt], racc [K][nt] (WGRAD); spill [2 DP][nt]
+    const int u_floats = WGRAD ? max(3 * K * nt, 2 * DP * nt) : (ANYGRAD ? 2 * DP * nt : 0);
+    double *scratch = reinterpret_cast<double *>(sU + ((u_floats + 3) & ~3));
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double sig_j = sigma[j];
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    for (int i = tid; i < K * DP; i += nt) {
+        const int k = i / DP, d = i - k * DP;
+        sDl[i] = (d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) / lambd[d]) : 0.0f;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        const double sk = sigma[k];
+        const double hk = kHalfLog2e / (sk * sk), hjd = kHalfLog2e / (sig_j * sig_j);
+        const double ck = D * (log2(sig_j) - log2(sk));
+        double A = 0.0;  // |Delta_k|^2 of the ROUNDED table entries (what the FFMA2s will see)
+        for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
+        // bound on E = sigma_j^2 |eps|^2 : |eps|^2 <= D + 8 sqrt(2 D) + 32 except with probability < 1e-12
+        const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+        KFast c;
+        c.ck2 = (float)(ck - hk * A);
+        c.h2 = (float)(2.0 * hk);
+        c.hd = (float)(hjd - hk);
+        c.w = (float)w[k];
+        c.wis2 = (float)(w[k] / (sk * sk));
+        c.flag = (hk * (A + Emax) > (double)guard && k != j) ? 1.0f : 0.0f;
+        c.ck = (float)ck;
+        c.h = (float)hk;
+        sKc[k] = c;
+    }
+    if (WGRAD)
+        for (int i = tid; i < K * nt; i += nt) sU[2 * K * nt + i] = 0.0f;
+    __syncthreads();
+
+    float *Up = sU + tid, *Um = sU + K * nt + tid, *racc = sU + 2 * K * nt + tid;
+    const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+    const double is2j = 1.0 / (sig_j * sig_j);
+    const float sj = (float)sig_j;
+    double hacc = 0.0;
+    float2 accA[ANYGRAD ? H : 1], accB[ANYGRAD ? H : 1];
+    if constexpr (ANYGRAD) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+    }
+
+    const int64_t slab_base = (int64_t)slab * nt * R;
+    for (int r = 0; r < R; ++r) {
+        const int64_t p = slab_base + (int64_t)r * nt + tid;  // local pair index
+        if (p >= half) break;                                  // no barriers / shuffles inside the loop
+        const int64_t gpair = pair0 + p;
+
+        float2 e2[H];
+        {
+            float z[DP];
+            if (PHILOX) {
+                philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)gpair, D, z);
+            } else {
+                const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = (d < D) ? (float)__ldg(ep + d) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) e2[i] = make_float2(sj * z[2 * i], sj * z[2 * i + 1]);
+        }
+        float2 ee = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < H; ++i) ee = __ffma2_rn(e2[i], e2[i], ee);
+        const float E = ee.x + ee.y;
+        const float base = hj * E;
+
+        float2 lp[ANYGRAD ? H : 1], lm[ANYGRAD ? H : 1];
+        if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) lp[i] = lm[i] = make_float2(0.f, 0.f);
+        }
+        float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
+
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            const KFast c = sKc[k];
+            const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
+            float2 dl[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) dl[i] = dl2[i];
+            float up, um;
+            if (c.flag == 0.0f) {
+                float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+#pragma unroll
+                for (int i = 0; i + 1 < H; i += 2) {
+                    b0 = __ffma2_rn(dl[i], e2[i], b0);
+                    b1 = __ffma2_rn(dl[i + 1], e2[i + 1], b1);
+                }
+                if (H & 1) b0 = __ffma2_rn(dl[H - 1], e2[H - 1], b0);
+                const float2 bb = __fadd2_rn(b0, b1);
+                const float B = bb.x + bb.y;
+                const float s0 = fmaf(c.hd, E, c.ck2);
+                up = M<float>::ex2(fmaf(-c.h2, B, s0));
+                um = M<float>::ex2(fmaf(c.h2, B, s0));
+                qp = fmaf(c.w, up, qp);
+                qm = fmaf(c.w, um, qm);
+                if constexpr (ANYGRAD) {
+                    const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                    Gp += gpv;
+                    Gm += gmv;
+                    const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        lp[i] = __ffma2_rn(gp2, dl[i], lp[i]);
+                        lm[i] = __ffma2_rn(gm2, dl[i], lm[i]);
+                    }
+                }
+            } else {
+                // direct path: differences first, squared term by term (no cancellation)
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+                float2 tp[H], tm[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    tp[i] = __fadd2_rn(dl[i], e2[i]);
+                    tm[i] = __fadd2_rn(dl[i], make_float2(-e2[i].x, -e2[i].y));
+                    a0 = __ffma2_rn(tp[i], tp[i], a0);
+                    a1 = __ffma2_rn(tm[i], tm[i], a1);
+                }
+                const float cb = c.ck + base;
+                up = M<float>::ex2(fmaf(-c.h, a0.x + a0.y, cb));
+                um = M<float>::ex2(fmaf(-c.h, a1.x + a1.y, cb));
+                qp = fmaf(c.w, up, qp);
+                qm = fmaf(c.w, um, qm);
+                if constexpr (ANYGRAD) {
+                    const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                    const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
+                        lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
+                    }
+                }
+            }
+            if (WGRAD) {
+                Up[k * nt] = up;
+                Um[k * nt] = um;
+            }
+        }
+
+        hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
+        if constexpr (ANYGRAD) {
+            const float iqp = __frcp_rn(qp), iqm = __frcp_rn(qm);
+            const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm);
+            const float2 Gp2 = make_float2(Gp, Gp), nGm2 = make_float2(-Gm, -Gm);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const float2 a = __fmul2_rn(__ffma2_rn(e2[i], Gp2, lp[i]), ip2);   // l+ / q+
+                const float2 b = __fmul2_rn(__ffma2_rn(e2[i], nGm2, lm[i]), im2);  // l- / q-
+                accA[i] = __fadd2_rn(accA[i], __fadd2_rn(a, b));
+                accB[i] = __ffma2_rn(e2[i], __fadd2_rn(a, make_float2(-b.x, -b.y)), accB[i]);
+            }
+            if (WGRAD) {
+                for (int k = 0; k < K; ++k) racc[k * nt] += fmaf(Up[k * nt], iqp, Um[k * nt] * iqm);
+            }
+        }
+    }
+
+    // ---- CTA record: fixed-order fp64 reduction over the thread columns ------------------
+    double *rec = part + ((size_t)j * gridDim.x + slab) * (size_t)part_stride;
+    const double hs = block_sum(hacc, scratch);
+    if (tid == 0) rec[0] = hs;
+    if constexpr (ANYGRAD) {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        __syncthreads();
+        if (WGRAD) {
+            for (int row = wid; row < K; row += nw) {
+                const float *src = sU + 2 * K * nt + row * nt;
+                double v = 0.0;
+                for (int c = lane; c < nt; c += 32) v += (double)src[c];
+                v = warp_sum(v);
+                if (lane == 0) rec[1 + 2 * DP + row] = v;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            sU[(2 * i) * nt + tid] = accA[i].x;
+            sU[(2 * i + 1) * nt + tid] = accA[i].y;
+            sU[(DP + 2 * i) * nt + tid] = accB[i].x;
+            sU[(DP + 2 * i + 1) * nt + tid] = accB[i].y;
+        }
+        __syncthreads();
+        for (int row = wid; row < 2 * DP; row += nw) {
+            const float *src = sU + row * nt;
+            double v = 0.0;
+            for (int c = lane; c < nt; c += 32) v += (double)src[c];
+            v = warp_sum(v);
+            if (lane == 0) rec[1 + row] = v;
+        }
+    }
+}
+
+static size_t entmc_smem_fast(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    size_t b = (size_t)K * DP * sizeof(float) + (size_t)K * sizeof(KFast);
+    size_t u = wgrad ? (size_t)3 * K * nt : 0;
+    if (anygrad && u < (size_t)2 * DP * nt) u = (size_t)2 * DP * nt;
+    u = (u + 3) & ~(size_t)3;
+    b += u * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    return b + 32 * sizeof(double);
+}
+
 static size_t entmc_smem_ds(int DP, int K, int nt, bool wgrad, bool anygrad) {
     const int DHP = ((DP / 2) + 3) & ~3;
     size_t b = (size_t)K * 2 * DHP * sizeof(float) + (size_t)K * sizeof(KConst<float>);
@@ -635,19 +876,32 @@ int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan
                 uint64_t seed, uint64_t offset, double *d_part) {
     dim3 grid(plan.slabs, lay.K);
     if (c->time_entmc) VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+#define VBMC_LAUNCH(KERN, ...)                                                                                   \
+    do {                                                                                                         \
+        auto kern = KERN;                                                                                        \
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem)); \
+        kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,  \
+                                                           plan.pairs_per_thread, d_eps, seed, offset, d_part,   \
+                                                           entpart_stride(DP, lay.K) __VA_ARGS__);               \
+    } while (0)
     if constexpr (sizeof(T) == 4) {
-        auto kern = entmc_kernel_f32x2_ds<DP, WGRAD, ANYGRAD, PHILOX>;
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
-                                                           plan.pairs_per_thread, d_eps, seed, offset, d_part,
-                                                           entpart_stride(DP, lay.K));
+        switch (plan.variant) {
+            case ENTMC_FAST:
+                VBMC_LAUNCH((entmc_kernel_fast<DP, WGRAD, ANYGRAD, PHILOX>), , c->entmc_guard);
+                break;
+            case ENTMC_DSPLIT:
+                VBMC_LAUNCH((entmc_kernel_f32x2_ds<DP, WGRAD, ANYGRAD, PHILOX>));
+                break;
+            case ENTMC_PACKED:
+                VBMC_LAUNCH((entmc_kernel_f32x2<DP, WGRAD, ANYGRAD, PHILOX>));
+                break;
+            default:
+                VBMC_LAUNCH((entmc_kernel<float, DP, WGRAD, ANYGRAD, PHILOX>));
+        }
     } else {
-        auto kern = entmc_kernel<T, DP, WGRAD, ANYGRAD, PHILOX>;
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
-                                                           plan.pairs_per_thread, d_eps, seed, offset, d_part,
-                                                           entpart_stride(DP, lay.K));
+        VBMC_LAUNCH((entmc_kernel<T, DP, WGRAD, ANYGRAD, PHILOX>));
     }
+#undef VBMC_LAUNCH
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     if (c->time_entmc) {
@@ -716,28 +970,39 @@ __global__ void philox_dump_kernel(int D, int K, int64_t half, uint64_t seed, ui
 
 // Choose threads / pairs-per-thread so that the grid is a whole number of waves of the
 // resident-CTA capacity whenever possible (148 SMs x CTAs that fit by shared memory).
+static size_t entmc_smem_variant(int variant, int precision, int DP, int K, int nt, bool wgrad, bool anygrad) {
+    if (precision == VBMC_PREC_F64) return entmc_smem<double>(DP, K, nt, wgrad, anygrad);
+    switch (variant) {
+        case ENTMC_FAST:
+            return entmc_smem_fast(DP, K, nt, wgrad, anygrad);
+        case ENTMC_DSPLIT:
+            return entmc_smem_ds(DP, K, nt, wgrad, anygrad);
+        case ENTMC_PACKED:
+            return entmc_smem_f32x2(DP, K, nt, wgrad, anygrad);
+        default:
+            return entmc_smem<float>(DP, K, nt, wgrad, anygrad);
+    }
+}
+
 int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int precision, EntmcPlan *plan) {
     const int DP = pad_dim(D);
     VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "entmc: D > 32 is not supported");
     VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
+    const int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
     const size_t smem_cap = 227 * 1024;
     int nt = 128;
-    auto smem_of = [&](int t) {
-        return precision == VBMC_PREC_F64 ? entmc_smem<double>(DP, K, t, wgrad, true)
-                                          : entmc_smem_ds(DP, K, t, wgrad, true);
-    };
+    auto smem_of = [&](int t) { return entmc_smem_variant(variant, precision, DP, K, t, wgrad, true); };
     while (nt > 32 && smem_of(nt) > smem_cap) nt >>= 1;
     VBMC_REQUIRE(smem_of(nt) <= smem_cap, VBMC_ERR_UNSUPPORTED, "entmc: K too large for shared memory");
     const size_t smem = smem_of(nt);
     int per_sm = (int)(smem_cap / (smem + 1024));
-    // registers: the fp64 kernel sits near 255/thread (2 CTAs of 128), the dimension-split fp32 kernel
-    // is built with __launch_bounds__(128, 4)
-    const int reg_limit = (precision == VBMC_PREC_F64 ? 2 : 4) * (128 / nt);
+    // register-limited CTAs per SM (see __launch_bounds__ of the kernels)
+    const int reg_limit = ((precision != VBMC_PREC_F64 && variant == ENTMC_DSPLIT) ? 4 : 2) * (128 / nt);
     if (per_sm > reg_limit) per_sm = reg_limit;
     if (per_sm < 1) per_sm = 1;
     const int64_t slots = (int64_t)c->sm_count * per_sm;
-    // pairs evaluated per CTA sweep: one per thread (fp64) or one per two lanes (fp32, dimension-split)
-    const int ppi = precision == VBMC_PREC_F64 ? nt : nt / 2;
+    // pairs evaluated per CTA sweep: one per thread, or one per two lanes (dimension-split kernel)
+    const int ppi = (precision != VBMC_PREC_F64 && variant == ENTMC_DSPLIT) ? nt / 2 : nt;
 
     // candidate R: cost ~ waves * (R + overhead); overhead ~ table set-up + record reduction
     int bestR = 1;
@@ -751,6 +1016,7 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
         if (cost < best - 1e-9) best = cost, bestR = R;
         if (slabs <= 1) break;
     }
+    plan->variant = variant;
     plan->threads = nt;
     plan->pairs_per_thread = bestR;
     plan->slabs = (int)((half_local + (int64_t)ppi * bestR - 1) / ((int64_t)ppi * bestR));
@@ -770,8 +1036,7 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
     VBMC_REQUIRE(plan.half_glob < ((int64_t)1 << 32), VBMC_ERR_UNSUPPORTED, "entmc: more than 2^32 pairs per component");
     // smem of the plan was sized for anygrad; recompute for the actual instantiation
     EntmcPlan p = plan;
-    p.smem = precision == VBMC_PREC_F64 ? entmc_smem<double>(lay.DP, K, plan.threads, wgrad, anygrad)
-                                        : entmc_smem_ds(lay.DP, K, plan.threads, wgrad, anygrad);
+    p.smem = entmc_smem_variant(plan.variant, precision, lay.DP, K, plan.threads, wgrad, anygrad);
     if (precision == VBMC_PREC_F64)
         return launch_t<double>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
     return launch_t<float>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
