@@ -161,6 +161,15 @@ typedef struct vbmc_elcbo_out {
 
 int vbmc_negelcbo(vbmc_ctx *ctx, const vbmc_elcbo_in *in, vbmc_elcbo_out *out);
 
+/* Same evaluation (value + gradient, no variance path) with ONE packed input and ONE packed output --
+ * the low-overhead form the Python shim uses inside the minimize_adam loop (:238-249).
+ *   params = [mu (K*D, component-major) | sigma (K) | lambd (D) | w (K) | eta (K) |
+ *             ln_sigma_b (K) | ln_lambd_b (D) | eta_b (K)]           (D*K + 5K + 2D doubles)
+ *   out    = [F, G, H, 0, 0, L_bound, L_penalty, nonfinite | dF (P) | dH (P) if want_dH]       */
+int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const int optimize[4], int64_t Ns,
+                       int compute_grad, int use_bounds, int rng_mode, const double *eps, uint64_t seed,
+                       uint64_t offset, int precision, int want_dH, double *out);
+
 /* ---- split-phase, device-resident variants ----------------------------------------
  * One evaluation = partials (this rank's shard of draws and hyper-samples, raw sums
  * BEFORE the sigma/lambda/softmax Jacobians, already scaled by the GLOBAL 1/Ns and 1/S)

@@ -95,6 +95,11 @@ PROTOTYPES = {
     ),
     "vbmc_set_bounds": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double]),
     "vbmc_negelcbo": (C.c_int, [C.c_void_p, C.POINTER(ElcboIn), C.POINTER(ElcboOut)]),
+    "vbmc_negelcbo_flat": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_int_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+         C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p],
+    ),
     "vbmc_raw_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_out_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_negelcbo_upload": (C.c_int, [C.c_void_p, C.POINTER(ElcboIn)]),

@@ -120,6 +120,9 @@ class Context:
         self._gp_token = None
         self._gp_has_L = False
         self._bnd_cache = None
+        self._bnd_ids = None
+        self._flat = {}
+        self._opt_c = {}
         self.S = 0
         self.N = 0
         self.D = 0
@@ -210,6 +213,13 @@ class Context:
         """Upload ``theta_bnd`` (variational_posterior.py:225-239) unless unchanged."""
         if theta_bnd is None:
             return False
+        # fast path: the very same dict / arrays as last time (get_bounds builds fresh arrays per call,
+        # variational_posterior.py:213-228, and nothing in the reference mutates them afterwards)
+        ids = (id(theta_bnd), id(theta_bnd["lb"]), id(theta_bnd["ub"]), theta_bnd["tol_con"],
+               theta_bnd.get("weight_threshold"), theta_bnd.get("weight_penalty"))
+        if ids == self._bnd_ids:
+            return True
+        self._bnd_ids = ids
         lb = _arr(theta_bnd["lb"]).reshape(-1)
         ub = _arr(theta_bnd["ub"]).reshape(-1)
         tol = float(theta_bnd["tol_con"])
@@ -354,6 +364,36 @@ class Context:
             I_sk=I_sk, J_sjk=J_sjk,
         )
 
+    # ------------------------------------------------------------------ low-overhead flat path
+    def flat_buffers(self, D, K):
+        """Preallocated host arrays of the flat entry point: (params, out)."""
+        key = (D, K)
+        buf = self._flat.get(key)
+        if buf is None:
+            n_in = D * K + 5 * K + 2 * D
+            n_out = 8 + 2 * (D * K + 2 * K + D)
+            buf = (np.zeros(n_in, dtype=_F64), np.zeros(n_out, dtype=_F64))
+            self._flat[key] = buf
+        return buf
+
+    def negelcbo_flat(self, D, K, params, optimize, Ns_even, compute_grad, use_bounds, eps, seed, precision, want_dH,
+                      out):
+        """``vbmc_negelcbo_flat``: one packed parameter block in, ``out`` filled in place."""
+        og = self._opt_c.get(optimize)
+        if og is None:
+            og = self._opt_c[optimize] = (C.c_int * 4)(*[int(bool(o)) for o in optimize])
+        if eps is not None:
+            mode, eptr = _capi.RNG_EPS, eps.ctypes.data
+        else:
+            mode, eptr = _capi.RNG_PHILOX, None
+        prec = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
+        rc = self._lib.vbmc_negelcbo_flat(
+            self._h, D, K, params.ctypes.data, og, Ns_even, int(compute_grad), int(use_bounds), mode, eptr, seed, 0,
+            prec, int(want_dH), out.ctypes.data,
+        )
+        if rc:
+            _capi.check(rc)
+
     # split-phase API (multi-GPU / kernel-only timing); device pointers are plain ints
     def upload(self, vp, optimize, Ns, compute_grad=True, use_bounds=False, ln_sigma_b=None, ln_lambd_b=None,
                eta_b=None, eps=None, seed=0, offset=0, precision=None):
@@ -380,6 +420,7 @@ class Context:
 
 # ---------------------------------------------------------------------- per-process caches
 _entropy_ctx = {}
+_last_gp = None
 _gp_ctx = OrderedDict()
 _GP_CTX_MAX = 4
 
@@ -399,6 +440,23 @@ def context_for_gp(gp, need_L=False, device=None) -> Context:
     posterior records, which invalidates the entry.  Nothing is attached to ``gp`` itself.
     """
     dev = config.device if device is None else int(device)
+    global _last_gp
+    posts = gp.posteriors
+    quick = (dev, id(gp), id(posts), len(posts), id(posts[0].alpha), id(posts[-1].alpha))
+    if _last_gp is not None and _last_gp[0] == quick and (_last_gp[2] is None or _last_gp[2]() is gp):
+        ctx = _last_gp[1]
+        if ctx._h and (not need_L or ctx._gp_has_L):
+            return ctx
+    ctx = _context_for_gp_slow(gp, need_L, dev)
+    try:
+        ref = weakref.ref(gp)
+    except TypeError:
+        ref = None
+    _last_gp = (quick, ctx, ref)
+    return ctx
+
+
+def _context_for_gp_slow(gp, need_L, dev) -> Context:
     tok = (dev,) + Context.gp_token(gp, False)
     hit = _gp_ctx.get(tok)
     if hit is not None:
@@ -424,6 +482,8 @@ def context_for_gp(gp, need_L=False, device=None) -> Context:
 
 
 def clear_caches():
+    global _last_gp
+    _last_gp = None
     for ctx, _ in _gp_ctx.values():
         ctx.close()
     _gp_ctx.clear()

@@ -42,8 +42,8 @@ struct Bind {
     explicit Bind(Ctx *c) { cudaSetDevice(c->device); }
 };
 
-int check_vp(const vbmc_vp *vp) {
-    VBMC_REQUIRE(vp && vp->mu && vp->sigma && vp->lambd && vp->w && vp->eta, VBMC_ERR_ARG, "vp: null field");
+int check_vp(const vbmc_vp *vp, bool flat) {
+    VBMC_REQUIRE(vp && (flat || (vp->mu && vp->sigma && vp->lambd && vp->w && vp->eta)), VBMC_ERR_ARG, "vp: null field");
     VBMC_REQUIRE(vp->D >= 1 && vp->K >= 1, VBMC_ERR_ARG, "vp: D and K must be >= 1");
     VBMC_REQUIRE(vp->D <= kMaxD, VBMC_ERR_UNSUPPORTED, "D > 32 is not supported by the CUDA path");
     return VBMC_OK;
@@ -57,6 +57,7 @@ int packed_len(int D, int K, const int g[4]) {
 
 // internal description of one evaluation
 struct Spec {
+    const double *flat = nullptr;  // whole parameter block in ParamLayout order (fast path), else vp + *_b
     vbmc_vp vp;
     int grad[4];
     int jacobian = 1;
@@ -92,7 +93,7 @@ CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
 
 int stage(CtxEx *x, const Spec &s) {
     Ctx *c = &x->c;
-    VBMC_TRY(check_vp(&s.vp));
+    VBMC_TRY(check_vp(&s.vp, s.flat != nullptr));
     const int D = s.vp.D, K = s.vp.K, DP = pad_dim(D);
     if (s.have_gp) {
         VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "no GP packed (call vbmc_gp_pack first)");
@@ -102,14 +103,18 @@ int stage(CtxEx *x, const Spec &s) {
     RawLayout rl{D, K};
     VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total()));
     double *h = c->h_in;
-    memcpy(h + lay.mu(), s.vp.mu, sizeof(double) * K * D);
-    memcpy(h + lay.sigma(), s.vp.sigma, sizeof(double) * K);
-    memcpy(h + lay.lambd(), s.vp.lambd, sizeof(double) * D);
-    memcpy(h + lay.w(), s.vp.w, sizeof(double) * K);
-    memcpy(h + lay.eta(), s.vp.eta, sizeof(double) * K);
-    for (int k = 0; k < K; ++k) h[lay.lnsig_b() + k] = s.ln_sigma_b ? s.ln_sigma_b[k] : log(s.vp.sigma[k]);
-    for (int d = 0; d < D; ++d) h[lay.lnlam_b() + d] = s.ln_lambd_b ? s.ln_lambd_b[d] : log(s.vp.lambd[d]);
-    for (int k = 0; k < K; ++k) h[lay.eta_b() + k] = s.eta_b ? s.eta_b[k] : s.vp.eta[k];
+    if (s.flat) {
+        memcpy(h, s.flat, sizeof(double) * lay.total());
+    } else {
+        memcpy(h + lay.mu(), s.vp.mu, sizeof(double) * K * D);
+        memcpy(h + lay.sigma(), s.vp.sigma, sizeof(double) * K);
+        memcpy(h + lay.lambd(), s.vp.lambd, sizeof(double) * D);
+        memcpy(h + lay.w(), s.vp.w, sizeof(double) * K);
+        memcpy(h + lay.eta(), s.vp.eta, sizeof(double) * K);
+        for (int k = 0; k < K; ++k) h[lay.lnsig_b() + k] = s.ln_sigma_b ? s.ln_sigma_b[k] : log(s.vp.sigma[k]);
+        for (int d = 0; d < D; ++d) h[lay.lnlam_b() + d] = s.ln_lambd_b ? s.ln_lambd_b[d] : log(s.vp.lambd[d]);
+        for (int k = 0; k < K; ++k) h[lay.eta_b() + k] = s.eta_b ? s.eta_b[k] : s.vp.eta[k];
+    }
     VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * lay.total(), cudaMemcpyHostToDevice, c->stream));
 
     if (s.use_bounds) {
@@ -549,6 +554,40 @@ int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
         for (int si = 0; si < c->S; ++si)
             for (int k = 0; k < K; ++k) out->I_sk[(size_t)si * K + k] = gps[(size_t)si * (1 + Pfull) + 1 + rl.o_w() + k];
     }
+    return VBMC_OK;
+}
+
+int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const int optimize[4], int64_t Ns,
+                       int compute_grad, int use_bounds, int rng_mode, const double *eps, uint64_t seed,
+                       uint64_t offset, int precision, int want_dH, double *out) {
+    VBMC_REQUIRE(p && params && optimize && out, VBMC_ERR_ARG, "negelcbo_flat: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    Spec s;
+    s.flat = params;
+    s.vp.D = D, s.vp.K = K;
+    s.vp.mu = s.vp.sigma = s.vp.lambd = s.vp.w = s.vp.eta = nullptr;
+    for (int i = 0; i < 4; ++i) {
+        s.optimize[i] = optimize[i] != 0;
+        s.grad[i] = compute_grad ? s.optimize[i] : 0;
+    }
+    s.jacobian = 1;
+    s.Ns = Ns;
+    s.use_bounds = use_bounds != 0;
+    s.rng_mode = rng_mode, s.eps = eps, s.seed = seed, s.offset = offset, s.precision = precision;
+    const int P = packed_len(D, K, s.grad);
+    const size_t Pfull = RawLayout{D, K}.block();
+    const size_t n_dev = kOutHead + (compute_grad ? (want_dH ? 2 * Pfull : (size_t)P) : 0);
+    VBMC_TRY(run_single(x, s, n_dev));
+    const double *o = c->h_out;
+    if (o[7] != 0.0 && s.precision == VBMC_PREC_F32 && s.Ns > 0) {
+        s.precision = VBMC_PREC_F64;  // fp32 density ratios overflowed: redo the entropy in fp64 on the GPU
+        VBMC_TRY(run_single(x, s, n_dev));
+        o = c->h_out;
+    }
+    memcpy(out, o, sizeof(double) * (kOutHead + (compute_grad ? P : 0)));
+    if (compute_grad && want_dH) memcpy(out + kOutHead + P, o + kOutHead + Pfull, sizeof(double) * P);
     return VBMC_OK;
 }
 

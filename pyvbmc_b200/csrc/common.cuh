@@ -222,16 +222,21 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// block-wide sum, result valid in every thread; scratch must hold 32 doubles
+// block-wide sum, result valid in every thread; scratch must hold 33 doubles.  Fixed order:
+// butterfly inside each warp, then a butterfly over the (<= 32) warp sums => deterministic.
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_sum(v);
     __syncthreads();
     if (lane == 0) scratch[wid] = v;
     __syncthreads();
-    double r = 0.0;
-    for (int i = 0; i < nw; ++i) r += scratch[i];  // fixed order: deterministic
-    return r;
+    if (wid == 0) {
+        double r = lane < nw ? scratch[lane] : 0.0;
+        r = warp_sum(r);
+        if (lane == 0) scratch[32] = r;
+    }
+    __syncthreads();
+    return scratch[32];
 }
 __device__ __forceinline__ double block_max(double v, double *scratch) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -16,7 +16,7 @@ constexpr double kLog2Pi = 1.8378770664093454836;
 __global__ void entlb_a_kernel(const double *__restrict__ prm, ParamLayout lay, double *__restrict__ lg,
                                double *__restrict__ r2o, double *__restrict__ lgs) {
     const int D = lay.D, K = lay.K, i = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[32];
+    __shared__ double scratch[40];
     const double *mu = prm + lay.mu(), *sigma = prm + lay.sigma(), *lambd = prm + lay.lambd(), *w = prm + lay.w();
     double sumlnl = 0.0;
     for (int d = 0; d < D; ++d) sumlnl += log(lambd[d]);
@@ -51,7 +51,7 @@ __global__ void entlb_b_kernel(const double *__restrict__ prm, ParamLayout lay, 
     double *pw = sm;          // pair_ij / s2_ij
     double *gj = sm + K;      // w_i gamma_ij / gammasum_j
     double *is2 = sm + 2 * K; // 1 / s2_ij
-    __shared__ double scratch[32];
+    __shared__ double scratch[40];
     const double *mu = prm + lay.mu(), *sigma = prm + lay.sigma(), *lambd = prm + lay.lambd(), *w = prm + lay.w();
     const double sj2 = sigma[j] * sigma[j], lgsj = lgs[j], wj = w[j];
     double acc_sig = 0.0, acc_w = 0.0;
@@ -96,7 +96,7 @@ __global__ void entlb_c_kernel(const double *__restrict__ prm, ParamLayout lay, 
                                const double *__restrict__ lamp, double *__restrict__ raw_ent, RawLayout rl,
                                double *__restrict__ Hout) {
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[32];
+    __shared__ double scratch[40];
     const double *sigma = prm + lay.sigma(), *lambd = prm + lay.lambd(), *w = prm + lay.w();
     if (K == 1) {
         if (tid == 0) {

@@ -837,7 +837,7 @@ static size_t entmc_smem_fast(int DP, int K, int nt, bool wgrad, bool anygrad) {
     u = (u + 3) & ~(size_t)3;
     b += u * sizeof(float);
     b = (b + 15) & ~(size_t)15;
-    return b + 32 * sizeof(double);
+    return b + 40 * sizeof(double);
 }
 
 static size_t entmc_smem_ds(int DP, int K, int nt, bool wgrad, bool anygrad) {
@@ -848,7 +848,7 @@ static size_t entmc_smem_ds(int DP, int K, int nt, bool wgrad, bool anygrad) {
     u = (u + 3) & ~(size_t)3;
     b += u * sizeof(float);
     b = (b + 15) & ~(size_t)15;
-    return b + 32 * sizeof(double);
+    return b + 40 * sizeof(double);
 }
 
 static size_t entmc_smem_f32x2(int DP, int K, int nt, bool wgrad, bool anygrad) {
@@ -859,7 +859,7 @@ static size_t entmc_smem_f32x2(int DP, int K, int nt, bool wgrad, bool anygrad) 
     u = (u + 3) & ~(size_t)3;
     b += u * sizeof(float);
     b = (b + 15) & ~(size_t)15;
-    return b + 32 * sizeof(double);
+    return b + 40 * sizeof(double);
 }
 
 template <typename T>
@@ -868,7 +868,7 @@ size_t entmc_smem(int DP, int K, int nt, bool wgrad, bool anygrad) {
     if (anygrad) b += (size_t)2 * DP * nt * sizeof(T);
     if (wgrad) b += (size_t)3 * K * nt * sizeof(T);
     b = (b + 15) & ~(size_t)15;
-    return b + 32 * sizeof(double);
+    return b + 40 * sizeof(double);
 }
 
 template <typename T, int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>

@@ -40,7 +40,7 @@ struct ReduceArgs {
 // CTA K + i turns the (s_i, k) log-joint records into G_s and the raw per-sample gradients.
 __global__ void __launch_bounds__(128) reduce_kernel(const double *__restrict__ prm, ReduceArgs a) {
     const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[32];
+    __shared__ double scratch[40];
     const double *mu = prm + a.lay.mu(), *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(),
                  *w = prm + a.lay.w();
     const RawLayout rl = a.rl;
@@ -277,53 +277,56 @@ struct FinalArgs {
 
 // Stage 2 (single CTA, 1024 threads): [assemble raw] and/or [finalize].  On one GPU both run in one
 // launch; with several ranks the all-reduce of raw sits between an assemble-only and a finalize-only launch.
+// Every output element is written exactly once; cross-element sums (softmax, the reference's row-major
+// reshape of the ln-scale block) go through shared memory with one warp per output entry.
 __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[32];
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    __shared__ double scratch[40];
+    extern __shared__ double fsm[];  // tmp [K*D] | add_sig [K] | add_lam [D] | add_eta [K]
+    double *tmp = fsm, *add_sig = tmp + K * D, *add_lam = add_sig + K, *add_eta = add_lam + D;
     if (a.do_assemble) assemble_raw(prm, a.red, scratch);
     if (!a.do_finalize) return;
+
     const RawLayout rl = a.rl;
     const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
     double *out = a.out;
-    double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull, *tmp = dG + a.Pfull;  // tmp: [K*D]
+    double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+    const bool bounds = a.f.use_bounds && a.n_bnd > 0;
 
-    // softmax pieces
-    double es = 0.0, dote = 0.0, dotg = 0.0;
-    if (anyg && a.f.grad[3] && a.f.jacobian) {
+    for (int i = tid; i < 2 * K + D; i += nt) add_sig[i] = 0.0;  // add_sig | add_lam | add_eta are contiguous
+
+    // ---- softmax pieces: es = sum exp(eta), <exp(eta), gw> for both blocks, and for the weight penalty
+    double es = 0.0, dote = 0.0, dotg = 0.0, dotp = 0.0, Lp = 0.0;
+    const bool need_sm = (anyg && a.f.grad[3] && a.f.jacobian) || (bounds && a.f.optimize[3]);
+    if (need_sm) {
         for (int k = tid; k < K; k += nt) {
             const double ek = exp(eta[k]);
             es += ek;
             dote += ek * a.raw[rl.ent() + rl.o_w() + k];
             dotg += ek * a.raw[rl.gp() + rl.o_w() + k];
+            if (bounds && a.f.optimize[3]) {
+                const double wk = w[k];
+                Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;       // :1213-1219
+                dotp += ek * (wk < a.w_thr ? a.w_pen : 0.0);
+            }
         }
         es = block_sum(es, scratch);
         dote = block_sum(dote, scratch);
         dotg = block_sum(dotg, scratch);
+        if (bounds && a.f.optimize[3]) {
+            Lp = block_sum(Lp, scratch);
+            dotp = block_sum(dotp, scratch);
+        }
     }
-    if (anyg) {
-        pack_block(a.raw + rl.ent(), rl, prm, a.lay, a.f.grad, a.f.jacobian, es, dote, 1.0, dH, false);
-        pack_block(a.raw + rl.gp(), rl, prm, a.lay, a.f.grad, a.f.jacobian, es, dotg, 1.0, dG, false);
-        __syncthreads();
-        int P = 0;
-        if (a.f.grad[0]) P += K * D;
-        if (a.f.grad[1]) P += K;
-        if (a.f.grad[2]) P += D;
-        if (a.f.grad[3]) P += K;
-        for (int e = tid; e < P; e += nt) dF[e] = -dG[e] - dH[e];  // variational_optimization.py:1171-1173
-    }
-    __syncthreads();
 
     // ---- soft bounds on [mu | ln sigma_k + ln lambda_d | eta]  (:503-657) -----------------
-    double Lb = 0.0, Lp = 0.0;
-    if (a.f.use_bounds && a.n_bnd > 0) {
+    double Lb = 0.0;
+    const int n_mu = a.f.optimize[0] ? K * D : 0, n_sc = K * D, n_eta = a.f.optimize[3] ? K : 0;
+    if (bounds) {
         const double *lnsig = prm + a.lay.lnsig_b(), *lnlam = prm + a.lay.lnlam_b(), *etab = prm + a.lay.eta_b();
         const double *mu = prm + a.lay.mu();
-        const int n_mu = a.f.optimize[0] ? K * D : 0;
-        const int n_sc = K * D;
-        const int n_eta = a.f.optimize[3] ? K : 0;
-        // offsets of the groups in the packed gradient (grad == optimize when compute_grad)
-        int o_sig = n_mu, o_lam = o_sig + (a.f.optimize[1] ? K : 0), o_eta = o_lam + (a.f.optimize[2] ? D : 0);
         for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) {
             double x;
             if (e < n_mu)
@@ -335,66 +338,85 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
                 x = etab[e - n_mu - n_sc];
             const double lo = a.lb[e], hi = a.ub[e];
             const double ell = (hi - lo) * a.tol_con;
-            double viol = 0.0;
-            if (x < lo)
-                viol = x - lo;
-            else if (x > hi)
-                viol = x - hi;
+            const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
             double dy = 0.0;
             if (viol != 0.0) {
                 const double r = viol / ell;
                 Lb += 0.5 * r * r;
                 dy = viol / (ell * ell);
             }
-            if (anyg) {
-                if (e < n_mu)
-                    dF[e] += dy;
-                else if (e < n_mu + n_sc)
-                    tmp[e - n_mu] = dy;
-                else
-                    dF[o_eta + (e - n_mu - n_sc)] += dy;
-            }
+            // mu part is re-derived element-wise in the final pass; keep the other two in shared memory
+            if (e >= n_mu && e < n_mu + n_sc)
+                tmp[e - n_mu] = dy;
+            else if (e >= n_mu + n_sc)
+                add_eta[e - n_mu - n_sc] = dy;
         }
-        Lb = block_sum(Lb, scratch);
-        __syncthreads();
+        Lb = block_sum(Lb, scratch);  // (contains the barrier that publishes tmp / add_eta)
         if (anyg) {
-            // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[a][b] = tmp[a*K + b]
-            if (a.f.optimize[1])
-                for (int b = tid; b < K; b += nt) {
-                    double v = 0.0;
-                    for (int r = 0; r < D; ++r) v += tmp[r * K + b];
-                    dF[o_sig + b] += v;
+            // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = tmp[r*K + b]
+            // (:584-586); sigma gets the column sums, lambda the row sums.  One warp per output entry.
+            for (int idx = wid; idx < K + D; idx += nw) {
+                double v = 0.0;
+                if (idx < K) {
+                    for (int r = lane; r < D; r += 32) v += tmp[r * K + idx];
+                    v = warp_sum(v);
+                    if (lane == 0) add_sig[idx] = v;
+                } else {
+                    const int r = idx - K;
+                    for (int b = lane; b < K; b += 32) v += tmp[r * K + b];
+                    v = warp_sum(v);
+                    if (lane == 0) add_lam[r] = v;
                 }
-            if (a.f.optimize[2])
-                for (int r = tid; r < D; r += nt) {
-                    double v = 0.0;
-                    for (int b = 0; b < K; ++b) v += tmp[r * K + b];
-                    dF[o_lam + r] += v;
-                }
-        }
-        // ---- weight penalty (:1212-1229) ---------------------------------------------------
-        if (a.f.optimize[3]) {
-            double es2 = 0.0, dot = 0.0;
-            for (int k = tid; k < K; k += nt) {
-                const double wk = w[k];
-                Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;
-                const double ek = exp(eta[k]);
-                es2 += ek;
-                dot += ek * (wk < a.w_thr ? a.w_pen : 0.0);
             }
-            Lp = block_sum(Lp, scratch);
-            es2 = block_sum(es2, scratch);
-            dot = block_sum(dot, scratch);
-            __syncthreads();
-            if (anyg)
-                for (int k = tid; k < K; k += nt) {
-                    const double ek = exp(eta[k]);
-                    const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
-                    dF[o_eta + k] += ek / es2 * g - ek / (es2 * es2) * dot;
-                }
         }
     }
     __syncthreads();
+
+    // ---- gradients: Jacobians (entmc_vbmc.py:114-130, variational_optimization.py:1522-1548) and dF -----
+    if (anyg) {
+        const double *be = a.raw + rl.ent(), *bg = a.raw + rl.gp();
+        const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *mu = prm + a.lay.mu();
+        const int jac = a.f.jacobian;
+        const int n0 = a.f.grad[0] ? K * D : 0, n1 = a.f.grad[1] ? K : 0, n2 = a.f.grad[2] ? D : 0,
+                  n3 = a.f.grad[3] ? K : 0;
+        for (int e = tid; e < n0 + n1 + n2 + n3; e += nt) {
+            double gh, gg, add = 0.0;
+            if (e < n0) {
+                gh = be[rl.o_mu() + e], gg = bg[rl.o_mu() + e];
+                if (bounds && n_mu) {  // d(bound loss)/d mu, recomputed element-wise
+                    const double x = mu[e], lo = a.lb[e], hi = a.ub[e], ell = (hi - lo) * a.tol_con;
+                    const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
+                    if (viol != 0.0) add = viol / (ell * ell);
+                }
+            } else if (e < n0 + n1) {
+                const int k = e - n0;
+                const double sc = jac ? sigma[k] : 1.0;
+                gh = be[rl.o_sig() + k] * sc, gg = bg[rl.o_sig() + k] * sc;
+                add = add_sig[k];
+            } else if (e < n0 + n1 + n2) {
+                const int d = e - n0 - n1;
+                const double sc = jac ? lambd[d] : 1.0;
+                gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
+                add = add_lam[d];
+            } else {
+                const int k = e - n0 - n1 - n2;
+                gh = be[rl.o_w() + k], gg = bg[rl.o_w() + k];
+                const double ek = jac || bounds ? exp(eta[k]) : 0.0;
+                if (jac) {  // row k of J_w @ g
+                    gh = ek / es * gh - ek / (es * es) * dote;
+                    gg = ek / es * gg - ek / (es * es) * dotg;
+                }
+                add = add_eta[k];
+                if (bounds && a.f.optimize[3]) {  // weight penalty through the softmax Jacobian (:1221-1229)
+                    const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
+                    add += ek / es * g - ek / (es * es) * dotp;
+                }
+            }
+            dH[e] = gh;
+            dG[e] = gg;
+            dF[e] = -gg - gh + add;  // :1171-1173, :1200, :1227-1229
+        }
+    }
     if (tid == 0) {
         const double H = a.raw[0], G = a.raw[1];
         const double F = -G - H + Lb + Lp;
@@ -414,7 +436,7 @@ __global__ void __launch_bounds__(256)
 gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout rl, EvalFlags f,
                     const double *__restrict__ gps, double *__restrict__ out_s, int Pfull) {
     const int K = lay.K, s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[32];
+    __shared__ double scratch[40];
     const double *blk = gps + (size_t)s * (1 + rl.block()) + 1;
     double *dst = out_s + (size_t)s * (1 + Pfull);
     double es = 0.0, dot = 0.0;
@@ -432,6 +454,8 @@ gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout r
 }
 
 }  // namespace
+
+static size_t finalize_smem(int D, int K) { return sizeof(double) * ((size_t)K * D + 2 * K + D); }
 
 static ReduceArgs make_reduce_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *plan, int64_t Ns_glob,
                                    int s_begin, int s_step, int S_glob, double *d_raw) {
@@ -484,7 +508,7 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
         fa.lay = a.lay, fa.rl = a.rl, fa.f = f;
         fa.do_assemble = 1, fa.do_finalize = 0;
         fa.red = a;
-        finalize_kernel<<<1, 1024, 0, c->stream>>>(d_params, fa);
+        finalize_kernel<<<1, 1024, finalize_smem(D, K), c->stream>>>(d_params, fa);
         VBMC_CUDA_CHECK(cudaGetLastError());
         c->launches++;
     }
@@ -514,7 +538,10 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.w_pen = c->w_pen;
     a.out = d_out;
     a.Pfull = a.rl.block();
-    finalize_kernel<<<1, 1024, 0, c->stream>>>(d_params, a);
+    const size_t fsmem = finalize_smem(D, K);
+    if (fsmem > 48 * 1024)
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    finalize_kernel<<<1, 1024, fsmem, c->stream>>>(d_params, a);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

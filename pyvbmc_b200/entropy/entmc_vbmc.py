@@ -8,11 +8,10 @@ from ..context import entropy_context
 
 
 def draw_seed() -> int:
-    """63-bit Philox seed taken from the GLOBAL NumPy RNG, so that ``np.random.seed(s)``
+    """53-bit Philox seed taken from the GLOBAL NumPy RNG, so that ``np.random.seed(s)``
     makes the estimate a deterministic function of the parameters, as in the reference
     (whose draws come from the same global state, entmc_vbmc.py:67)."""
-    hi, lo = np.random.randint(0, 2**31 - 1, size=2)
-    return (int(hi) << 31) | int(lo)
+    return int(np.random.random_sample() * 9007199254740992.0)  # 53 bits, one draw of the global stream
 
 
 def draw_eps_numpy(K: int, Ns_even: int, D: int) -> np.ndarray:

@@ -165,12 +165,9 @@ def _neg_elcbo(
         vp.eta -= np.amax(vp.eta)
         vp.eta = np.reshape(vp.eta, (1, -1))  # :1082-1085
 
-    optimize = (vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights)
+    optimize = (bool(vp.optimize_mu), bool(vp.optimize_sigma), bool(vp.optimize_lambd), bool(vp.optimize_weights))
     ctx = context_for_gp(gp, need_L=bool(compute_var))
     use_bounds = ctx.set_bounds(theta_bnd)
-    ln_sigma_b = ln_lambd_b = eta_b = None
-    if use_bounds:
-        ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
 
     Ns_even = int(np.ceil(Ns / 2)) * 2 if Ns > 0 else 0
     if Ns_even > 0 and eps is None and seed is None:
@@ -178,7 +175,37 @@ def _neg_elcbo(
             eps = draw_eps_numpy(K, Ns_even, D)
         else:
             seed = draw_seed()
+    if eps is not None:
+        eps = np.ascontiguousarray(eps, dtype=float)
+        if eps.size != K * (Ns_even // 2) * D:
+            raise ValueError("eps must have shape (K, Ns/2, D)")
 
+    if not compute_var and not separate_K:
+        # hot path (minimize_adam / BFGS / sieve objective): one packed block in, one packed block out
+        prm, out = ctx.flat_buffers(D, K)
+        DK = D * K
+        prm[:DK] = theta[:DK] if optimize[0] else np.ravel(vp.mu, order="F")
+        prm[DK : DK + K] = np.ravel(vp.sigma)
+        prm[DK + K : DK + K + D] = np.ravel(vp.lambd)
+        prm[DK + K + D : DK + 2 * K + D] = np.ravel(vp.w)
+        prm[DK + 2 * K + D : DK + 3 * K + D] = np.ravel(vp.eta)
+        if use_bounds:
+            ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
+            prm[DK + 3 * K + D : DK + 4 * K + D] = ln_sigma_b
+            prm[DK + 4 * K + D : DK + 4 * K + 2 * D] = ln_lambd_b
+            if eta_b is not None:
+                prm[DK + 4 * K + 2 * D :] = eta_b
+        ctx.negelcbo_flat(D, K, prm, optimize, Ns_even, compute_grad, use_bounds, eps, seed or 0, None, False, out)
+        F, G, H = float(out[0]), float(out[1]), float(out[2])
+        dF = None
+        if compute_grad:
+            P = (DK if optimize[0] else 0) + (K if optimize[1] else 0) + (D if optimize[2] else 0) + (K if optimize[3] else 0)
+            dF = out[8 : 8 + P].copy()
+        return F, dF, G, H, 0  # (beta != 0 implies compute_var and never takes this branch)
+
+    ln_sigma_b = ln_lambd_b = eta_b = None
+    if use_bounds:
+        ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
     r = ctx.negelcbo(
         vp, optimize, Ns_even, compute_grad, bool(compute_var), separate_K, use_bounds,
         ln_sigma_b, ln_lambd_b, eta_b, eps=eps, seed=seed or 0,
