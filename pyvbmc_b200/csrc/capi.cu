@@ -70,6 +70,8 @@ struct Spec {
     const double *eps = nullptr;
     uint64_t seed = 0, offset = 0;
     int precision = VBMC_PREC_F32;
+    bool compute_var = false;
+    int avg = 1;
 };
 
 struct Staged {
@@ -167,7 +169,13 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
             VBMC_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
             VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
         }
-        VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart, fork ? c->stream2 : c->stream));
+        double *Zout = nullptr;
+        if (s.compute_var) {
+            VBMC_REQUIRE(world == 1, VBMC_ERR_UNSUPPORTED, "the variance path is not sharded");
+            VBMC_TRY(ensure(&c->d_var, &c->var_cap, gpvar_workspace(c->S, K, c->N)));
+            Zout = gpvar_Z(c);
+        }
+        VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart, fork ? c->stream2 : c->stream, Zout));
         if (fork) VBMC_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
     }
     if (s.have_ent) {
@@ -192,6 +200,7 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     st.f_partials = f;
     st.assemble_pending = (world == 1);
     VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, !st.assemble_pending));
+    if (s.compute_var) VBMC_TRY(gpvar_launch(c, c->d_in, K, s.avg));
     return VBMC_OK;
 }
 
@@ -266,7 +275,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     Ctx *c = &x->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_crec,
+    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_crec, c->d_outs,
                      c->d_entpart, c->d_gppart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
@@ -451,6 +460,8 @@ int vbmc_gplogjoint(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int
                  "gradient of the log-joint variance is not available (reference raises at :1302-1307)");
     VBMC_REQUIRE(compute_var == 0 || compute_var == 1, VBMC_ERR_UNSUPPORTED,
                  "diagonal variance approximation is not implemented (reference raises at :1467-1471)");
+    s.compute_var = compute_var != 0;
+    s.avg = avg_flag != 0;
     const int D = vp->D, K = vp->K;
     const int P = packed_len(D, K, s.grad);
     const size_t Pfull = RawLayout{D, K}.block();
@@ -459,7 +470,7 @@ int vbmc_gplogjoint(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int
     const double *o = c->h_out;
     const bool per_s = !(avg_flag && S > 1) && S > 1;
     std::vector<double> gps;
-    if (per_s || separate_K || compute_var) {
+    if (per_s || separate_K) {
         gps.resize((size_t)S * (1 + Pfull));
         VBMC_CUDA_CHECK(cudaMemcpyAsync(gps.data(), c->d_gps, gps.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -471,14 +482,10 @@ int vbmc_gplogjoint(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int
     } else {
         // per-sample Jacobians on the device, then [S][1+P] -> G[S], dG[P][S]
         x->st.f.avg = 0;
-        double *d_out_s = nullptr;
-        size_t cap = 0;
-        VBMC_TRY(ensure(&c->d_var, &c->var_cap, (size_t)S * (1 + Pfull)));
-        d_out_s = c->d_var;
-        (void)cap;
-        VBMC_TRY(gps_finalize_launch(c, c->d_in, D, K, x->st.f, d_out_s));
+        VBMC_TRY(ensure(&c->d_outs, &c->outs_cap, (size_t)S * (1 + Pfull)));
+        VBMC_TRY(gps_finalize_launch(c, c->d_in, D, K, x->st.f, c->d_outs));
         std::vector<double> hs((size_t)S * (1 + Pfull));
-        VBMC_CUDA_CHECK(cudaMemcpyAsync(hs.data(), d_out_s, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(hs.data(), c->d_outs, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         for (int si = 0; si < S; ++si) {
             if (G) G[si] = hs[(size_t)si * (1 + Pfull)];
@@ -492,9 +499,18 @@ int vbmc_gplogjoint(vbmc_ctx *p, const vbmc_vp *vp, const int grad_flags[4], int
             for (int k = 0; k < K; ++k) I_sk[(size_t)si * K + k] = gps[(size_t)si * (1 + Pfull) + 1 + rl.o_w() + k];
     }
     if (compute_var) {
-        (void)varG, (void)var_ss, (void)J_sjk;
-        set_error("gp_log_joint: variance path not built yet");
-        return VBMC_ERR_UNSUPPORTED;
+        std::vector<double> ov(2 + S);
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(ov.data(), gpvar_out(c, K), ov.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (separate_K && J_sjk)
+            VBMC_CUDA_CHECK(cudaMemcpyAsync(J_sjk, gpvar_J(c, K), (size_t)S * K * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (var_ss) *var_ss = ov[1];
+        if (varG) {
+            if (per_s || S == 1)
+                for (int si = 0; si < S; ++si) varG[si] = ov[2 + si];
+            else
+                *varG = ov[0];
+        }
     }
     return VBMC_OK;
 }
@@ -524,10 +540,9 @@ int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
     Bind b(c);
     Spec s;
     VBMC_TRY(spec_from_in(in, &s));
-    if (in->compute_var) {
-        set_error("neg_elcbo: variance path not built yet");
-        return VBMC_ERR_UNSUPPORTED;
-    }
+    s.compute_var = in->compute_var != 0;
+    VBMC_REQUIRE(!(s.compute_var && in->compute_grad), VBMC_ERR_UNSUPPORTED,
+                 "gradient of the ELBO variance is not available (reference raises at :1066-1070 / :1302-1307)");
     const int D = in->vp.D, K = in->vp.K;
     const int P = packed_len(D, K, s.grad);
     const size_t Pfull = RawLayout{D, K}.block();
@@ -540,6 +555,16 @@ int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
         o = c->h_out;
     }
     out->F = o[0], out->G = o[1], out->H = o[2], out->varF = 0.0, out->varG_ss = 0.0;
+    if (s.compute_var) {
+        std::vector<double> ov(2 + c->S);
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(ov.data(), gpvar_out(c, K), ov.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (in->separate_K && out->J_sjk)
+            VBMC_CUDA_CHECK(cudaMemcpyAsync(out->J_sjk, gpvar_J(c, K), (size_t)c->S * K * K * sizeof(double),
+                                            cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        out->varF = ov[0];     // varG (+ varH == 0, :1179-1181)
+        out->varG_ss = ov[1];  // the 5th output of _gp_log_joint, i.e. var_ss (:1121,1586)
+    }
     if (in->compute_grad) {
         if (out->dF)
             for (int i = 0; i < P; ++i) out->dF[i] = o[kOutHead + i];

@@ -156,6 +156,8 @@ struct Ctx {
     size_t lbws_cap = 0;
     double *d_var = nullptr;  // variance-path workspace
     size_t var_cap = 0;
+    double *d_outs = nullptr; // per-sample finalize outputs (avg_flag == 0)
+    size_t outs_cap = 0;
 
     // state of the evaluation uploaded by vbmc_negelcbo_upload
     bool staged = false;
@@ -196,8 +198,13 @@ int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uin
 
 // gplj.cu
 int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
-                cudaStream_t stream);
-int gpvar_launch(Ctx *c, const double *d_params, int K, double *d_J /*[S][K][K]*/);
+                cudaStream_t stream, double *Zout /* [S][K][N] or null */);
+// gpvar.cu
+size_t gpvar_workspace(int S, int K, int N);
+double *gpvar_Z(Ctx *c);
+double *gpvar_J(Ctx *c, int K);
+double *gpvar_out(Ctx *c, int K);  // [varG, var_ss, varG_s (S)]
+int gpvar_launch(Ctx *c, const double *d_params, int K, int avg);
 
 // entlb.cu
 int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4], double *d_raw_ent /*H at [0], block*/,

@@ -103,7 +103,7 @@ gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__res
 }  // namespace
 
 int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
-                cudaStream_t stream) {
+                cudaStream_t stream, double *Zout) {
     VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "gp_log_joint: no GP packed (call vbmc_gp_pack first)");
     const int D = c->gD, DP = c->gDP;
     ParamLayout lay{D, DP, K};
@@ -112,7 +112,6 @@ int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, 
     dim3 grid(K, S_local);
     const int nt = c->N >= 96 ? 128 : (c->N >= 48 ? 64 : 32);
     const int hs = hyp_stride(DP);
-    double *Zout = nullptr;
 #define VBMC_CASE(NDP)                                                                                          \
     case NDP:                                                                                                   \
         if (anygrad)                                                                                            \
@@ -139,12 +138,6 @@ int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, 
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;
-}
-
-int gpvar_launch(Ctx *c, const double *d_params, int K, double *d_J) {
-    (void)c, (void)d_params, (void)K, (void)d_J;
-    set_error("gp_log_joint: variance path not built yet");
-    return VBMC_ERR_UNSUPPORTED;
 }
 
 }  // namespace vbmc

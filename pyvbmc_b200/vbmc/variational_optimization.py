@@ -215,6 +215,8 @@ def _neg_elcbo(
     dH = r["dH"] if compute_grad else None
     varH = 0  # :1179
     varG = r["varF"] if compute_var else 0
+    if compute_var and ctx.S == 1:
+        varG = np.array([varG])  # the reference only unwraps G and dG for a single hyper-sample (:1598-1602)
     varG_ss = r["varG_ss"] if compute_var else 0
     varF = varG + varH if compute_var else 0
     if beta != 0:  # dead in practice: elcbo_beta is hard-wired to 0 (:743); value-only branch

@@ -9,7 +9,7 @@ kernel; the all-fp64 kernel and the fp64 log-joint / lower-bound kernels are hel
 import numpy as np
 import pytest
 
-from golden_util import REF_CASES, eps_for, load_case, load_npz, relerr, relmax
+from golden_util import REF_CASES, VAR_CASES, eps_for, load_case, load_npz, relerr, relmax
 from oracle import elbo_oracle as eo
 from oracle import gp_posterior as gpp
 from oracle import synthetic as syn
@@ -223,6 +223,62 @@ def test_negelcbo_errors(pv):
         pv._neg_elcbo(c.g["theta2"], c.gp, case_vp(pv, c), 1.0, 0, True, None, None)
     with pytest.raises(NotImplementedError):
         pv._gp_log_joint(case_vp(pv, c), c.gp, True, True, True, True)
+    with pytest.raises(NotImplementedError):
+        pv._gp_log_joint(case_vp(pv, c), c.gp, False, True, True, 2)
+
+
+# ------------------------------------------------------------------ variance path (full ELCBO evaluation)
+@pytest.mark.parametrize("stem", VAR_CASES)
+def test_variance_path_golden(pv, stem):
+    """_eval_full_elcbo's call: value + variance + per-component terms (variational_optimization.py:474-485).
+    varG = prior - explained is a cancellation; 1e-7 relative is the agreed fp64 noise floor between two
+    orderings of the same triangular solves."""
+    c = load_case(stem)
+    g = c.g
+    eps = eps_for(g["var_seed"], c.K, c.Ns_K, c.D)
+    r = pv._neg_elcbo(g["theta2"], c.gp, case_vp(pv, c), 0.0, c.Ns_K, False, True, None, 0.0, True, eps=eps)
+    F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk = r
+    assert dF is None and dH is None and varH == 0
+    assert relerr(F, g["var_F"]) < TOL_F32_VAL and relerr(G, g["var_G"]) < TOL_F64 and relerr(H, g["var_H"]) < TOL_F32_VAL
+    assert relerr(varF, g["var_varF"]) < 1e-7 and relerr(varG, g["var_varG"]) < 1e-7
+    if c.S > 1:
+        assert relerr(varG_ss, g["var_varG_ss"]) < 1e-7
+    else:
+        assert varG_ss == 0
+    assert I_sk.shape == (c.S, c.K) and relmax(I_sk, g["var_I_sk"]) < TOL_F64
+    assert J_sjk.shape == (c.S, c.K, c.K) and relmax(J_sjk, g["var_J_sjk"]) < 1e-7
+    G, dG, varG, dvarG, var_ss = pv._gp_log_joint(case_vp(pv, c, "sa"), c.gp, False, True, True, True)
+    assert dG is None and dvarG is None
+    assert relerr(G, g["gpv_G"]) < TOL_F64 and relerr(varG, g["gpv_varG"]) < 1e-7
+    if c.S > 1:
+        assert relerr(var_ss, g["gpv_var_ss"]) < 1e-7
+
+
+def test_matlab_variance(pv):
+    # pyvbmc/testing/vbmc/test_variational_optimization.py:120-149 and :165-199 (variance parts)
+    m = load_npz("matlab_vbmc")
+    D = K = 2
+    posts = gpp.posteriors(m["X"], m["y"], m["hyp"])
+    gp = eo.make_gp(m["X"], posts)
+    vp = make_vp(pv, D, K, m["mu"], 1e-3 * np.ones(K), np.ones(D), np.ones(K) / K, np.ones(K) / K)
+    G, dG, varG, dvarG, var_ss, I_sk, J_sjk = pv._gp_log_joint(vp, gp, False, True, True, True, True)
+    assert np.isclose(G, m["G"]) and dG is None and dvarG is None
+    assert np.isclose(varG, m["varG"]) and np.isclose(var_ss, m["var_ss"])
+    assert I_sk.shape == (8, 2) and J_sjk.shape == (8, 2, 2)
+    theta = vp.get_parameters()
+    F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk = pv._neg_elcbo(theta, gp, vp, 0.0, 0, False, True, None, 0.0, True)
+    assert np.isclose(F, m["F"]) and dF is None and np.isclose(G, m["G"]) and np.isclose(H, m["H"])
+    assert np.isclose(varF, m["varG"]) and dH is None and np.isclose(varG, m["varG"]) and varH == 0.0
+
+
+def test_variance_full_size_c3(pv):
+    """N = 400, K = 50, S = 8 (10 MB of Cholesky factors): CUDA vs the oracle's triangular solves."""
+    pr = syn.make_problem("C3")
+    vp = make_vp(pv, pr.D, pr.K, pr.vp.mu, pr.vp.sigma, pr.vp.lambd, pr.vp.w, pr.vp.eta)
+    G, dG, varG, dvarG, var_ss, I_sk, J_sjk = pv._gp_log_joint(vp, pr.gp, False, True, True, True, True)
+    Go, _, varGo, _, var_sso, I_o, J_o = eo.gp_log_joint(pr.vp.copy(), pr.gp, False, True, True, True, True)
+    assert relerr(G, Go) < TOL_F64 and relerr(varG, varGo) < 1e-7 and relerr(var_ss, var_sso) < 1e-7
+    assert relmax(I_sk, I_o) < TOL_F64 and relmax(J_sjk, J_o) < 1e-7
 
 
 # ------------------------------------------------------------------ full-size workloads vs the oracle
