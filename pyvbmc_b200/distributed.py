@@ -41,15 +41,16 @@ class ShardedNegElcbo:
     ``(F, dF, G, H, varF)``.
     """
 
-    def __init__(self, gp, device=None, group=None, seed=0):
+    def __init__(self, gp, device=None, group=None, seed=0, single=False):
         import torch
         import torch.distributed as dist
 
         from .context import Context
 
         self.torch, self.dist, self.group = torch, dist, group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        use_dist = dist.is_initialized() and not single  # single=True: this rank evaluates everything itself
+        self.rank = dist.get_rank(group) if use_dist else 0
+        self.world = dist.get_world_size(group) if use_dist else 1
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.ctx = Context(self.device)
         self.ctx.pack_gp(gp)

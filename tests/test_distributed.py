@@ -1,0 +1,103 @@
+"""Multi-GPU sharding.  CPU part: the partition arithmetic and, with a world_size-2 gloo group, the
+linearity that the single all-reduce relies on (shard partial sums, scaled by the GLOBAL 1/Ns and 1/S,
+add up to the full evaluation BEFORE the Jacobians).  GPU part: torchrun on 2 GPUs vs one GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import elbo_oracle as eo
+from oracle import synthetic as syn
+from pyvbmc_b200.distributed import pair_range, raw_layout, sample_indices
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partition_covers_everything_once():
+    for half in (1, 7, 1001, 4000):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(half, dtype=int)
+            for r in range(world):
+                lo, hi = pair_range(half, r, world)
+                assert 0 <= lo <= hi <= half
+                seen[lo:hi] += 1
+            assert np.all(seen == 1)
+    for S in (1, 3, 8, 32):
+        for world in (1, 2, 4, 8):
+            got = sorted(s for r in range(world) for s in sample_indices(S, r, world))
+            assert got == list(range(S))
+
+
+def test_raw_layout_matches_abi():
+    lay = raw_layout(20, 50)
+    assert lay["block"] == 20 * 50 + 2 * 50 + 20 and lay["total"] == 4 + 2 * lay["block"]
+    from pyvbmc_b200 import _capi
+
+    lib = _capi.load()
+    assert lib.vbmc_raw_len(20, 50) == lay["total"]
+    assert lib.vbmc_out_len(20, 50) == 8 + 3 * lay["block"] + 20 * 50
+
+
+def _shard_partial(rank, world, pr, eps):
+    """What one rank contributes to the raw vector, computed with the oracle: pre-Jacobian sums scaled by
+    the global 1/Ns and 1/S."""
+    K, D, S = pr.K, pr.D, pr.S
+    half = eps.shape[1]
+    lo, hi = pair_range(half, rank, world)
+    vp = pr.vp.copy()
+    H_r, dH_r = eo.entmc(vp, eps[:, lo:hi], (True,) * 4, jacobian_flag=False)
+    frac = (hi - lo) / half
+    sidx = sample_indices(S, rank, world)
+    gp_r = eo.make_gp(pr.X, [pr.posts[s] for s in sidx], mean_kind=pr.mean_kind)
+    # jacobian_flag=True is needed to get all four gradient blocks; undo the (linear, shared) Jacobians after
+    G_r, dG_r, *_ = eo.gp_log_joint(vp, gp_r, (True, False, False, False), True, True, False)
+    return np.concatenate([[H_r * frac, G_r * len(sidx) / S], dH_r * frac, dG_r * len(sidx) / S])
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr = syn.make_problem("C2", S=4)
+    eps = syn.draw_eps(pr.K, 202, pr.D, seed=1)
+    part = torch.from_numpy(_shard_partial(rank, world, pr, eps))
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(part.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_allreduce_of_shard_partials_equals_full():
+    import torch.multiprocessing as mp
+
+    world, port = 2, 29533
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pr = syn.make_problem("C2", S=4)
+    eps = syn.draw_eps(pr.K, 202, pr.D, seed=1)
+    full = _shard_partial(0, 1, pr, eps)
+    assert np.allclose(got, full, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_equals_single():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29511", os.path.join(ROOT, "scripts", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
