@@ -1,0 +1,194 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vbmc_b200.h declares (no compute calls
+without a GPU), the product refuses to run without a CUDA device, and the host-side plumbing (theta
+packing, soft bounds, name rebinding) matches the oracle / the reference's MATLAB fixtures."""
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from golden_util import load_npz
+from oracle import elbo_oracle as eo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "vbmc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vbmc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from pyvbmc_b200 import _capi
+
+    lib = _capi.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vbmc_b200.h but not exported by libvbmc_b200.so"
+        assert n in _capi.PROTOTYPES, f"{n} has no ctypes prototype in pyvbmc_b200/_capi.py"
+    assert lib.vbmc_abi_version() == 1
+    assert isinstance(lib.vbmc_device_count(), int)
+
+
+def test_no_cpu_fallback():
+    import pyvbmc_b200 as pv
+
+    if pv._capi.load().vbmc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    vp = pv.VariationalPosterior(2, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pv.entlb_vbmc(vp)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pv.entmc_vbmc(vp, 10)
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under pyvbmc_b200/ may import oracle/ (the checker) or the reference."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pyvbmc_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+(oracle|pyvbmc\b(?!_))", txt, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def _pair(D, K, seed, opt=(True,) * 4):
+    import pyvbmc_b200 as pv
+
+    rng = np.random.default_rng(seed)
+    mu, sigma, lambd = rng.normal(size=(D, K)), np.exp(rng.normal(size=K)), np.exp(rng.normal(size=D))
+    w = rng.dirichlet(np.ones(K))
+    a = pv.VariationalPosterior(D, K)
+    a.mu, a.sigma, a.lambd, a.w, a.eta = mu.copy(), sigma.reshape(1, -1).copy(), lambd.reshape(-1, 1).copy(), w.reshape(1, -1).copy(), np.log(w).reshape(1, -1)
+    a.optimize_mu, a.optimize_sigma, a.optimize_lambd, a.optimize_weights = opt
+    b = eo.OracleVP.create(D, K, mu, sigma, lambd, w, np.log(w), opt)
+    return a, b
+
+
+@pytest.mark.parametrize("opt", [(True,) * 4, (True, True, True, False), (True, True, False, True), (False, True, True, True)])
+def test_theta_packing_matches_oracle(opt):
+    a, b = _pair(3, 4, 0, opt)
+    ta, tb = a.get_parameters(), eo.get_parameters(b)
+    assert np.array_equal(ta, tb)
+    t2 = ta + 0.1 * np.random.default_rng(1).normal(size=ta.size)
+    a.set_parameters(t2)
+    eo.set_parameters(b, t2)
+    for f in ("mu", "sigma", "lambd", "w"):
+        assert np.array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f))), f
+    assert a.sigma.shape == (1, 4) and a.lambd.shape == (3, 1) and a.w.shape == (1, 4) and a.mu.shape == (3, 4)
+    # raw_flag=False round trip and its positivity check (variational_posterior.py:706-718)
+    tn = a.get_parameters(raw_flag=False)
+    a.set_parameters(tn, raw_flag=False)
+    assert np.allclose(a.get_parameters(raw_flag=False), tn)
+    bad = tn.copy()
+    bad[-1] = -1.0
+    with pytest.raises(ValueError):
+        a.set_parameters(bad, raw_flag=False)
+    # theta is copied, never aliased (reference regression test test_variational_posterior.py:501-513)
+    t3 = a.get_parameters()
+    a.set_parameters(t3)
+    t3[:] = 0
+    assert not np.all(np.ravel(a.mu) == 0) or not opt[0]
+
+
+def test_get_bounds_matlab_fixture():
+    # pyvbmc/testing/variational_posterior/test_variational_posterior.py:761-791
+    import pyvbmc_b200 as pv
+
+    m = load_npz("matlab_bounds")
+    vp = pv.VariationalPosterior(2, 2)
+    vp.mu = m["mu"]
+    options = {"tol_con_loss": 0.01, "tol_weight": 1e-2, "weight_penalty": 0.1, "tol_length": 1e-6}
+    bnd = vp.get_bounds(m["X"], options)
+    assert np.allclose(bnd["lb"], m["lb"]) and np.allclose(bnd["ub"], m["ub"])
+    assert bnd["tol_con"] == 0.01 and bnd["weight_threshold"] == 0.125 and bnd["weight_penalty"] == 0.1
+    # accumulating bounds over calls + tol_weight == 0 (final boost, :207-208)
+    bnd2 = vp.get_bounds(m["X"] * 2.0, dict(options, tol_weight=0), K=3)
+    assert bnd2["lb"].size == 2 * 3 + 2 * 3 + 3 and np.all(np.isneginf(bnd2["lb"][-3:]))
+    assert np.all(bnd2["lb"][:2] <= bnd["lb"][:2])
+
+
+def test_bound_loss_host_mirror_matches_oracle_and_matlab():
+    import pyvbmc_b200 as pv
+
+    m = load_npz("matlab_vbmc")
+    vp = pv.VariationalPosterior(2, 2)
+    vp.mu = m["mu"]
+    options = {"tol_con_loss": 0.01, "tol_weight": 1e-2, "weight_penalty": 0.1, "tol_length": 1e-6}
+    theta = vp.get_parameters()
+    bnd = vp.get_bounds(m["X"], options, 2)
+    L, dL = pv._vp_bound_loss(vp, theta, bnd)
+    assert L == 0.0 and np.all(dL == 0.0)
+    theta[-1] = 1.0
+    L, dL = pv._vp_bound_loss(vp, theta, bnd, tol_con=0.01)
+    assert np.isclose(L, m["bound_L"]) and np.isclose(dL[-1], m["bound_dL_last"]) and np.all(dL[:-1] == 0.0)
+    x = np.zeros(3)
+    x[0], x[1] = 15.0, -20.0
+    L, dL = pv._soft_bound_loss(x, np.full(3, -10.0), np.full(3, 10.0), compute_grad=True)
+    assert np.isclose(L, 156250.0) and np.isclose(dL[0], 12500.0) and np.isclose(dL[1], -25000.0)
+    # D != K with violations in every block: must equal the oracle (which equals the reference incl. its reshape quirk)
+    a, b = _pair(3, 5, 3)
+    X = np.random.default_rng(0).normal(size=(30, 3))
+    bnd = a.get_bounds(X, options)
+    th = a.get_parameters()
+    th[1] += 9.0
+    th[3 * 5 + 2] += 7.0
+    th[3 * 5 + 5 + 1] -= 30.0
+    th[-1] -= 12.0
+    La, dLa = pv._vp_bound_loss(a, th, bnd, tol_con=0.01)
+    Lb, dLb = eo.vp_bound_loss(b, th, bnd, tol_con=0.01)
+    assert np.isclose(La, Lb, rtol=1e-14) and np.allclose(dLa, dLb, rtol=1e-14, atol=0)
+
+
+def test_install_rebinds_every_site(monkeypatch):
+    import pyvbmc_b200 as pv
+    import importlib
+
+    inst = importlib.import_module("pyvbmc_b200.install")
+
+    def mk(name, attrs):
+        m = types.ModuleType(name)
+        for a in attrs:
+            setattr(m, a, object())
+        return m
+
+    fake = {
+        "pyvbmc": mk("pyvbmc", []),
+        "pyvbmc.entropy": mk("pyvbmc.entropy", ["entmc_vbmc", "entlb_vbmc"]),
+        "pyvbmc.vbmc": mk("pyvbmc.vbmc", []),
+        "pyvbmc.vbmc.variational_optimization": mk(
+            "pyvbmc.vbmc.variational_optimization",
+            ["entmc_vbmc", "entlb_vbmc", "_gp_log_joint", "_neg_elcbo", "_vp_bound_loss", "_soft_bound_loss"],
+        ),
+        "pyvbmc.vbmc.active_sample": mk("pyvbmc.vbmc.active_sample", ["_gp_log_joint", "_neg_elcbo"]),
+    }
+    for k, v in fake.items():
+        monkeypatch.setitem(sys.modules, k, v)
+    before = fake["pyvbmc.vbmc.active_sample"]._neg_elcbo
+    done = inst.install()
+    assert len(done) == 10
+    assert fake["pyvbmc.entropy"].entmc_vbmc is pv.entmc_vbmc
+    assert fake["pyvbmc.vbmc.variational_optimization"]._neg_elcbo is pv._neg_elcbo
+    assert fake["pyvbmc.vbmc.active_sample"]._gp_log_joint is pv._gp_log_joint
+    inst.uninstall()
+    assert fake["pyvbmc.vbmc.active_sample"]._neg_elcbo is before
+
+
+def test_neg_elcbo_argument_errors_without_gpu():
+    """Argument validation happens before any device work (reference :1066-1070, :1114-1118)."""
+    import pyvbmc_b200 as pv
+
+    vp = pv.VariationalPosterior(2, 2)
+    theta = vp.get_parameters()
+    with pytest.raises(NotImplementedError):
+        pv._neg_elcbo(theta, None, vp, 1.0, 0, True, None, None)
+    with pytest.raises(ValueError):
+        pv._neg_elcbo(theta, None, vp, 0.0, 0, True, False, None, 0.0, True)
+    with pytest.raises(NotImplementedError):
+        pv._gp_log_joint(vp, None, True, True, True, True)
