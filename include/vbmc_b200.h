@@ -192,6 +192,11 @@ int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst
  * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */
 int vbmc_set_kernel_timing(vbmc_ctx *ctx, int on);
 int vbmc_entmc_kernel_ms(vbmc_ctx *ctx, double *avg_ms, int64_t *launches);
+/* measurement only (VBMC_STAGE_TIMING=1 in the environment when the context is created): device time in
+ * microseconds between the stage marks of the last synchronous evaluation --
+ * us[0] H2D, [1] entmc (+ launch of gplj), [2] wait for the side stream, [3] reduce, [4] finalize,
+ * [5] D2H, and us[6] = host wall time of the whole call                                          */
+int vbmc_stage_times(vbmc_ctx *ctx, double *us);
 /* measurement only: best-of-5 FMA issue peak of this device in TFLOP/s
  * (fp64: 0 -> FFMA, 1 -> DFMA, 2 -> packed FFMA2)                                         */
 int vbmc_fma_peak(vbmc_ctx *ctx, int fp64, double *tflops);

@@ -170,6 +170,12 @@ class Context:
         _capi.check(self._lib.vbmc_entmc_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def stage_times(self):
+        """Device microseconds per stage of the last synchronous evaluation (needs VBMC_STAGE_TIMING=1)."""
+        us = (C.c_double * 7)()
+        _capi.check(self._lib.vbmc_stage_times(self._h, us))
+        return dict(zip(("h2d", "entmc", "join_gplj", "reduce", "finalize", "d2h", "host_call"), [float(u) for u in us]))
+
     def fma_peak(self, kind=0) -> float:
         """Measured FMA issue peak of this device in TFLOP/s (bench.py's compute denominator);
         kind 0 = FFMA, 1 = DFMA, 2 = packed FFMA2."""

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -126,7 +127,7 @@ int stage(CtxEx *x, const Spec &s) {
     VBMC_TRY(ensure(&c->d_raw, &c->raw_cap, (size_t)rl.total()));
     VBMC_TRY(ensure_pinned(&c->d_out, &c->h_out, &c->out_cap, vbmc_out_len(D, K)));
     if (s.have_gp) {
-        VBMC_TRY(ensure(&c->d_gppart, &c->gppart_cap, (size_t)c->S * K * gppart_stride(DP)));
+        VBMC_TRY(ensure(&c->d_lamc, &c->lamc_cap, (size_t)c->S * K * D));
         VBMC_TRY(ensure(&c->d_gps, &c->gps_cap, (size_t)c->S * (1 + rl.block())));
     }
     if (s.have_ent && s.Ns > 0 && s.rng_mode == VBMC_RNG_EPS) {
@@ -175,7 +176,7 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
             VBMC_TRY(ensure(&c->d_var, &c->var_cap, gpvar_workspace(c->S, K, c->N)));
             Zout = gpvar_Z(c);
         }
-        VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, c->d_gppart, fork ? c->stream2 : c->stream, Zout));
+        VBMC_TRY(gplj_launch(c, c->d_in, K, rank, world, anyg, fork ? c->stream2 : c->stream, Zout));
         if (fork) VBMC_CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
     }
     if (s.have_ent) {
@@ -196,11 +197,12 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
             f.have_ent = 0;
         }
     }
+    stage_mark(c, 2);
     if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    stage_mark(c, 3);
     st.f_partials = f;
     st.assemble_pending = (world == 1);
     VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, !st.assemble_pending));
-    if (s.compute_var) VBMC_TRY(gpvar_launch(c, c->d_in, K, s.avg));
     return VBMC_OK;
 }
 
@@ -210,17 +212,27 @@ int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
     VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged");
     const bool fuse = st.assemble_pending;
     st.assemble_pending = false;
-    return finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev, fuse);
+    VBMC_TRY(finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev, fuse));
+    // the variance path needs the per-sample G_s completed by the assemble phase
+    if (st.s.compute_var) VBMC_TRY(gpvar_launch(c, c->d_in, st.K, st.s.avg));
+    return VBMC_OK;
 }
 
 // run everything on one GPU and bring `n` leading doubles of out back to the host
 int run_single(CtxEx *x, const Spec &s, size_t n_out) {
     Ctx *c = &x->c;
+    const auto t0 = std::chrono::steady_clock::now();
+    stage_mark(c, 0);
     VBMC_TRY(stage(x, s));
+    stage_mark(c, 1);  // after the H2D copies
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
+    stage_mark(c, 4);  // after the reduce stage (2 = entmc done, 3 = side stream joined)
     VBMC_TRY(finalize(x, c->d_raw, c->d_out));
+    stage_mark(c, 5);
     VBMC_CUDA_CHECK(cudaMemcpyAsync(c->h_out, c->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    stage_mark(c, 6);
     VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     return VBMC_OK;
 }
 
@@ -257,6 +269,9 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     CtxEx *x = new CtxEx();
     x->c.device = device;
     x->c.sm_count = prop.multiProcessorCount;
+    if (const char *t = getenv("VBMC_STAGE_TIMING")) x->c.stage_timing = atoi(t) != 0;
+    if (x->c.stage_timing)
+        for (int i = 0; i < 8; ++i) VBMC_CUDA_CHECK(cudaEventCreate(&x->c.sev[i]));
     if (const char *v = getenv("VBMC_ENTMC_VARIANT")) x->c.entmc_variant = atoi(v);
     if (const char *g = getenv("VBMC_ENTMC_GUARD")) x->c.entmc_guard = (float)atof(g);
     VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
@@ -275,8 +290,8 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     Ctx *c = &x->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_crec, c->d_outs,
-                     c->d_entpart, c->d_gppart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+    double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -654,6 +669,19 @@ int vbmc_read_device(vbmc_ctx *p, const double *src_dev, size_t n, double *dst_h
         VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         memcpy(dst_host + off, c->h_out, m * sizeof(double));
     }
+    return VBMC_OK;
+}
+
+int vbmc_stage_times(vbmc_ctx *p, double *us) {
+    VBMC_REQUIRE(p && us, VBMC_ERR_ARG, "stage_times: null argument");
+    Ctx *c = &ex(p)->c;
+    VBMC_REQUIRE(c->stage_timing, VBMC_ERR_STATE, "stage timing is off (set VBMC_STAGE_TIMING=1 before creating the context)");
+    for (int i = 0; i < 6; ++i) {
+        float ms = 0;
+        VBMC_CUDA_CHECK(cudaEventElapsedTime(&ms, c->sev[i], c->sev[i + 1]));
+        us[i] = 1e3 * ms;
+    }
+    us[6] = c->host_us;
     return VBMC_OK;
 }
 

@@ -94,8 +94,6 @@ constexpr int kOutHead = 8;
 
 // entmc per-CTA partial record (doubles): [hacc | A (DP) | Be (DP) | racc (K)]
 static inline int entpart_stride(int DP, int K) { return 1 + 2 * DP + K; }
-// gplj per-(s,k) record (doubles): [U | M (DP) | Q2 (DP)]
-static inline int gppart_stride(int DP) { return 1 + 2 * DP; }
 
 struct EvalFlags {
     int grad[4];       // which gradient groups are wanted
@@ -136,12 +134,11 @@ struct Ctx {
     size_t in_cap = 0;
     double *d_entpart = nullptr;
     size_t entpart_cap = 0;
-    double *d_gppart = nullptr;
-    size_t gppart_cap = 0;
+    double *d_lamc = nullptr; // [S][K][D] lambda-gradient contributions of the log joint
+    size_t lamc_cap = 0;
     double *d_gps = nullptr; // [S][1 + block] per-sample raw log-joint terms
     size_t gps_cap = 0;
-    double *d_crec = nullptr; // [K][entpart_stride] per-component entropy records
-    size_t crec_cap = 0;
+    size_t finalize_smem_set = 0;
     // arguments of the last reduce stage (for the fused assemble+finalize launch)
     bool red_args_valid = false;
     int red_plan_slabs = 0, red_s_begin = 0, red_s_step = 1, red_S_glob = 1;
@@ -169,6 +166,11 @@ struct Ctx {
     int entmc_variant = 0;
     float entmc_guard = 128.0f;
 
+    // optional per-stage timeline (VBMC_STAGE_TIMING=1): events on the main stream
+    bool stage_timing = false;
+    cudaEvent_t sev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double host_us = 0;  // wall time of the last synchronous evaluation call
+
     // entmc kernel timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool time_entmc = false;
@@ -176,6 +178,9 @@ struct Ctx {
     int64_t entmc_ms_n = 0;
 };
 
+static inline void stage_mark(Ctx *c, int i) {
+    if (c->stage_timing) cudaEventRecord(c->sev[i], c->stream);
+}
 int ensure(double **p, size_t *cap, size_t need);
 int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
@@ -197,8 +202,8 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
 int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
 
 // gplj.cu
-int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
-                cudaStream_t stream, double *Zout /* [S][K][N] or null */);
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, cudaStream_t stream,
+                double *Zout /* [S][K][N] or null */);
 // gpvar.cu
 size_t gpvar_workspace(int S, int K, int N);
 double *gpvar_Z(Ctx *c);

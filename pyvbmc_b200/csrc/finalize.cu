@@ -1,15 +1,19 @@
-// finalize.cu -- fixed-order reduction of the kernel partials into the RAW vector, and the
-// final assembly (Jacobians, soft-bound loss, weight penalty) of F and dF.
+// finalize.cu -- fixed-order reduction of the kernel outputs into the RAW vector, and the final
+// assembly (Jacobians, soft-bound loss, weight penalty) of F and dF.
 //
-//   reduce_kernel   : entmc CTA records + gplj (s,k) records  ->  raw = [H, G, .. | ent | gp]
-//                     (raw = pre-Jacobian sums, already scaled by the GLOBAL 1/Ns and 1/S, so a
-//                      SUM all-reduce over ranks yields the single-GPU value)
-//   finalize_kernel : raw -> out = [F, G, H, .., | dF | dH | dG]
-//                     log/softmax Jacobians  entmc_vbmc.py:114-130, variational_optimization.py:1522-1548
-//                     soft bounds            variational_optimization.py:503-657 (incl. the row-major
-//                                            reshape of the column-major ln-scale block at :584-586)
-//                     weight penalty         variational_optimization.py:1212-1229
-// Both are single-CTA kernels: O(S K D) work, fp64, deterministic summation order.
+//   finalize_kernel (ONE CTA, 1024 threads), two phases that can run in one launch or in two:
+//     assemble : entmc CTA records + per-(s,k) log-joint terms  ->  raw = [H, G, .., .. | ent | gp]
+//                (raw = pre-Jacobian sums, already scaled by the GLOBAL 1/Ns and 1/S, so a SUM
+//                 all-reduce over ranks yields the single-GPU value)
+//     finalize : raw -> out = [F, G, H, .., | dF | dH | dG]
+//                log/softmax Jacobians  entmc_vbmc.py:114-130, variational_optimization.py:1522-1548
+//                soft bounds            variational_optimization.py:503-657 (incl. the row-major
+//                                       reshape of the column-major ln-scale block at :584-586)
+//                weight penalty         variational_optimization.py:1212-1229
+//   On one GPU both phases share a launch; with W ranks the all-reduce sits between them.
+//   Latency is what matters here (O(S K D) work): the parameter block, the bounds and the raw vector
+//   are staged into shared memory once and every later phase runs out of shared memory; cross-element
+//   sums use one warp per output entry with a butterfly tree => deterministic order.
 #include "common.cuh"
 
 namespace vbmc {
@@ -17,197 +21,169 @@ namespace {
 
 constexpr double kLog2Pi = 1.8378770664093454836;
 
-struct ReduceArgs {
+struct AsmArgs {
+    // entmc CTA records: component j owns records [j*slabs, (j+1)*slabs)
+    const double *entpart;
+    int slabs, ent_stride;
+    double Ns_glob;      // draws per component over all ranks
+    double draws_local;  // draws per component on this rank
+    // log joint: gps[s] = [G_s | mu | sigma | lambda | w] per-sample raw block, lamc[s][k][d]
+    double *gps;
+    const double *lamc;
+    int gps_stride, s_begin, s_step, S, S_glob;
+    double *raw_out;  // global raw vector
+};
+
+struct FinalArgs {
     ParamLayout lay;
     RawLayout rl;
     EvalFlags f;
-    // entmc
-    const double *entpart;
-    int slabs, ent_stride;
-    double Ns_glob;     // draws per component over all ranks
-    double draws_local; // draws per component on this rank
-    double *crec;       // [K][ent_stride] per-component records
-    // gp
-    const double *gppart;
-    const double *hyp;
-    int hs, s_begin, s_step, S, S_glob;
-    int mean_kind;
-    double *gps;  // [S][1 + block]
-    double *raw;
+    int do_assemble, do_finalize, stage_bounds;
+    AsmArgs as;
+    const double *raw_in;  // global raw vector (all-reduced) when !do_assemble; entlb output when ent_lb
+    const double *lb, *ub;
+    int n_bnd;
+    double tol_con, w_thr, w_pen;
+    double *out;
+    int Pfull;
 };
 
-// Stage 1 (many CTAs): CTA j < K sums the slab records of mixture component j in slab order;
-// CTA K + i turns the (s_i, k) log-joint records into G_s and the raw per-sample gradients.
-__global__ void __launch_bounds__(128) reduce_kernel(const double *__restrict__ prm, ReduceArgs a) {
-    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[40];
-    const double *mu = prm + a.lay.mu(), *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(),
-                 *w = prm + a.lay.w();
-    const RawLayout rl = a.rl;
-    const bool ent_on = a.f.have_ent && a.f.use_ent_mc;
-    const int n_ent = ent_on ? K : 0;
+struct Smem {
+    double *prm, *raw, *tmp, *add_sig, *add_lam, *add_eta, *part, *gsig, *sgs, *lb, *ub;
+};
 
-    if ((int)blockIdx.x < n_ent) {
-        // ---------------------------------------------------------- Monte-Carlo entropy, component j
-        const int j = blockIdx.x, st = a.ent_stride;
-        // last warp: sum_d ln lambda_d (lanes over d) while the others stream the slab records
-        if (tid >= nt - 32) {
-            double sl = 0.0;
-            for (int d = tid - (nt - 32); d < D; d += 32) sl += log(lambd[d]);
-            sl = warp_sum(sl);
-            if (tid == nt - 32) scratch[0] = sl;
-        }
-        double v0 = 0.0;
-        for (int t = tid; t < st; t += nt) {
-            double v = 0.0;
-#pragma unroll 4
-            for (int s = 0; s < a.slabs; ++s) v += a.entpart[((size_t)j * a.slabs + s) * st + t];
-            if (t == 0)
-                v0 = v;
-            else
-                a.crec[(size_t)j * st + t] = v;
-        }
-        __syncthreads();
-        // + (draws of this rank) * log( nconst / sigma_j^D )   (entmc_vbmc.py:53-56,77)
-        if (tid == 0) a.crec[(size_t)j * st] = v0 + a.draws_local * (-0.5 * D * kLog2Pi - scratch[0] - D * log(sigma[j]));
-        return;
-    }
-    if (!a.f.have_gp) return;
-    // -------------------------------------------------------------- GP expected log joint, sample s
-    const int s = a.s_begin + ((int)blockIdx.x - n_ent) * a.s_step;
-    if (s >= a.S) return;
-    const int gst = 1 + 2 * DP;
-    const int blk = rl.block();
-    const bool quad = a.mean_kind == VBMC_MEAN_NEGQUAD, zero = a.mean_kind == VBMC_MEAN_ZERO;
-    const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
-    const double *h = a.hyp + (size_t)s * a.hs;
-    const double *ell = h, *xm = h + DP, *iom2 = h + 2 * DP;
-    const double m0 = zero ? 0.0 : h[3 * DP + 2];
-    double *gs = a.gps + (size_t)s * (1 + blk);
-    const double *rec_s = a.gppart + (size_t)s * K * gst;
-    // I_sk -> the w block (variational_optimization.py:1407-1428,1464-1465)
-    double gpart = 0.0;
-    for (int k = tid; k < K; k += nt) {
-        double I = rec_s[(size_t)k * gst] + m0;
-        if (quad) {
-            const double s2 = sigma[k] * sigma[k];
-            double nu = 0.0;
-            for (int d = 0; d < D; ++d) {
-                const double m = mu[k * D + d];
-                nu += iom2[d] * (m * m + s2 * lambd[d] * lambd[d] - 2.0 * m * xm[d] + xm[d] * xm[d]);
-            }
-            I -= 0.5 * nu;
-        }
-        gs[1 + rl.o_w() + k] = I;
-        gpart += w[k] * I;
-    }
-    gpart = block_sum(gpart, scratch);
-    if (tid == 0) gs[0] = gpart;  // G_s (:1425)
-    if (!anyg) return;
-    // d/dmu (:1430-1436)
-    for (int e = tid; e < K * D; e += nt) {
-        const int k = e / D, d = e - k * D;
-        const double sl = sigma[k] * lambd[d];
-        const double tau = sqrt(sl * sl + ell[d] * ell[d]);
-        double g = -rec_s[(size_t)k * gst + 1 + d] / tau;
-        if (quad) g -= iom2[d] * (mu[e] - xm[d]);
-        gs[1 + rl.o_mu() + e] = w[k] * g;
-    }
-    // d/dsigma (:1438-1450)
-    for (int k = tid; k < K; k += nt) {
-        const double U = rec_s[(size_t)k * gst];
-        double acc = 0.0, accq = 0.0;
-        for (int d = 0; d < D; ++d) {
-            const double sl = sigma[k] * lambd[d];
-            const double t2 = sl * sl + ell[d] * ell[d];
-            acc += lambd[d] * lambd[d] / t2 * (rec_s[(size_t)k * gst + 1 + DP + d] - U);
-            accq += lambd[d] * lambd[d] * iom2[d];
-        }
-        double g = sigma[k] * acc;
-        if (quad) g -= sigma[k] * accq;
-        gs[1 + rl.o_sig() + k] = w[k] * g;
-    }
-    // d/dlambda (:1452-1462): warp per dimension, lanes over components, fixed-order shuffle tree
-    {
-        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-        for (int d = wid; d < D; d += nw) {
-            double acc = 0.0;
-            for (int k = lane; k < K; k += 32) {
-                const double s2 = sigma[k] * sigma[k];
-                const double t2 = s2 * lambd[d] * lambd[d] + ell[d] * ell[d];
-                double g = s2 / t2 * lambd[d] * (rec_s[(size_t)k * gst + 1 + DP + d] - rec_s[(size_t)k * gst]);
-                if (quad) g -= s2 * lambd[d] * iom2[d];
-                acc += w[k] * g;
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) gs[1 + rl.o_lam() + d] = acc;
-        }
-    }
+__device__ __forceinline__ Smem carve(double *base, const FinalArgs &a) {
+    const int D = a.lay.D, K = a.lay.K;
+    Smem m;
+    m.prm = base;
+    m.raw = m.prm + a.lay.total();
+    m.tmp = m.raw + a.rl.total();
+    m.add_sig = m.tmp + K * D;
+    m.add_lam = m.add_sig + K;
+    m.add_eta = m.add_lam + D;
+    m.part = m.add_eta + K;                       // [32][ent_stride + 1]
+    m.gsig = m.part + 32 * (a.as.ent_stride + 1);  // [K]
+    m.sgs = m.gsig + K;                            // [S][D + 1]
+    m.lb = m.sgs + a.as.S * (D + 1);
+    m.ub = m.lb + (a.stage_bounds ? a.n_bnd : 0);
+    return m;
 }
 
-// Stage 2, part A (device function, whole CTA): per-component / per-sample records -> raw vector.
-__device__ void assemble_raw(const double *__restrict__ prm, const ReduceArgs &a, double *scratch) {
+// ---- assemble: records -> raw (in shared memory, then copied to global) -------------------------------
+__device__ void assemble_raw(const FinalArgs &a, const Smem &m, double *scratch) {
     const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const AsmArgs &as = a.as;
     const RawLayout rl = a.rl;
-    double *raw = a.raw;
+    const double *sigma = m.prm + a.lay.sigma(), *lambd = m.prm + a.lay.lambd(), *w = m.prm + a.lay.w();
+    double *raw = m.raw;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
     const bool ent_mc = a.f.have_ent && a.f.use_ent_mc;
-    const bool ent_lb = a.f.have_ent && !a.f.use_ent_mc;  // entlb kernels already wrote raw[0] and the block
+    const bool ent_lb = a.f.have_ent && !a.f.use_ent_mc;  // the entlb kernels wrote H and the block to global raw
 
-    if (tid >= 1 && tid < 4) raw[tid] = 0.0;
-    if (tid == 0 && !ent_lb) raw[0] = 0.0;
-    if (!a.f.have_ent)
-        for (int e = tid; e < rl.block(); e += nt) raw[rl.ent() + e] = 0.0;
-    if (!a.f.have_gp)
-        for (int e = tid; e < rl.block(); e += nt) raw[rl.gp() + e] = 0.0;
+    for (int e = tid; e < rl.total(); e += nt) {
+        const bool in_ent = e >= rl.ent() && e < rl.gp();
+        raw[e] = (ent_lb && (e == 0 || in_ent)) ? a.raw_in[e] : 0.0;
+    }
+    for (int k = tid; k < K; k += nt) m.gsig[k] = 0.0;
+    __syncthreads();
 
     if (ent_mc) {
-        const double inv_ns = 1.0 / a.Ns_glob;
-        const int st = a.ent_stride;
+        const double inv_ns = 1.0 / as.Ns_glob;
+        const int st = as.ent_stride;
+        // fields the producer actually wrote: [sum log q] always, [A | Be] with any gradient, [racc] with d/dw
+        const int st_eff = !anyg ? 1 : (a.f.grad[3] ? st : 1 + 2 * DP);
         double *ent = raw + rl.ent();
-        double hpart = 0.0;
-        for (int j = tid; j < K; j += nt) hpart -= w[j] * a.crec[(size_t)j * st] * inv_ns;  // entmc_vbmc.py:80
-        hpart = block_sum(hpart, scratch);
-        if (tid == 0) raw[0] = hpart;
-        if (anyg) {
-            // d/dmu_j (:98): element-wise
-            for (int e = tid; e < K * D; e += nt) {
-                const int j = e / D, d = e - j * D;
-                ent[rl.o_mu() + e] = w[j] * a.crec[(size_t)j * st + 1 + d] * inv_ns / lambd[d];
+        double sumlnl = 0.0;
+        for (int d = lane; d < D; d += 32) sumlnl += log(lambd[d]);
+        sumlnl = warp_sum(sumlnl);  // every warp computes the same value
+        double hpart = 0.0;         // lane 0 of each warp
+        for (int f = tid; f < 32 * (st + 1); f += nt) m.part[f] = 0.0;
+        __syncthreads();
+        for (int f0 = 0; f0 < st_eff; f0 += 32) {
+            const int f = f0 + lane;
+            const bool fin = f < st_eff;
+            const bool is_be = fin && f >= 1 + DP && f < 1 + DP + D;
+            double colacc = 0.0;  // sum_j w_j v_j[f] over this warp's components
+            for (int j = wid; j < K; j += nw) {
+                double v = 0.0;
+                if (fin) {
+                    const double *rec = as.entpart + (size_t)j * as.slabs * st + f;
+#pragma unroll 4
+                    for (int s = 0; s < as.slabs; ++s) v += rec[(size_t)s * st];
+                }
+                const double wj = w[j];
+                if (f == 0) {
+                    // + (draws of this rank) * log(nconst / sigma_j^D)   (entmc_vbmc.py:53-56,77)
+                    const double hs = v + as.draws_local * (-0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]));
+                    hpart -= wj * hs * inv_ns;        // :80
+                    ent[rl.o_w() + j] = -hs * inv_ns;  // :111 (cross term added below)
+                } else if (fin && f < 1 + D) {
+                    ent[rl.o_mu() + j * D + (f - 1)] = wj * v * inv_ns / lambd[f - 1];  // :98
+                }
+                if (anyg && f0 < 1 + DP + D && f0 + 32 > 1 + DP) {  // chunk holds Be fields: d/dsigma_j (:102-103)
+                    const double sb = warp_sum(is_be ? v : 0.0);
+                    if (lane == 0) m.gsig[j] += sb;
+                }
+                if (fin && f >= 1 + DP) colacc += wj * v;
             }
-            // cross sums: one WARP per output entry, lanes over the summed index, butterfly tree
-            const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-            for (int idx = wid; idx < 2 * K + D; idx += nw) {
-                double u = 0.0;
-                if (idx < K) {  // d/dsigma_j (:102-103): sum over dimensions
-                    for (int d = lane; d < D; d += 32) u += a.crec[(size_t)idx * st + 1 + DP + d];
-                    u = warp_sum(u);
-                    if (lane == 0) ent[rl.o_sig() + idx] = w[idx] * u * inv_ns / sigma[idx];
-                } else if (idx < K + D) {  // d/dlambda_d (:106-108): sum over components
-                    const int d = idx - K;
-                    for (int j = lane; j < K; j += 32) u += w[j] * a.crec[(size_t)j * st + 1 + DP + d];
-                    u = warp_sum(u);
-                    if (lane == 0) ent[rl.o_lam() + d] = u * inv_ns / lambd[d];
-                } else {  // d/dw_k (:111-112): direct term + sum over components
-                    const int k = idx - K - D;
-                    if (a.f.grad[3])
-                        for (int j = lane; j < K; j += 32) u += w[j] * a.crec[(size_t)j * st + 1 + 2 * DP + k];
-                    u = warp_sum(u);
-                    if (lane == 0) ent[rl.o_w() + k] = -(a.crec[(size_t)k * st] + u) * inv_ns;
+            if (fin) m.part[wid * (st + 1) + f] = colacc;
+        }
+        if (lane == 0) m.part[wid * (st + 1) + st] = hpart;
+        __syncthreads();
+        // cross-warp sums in fixed order
+        for (int f = tid; f <= st; f += nt) {
+            double v = 0.0;
+            for (int ww = 0; ww < nw; ++ww) v += m.part[ww * (st + 1) + f];
+            if (f == st)
+                raw[0] = v;  // H
+            else if (f >= 1 + DP && f < 1 + DP + D)
+                ent[rl.o_lam() + (f - 1 - DP)] = v * inv_ns / lambd[f - 1 - DP];  // :106-108
+            else if (f >= 1 + 2 * DP && a.f.grad[3])
+                ent[rl.o_w() + (f - 1 - 2 * DP)] -= v * inv_ns;  // :112
+        }
+        for (int j = tid; j < K; j += nt) ent[rl.o_sig() + j] = w[j] * m.gsig[j] * inv_ns / sigma[j];
+        __syncthreads();
+    }
+
+    if (a.f.have_gp) {
+        // per-sample cross-component sums: G_s = sum_k w_k I_sk (:1425), lambda block = sum_k lamc (:1452-1462)
+        const int blk = rl.block();
+        int si = 0;
+        for (int s = as.s_begin; s < as.S; s += as.s_step, ++si) {
+            double *gs = as.gps + (size_t)s * as.gps_stride;
+            for (int idx = wid; idx < D + 1; idx += nw) {
+                double v = 0.0;
+                if (idx == 0) {
+                    for (int k = lane; k < K; k += 32) v += w[k] * gs[1 + rl.o_w() + k];
+                } else if (anyg) {
+                    for (int k = lane; k < K; k += 32) v += as.lamc[((size_t)s * K + k) * D + idx - 1];
+                }
+                v = warp_sum(v);
+                if (lane == 0) {
+                    m.sgs[si * (D + 1) + idx] = v;
+                    if (idx == 0)
+                        gs[0] = v;
+                    else
+                        gs[1 + rl.o_lam() + idx - 1] = v;  // complete the per-sample block for its consumers
                 }
             }
         }
-    }
-    if (a.f.have_gp) {
+        const int S_local = si;
+        __syncthreads();
         // average over hyper-samples (:1578-1596); this rank contributes its own s / S_glob
-        const int blk = rl.block();
-        const double inv_S = 1.0 / (double)a.S_glob;
+        const double inv_S = 1.0 / (double)as.S_glob;
         for (int e = tid; e < blk + 1; e += nt) {
             if (e > 0 && !anyg) break;
             double v = 0.0;
+            const bool lam = e >= 1 + rl.o_lam() && e < 1 + rl.o_w();
+            if (e == 0 || lam) {
+                const int col = e == 0 ? 0 : e - rl.o_lam();
+                for (int i = 0; i < S_local; ++i) v += m.sgs[i * (D + 1) + col];
+            } else {
 #pragma unroll 4
-            for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * (1 + blk) + e];
+                for (int s = as.s_begin; s < as.S; s += as.s_step) v += as.gps[(size_t)s * as.gps_stride + e];
+            }
             v *= inv_S;
             if (e == 0)
                 raw[1] = v;
@@ -216,6 +192,7 @@ __device__ void assemble_raw(const double *__restrict__ prm, const ReduceArgs &a
         }
     }
     __syncthreads();
+    for (int e = tid; e < rl.total(); e += nt) as.raw_out[e] = raw[e];
 }
 
 // Apply the reparameterisation Jacobians to one raw block and scatter it into theta order.
@@ -261,41 +238,33 @@ __device__ __forceinline__ void pack_block(const double *__restrict__ blk, const
     }
 }
 
-struct FinalArgs {
-    ParamLayout lay;
-    RawLayout rl;
-    EvalFlags f;
-    int do_assemble, do_finalize;
-    ReduceArgs red;  // used when do_assemble
-    const double *raw;
-    const double *lb, *ub;
-    int n_bnd;
-    double tol_con, w_thr, w_pen;
-    double *out;
-    int Pfull;
-};
 
-// Stage 2 (single CTA, 1024 threads): [assemble raw] and/or [finalize].  On one GPU both run in one
-// launch; with several ranks the all-reduce of raw sits between an assemble-only and a finalize-only launch.
-// Every output element is written exactly once; cross-element sums (softmax, the reference's row-major
-// reshape of the ln-scale block) go through shared memory with one warp per output entry.
 __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     __shared__ double scratch[40];
-    extern __shared__ double fsm[];  // tmp [K*D] | add_sig [K] | add_lam [D] | add_eta [K]
-    double *tmp = fsm, *add_sig = tmp + K * D, *add_lam = add_sig + K, *add_eta = add_lam + D;
-    if (a.do_assemble) assemble_raw(prm, a.red, scratch);
+    extern __shared__ double fsm[];
+    const Smem m = carve(fsm, a);
+
+    // ---- stage: parameter block, (all-reduced) raw vector, bounds -> shared memory -------------------
+    for (int i = tid; i < a.lay.total(); i += nt) m.prm[i] = prm[i];
+    if (!a.do_assemble)
+        for (int i = tid; i < a.rl.total(); i += nt) m.raw[i] = a.raw_in[i];
+    const bool bounds = a.do_finalize && a.f.use_bounds && a.n_bnd > 0;
+    if (bounds && a.stage_bounds)
+        for (int i = tid; i < a.n_bnd; i += nt) m.lb[i] = a.lb[i], m.ub[i] = a.ub[i];
+    for (int i = tid; i < 2 * K + D; i += nt) m.add_sig[i] = 0.0;  // add_sig | add_lam | add_eta are contiguous
+    __syncthreads();
+    if (a.do_assemble) assemble_raw(a, m, scratch);
     if (!a.do_finalize) return;
 
     const RawLayout rl = a.rl;
-    const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
+    const double *raw = m.raw;
+    const double *lb = a.stage_bounds ? m.lb : a.lb, *ub = a.stage_bounds ? m.ub : a.ub;
+    const double *eta = m.prm + a.lay.eta(), *w = m.prm + a.lay.w();
     double *out = a.out;
     double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
-    const bool bounds = a.f.use_bounds && a.n_bnd > 0;
-
-    for (int i = tid; i < 2 * K + D; i += nt) add_sig[i] = 0.0;  // add_sig | add_lam | add_eta are contiguous
 
     // ---- softmax pieces: es = sum exp(eta), <exp(eta), gw> for both blocks, and for the weight penalty
     double es = 0.0, dote = 0.0, dotg = 0.0, dotp = 0.0, Lp = 0.0;
@@ -304,11 +273,11 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
         for (int k = tid; k < K; k += nt) {
             const double ek = exp(eta[k]);
             es += ek;
-            dote += ek * a.raw[rl.ent() + rl.o_w() + k];
-            dotg += ek * a.raw[rl.gp() + rl.o_w() + k];
+            dote += ek * raw[rl.ent() + rl.o_w() + k];
+            dotg += ek * raw[rl.gp() + rl.o_w() + k];
             if (bounds && a.f.optimize[3]) {
                 const double wk = w[k];
-                Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;       // :1213-1219
+                Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;  // :1213-1219
                 dotp += ek * (wk < a.w_thr ? a.w_pen : 0.0);
             }
         }
@@ -325,8 +294,8 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
     double Lb = 0.0;
     const int n_mu = a.f.optimize[0] ? K * D : 0, n_sc = K * D, n_eta = a.f.optimize[3] ? K : 0;
     if (bounds) {
-        const double *lnsig = prm + a.lay.lnsig_b(), *lnlam = prm + a.lay.lnlam_b(), *etab = prm + a.lay.eta_b();
-        const double *mu = prm + a.lay.mu();
+        const double *lnsig = m.prm + a.lay.lnsig_b(), *lnlam = m.prm + a.lay.lnlam_b(), *etab = m.prm + a.lay.eta_b();
+        const double *mu = m.prm + a.lay.mu();
         for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) {
             double x;
             if (e < n_mu)
@@ -336,7 +305,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
                 x = lnlam[d] + lnsig[k];
             } else
                 x = etab[e - n_mu - n_sc];
-            const double lo = a.lb[e], hi = a.ub[e];
+            const double lo = lb[e], hi = ub[e];
             const double ell = (hi - lo) * a.tol_con;
             const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
             double dy = 0.0;
@@ -345,11 +314,11 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
                 Lb += 0.5 * r * r;
                 dy = viol / (ell * ell);
             }
-            // mu part is re-derived element-wise in the final pass; keep the other two in shared memory
+            // the mu part is re-derived element-wise in the final pass; keep the other two in shared memory
             if (e >= n_mu && e < n_mu + n_sc)
-                tmp[e - n_mu] = dy;
+                m.tmp[e - n_mu] = dy;
             else if (e >= n_mu + n_sc)
-                add_eta[e - n_mu - n_sc] = dy;
+                m.add_eta[e - n_mu - n_sc] = dy;
         }
         Lb = block_sum(Lb, scratch);  // (contains the barrier that publishes tmp / add_eta)
         if (anyg) {
@@ -358,14 +327,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
             for (int idx = wid; idx < K + D; idx += nw) {
                 double v = 0.0;
                 if (idx < K) {
-                    for (int r = lane; r < D; r += 32) v += tmp[r * K + idx];
+                    for (int r = lane; r < D; r += 32) v += m.tmp[r * K + idx];
                     v = warp_sum(v);
-                    if (lane == 0) add_sig[idx] = v;
+                    if (lane == 0) m.add_sig[idx] = v;
                 } else {
                     const int r = idx - K;
-                    for (int b = lane; b < K; b += 32) v += tmp[r * K + b];
+                    for (int b = lane; b < K; b += 32) v += m.tmp[r * K + b];
                     v = warp_sum(v);
-                    if (lane == 0) add_lam[r] = v;
+                    if (lane == 0) m.add_lam[r] = v;
                 }
             }
         }
@@ -374,8 +343,8 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
 
     // ---- gradients: Jacobians (entmc_vbmc.py:114-130, variational_optimization.py:1522-1548) and dF -----
     if (anyg) {
-        const double *be = a.raw + rl.ent(), *bg = a.raw + rl.gp();
-        const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *mu = prm + a.lay.mu();
+        const double *be = raw + rl.ent(), *bg = raw + rl.gp();
+        const double *sigma = m.prm + a.lay.sigma(), *lambd = m.prm + a.lay.lambd(), *mu = m.prm + a.lay.mu();
         const int jac = a.f.jacobian;
         const int n0 = a.f.grad[0] ? K * D : 0, n1 = a.f.grad[1] ? K : 0, n2 = a.f.grad[2] ? D : 0,
                   n3 = a.f.grad[3] ? K : 0;
@@ -384,7 +353,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
             if (e < n0) {
                 gh = be[rl.o_mu() + e], gg = bg[rl.o_mu() + e];
                 if (bounds && n_mu) {  // d(bound loss)/d mu, recomputed element-wise
-                    const double x = mu[e], lo = a.lb[e], hi = a.ub[e], ell = (hi - lo) * a.tol_con;
+                    const double x = mu[e], lo = lb[e], hi = ub[e], ell = (hi - lo) * a.tol_con;
                     const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
                     if (viol != 0.0) add = viol / (ell * ell);
                 }
@@ -392,12 +361,12 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
                 const int k = e - n0;
                 const double sc = jac ? sigma[k] : 1.0;
                 gh = be[rl.o_sig() + k] * sc, gg = bg[rl.o_sig() + k] * sc;
-                add = add_sig[k];
+                add = m.add_sig[k];
             } else if (e < n0 + n1 + n2) {
                 const int d = e - n0 - n1;
                 const double sc = jac ? lambd[d] : 1.0;
                 gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
-                add = add_lam[d];
+                add = m.add_lam[d];
             } else {
                 const int k = e - n0 - n1 - n2;
                 gh = be[rl.o_w() + k], gg = bg[rl.o_w() + k];
@@ -406,7 +375,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
                     gh = ek / es * gh - ek / (es * es) * dote;
                     gg = ek / es * gg - ek / (es * es) * dotg;
                 }
-                add = add_eta[k];
+                add = m.add_eta[k];
                 if (bounds && a.f.optimize[3]) {  // weight penalty through the softmax Jacobian (:1221-1229)
                     const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
                     add += ek / es * g - ek / (es * es) * dotp;
@@ -418,7 +387,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
         }
     }
     if (tid == 0) {
-        const double H = a.raw[0], G = a.raw[1];
+        const double H = raw[0], G = raw[1];
         const double F = -G - H + Lb + Lp;
         out[0] = F;
         out[1] = G;
@@ -455,64 +424,67 @@ gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout r
 
 }  // namespace
 
-static size_t finalize_smem(int D, int K) { return sizeof(double) * ((size_t)K * D + 2 * K + D); }
-
-static ReduceArgs make_reduce_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *plan, int64_t Ns_glob,
-                                   int s_begin, int s_step, int S_glob, double *d_raw) {
-    ReduceArgs a{};
-    const int DP = pad_dim(D);
-    a.lay = ParamLayout{D, DP, K};
-    a.rl = RawLayout{D, K};
-    a.f = f;
-    a.entpart = c->d_entpart;
-    a.crec = c->d_crec;
-    a.ent_stride = entpart_stride(DP, K);
-    if (plan) {
-        a.slabs = plan->slabs;
-        a.Ns_glob = (double)Ns_glob;
-        a.draws_local = 2.0 * (double)plan->half;
-    }
-    a.gppart = c->d_gppart;
-    a.hyp = c->d_hyp;
-    a.hs = hyp_stride(DP);
-    a.s_begin = s_begin;
-    a.s_step = s_step;
-    a.S = c->S;
-    a.S_glob = S_glob;
-    a.mean_kind = c->mean_kind;
-    a.gps = c->d_gps;
-    a.raw = d_raw;
-    return a;
+static size_t finalize_smem(const FinalArgs &a, bool stage_bounds) {
+    const int D = a.lay.D, K = a.lay.K;
+    size_t n = (size_t)a.lay.total() + a.rl.total() + (size_t)K * D + 2 * K + D + 32 * (size_t)(a.as.ent_stride + 1) + K +
+               (size_t)a.as.S * (D + 1);
+    if (stage_bounds) n += 2 * (size_t)a.n_bnd;
+    return n * sizeof(double);
 }
 
-// records -> (optionally) raw vector.  With assemble == false the caller fuses the assembly into
-// finalize_launch (single-GPU fast path: one launch less).
+static int launch_finalize(Ctx *c, const double *d_params, FinalArgs &a) {
+    a.stage_bounds = 1;
+    size_t smem = finalize_smem(a, true);
+    if (smem > 200 * 1024) {
+        a.stage_bounds = 0;
+        smem = finalize_smem(a, false);
+    }
+    VBMC_REQUIRE(smem <= 220 * 1024, VBMC_ERR_UNSUPPORTED, "finalize: D*K too large for the shared-memory staging");
+    if (smem > c->finalize_smem_set) {
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->finalize_smem_set = smem;
+    }
+    finalize_kernel<<<1, 1024, smem, c->stream>>>(d_params, a);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+static void fill_asm(Ctx *c, int D, int K, FinalArgs &a, double *d_raw) {
+    const int DP = pad_dim(D);
+    a.as.entpart = c->d_entpart;
+    a.as.ent_stride = entpart_stride(DP, K);
+    a.as.slabs = c->red_plan_slabs;
+    a.as.Ns_glob = c->red_Ns_glob;
+    a.as.draws_local = c->red_draws_local;
+    a.as.gps = c->d_gps;
+    a.as.lamc = c->d_lamc;
+    a.as.gps_stride = 1 + RawLayout{D, K}.block();
+    a.as.s_begin = c->red_s_begin;
+    a.as.s_step = c->red_s_step;
+    a.as.S = c->S;
+    a.as.S_glob = c->red_S_glob;
+    a.as.raw_out = d_raw;
+}
+
+// Record the shard description of this evaluation; with assemble == true also launch the
+// assemble-only pass (multi-GPU: the all-reduce of d_raw follows).
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
                   int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool assemble) {
-    const int DP = pad_dim(D);
-    const bool ent_on = f.have_ent && f.use_ent_mc;
-    if (ent_on) VBMC_TRY(ensure(&c->d_crec, &c->crec_cap, (size_t)K * entpart_stride(DP, K)));
-    ReduceArgs a = make_reduce_args(c, D, K, f, plan, Ns_glob, s_begin, s_step, S_glob, d_raw);
     c->red_args_valid = true;
-    c->red_plan_slabs = a.slabs, c->red_Ns_glob = a.Ns_glob, c->red_draws_local = a.draws_local;
+    c->red_plan_slabs = plan ? plan->slabs : 0;
+    c->red_Ns_glob = plan ? (double)Ns_glob : 0.0;
+    c->red_draws_local = plan ? 2.0 * (double)plan->half : 0.0;
     c->red_s_begin = s_begin, c->red_s_step = s_step, c->red_S_glob = S_glob;
-    const int S_local = f.have_gp ? (c->S - s_begin + s_step - 1) / s_step : 0;
-    const int grid = (ent_on ? K : 0) + (S_local > 0 ? S_local : 0);
-    if (grid > 0) {
-        reduce_kernel<<<grid, 128, 0, c->stream>>>(d_params, a);
-        VBMC_CUDA_CHECK(cudaGetLastError());
-        c->launches++;
-    }
-    if (assemble) {
-        FinalArgs fa{};
-        fa.lay = a.lay, fa.rl = a.rl, fa.f = f;
-        fa.do_assemble = 1, fa.do_finalize = 0;
-        fa.red = a;
-        finalize_kernel<<<1, 1024, finalize_smem(D, K), c->stream>>>(d_params, fa);
-        VBMC_CUDA_CHECK(cudaGetLastError());
-        c->launches++;
-    }
-    return VBMC_OK;
+    if (!assemble) return VBMC_OK;
+    FinalArgs a{};
+    a.lay = ParamLayout{D, pad_dim(D), K};
+    a.rl = RawLayout{D, K};
+    a.f = f;
+    a.do_assemble = 1, a.do_finalize = 0;
+    fill_asm(c, D, K, a, d_raw);
+    a.raw_in = d_raw;
+    return launch_finalize(c, d_params, a);
 }
 
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
@@ -523,28 +495,18 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.f = f;
     a.do_assemble = assemble_first ? 1 : 0;
     a.do_finalize = 1;
-    if (assemble_first) {
-        VBMC_REQUIRE(c->red_args_valid, VBMC_ERR_STATE, "finalize: no reduce stage to assemble from");
-        a.red = make_reduce_args(c, D, K, f, nullptr, 0, c->red_s_begin, c->red_s_step, c->red_S_glob,
-                                 const_cast<double *>(d_raw));
-        a.red.slabs = c->red_plan_slabs, a.red.Ns_glob = c->red_Ns_glob, a.red.draws_local = c->red_draws_local;
-    }
-    a.raw = d_raw;
+    if (assemble_first) VBMC_REQUIRE(c->red_args_valid, VBMC_ERR_STATE, "finalize: no partials to assemble from");
+    fill_asm(c, D, K, a, const_cast<double *>(d_raw));
+    a.raw_in = d_raw;
     a.lb = c->d_lb;
     a.ub = c->d_ub;
-    a.n_bnd = c->n_bnd;
+    a.n_bnd = f.use_bounds ? c->n_bnd : 0;
     a.tol_con = c->tol_con;
     a.w_thr = c->w_thr;
     a.w_pen = c->w_pen;
     a.out = d_out;
     a.Pfull = a.rl.block();
-    const size_t fsmem = finalize_smem(D, K);
-    if (fsmem > 48 * 1024)
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    finalize_kernel<<<1, 1024, fsmem, c->stream>>>(d_params, a);
-    VBMC_CUDA_CHECK(cudaGetLastError());
-    c->launches++;
-    return VBMC_OK;
+    return launch_finalize(c, d_params, a);
 }
 
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s) {

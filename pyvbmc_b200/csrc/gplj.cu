@@ -10,7 +10,9 @@
 //   U   = sum_n alpha_n z_n                      -> I_k = U + m0 + nu_k               (:1407-1424)
 //   M_d = sum_n alpha_n z_n delta_dn             -> d/dmu      = -w_k M_d / tau_kd    (:1430-1436)
 //   Q_d = sum_n alpha_n z_n delta_dn^2           -> d/dsigma, d/dlambda via (Q_d - U) (:1438-1462)
-// The (s,k) record [U | M | Q] is turned into G_s and raw gradients by reduce_kernel.
+// The CTA's tail turns the three moments into the finished per-(s,k) terms: I_sk, and the w_k-weighted raw
+// gradients w.r.t. mu_k, sigma_k (written into the per-sample block gps[s]) and the lambda contribution
+// lamc[s][k][:] (summed over k by finalize_kernel).
 #include "common.cuh"
 
 namespace vbmc {
@@ -20,7 +22,8 @@ template <int DP, bool GRAD>
 __global__ void __launch_bounds__(128)
 gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__restrict__ Xt,
             const double *__restrict__ alpha, const double *__restrict__ hyp, int hs, int N, int s_begin,
-            int s_step, double *__restrict__ part, double *__restrict__ Zout) {
+            int s_step, int mean_kind, double *__restrict__ gps, int gps_stride, double *__restrict__ lamc,
+            double *__restrict__ Zout) {
     const int D = lay.D, K = lay.K;
     const int k = blockIdx.x, s = s_begin + blockIdx.y * s_step;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -91,19 +94,49 @@ gplj_kernel(const double *__restrict__ prm, ParamLayout lay, const double *__res
         }
     }
     __syncthreads();
-    double *rec = part + ((size_t)s * K + k) * (1 + 2 * DP);
-    const int rows = GRAD ? 1 + 2 * DP : 1;
-    for (int r = tid; r < rows; r += nt) {
-        double v = 0.0;
-        for (int w = 0; w < nw; ++w) v += s_red[w][r];
-        rec[r] = v;
+    // ---- tail (first warp): moments -> finished per-(s,k) terms ------------------------------------
+    if (tid < 32) {
+        const RawLayout rl{D, K};
+        const bool quad = mean_kind == VBMC_MEAN_NEGQUAD, zero = mean_kind == VBMC_MEAN_ZERO;
+        double U = 0.0;
+        for (int w = 0; w < nw; ++w) U += s_red[w][0];
+        const double sg = prm[lay.sigma() + k], wk = prm[lay.w() + k], s2 = sg * sg;
+        double nu = 0.0, asig = 0.0;
+        const int d = tid;
+        double *gs = gps + (size_t)s * gps_stride;
+        if (d < D) {
+            const double lm = prm[lay.lambd() + d], m = s_mu[d], it = s_itau[d];
+            const double xm = h[DP + d], iom2 = h[2 * DP + d];
+            if (quad) nu = iom2 * (m * m + s2 * lm * lm - 2.0 * m * xm + xm * xm);  // :1409-1424
+            if constexpr (GRAD) {
+                double M = 0.0, Q = 0.0;
+                for (int w = 0; w < nw; ++w) M += s_red[w][1 + d], Q += s_red[w][1 + DP + d];
+                double gm = -M * it;  // :1430-1436
+                double gl = s2 * it * it * lm * (Q - U);  // :1452-1462
+                asig = lm * lm * it * it * (Q - U);       // :1438-1450
+                if (quad) {
+                    gm -= iom2 * (m - xm);
+                    gl -= s2 * lm * iom2;
+                    asig -= lm * lm * iom2;
+                }
+                gs[1 + rl.o_mu() + k * D + d] = wk * gm;
+                lamc[((size_t)s * K + k) * D + d] = wk * gl;
+            }
+        }
+        nu = warp_sum(nu);
+        asig = warp_sum(asig);
+        if (tid == 0) {
+            const double m0 = zero ? 0.0 : h[3 * DP + 2];
+            gs[1 + rl.o_w() + k] = U + m0 - 0.5 * nu;          // I_sk  (:1407-1428, :1464-1465)
+            if constexpr (GRAD) gs[1 + rl.o_sig() + k] = wk * sg * asig;
+        }
     }
 }
 
 }  // namespace
 
-int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, double *d_part,
-                cudaStream_t stream, double *Zout) {
+int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, cudaStream_t stream,
+                double *Zout) {
     VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "gp_log_joint: no GP packed (call vbmc_gp_pack first)");
     const int D = c->gD, DP = c->gDP;
     ParamLayout lay{D, DP, K};
@@ -112,14 +145,17 @@ int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, 
     dim3 grid(K, S_local);
     const int nt = c->N >= 96 ? 128 : (c->N >= 48 ? 64 : 32);
     const int hs = hyp_stride(DP);
+    const int gst = 1 + RawLayout{D, K}.block();
 #define VBMC_CASE(NDP)                                                                                          \
     case NDP:                                                                                                   \
         if (anygrad)                                                                                            \
-            gplj_kernel<NDP, true><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, \
-                                                               c->N, s_begin, s_step, d_part, Zout);            \
+            gplj_kernel<NDP, true><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, c->N,   \
+                                                            s_begin, s_step, c->mean_kind, c->d_gps, gst,       \
+                                                            c->d_lamc, Zout);                                   \
         else                                                                                                    \
-            gplj_kernel<NDP, false><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp,   \
-                                                                hs, c->N, s_begin, s_step, d_part, Zout);       \
+            gplj_kernel<NDP, false><<<grid, nt, 0, stream>>>(d_params, lay, c->d_Xt, c->d_alpha, c->d_hyp, hs, c->N,  \
+                                                             s_begin, s_step, c->mean_kind, c->d_gps, gst,      \
+                                                             c->d_lamc, Zout);                                  \
         break
     switch (DP) {
         VBMC_CASE(4);
