@@ -179,8 +179,6 @@ int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const 
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
-/* NOTE: with world == 1 the cross-component assembly of raw_dev is deferred into the finalize
- * launch (one kernel less); raw_dev is only complete after partials when world > 1.          */
 int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
 int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
 int vbmc_stream_synchronize(vbmc_ctx *ctx);

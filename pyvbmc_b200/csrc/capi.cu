@@ -201,8 +201,7 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     stage_mark(c, 3);
     st.f_partials = f;
-    st.assemble_pending = (world == 1);
-    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, !st.assemble_pending));
+    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev));
     return VBMC_OK;
 }
 
@@ -210,9 +209,7 @@ int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
     Ctx *c = &x->c;
     Staged &st = x->st;
     VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged");
-    const bool fuse = st.assemble_pending;
-    st.assemble_pending = false;
-    VBMC_TRY(finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev, fuse));
+    VBMC_TRY(finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev));
     // the variance path needs the per-sample G_s completed by the assemble phase
     if (st.s.compute_var) VBMC_TRY(gpvar_launch(c, c->d_in, st.K, st.s.avg));
     return VBMC_OK;

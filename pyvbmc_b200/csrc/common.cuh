@@ -217,9 +217,9 @@ int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4]
 
 // finalize.cu
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool assemble);
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw);
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
-                    double *d_out, bool assemble_first);
+                    double *d_out);
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s);
 
 // ----------------------------------------------------------------------------- device helpers

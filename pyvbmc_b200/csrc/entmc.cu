@@ -879,7 +879,11 @@ int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan
 #define VBMC_LAUNCH(KERN, ...)                                                                                   \
     do {                                                                                                         \
         auto kern = KERN;                                                                                        \
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem)); \
+        static size_t smem_set = 0; /* per instantiation: the attribute call costs microseconds */              \
+        if (plan.smem > smem_set) {                                                                              \
+            VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem)); \
+            smem_set = plan.smem;                                                                                \
+        }                                                                                                        \
         kern<<<grid, plan.threads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,  \
                                                            plan.pairs_per_thread, d_eps, seed, offset, d_part,   \
                                                            entpart_stride(DP, lay.K) __VA_ARGS__);               \

@@ -1,19 +1,18 @@
 // finalize.cu -- fixed-order reduction of the kernel outputs into the RAW vector, and the final
 // assembly (Jacobians, soft-bound loss, weight penalty) of F and dF.
 //
-//   finalize_kernel (ONE CTA, 1024 threads), two phases that can run in one launch or in two:
-//     assemble : entmc CTA records + per-(s,k) log-joint terms  ->  raw = [H, G, .., .. | ent | gp]
-//                (raw = pre-Jacobian sums, already scaled by the GLOBAL 1/Ns and 1/S, so a SUM
-//                 all-reduce over ranks yields the single-GPU value)
-//     finalize : raw -> out = [F, G, H, .., | dF | dH | dG]
-//                log/softmax Jacobians  entmc_vbmc.py:114-130, variational_optimization.py:1522-1548
-//                soft bounds            variational_optimization.py:503-657 (incl. the row-major
-//                                       reshape of the column-major ln-scale block at :584-586)
-//                weight penalty         variational_optimization.py:1212-1229
-//   On one GPU both phases share a launch; with W ranks the all-reduce sits between them.
-//   Latency is what matters here (O(S K D) work): the parameter block, the bounds and the raw vector
-//   are staged into shared memory once and every later phase runs out of shared memory; cross-element
-//   sums use one warp per output entry with a butterfly tree => deterministic order.
+//   raw_kernel   : entmc CTA records + per-(s,k) log-joint terms  ->  raw = [H, G, .., .. | ent | gp]
+//                  (raw = pre-Jacobian sums, already scaled by the GLOBAL 1/Ns and 1/S, so a SUM
+//                   all-reduce over ranks yields the single-GPU value)
+//   final_kernel : raw -> out = [F, G, H, .., | dF | dH | dG]
+//                  log/softmax Jacobians  entmc_vbmc.py:114-130, variational_optimization.py:1522-1548
+//                  soft bounds            variational_optimization.py:503-657 (incl. the row-major
+//                                         reshape of the column-major ln-scale block at :584-586)
+//                  weight penalty         variational_optimization.py:1212-1229
+// Both are latency-bound O(S K D) passes, so both are spread over many small CTAs with ONE output entry
+// per thread (element-wise entries) or per warp (entries that are sums over components / samples / slabs:
+// lanes stride over the summed index, butterfly tree => fixed summation order, bitwise reproducible).
+// Small global scalars (softmax sums, penalty) are recomputed by every CTA instead of being exchanged.
 #include "common.cuh"
 
 namespace vbmc {
@@ -21,8 +20,11 @@ namespace {
 
 constexpr double kLog2Pi = 1.8378770664093454836;
 
-struct AsmArgs {
-    // entmc CTA records: component j owns records [j*slabs, (j+1)*slabs)
+struct RawArgs {
+    ParamLayout lay;
+    RawLayout rl;
+    EvalFlags f;
+    // entmc CTA records: component j owns records [j*slabs, (j+1)*slabs), each of ent_stride doubles
     const double *entpart;
     int slabs, ent_stride;
     double Ns_glob;      // draws per component over all ranks
@@ -30,169 +32,158 @@ struct AsmArgs {
     // log joint: gps[s] = [G_s | mu | sigma | lambda | w] per-sample raw block, lamc[s][k][d]
     double *gps;
     const double *lamc;
-    int gps_stride, s_begin, s_step, S, S_glob;
-    double *raw_out;  // global raw vector
+    int gps_stride, s_begin, s_step, S, S_glob, S_local;
+    double *raw;  // global raw vector (the entlb kernels may already have written H and the ent block)
+    int n_warp_entries, n_thread_entries;
 };
 
-struct FinalArgs {
-    ParamLayout lay;
-    RawLayout rl;
-    EvalFlags f;
-    int do_assemble, do_finalize, stage_bounds;
-    AsmArgs as;
-    const double *raw_in;  // global raw vector (all-reduced) when !do_assemble; entlb output when ent_lb
-    const double *lb, *ub;
-    int n_bnd;
-    double tol_con, w_thr, w_pen;
-    double *out;
-    int Pfull;
-};
-
-struct Smem {
-    double *prm, *raw, *tmp, *add_sig, *add_lam, *add_eta, *part, *gsig, *sgs, *lb, *ub;
-};
-
-__device__ __forceinline__ Smem carve(double *base, const FinalArgs &a) {
-    const int D = a.lay.D, K = a.lay.K;
-    Smem m;
-    m.prm = base;
-    m.raw = m.prm + a.lay.total();
-    m.tmp = m.raw + a.rl.total();
-    m.add_sig = m.tmp + K * D;
-    m.add_lam = m.add_sig + K;
-    m.add_eta = m.add_lam + D;
-    m.part = m.add_eta + K;                       // [32][ent_stride + 1]
-    m.gsig = m.part + 32 * (a.as.ent_stride + 1);  // [K]
-    m.sgs = m.gsig + K;                            // [S][D + 1]
-    m.lb = m.sgs + a.as.S * (D + 1);
-    m.ub = m.lb + (a.stage_bounds ? a.n_bnd : 0);
-    return m;
+// sum over the slab records of component j of field f (fixed order)
+__device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
+    const double *rec = a.entpart + (size_t)j * a.slabs * a.ent_stride + f;
+    double v = 0.0;
+#pragma unroll 4
+    for (int s = 0; s < a.slabs; ++s) v += rec[(size_t)s * a.ent_stride];
+    return v;
 }
 
-// ---- assemble: records -> raw (in shared memory, then copied to global) -------------------------------
-__device__ void assemble_raw(const FinalArgs &a, const Smem &m, double *scratch) {
-    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    const AsmArgs &as = a.as;
+__global__ void __launch_bounds__(256) raw_kernel(const double *__restrict__ prm, RawArgs a) {
+    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K;
+    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
     const RawLayout rl = a.rl;
-    const double *sigma = m.prm + a.lay.sigma(), *lambd = m.prm + a.lay.lambd(), *w = m.prm + a.lay.w();
-    double *raw = m.raw;
+    double *raw = a.raw;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
     const bool ent_mc = a.f.have_ent && a.f.use_ent_mc;
-    const bool ent_lb = a.f.have_ent && !a.f.use_ent_mc;  // the entlb kernels wrote H and the block to global raw
+    const bool ent_lb = a.f.have_ent && !a.f.use_ent_mc;
+    const double inv_ns = ent_mc ? 1.0 / a.Ns_glob : 0.0, inv_S = 1.0 / (double)a.S_glob;
+    const int st = a.ent_stride;
+    double *ent = raw + rl.ent(), *gpb = raw + rl.gp();
 
-    for (int e = tid; e < rl.total(); e += nt) {
-        const bool in_ent = e >= rl.ent() && e < rl.gp();
-        raw[e] = (ent_lb && (e == 0 || in_ent)) ? a.raw_in[e] : 0.0;
-    }
-    for (int k = tid; k < K; k += nt) m.gsig[k] = 0.0;
-    __syncthreads();
-
-    if (ent_mc) {
-        const double inv_ns = 1.0 / as.Ns_glob;
-        const int st = as.ent_stride;
-        // fields the producer actually wrote: [sum log q] always, [A | Be] with any gradient, [racc] with d/dw
-        const int st_eff = !anyg ? 1 : (a.f.grad[3] ? st : 1 + 2 * DP);
-        double *ent = raw + rl.ent();
-        double sumlnl = 0.0;
-        for (int d = lane; d < D; d += 32) sumlnl += log(lambd[d]);
-        sumlnl = warp_sum(sumlnl);  // every warp computes the same value
-        double hpart = 0.0;         // lane 0 of each warp
-        for (int f = tid; f < 32 * (st + 1); f += nt) m.part[f] = 0.0;
-        __syncthreads();
-        for (int f0 = 0; f0 < st_eff; f0 += 32) {
-            const int f = f0 + lane;
-            const bool fin = f < st_eff;
-            const bool is_be = fin && f >= 1 + DP && f < 1 + DP + D;
-            double colacc = 0.0;  // sum_j w_j v_j[f] over this warp's components
-            for (int j = wid; j < K; j += nw) {
-                double v = 0.0;
-                if (fin) {
-                    const double *rec = as.entpart + (size_t)j * as.slabs * st + f;
-#pragma unroll 4
-                    for (int s = 0; s < as.slabs; ++s) v += rec[(size_t)s * st];
+    if (gw < a.n_warp_entries) {
+        // ------------------------------------------------------------ one WARP per summed entry
+        // order: [H | ent sigma (K) | ent lambda (D) | ent w (K) | G | gp lambda (D) | per-sample (S_local x (D+1))]
+        int idx = gw;
+        if (idx == 0) {  // H = -sum_j w_j mean log q  (entmc_vbmc.py:80)
+            if (ent_mc) {
+                double sl = 0.0;
+                for (int d = lane; d < D; d += 32) sl += log(lambd[d]);
+                sl = warp_sum(sl);
+                double h = 0.0;
+                for (int j = lane; j < K; j += 32) {
+                    const double hs = slab_sum(a, j, 0) + a.draws_local * (-0.5 * D * kLog2Pi - sl - D * log(sigma[j]));
+                    h -= w[j] * hs;
                 }
-                const double wj = w[j];
-                if (f == 0) {
-                    // + (draws of this rank) * log(nconst / sigma_j^D)   (entmc_vbmc.py:53-56,77)
-                    const double hs = v + as.draws_local * (-0.5 * D * kLog2Pi - sumlnl - D * log(sigma[j]));
-                    hpart -= wj * hs * inv_ns;        // :80
-                    ent[rl.o_w() + j] = -hs * inv_ns;  // :111 (cross term added below)
-                } else if (fin && f < 1 + D) {
-                    ent[rl.o_mu() + j * D + (f - 1)] = wj * v * inv_ns / lambd[f - 1];  // :98
-                }
-                if (anyg && f0 < 1 + DP + D && f0 + 32 > 1 + DP) {  // chunk holds Be fields: d/dsigma_j (:102-103)
-                    const double sb = warp_sum(is_be ? v : 0.0);
-                    if (lane == 0) m.gsig[j] += sb;
-                }
-                if (fin && f >= 1 + DP) colacc += wj * v;
+                h = warp_sum(h);
+                if (lane == 0) raw[0] = h * inv_ns;
+            } else if (!ent_lb && lane == 0) {
+                raw[0] = 0.0;
             }
-            if (fin) m.part[wid * (st + 1) + f] = colacc;
+            if (lane == 0) raw[2] = raw[3] = 0.0;
+            return;
         }
-        if (lane == 0) m.part[wid * (st + 1) + st] = hpart;
-        __syncthreads();
-        // cross-warp sums in fixed order
-        for (int f = tid; f <= st; f += nt) {
-            double v = 0.0;
-            for (int ww = 0; ww < nw; ++ww) v += m.part[ww * (st + 1) + f];
-            if (f == st)
-                raw[0] = v;  // H
-            else if (f >= 1 + DP && f < 1 + DP + D)
-                ent[rl.o_lam() + (f - 1 - DP)] = v * inv_ns / lambd[f - 1 - DP];  // :106-108
-            else if (f >= 1 + 2 * DP && a.f.grad[3])
-                ent[rl.o_w() + (f - 1 - 2 * DP)] -= v * inv_ns;  // :112
-        }
-        for (int j = tid; j < K; j += nt) ent[rl.o_sig() + j] = w[j] * m.gsig[j] * inv_ns / sigma[j];
-        __syncthreads();
-    }
-
-    if (a.f.have_gp) {
-        // per-sample cross-component sums: G_s = sum_k w_k I_sk (:1425), lambda block = sum_k lamc (:1452-1462)
-        const int blk = rl.block();
-        int si = 0;
-        for (int s = as.s_begin; s < as.S; s += as.s_step, ++si) {
-            double *gs = as.gps + (size_t)s * as.gps_stride;
-            for (int idx = wid; idx < D + 1; idx += nw) {
+        idx -= 1;
+        if (idx < K) {  // d/dsigma_j (:102-103): sum over dimensions of Be
+            if (ent_mc && anyg) {
                 double v = 0.0;
-                if (idx == 0) {
-                    for (int k = lane; k < K; k += 32) v += w[k] * gs[1 + rl.o_w() + k];
-                } else if (anyg) {
-                    for (int k = lane; k < K; k += 32) v += as.lamc[((size_t)s * K + k) * D + idx - 1];
-                }
+                for (int d = lane; d < D; d += 32) v += slab_sum(a, idx, 1 + DP + d);
+                v = warp_sum(v);
+                if (lane == 0) ent[rl.o_sig() + idx] = w[idx] * v * inv_ns / sigma[idx];
+            } else if (!ent_lb && lane == 0) {
+                ent[rl.o_sig() + idx] = 0.0;
+            }
+            return;
+        }
+        idx -= K;
+        if (idx < D) {  // d/dlambda_d (:106-108): sum over components
+            if (ent_mc && anyg) {
+                double v = 0.0;
+                for (int j = lane; j < K; j += 32) v += w[j] * slab_sum(a, j, 1 + DP + idx);
+                v = warp_sum(v);
+                if (lane == 0) ent[rl.o_lam() + idx] = v * inv_ns / lambd[idx];
+            } else if (!ent_lb && lane == 0) {
+                ent[rl.o_lam() + idx] = 0.0;
+            }
+            return;
+        }
+        idx -= D;
+        if (idx < K) {  // d/dw_k (:111-112): -E_k[log q] - sum_j w_j E_j[N_k / q]
+            if (ent_mc && anyg) {
+                double v = 0.0;
+                if (a.f.grad[3])
+                    for (int j = lane; j < K; j += 32) v += w[j] * slab_sum(a, j, 1 + 2 * DP + idx);
+                double sl = 0.0;
+                for (int d = lane; d < D; d += 32) sl += log(lambd[d]);
+                sl = warp_sum(sl);
                 v = warp_sum(v);
                 if (lane == 0) {
-                    m.sgs[si * (D + 1) + idx] = v;
-                    if (idx == 0)
-                        gs[0] = v;
-                    else
-                        gs[1 + rl.o_lam() + idx - 1] = v;  // complete the per-sample block for its consumers
+                    const double hs = slab_sum(a, idx, 0) + a.draws_local * (-0.5 * D * kLog2Pi - sl - D * log(sigma[idx]));
+                    ent[rl.o_w() + idx] = -(hs + v) * inv_ns;
                 }
+            } else if (!ent_lb && lane == 0) {
+                ent[rl.o_w() + idx] = 0.0;
             }
+            return;
         }
-        const int S_local = si;
-        __syncthreads();
-        // average over hyper-samples (:1578-1596); this rank contributes its own s / S_glob
-        const double inv_S = 1.0 / (double)as.S_glob;
-        for (int e = tid; e < blk + 1; e += nt) {
-            if (e > 0 && !anyg) break;
+        idx -= K;
+        if (idx == 0) {  // G = mean_s sum_k w_k I_sk  (:1425, :1581)
             double v = 0.0;
-            const bool lam = e >= 1 + rl.o_lam() && e < 1 + rl.o_w();
-            if (e == 0 || lam) {
-                const int col = e == 0 ? 0 : e - rl.o_lam();
-                for (int i = 0; i < S_local; ++i) v += m.sgs[i * (D + 1) + col];
-            } else {
-#pragma unroll 4
-                for (int s = as.s_begin; s < as.S; s += as.s_step) v += as.gps[(size_t)s * as.gps_stride + e];
-            }
-            v *= inv_S;
-            if (e == 0)
-                raw[1] = v;
-            else
-                raw[rl.gp() + e - 1] = v;
+            if (a.f.have_gp)
+                for (int i = lane; i < a.S_local * K; i += 32) {
+                    const int s = a.s_begin + (i / K) * a.s_step, k = i % K;
+                    v += w[k] * a.gps[(size_t)s * a.gps_stride + 1 + rl.o_w() + k];
+                }
+            v = warp_sum(v);
+            if (lane == 0) raw[1] = v * inv_S;
+            return;
         }
+        idx -= 1;
+        if (idx < D) {  // gp d/dlambda_d: mean_s sum_k lamc  (:1452-1462, :1596)
+            double v = 0.0;
+            if (a.f.have_gp && anyg)
+                for (int i = lane; i < a.S_local * K; i += 32) {
+                    const int s = a.s_begin + (i / K) * a.s_step, k = i % K;
+                    v += a.lamc[((size_t)s * K + k) * D + idx];
+                }
+            v = warp_sum(v);
+            if (lane == 0) gpb[rl.o_lam() + idx] = v * inv_S;
+            return;
+        }
+        idx -= D;
+        if (a.f.have_gp) {  // per-sample G_s and lambda block (consumers: variance path, avg_flag = 0, I_sk)
+            const int si = idx / (D + 1), col = idx - si * (D + 1), s = a.s_begin + si * a.s_step;
+            double *gs = a.gps + (size_t)s * a.gps_stride;
+            double v = 0.0;
+            if (col == 0)
+                for (int k = lane; k < K; k += 32) v += w[k] * gs[1 + rl.o_w() + k];
+            else if (anyg)
+                for (int k = lane; k < K; k += 32) v += a.lamc[((size_t)s * K + k) * D + col - 1];
+            v = warp_sum(v);
+            if (lane == 0) gs[col == 0 ? 0 : 1 + rl.o_lam() + col - 1] = v;
+        }
+        return;
     }
-    __syncthreads();
-    for (int e = tid; e < rl.total(); e += nt) as.raw_out[e] = raw[e];
+    // ---------------------------------------------------------------- one THREAD per element-wise entry
+    // order: [ent mu (K*D) | gp mu (K*D) | gp sigma (K) | gp w (K)]
+    int e = (gw - a.n_warp_entries) * 32 + lane;
+    if (e >= a.n_thread_entries) return;
+    if (e < K * D) {  // d/dmu_j (:98)
+        if (ent_mc && anyg) {
+            const int j = e / D, d = e - j * D;
+            ent[rl.o_mu() + e] = w[j] * slab_sum(a, j, 1 + d) * inv_ns / lambd[d];
+        } else if (!ent_lb) {
+            ent[rl.o_mu() + e] = 0.0;
+        }
+        return;
+    }
+    e -= K * D;
+    // gp blocks: average over this rank's hyper-samples (:1578-1596)
+    const int off = e < K * D ? rl.o_mu() + e : (e < K * D + K ? rl.o_sig() + (e - K * D) : rl.o_w() + (e - K * D - K));
+    double v = 0.0;
+    if (a.f.have_gp && anyg) {
+#pragma unroll 4
+        for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * a.gps_stride + 1 + off];
+    }
+    gpb[off] = v * inv_S;
 }
 
 // Apply the reparameterisation Jacobians to one raw block and scatter it into theta order.
@@ -239,144 +230,110 @@ __device__ __forceinline__ void pack_block(const double *__restrict__ blk, const
 }
 
 
-__global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict__ prm, FinalArgs a) {
+struct FinalArgs {
+    ParamLayout lay;
+    RawLayout rl;
+    EvalFlags f;
+    const double *raw;
+    const double *lb, *ub;
+    int n_bnd;
+    double tol_con, w_thr, w_pen;
+    double *out;
+    int Pfull;
+};
+
+// violation derivative of extended-theta entry e (and its loss), variational_optimization.py:639-653
+__device__ __forceinline__ double bound_dy(const FinalArgs &a, const double *prm, int e, int n_mu, int n_sc,
+                                           double *loss) {
+    const int D = a.lay.D;
+    double x;
+    if (e < n_mu)
+        x = prm[a.lay.mu() + e];
+    else if (e < n_mu + n_sc) {
+        const int i = e - n_mu, k = i / D, d = i - k * D;  // column-major (D,K) ravel (:557-562)
+        x = prm[a.lay.lnlam_b() + d] + prm[a.lay.lnsig_b() + k];
+    } else
+        x = prm[a.lay.eta_b() + e - n_mu - n_sc];
+    const double lo = a.lb[e], hi = a.ub[e];
+    const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
+    if (viol == 0.0) return 0.0;
+    const double ell = (hi - lo) * a.tol_con, r = viol / ell;
+    if (loss) *loss += 0.5 * r * r;
+    return r / ell;
+}
+
+__global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ prm, FinalArgs a) {
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     __shared__ double scratch[40];
-    extern __shared__ double fsm[];
-    const Smem m = carve(fsm, a);
-
-    // ---- stage: parameter block, (all-reduced) raw vector, bounds -> shared memory -------------------
-    for (int i = tid; i < a.lay.total(); i += nt) m.prm[i] = prm[i];
-    if (!a.do_assemble)
-        for (int i = tid; i < a.rl.total(); i += nt) m.raw[i] = a.raw_in[i];
-    const bool bounds = a.do_finalize && a.f.use_bounds && a.n_bnd > 0;
-    if (bounds && a.stage_bounds)
-        for (int i = tid; i < a.n_bnd; i += nt) m.lb[i] = a.lb[i], m.ub[i] = a.ub[i];
-    for (int i = tid; i < 2 * K + D; i += nt) m.add_sig[i] = 0.0;  // add_sig | add_lam | add_eta are contiguous
-    __syncthreads();
-    if (a.do_assemble) assemble_raw(a, m, scratch);
-    if (!a.do_finalize) return;
-
+    __shared__ double ssm[5];  // es, dote, dotg, dotp, Lp
     const RawLayout rl = a.rl;
-    const double *raw = m.raw;
-    const double *lb = a.stage_bounds ? m.lb : a.lb, *ub = a.stage_bounds ? m.ub : a.ub;
-    const double *eta = m.prm + a.lay.eta(), *w = m.prm + a.lay.w();
+    const double *raw = a.raw;
+    const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
     double *out = a.out;
     double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+    const bool bounds = a.f.use_bounds && a.n_bnd > 0;
+    const bool pen = bounds && a.f.optimize[3];
+    const int n_mu = a.f.optimize[0] ? K * D : 0, n_sc = K * D, n_eta = a.f.optimize[3] ? K : 0;
 
-    // ---- softmax pieces: es = sum exp(eta), <exp(eta), gw> for both blocks, and for the weight penalty
-    double es = 0.0, dote = 0.0, dotg = 0.0, dotp = 0.0, Lp = 0.0;
-    const bool need_sm = (anyg && a.f.grad[3] && a.f.jacobian) || (bounds && a.f.optimize[3]);
-    if (need_sm) {
-        for (int k = tid; k < K; k += nt) {
+    // ---- softmax pieces (every CTA, first warp): es = sum exp(eta), <exp(eta), gw>, penalty terms
+    const bool need_sm = (anyg && a.f.grad[3] && a.f.jacobian) || pen;
+    if (tid < 32 && need_sm) {
+        double es = 0.0, dote = 0.0, dotg = 0.0, dotp = 0.0, Lp = 0.0;
+        for (int k = tid; k < K; k += 32) {
             const double ek = exp(eta[k]);
             es += ek;
             dote += ek * raw[rl.ent() + rl.o_w() + k];
             dotg += ek * raw[rl.gp() + rl.o_w() + k];
-            if (bounds && a.f.optimize[3]) {
+            if (pen) {
                 const double wk = w[k];
                 Lp += (wk < a.w_thr ? wk : a.w_thr) * a.w_pen;  // :1213-1219
                 dotp += ek * (wk < a.w_thr ? a.w_pen : 0.0);
             }
         }
-        es = block_sum(es, scratch);
-        dote = block_sum(dote, scratch);
-        dotg = block_sum(dotg, scratch);
-        if (bounds && a.f.optimize[3]) {
-            Lp = block_sum(Lp, scratch);
-            dotp = block_sum(dotp, scratch);
-        }
-    }
-
-    // ---- soft bounds on [mu | ln sigma_k + ln lambda_d | eta]  (:503-657) -----------------
-    double Lb = 0.0;
-    const int n_mu = a.f.optimize[0] ? K * D : 0, n_sc = K * D, n_eta = a.f.optimize[3] ? K : 0;
-    if (bounds) {
-        const double *lnsig = m.prm + a.lay.lnsig_b(), *lnlam = m.prm + a.lay.lnlam_b(), *etab = m.prm + a.lay.eta_b();
-        const double *mu = m.prm + a.lay.mu();
-        for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) {
-            double x;
-            if (e < n_mu)
-                x = mu[e];
-            else if (e < n_mu + n_sc) {
-                const int i = e - n_mu, k = i / D, d = i - k * D;  // column-major (D,K) ravel (:557-562)
-                x = lnlam[d] + lnsig[k];
-            } else
-                x = etab[e - n_mu - n_sc];
-            const double lo = lb[e], hi = ub[e];
-            const double ell = (hi - lo) * a.tol_con;
-            const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
-            double dy = 0.0;
-            if (viol != 0.0) {
-                const double r = viol / ell;
-                Lb += 0.5 * r * r;
-                dy = viol / (ell * ell);
-            }
-            // the mu part is re-derived element-wise in the final pass; keep the other two in shared memory
-            if (e >= n_mu && e < n_mu + n_sc)
-                m.tmp[e - n_mu] = dy;
-            else if (e >= n_mu + n_sc)
-                m.add_eta[e - n_mu - n_sc] = dy;
-        }
-        Lb = block_sum(Lb, scratch);  // (contains the barrier that publishes tmp / add_eta)
-        if (anyg) {
-            // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = tmp[r*K + b]
-            // (:584-586); sigma gets the column sums, lambda the row sums.  One warp per output entry.
-            for (int idx = wid; idx < K + D; idx += nw) {
-                double v = 0.0;
-                if (idx < K) {
-                    for (int r = lane; r < D; r += 32) v += m.tmp[r * K + idx];
-                    v = warp_sum(v);
-                    if (lane == 0) m.add_sig[idx] = v;
-                } else {
-                    const int r = idx - K;
-                    for (int b = lane; b < K; b += 32) v += m.tmp[r * K + b];
-                    v = warp_sum(v);
-                    if (lane == 0) m.add_lam[r] = v;
-                }
-            }
-        }
+        es = warp_sum(es), dote = warp_sum(dote), dotg = warp_sum(dotg), dotp = warp_sum(dotp), Lp = warp_sum(Lp);
+        if (tid == 0) ssm[0] = es, ssm[1] = dote, ssm[2] = dotg, ssm[3] = dotp, ssm[4] = Lp;
     }
     __syncthreads();
+    const double es = ssm[0], dote = ssm[1], dotg = ssm[2], dotp = ssm[3];
 
-    // ---- gradients: Jacobians (entmc_vbmc.py:114-130, variational_optimization.py:1522-1548) and dF -----
+    // ---- one output entry per thread: Jacobians, bound-loss and penalty gradients, dF ---------------
     if (anyg) {
         const double *be = raw + rl.ent(), *bg = raw + rl.gp();
-        const double *sigma = m.prm + a.lay.sigma(), *lambd = m.prm + a.lay.lambd(), *mu = m.prm + a.lay.mu();
+        const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd();
         const int jac = a.f.jacobian;
         const int n0 = a.f.grad[0] ? K * D : 0, n1 = a.f.grad[1] ? K : 0, n2 = a.f.grad[2] ? D : 0,
                   n3 = a.f.grad[3] ? K : 0;
-        for (int e = tid; e < n0 + n1 + n2 + n3; e += nt) {
+        const int e = blockIdx.x * nt + tid;
+        if (e < n0 + n1 + n2 + n3) {
             double gh, gg, add = 0.0;
             if (e < n0) {
                 gh = be[rl.o_mu() + e], gg = bg[rl.o_mu() + e];
-                if (bounds && n_mu) {  // d(bound loss)/d mu, recomputed element-wise
-                    const double x = mu[e], lo = lb[e], hi = ub[e], ell = (hi - lo) * a.tol_con;
-                    const double viol = x < lo ? x - lo : (x > hi ? x - hi : 0.0);
-                    if (viol != 0.0) add = viol / (ell * ell);
-                }
+                if (bounds && n_mu) add = bound_dy(a, prm, e, n_mu, n_sc, nullptr);
             } else if (e < n0 + n1) {
                 const int k = e - n0;
                 const double sc = jac ? sigma[k] : 1.0;
                 gh = be[rl.o_sig() + k] * sc, gg = bg[rl.o_sig() + k] * sc;
-                add = m.add_sig[k];
+                // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = dy[r*K + b]
+                // (:584-586); sigma_b gets the column sum over r
+                if (bounds)
+                    for (int r = 0; r < D; ++r) add += bound_dy(a, prm, n_mu + r * K + k, n_mu, n_sc, nullptr);
             } else if (e < n0 + n1 + n2) {
                 const int d = e - n0 - n1;
                 const double sc = jac ? lambd[d] : 1.0;
                 gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
-                add = m.add_lam[d];
+                if (bounds)  // ... and lambda_r the row sum over b
+                    for (int b = 0; b < K; ++b) add += bound_dy(a, prm, n_mu + d * K + b, n_mu, n_sc, nullptr);
             } else {
                 const int k = e - n0 - n1 - n2;
                 gh = be[rl.o_w() + k], gg = bg[rl.o_w() + k];
-                const double ek = jac || bounds ? exp(eta[k]) : 0.0;
+                const double ek = (jac || pen) ? exp(eta[k]) : 0.0;
                 if (jac) {  // row k of J_w @ g
                     gh = ek / es * gh - ek / (es * es) * dote;
                     gg = ek / es * gg - ek / (es * es) * dotg;
                 }
-                add = m.add_eta[k];
-                if (bounds && a.f.optimize[3]) {  // weight penalty through the softmax Jacobian (:1221-1229)
+                if (bounds && n_eta) add = bound_dy(a, prm, n_mu + n_sc + k, n_mu, n_sc, nullptr);
+                if (pen) {  // weight penalty through the softmax Jacobian (:1221-1229)
                     const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
                     add += ek / es * g - ek / (es * es) * dotp;
                 }
@@ -386,17 +343,25 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double *__restrict
             dF[e] = -gg - gh + add;  // :1171-1173, :1200, :1227-1229
         }
     }
-    if (tid == 0) {
-        const double H = raw[0], G = raw[1];
-        const double F = -G - H + Lb + Lp;
-        out[0] = F;
-        out[1] = G;
-        out[2] = H;
-        out[3] = 0.0;
-        out[4] = 0.0;
-        out[5] = Lb;
-        out[6] = Lp;
-        out[7] = isfinite(F) ? 0.0 : 1.0;
+
+    // ---- CTA 0: the scalars ----------------------------------------------------------------------------
+    if (blockIdx.x == 0) {
+        double Lb = 0.0;
+        if (bounds)
+            for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
+        Lb = block_sum(Lb, scratch);
+        if (tid == 0) {
+            const double H = raw[0], G = raw[1], Lp = pen ? ssm[4] : 0.0;
+            const double F = -G - H + Lb + Lp;
+            out[0] = F;
+            out[1] = G;
+            out[2] = H;
+            out[3] = 0.0;
+            out[4] = 0.0;
+            out[5] = Lb;
+            out[6] = Lp;
+            out[7] = isfinite(F) ? 0.0 : 1.0;
+        }
     }
 }
 
@@ -424,80 +389,44 @@ gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout r
 
 }  // namespace
 
-static size_t finalize_smem(const FinalArgs &a, bool stage_bounds) {
-    const int D = a.lay.D, K = a.lay.K;
-    size_t n = (size_t)a.lay.total() + a.rl.total() + (size_t)K * D + 2 * K + D + 32 * (size_t)(a.as.ent_stride + 1) + K +
-               (size_t)a.as.S * (D + 1);
-    if (stage_bounds) n += 2 * (size_t)a.n_bnd;
-    return n * sizeof(double);
-}
-
-static int launch_finalize(Ctx *c, const double *d_params, FinalArgs &a) {
-    a.stage_bounds = 1;
-    size_t smem = finalize_smem(a, true);
-    if (smem > 200 * 1024) {
-        a.stage_bounds = 0;
-        smem = finalize_smem(a, false);
+// records / per-sample terms -> raw vector (device pointer d_raw)
+int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw) {
+    RawArgs a{};
+    const int DP = pad_dim(D);
+    a.lay = ParamLayout{D, DP, K};
+    a.rl = RawLayout{D, K};
+    a.f = f;
+    a.entpart = c->d_entpart;
+    a.ent_stride = entpart_stride(DP, K);
+    if (plan) {
+        a.slabs = plan->slabs;
+        a.Ns_glob = (double)Ns_glob;
+        a.draws_local = 2.0 * (double)plan->half;
     }
-    VBMC_REQUIRE(smem <= 220 * 1024, VBMC_ERR_UNSUPPORTED, "finalize: D*K too large for the shared-memory staging");
-    if (smem > c->finalize_smem_set) {
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->finalize_smem_set = smem;
-    }
-    finalize_kernel<<<1, 1024, smem, c->stream>>>(d_params, a);
+    a.gps = c->d_gps;
+    a.lamc = c->d_lamc;
+    a.gps_stride = 1 + a.rl.block();
+    a.s_begin = s_begin, a.s_step = s_step, a.S = c->S, a.S_glob = S_glob;
+    a.S_local = f.have_gp ? (c->S - s_begin + s_step - 1) / s_step : 0;
+    if (a.S_local < 0) a.S_local = 0;
+    a.raw = d_raw;
+    a.n_warp_entries = 1 + K + D + K + 1 + D + a.S_local * (D + 1);
+    a.n_thread_entries = 2 * K * D + 2 * K;
+    const int warps = a.n_warp_entries + (a.n_thread_entries + 31) / 32;
+    raw_kernel<<<(warps + 7) / 8, 256, 0, c->stream>>>(d_params, a);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;
 }
 
-static void fill_asm(Ctx *c, int D, int K, FinalArgs &a, double *d_raw) {
-    const int DP = pad_dim(D);
-    a.as.entpart = c->d_entpart;
-    a.as.ent_stride = entpart_stride(DP, K);
-    a.as.slabs = c->red_plan_slabs;
-    a.as.Ns_glob = c->red_Ns_glob;
-    a.as.draws_local = c->red_draws_local;
-    a.as.gps = c->d_gps;
-    a.as.lamc = c->d_lamc;
-    a.as.gps_stride = 1 + RawLayout{D, K}.block();
-    a.as.s_begin = c->red_s_begin;
-    a.as.s_step = c->red_s_step;
-    a.as.S = c->S;
-    a.as.S_glob = c->red_S_glob;
-    a.as.raw_out = d_raw;
-}
-
-// Record the shard description of this evaluation; with assemble == true also launch the
-// assemble-only pass (multi-GPU: the all-reduce of d_raw follows).
-int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool assemble) {
-    c->red_args_valid = true;
-    c->red_plan_slabs = plan ? plan->slabs : 0;
-    c->red_Ns_glob = plan ? (double)Ns_glob : 0.0;
-    c->red_draws_local = plan ? 2.0 * (double)plan->half : 0.0;
-    c->red_s_begin = s_begin, c->red_s_step = s_step, c->red_S_glob = S_glob;
-    if (!assemble) return VBMC_OK;
-    FinalArgs a{};
-    a.lay = ParamLayout{D, pad_dim(D), K};
-    a.rl = RawLayout{D, K};
-    a.f = f;
-    a.do_assemble = 1, a.do_finalize = 0;
-    fill_asm(c, D, K, a, d_raw);
-    a.raw_in = d_raw;
-    return launch_finalize(c, d_params, a);
-}
-
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
-                    double *d_out, bool assemble_first) {
+                    double *d_out) {
     FinalArgs a{};
     a.lay = ParamLayout{D, pad_dim(D), K};
     a.rl = RawLayout{D, K};
     a.f = f;
-    a.do_assemble = assemble_first ? 1 : 0;
-    a.do_finalize = 1;
-    if (assemble_first) VBMC_REQUIRE(c->red_args_valid, VBMC_ERR_STATE, "finalize: no partials to assemble from");
-    fill_asm(c, D, K, a, const_cast<double *>(d_raw));
-    a.raw_in = d_raw;
+    a.raw = d_raw;
     a.lb = c->d_lb;
     a.ub = c->d_ub;
     a.n_bnd = f.use_bounds ? c->n_bnd : 0;
@@ -506,7 +435,12 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.w_pen = c->w_pen;
     a.out = d_out;
     a.Pfull = a.rl.block();
-    return launch_finalize(c, d_params, a);
+    const int P = (f.grad[0] ? K * D : 0) + (f.grad[1] ? K : 0) + (f.grad[2] ? D : 0) + (f.grad[3] ? K : 0);
+    const int grid = P > 0 ? (P + 255) / 256 : 1;
+    final_kernel<<<grid, 256, 0, c->stream>>>(d_params, a);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
 }
 
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s) {
