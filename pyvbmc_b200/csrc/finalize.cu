@@ -41,7 +41,7 @@ struct RawArgs {
 __device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
     const double *rec = a.entpart + (size_t)j * a.slabs * a.ent_stride + f;
     double v = 0.0;
-#pragma unroll 4
+#pragma unroll 8
     for (int s = 0; s < a.slabs; ++s) v += rec[(size_t)s * a.ent_stride];
     return v;
 }
@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[40];
     __shared__ double ssm[5];  // es, dote, dotg, dotp, Lp
+    extern __shared__ double tmp[];  // [K*D] d(bound loss)/d(ln-scale entry), recomputed by every CTA
     const RawLayout rl = a.rl;
     const double *raw = a.raw;
     const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
@@ -294,6 +295,16 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
         es = warp_sum(es), dote = warp_sum(dote), dotg = warp_sum(dotg), dotp = warp_sum(dotp), Lp = warp_sum(Lp);
         if (tid == 0) ssm[0] = es, ssm[1] = dote, ssm[2] = dotg, ssm[3] = dotp, ssm[4] = Lp;
     }
+    // ln-scale block of the bound loss: all K*D entries in one parallel pass (independent loads), the
+    // row / column sums below then run out of shared memory.  CTA 0 also collects the loss itself.
+    double Lb = 0.0;
+    if (bounds) {
+        for (int i = tid; i < n_sc; i += nt) tmp[i] = bound_dy(a, prm, n_mu + i, n_mu, n_sc, &Lb);
+        if (blockIdx.x == 0) {
+            for (int e = tid; e < n_mu; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
+            for (int e = n_mu + n_sc + tid; e < n_mu + n_sc + n_eta; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
+        }
+    }
     __syncthreads();
     const double es = ssm[0], dote = ssm[1], dotg = ssm[2], dotp = ssm[3];
 
@@ -317,13 +328,13 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
                 // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = dy[r*K + b]
                 // (:584-586); sigma_b gets the column sum over r
                 if (bounds)
-                    for (int r = 0; r < D; ++r) add += bound_dy(a, prm, n_mu + r * K + k, n_mu, n_sc, nullptr);
+                    for (int r = 0; r < D; ++r) add += tmp[r * K + k];
             } else if (e < n0 + n1 + n2) {
                 const int d = e - n0 - n1;
                 const double sc = jac ? lambd[d] : 1.0;
                 gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
                 if (bounds)  // ... and lambda_r the row sum over b
-                    for (int b = 0; b < K; ++b) add += bound_dy(a, prm, n_mu + d * K + b, n_mu, n_sc, nullptr);
+                    for (int b = 0; b < K; ++b) add += tmp[d * K + b];
             } else {
                 const int k = e - n0 - n1 - n2;
                 gh = be[rl.o_w() + k], gg = bg[rl.o_w() + k];
@@ -346,9 +357,6 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
 
     // ---- CTA 0: the scalars ----------------------------------------------------------------------------
     if (blockIdx.x == 0) {
-        double Lb = 0.0;
-        if (bounds)
-            for (int e = tid; e < n_mu + n_sc + n_eta; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
         Lb = block_sum(Lb, scratch);
         if (tid == 0) {
             const double H = raw[0], G = raw[1], Lp = pen ? ssm[4] : 0.0;
@@ -437,7 +445,13 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.Pfull = a.rl.block();
     const int P = (f.grad[0] ? K * D : 0) + (f.grad[1] ? K : 0) + (f.grad[2] ? D : 0) + (f.grad[3] ? K : 0);
     const int grid = P > 0 ? (P + 255) / 256 : 1;
-    final_kernel<<<grid, 256, 0, c->stream>>>(d_params, a);
+    const size_t smem = (size_t)K * D * sizeof(double);
+    VBMC_REQUIRE(smem <= 200 * 1024, VBMC_ERR_UNSUPPORTED, "finalize: D*K too large");
+    if (smem > c->finalize_smem_set && smem > 48 * 1024) {
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->finalize_smem_set = smem;
+    }
+    final_kernel<<<grid, 256, smem, c->stream>>>(d_params, a);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;
