@@ -15,8 +15,11 @@ namespace vbmc {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 
+static thread_local bool g_realloc = false;  // set whenever a device buffer moved: captured graphs are stale
+
 int ensure(double **p, size_t *cap, size_t need) {
     if (need <= *cap && *p) return VBMC_OK;
+    g_realloc = true;
     if (*p) VBMC_CUDA_CHECK(cudaFree(*p));
     *p = nullptr;
     size_t n = need + need / 4 + 64;
@@ -27,6 +30,7 @@ int ensure(double **p, size_t *cap, size_t need) {
 
 int ensure_pinned(double **d, double **h, size_t *cap, size_t need) {
     if (need <= *cap && *d && *h) return VBMC_OK;
+    g_realloc = true;
     if (*d) VBMC_CUDA_CHECK(cudaFree(*d));
     if (*h) VBMC_CUDA_CHECK(cudaFreeHost(*h));
     *d = *h = nullptr;
@@ -81,15 +85,33 @@ struct Staged {
     EvalFlags f{};
     EntmcPlan plan{};
     bool planned = false;
-    bool assemble_pending = false;  // world == 1: the raw vector is assembled inside the finalize launch
     EvalFlags f_partials{};
+    int launches_per_eval = 0;
 };
 
 // per-context staged state (kept outside Ctx to keep common.cuh light)
+// signature of the launch sequence of one flat evaluation (everything that is baked into a captured graph)
+struct GraphKey {
+    int D = 0, K = 0, flags = 0, n_bnd = 0, precision = 0, variant = 0, S = 0, N = 0;
+    int64_t Ns = -1;
+    uint64_t gen = 0;  // bumped by gp_pack / set_bounds / any reallocation
+    bool operator==(const GraphKey &o) const {
+        return D == o.D && K == o.K && flags == o.flags && n_bnd == o.n_bnd && precision == o.precision &&
+               variant == o.variant && S == o.S && N == o.N && Ns == o.Ns && gen == o.gen;
+    }
+};
+
 struct CtxEx {
     Ctx c;
     Staged st;
     std::vector<double> host_tmp;
+    // CUDA-graph replay of the flat evaluation
+    bool graphs_on = true;
+    uint64_t gen = 1;
+    GraphKey gkey, last_key;
+    cudaGraphExec_t gexec = nullptr;
+    cudaGraph_t graph = nullptr;
+    int64_t graph_launches = 0;
 };
 
 CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
@@ -104,7 +126,7 @@ int stage(CtxEx *x, const Spec &s) {
     }
     ParamLayout lay{D, DP, K};
     RawLayout rl{D, K};
-    VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total()));
+    VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total() + 2));
     double *h = c->h_in;
     if (s.flat) {
         memcpy(h, s.flat, sizeof(double) * lay.total());
@@ -118,7 +140,9 @@ int stage(CtxEx *x, const Spec &s) {
         for (int d = 0; d < D; ++d) h[lay.lnlam_b() + d] = s.ln_lambd_b ? s.ln_lambd_b[d] : log(s.vp.lambd[d]);
         for (int k = 0; k < K; ++k) h[lay.eta_b() + k] = s.eta_b ? s.eta_b[k] : s.vp.eta[k];
     }
-    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * lay.total(), cudaMemcpyHostToDevice, c->stream));
+    memcpy(h + lay.total(), &s.seed, sizeof(uint64_t));  // Philox key rides behind the parameter block
+    memcpy(h + lay.total() + 1, &s.offset, sizeof(uint64_t));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * (lay.total() + 2), cudaMemcpyHostToDevice, c->stream));
 
     if (s.use_bounds) {
         const int n_expect = (s.optimize[0] ? K * D : 0) + K * D + (s.optimize[3] ? K : 0);
@@ -235,6 +259,76 @@ int run_single(CtxEx *x, const Spec &s, size_t n_out) {
     return VBMC_OK;
 }
 
+void drop_graph(CtxEx *x) {
+    if (x->gexec) cudaGraphExecDestroy(x->gexec);
+    if (x->graph) cudaGraphDestroy(x->graph);
+    x->gexec = nullptr, x->graph = nullptr;
+    x->gkey = GraphKey{};
+}
+
+// Flat evaluation with CUDA-graph replay: the first call with a new launch signature runs eagerly (and
+// sizes every buffer), the second one is captured (H2D copy, gplj on the side stream, entmc, raw, final),
+// every later call only refreshes the pinned parameter block (theta + Philox key) and replays the graph:
+// one driver call instead of ~12, and no CPU-side gaps between the dependent kernels.
+int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
+    Ctx *c = &x->c;
+    if (g_realloc) {  // some buffer moved since the last look: every captured pointer is suspect
+        x->gen++;
+        g_realloc = false;
+    }
+    const bool eligible = x->graphs_on && !c->stage_timing && !c->time_entmc && s.flat != nullptr &&
+                          !(s.Ns > 0 && s.rng_mode == VBMC_RNG_EPS) && !s.compute_var;
+    if (!eligible) return run_single(x, s, n_out);
+    GraphKey k;
+    k.D = s.vp.D, k.K = s.vp.K, k.Ns = s.Ns, k.n_bnd = s.use_bounds ? c->n_bnd : 0, k.precision = s.precision;
+    k.variant = c->entmc_variant, k.S = c->S, k.N = c->N, k.gen = x->gen;
+    for (int i = 0; i < 4; ++i) k.flags |= (s.grad[i] ? 1 : 0) << i | (s.optimize[i] ? 1 : 0) << (4 + i);
+    k.flags |= (s.use_bounds ? 1 : 0) << 8 | (s.have_gp ? 1 : 0) << 9 | (s.have_ent ? 1 : 0) << 10;
+    if (x->gexec && k == x->gkey) {
+        const ParamLayout lay{k.D, pad_dim(k.D), k.K};
+        memcpy(c->h_in, s.flat, sizeof(double) * lay.total());
+        memcpy(c->h_in + lay.total(), &s.seed, sizeof(uint64_t));
+        memcpy(c->h_in + lay.total() + 1, &s.offset, sizeof(uint64_t));
+        VBMC_CUDA_CHECK(cudaGraphLaunch(x->gexec, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        x->graph_launches++;
+        c->launches += x->st.launches_per_eval;
+        return VBMC_OK;
+    }
+    if (!(k == x->last_key)) {  // first sighting: eager run (allocations happen here)
+        x->last_key = k;
+        return run_single(x, s, n_out);
+    }
+    // second call with the same signature: capture
+    drop_graph(x);
+    g_realloc = false;
+    const int64_t l0 = c->launches;
+    VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = stage(x, s);
+    if (rc == VBMC_OK) rc = partials(x, 0, 1, c->d_raw);
+    if (rc == VBMC_OK) rc = finalize(x, c->d_raw, c->h_out);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+    if (rc != VBMC_OK || ce != cudaSuccess || g_realloc) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        x->gen++;  // whatever moved, start over with eager runs
+        x->last_key = GraphKey{};
+        if (rc != VBMC_OK) return rc;
+        return run_single(x, s, n_out);
+    }
+    x->graph = g;
+    x->st.launches_per_eval = (int)(c->launches - l0);
+    c->launches = l0;
+    VBMC_CUDA_CHECK(cudaGraphInstantiate(&x->gexec, g, 0));
+    x->gkey = k;
+    VBMC_CUDA_CHECK(cudaGraphLaunch(x->gexec, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    x->graph_launches++;
+    c->launches += x->st.launches_per_eval;
+    return VBMC_OK;
+}
+
 }  // namespace
 }  // namespace vbmc
 
@@ -268,6 +362,7 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     CtxEx *x = new CtxEx();
     x->c.device = device;
     x->c.sm_count = prop.multiProcessorCount;
+    if (const char *gq = getenv("VBMC_GRAPH")) x->graphs_on = atoi(gq) != 0;
     if (const char *t = getenv("VBMC_STAGE_TIMING")) x->c.stage_timing = atoi(t) != 0;
     if (x->c.stage_timing)
         for (int i = 0; i < 8; ++i) VBMC_CUDA_CHECK(cudaEventCreate(&x->c.sev[i]));
@@ -289,6 +384,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     Ctx *c = &x->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    drop_graph(x);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
                      c->d_entpart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
@@ -371,6 +467,7 @@ int vbmc_gp_pack(vbmc_ctx *p, int D, int N, int S, const double *X, const double
     c->gD = D, c->gDP = DP, c->N = N, c->S = S, c->mean_kind = mean_kind;
     c->has_gp = true;
     c->staged = false;
+    ex(p)->gen++;  // captured graphs reference the old GP buffers
     return VBMC_OK;
 }
 
@@ -381,6 +478,7 @@ int vbmc_set_bounds(vbmc_ctx *p, int n, const double *lb, const double *ub, doub
     Bind b(c);
     VBMC_REQUIRE(n >= 0, VBMC_ERR_ARG, "set_bounds: negative length");
     c->n_bnd = 0;
+    ex(p)->gen++;
     if (n == 0) return VBMC_OK;
     VBMC_REQUIRE(lb && ub, VBMC_ERR_ARG, "set_bounds: null array");
     VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -396,6 +494,7 @@ int vbmc_set_bounds(vbmc_ctx *p, int n, const double *lb, const double *ub, doub
     VBMC_CUDA_CHECK(cudaMemcpy(c->d_ub, ub, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     c->n_bnd = n;
     c->tol_con = tol_con, c->w_thr = weight_threshold, c->w_pen = weight_penalty;
+    ex(p)->gen++;  // bounds (pointers and scalars) are baked into captured graphs
     return VBMC_OK;
 }
 
@@ -618,7 +717,7 @@ int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const in
     const int P = packed_len(D, K, s.grad);
     const size_t Pfull = RawLayout{D, K}.block();
     const size_t n_dev = kOutHead + (compute_grad ? (want_dH ? 2 * Pfull : (size_t)P) : 0);
-    VBMC_TRY(run_single(x, s, n_dev));
+    VBMC_TRY(run_flat(x, s, n_dev));
     const double *o = c->h_out;
     if (o[7] != 0.0 && s.precision == VBMC_PREC_F32 && s.Ns > 0) {
         s.precision = VBMC_PREC_F64;  // fp32 density ratios overflowed: redo the entropy in fp64 on the GPU

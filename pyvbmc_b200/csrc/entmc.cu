@@ -64,6 +64,10 @@ entmc_kernel(const double *__restrict__ prm, ParamLayout lay, int64_t half, int6
              int part_stride) {
     constexpr bool kKeepT = sizeof(T) == 4;  // fp32: keep t(+-) in registers; fp64: recompute
     const int D = lay.D, K = lay.K;
+    {  // the Philox key lives behind the parameter block so that a captured CUDA graph stays valid
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
     const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -226,6 +230,10 @@ entmc_kernel_f32x2(const double *__restrict__ prm, ParamLayout lay, int64_t half
                    double *__restrict__ part, int part_stride) {
     constexpr int H = DP / 2;  // packed pairs of dimensions
     const int D = lay.D, K = lay.K;
+    {  // the Philox key lives behind the parameter block so that a captured CUDA graph stays valid
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
     const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -416,6 +424,10 @@ entmc_kernel_f32x2_ds(const double *__restrict__ prm, ParamLayout lay, int64_t h
     constexpr int DHP = (DH + 3) & ~3;    // table row length per half (float4 addressable)
     constexpr int NQ = DHP / 4;
     const int D = lay.D, K = lay.K;
+    {  // the Philox key lives behind the parameter block so that a captured CUDA graph stays valid
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
     const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int h = tid & 1, pt = tid >> 1, npt = nt >> 1;
 
@@ -624,6 +636,10 @@ entmc_kernel_fast(const double *__restrict__ prm, ParamLayout lay, int64_t half,
                   int part_stride, float guard) {
     constexpr int H = DP / 2;  // packed pairs of dimensions
     const int D = lay.D, K = lay.K;
+    {  // the Philox key lives behind the parameter block so that a captured CUDA graph stays valid
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
     const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];

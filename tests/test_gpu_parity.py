@@ -227,6 +227,40 @@ def test_negelcbo_errors(pv):
         pv._gp_log_joint(case_vp(pv, c), c.gp, False, True, True, 2)
 
 
+def test_graph_replay_is_transparent(pv):
+    """The hot-loop entry runs eagerly, then captures a CUDA graph, then replays it: all three must give
+    bitwise the same answer for the same (theta, seed), follow theta and the seed, and survive a change of
+    bounds / GP / draw count in between."""
+    c = load_case("c2")
+    g = c.g
+    res = []
+    for it in range(5):
+        F, dF, G, H, _ = pv._neg_elcbo(g["theta"], c.gp, case_vp(pv, c), 0.0, 500, True, False, c.theta_bnd, seed=11)
+        res.append((F, dF))
+    for F, dF in res[1:]:
+        assert F == res[0][0] and np.array_equal(dF, res[0][1])
+    F2, dF2, *_ = pv._neg_elcbo(g["theta"], c.gp, case_vp(pv, c), 0.0, 500, True, False, c.theta_bnd, seed=12)
+    assert F2 != res[0][0]
+    th = g["theta"] + 1e-3
+    F3, dF3, *_ = pv._neg_elcbo(th, c.gp, case_vp(pv, c), 0.0, 500, True, False, c.theta_bnd, seed=11)
+    eps = pv.context_for_gp(c.gp).philox_normals(c.D, c.K, 500, seed=11, offset=0)
+    Fo, dFo, *_ = eo.neg_elcbo(th, c.gp, c.vp(), 0.0, 500, True, False, c.theta_bnd, eps_half=eps)
+    assert relerr(F3, Fo) < TOL_F32_VAL and relmax(dF3, dFo) < TOL_F32_GRAD
+    # change the signature (no bounds, other Ns), come back: still the first answer
+    pv._neg_elcbo(g["theta"], c.gp, case_vp(pv, c), 0.0, 300, True, False, None, seed=11)
+    pv._neg_elcbo(g["theta"], c.gp, case_vp(pv, c), 0.0, 0, False, False, c.theta_bnd)
+    for it in range(3):
+        F, dF, *_ = pv._neg_elcbo(g["theta"], c.gp, case_vp(pv, c), 0.0, 500, True, False, c.theta_bnd, seed=11)
+        assert F == res[0][0] and np.array_equal(dF, res[0][1])
+    # another GP on the same shapes (fresh posterior arrays => repack => graphs invalidated)
+    c2 = load_case("c2_ill")
+    Fa, dFa, *_ = pv._neg_elcbo(g["theta"], c2.gp, case_vp(pv, c2), 0.0, 500, True, False, c2.theta_bnd, seed=11)
+    for it in range(3):
+        Fb, dFb, *_ = pv._neg_elcbo(g["theta"], c2.gp, case_vp(pv, c2), 0.0, 500, True, False, c2.theta_bnd, seed=11)
+        assert Fb == Fa and np.array_equal(dFa, dFb)
+    assert Fa != res[0][0]
+
+
 # ------------------------------------------------------------------ variance path (full ELCBO evaluation)
 @pytest.mark.parametrize("stem", VAR_CASES)
 def test_variance_path_golden(pv, stem):
