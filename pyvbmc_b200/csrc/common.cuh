@@ -163,7 +163,7 @@ struct Ctx {
     int ent_grid_slabs = 0;
 
     // fp32 entropy kernel selection (VBMC_ENTMC_VARIANT / VBMC_ENTMC_GUARD environment overrides)
-    int entmc_variant = 0;
+    int entmc_variant = 4;  // ENTMC_WARP
     float entmc_guard = 128.0f;
 
     // optional per-stage timeline (VBMC_STAGE_TIMING=1): events on the main stream
@@ -186,9 +186,11 @@ int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
 // ----------------------------------------------------------------------------- launchers
 // entmc.cu
-enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3 };
+enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENTMC_WARP = 4 };
 struct EntmcPlan {
     int variant;
+    int64_t chunk;    // ENTMC_WARP: pairs of the flattened (component, pair) space per CTA
+    int grid, maxseg; // ENTMC_WARP: CTAs, records reserved per CTA
     int threads, slabs, pairs_per_thread;
     int64_t half;      // pairs per component handled by THIS rank
     int64_t pair0;     // first pair index (global) of this rank's range

@@ -26,6 +26,8 @@
 //
 // T = float : fp32 compute, fp64 accumulation across threads (default, ~6D+10 FP32-pipe
 //             instructions per (pair, k)).   T = double: everything fp64 (validation mode).
+#include <algorithm>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -856,6 +858,290 @@ static size_t entmc_smem_fast(int DP, int K, int nt, bool wgrad, bool anygrad) {
     return b + 40 * sizeof(double);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 production kernel, "warp-autonomous" (default).  Arithmetic = the expanded form of
+// entmc_kernel_fast (same guard, same direct-path fallback); what changes is the work distribution:
+//   * the K * half antithetic pairs form ONE index space cut into equal chunks, one per CTA (grid <= 3
+//     CTAs per SM: a single, balanced wave); a chunk that straddles components is processed segment by
+//     segment, the component tables being rebuilt at each boundary (at most twice for realistic sizes);
+//   * inside a segment every WARP is an independent worker on batches of 32 pairs: it owns a 32-column
+//     tile of the u(+-) scratch, keeps its d/dw sums racc_k in registers (lane l owns rows l, l+32, ...:
+//     after each batch it folds the tile row-wise with conflict-free LDS.128), and reduces its own
+//     gradient sums through its tile -- no block-wide barrier inside a segment, no per-thread racc
+//     columns (-200 B/thread of shared memory => 3 CTAs/SM instead of 2);
+//   * per segment the four warp records are combined through shared memory and ONE fp64 record is
+//     written: part[(cta * maxseg + seg)].  raw_kernel recomputes the same chunk arithmetic.
+constexpr int kUS = 132;  // row stride (floats) of the u tile: 128 columns + 4 => LDS.128 row reads are conflict-free
+
+template <int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128, (DP <= 20 ? 3 : 2))
+entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
+               int64_t chunk, int maxseg, const double *__restrict__ eps, uint64_t seed, uint64_t offset,
+               double *__restrict__ part, int part_stride, float guard) {
+    constexpr int H = DP / 2;
+    constexpr int NW = 4;
+    const int D = lay.D, K = lay.K;
+    {
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int urows = max(WGRAD ? 2 * K : 0, ANYGRAD ? 2 * DP : 0);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sDl = reinterpret_cast<float *>(smem_raw);             // [K][DP]
+    KFast *sKc = reinterpret_cast<KFast *>(sDl + K * DP);         // [K]
+    float *sU = reinterpret_cast<float *>(sKc + K);               // [urows][kUS]: u+ rows [0,K), u- rows [K,2K)
+    float *sIq = sU + urows * kUS;                                // [2][128]
+    double *sRec = reinterpret_cast<double *>(sIq + 2 * 128);     // [NW][part_stride]
+    double *sInvL = sRec + NW * part_stride;                      // [DP]
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    const int64_t T = (int64_t)K * half;
+    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, T);
+    if (g0 >= T) return;
+    if (tid < DP) sInvL[tid] = tid < D ? 1.0 / lambd[tid] : 0.0;
+
+    const int j_first = (int)(g0 / half);
+    for (int seg = 0;; ++seg) {
+        const int j = j_first + seg;
+        const int64_t lo = max(g0, (int64_t)j * half), hi = min(g1, (int64_t)(j + 1) * half);
+        if (j >= K || lo >= hi) break;
+        const int64_t p_lo = lo - (int64_t)j * half;
+        const int n = (int)(hi - lo);
+
+        // ---- component tables --------------------------------------------------------------
+        __syncthreads();
+        const double sig_j = sigma[j];
+        for (int i = tid; i < K * DP; i += 128) {
+            const int k = i / DP, d = i - k * DP;
+            sDl[i] = (d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * sInvL[d]) : 0.0f;
+        }
+        __syncthreads();
+        for (int k = tid; k < K; k += 128) {
+            const double sk = sigma[k];
+            const double hk = kHalfLog2e / (sk * sk), hjd = kHalfLog2e / (sig_j * sig_j);
+            const double ck = D * (log2(sig_j) - log2(sk));
+            double A = 0.0;  // |Delta_k|^2 of the ROUNDED table entries (what the FFMA2s will see)
+            for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
+            const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+            KFast c;
+            c.ck2 = (float)(ck - hk * A);
+            c.h2 = (float)(2.0 * hk);
+            c.hd = (float)(hjd - hk);
+            c.w = (float)w[k];
+            c.wis2 = (float)(w[k] / (sk * sk));
+            c.flag = (hk * (A + Emax) > (double)guard && k != j) ? 1.0f : 0.0f;
+            c.ck = (float)ck;
+            c.h = (float)hk;
+            sKc[k] = c;
+        }
+        __syncthreads();
+
+        const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+        const double is2j = 1.0 / (sig_j * sig_j);
+        const float sj = (float)sig_j;
+        double hacc = 0.0;
+        float2 accA[ANYGRAD ? H : 1], accB[ANYGRAD ? H : 1];
+        if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+        }
+        float racc[4] = {0.f, 0.f, 0.f, 0.f};  // rows lane, lane+32, lane+64, lane+96 (K <= 128 in this kernel)
+        float *Ucol = sU + tid;                 // column of this thread inside its warp's tile
+
+        for (int b = wid; b * 32 < n; b += NW) {
+            const int off = b * 32 + lane;
+            const bool live = off < n;
+            const int64_t gpair = pair0 + p_lo + (live ? off : 0);
+
+            float2 e2[H];
+            {
+                float z[DP];
+                if (PHILOX) {
+                    philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)gpair, D, z);
+                } else {
+                    const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) z[d] = (d < D) ? (float)__ldg(ep + d) : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < H; ++i) e2[i] = make_float2(sj * z[2 * i], sj * z[2 * i + 1]);
+            }
+            float2 ee = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < H; ++i) ee = __ffma2_rn(e2[i], e2[i], ee);
+            const float E = ee.x + ee.y;
+            const float base = hj * E;
+
+            float2 lp[ANYGRAD ? H : 1], lm[ANYGRAD ? H : 1];
+            if constexpr (ANYGRAD) {
+#pragma unroll
+                for (int i = 0; i < H; ++i) lp[i] = lm[i] = make_float2(0.f, 0.f);
+            }
+            float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
+
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const KFast c = sKc[k];
+                const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
+                float2 dl[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) dl[i] = dl2[i];
+                float up, um;
+                if (c.flag == 0.0f) {
+                    float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+#pragma unroll
+                    for (int i = 0; i + 1 < H; i += 2) {
+                        b0 = __ffma2_rn(dl[i], e2[i], b0);
+                        b1 = __ffma2_rn(dl[i + 1], e2[i + 1], b1);
+                    }
+                    if (H & 1) b0 = __ffma2_rn(dl[H - 1], e2[H - 1], b0);
+                    const float2 bb = __fadd2_rn(b0, b1);
+                    const float B = bb.x + bb.y;
+                    const float s0 = fmaf(c.hd, E, c.ck2);
+                    up = M<float>::ex2(fmaf(-c.h2, B, s0));
+                    um = M<float>::ex2(fmaf(c.h2, B, s0));
+                    qp = fmaf(c.w, up, qp);
+                    qm = fmaf(c.w, um, qm);
+                    if constexpr (ANYGRAD) {
+                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                        Gp += gpv;
+                        Gm += gmv;
+                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                        for (int i = 0; i < H; ++i) {
+                            lp[i] = __ffma2_rn(gp2, dl[i], lp[i]);
+                            lm[i] = __ffma2_rn(gm2, dl[i], lm[i]);
+                        }
+                    }
+                } else {
+                    // direct path: differences first, squared term by term (no cancellation)
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+                    float2 tp[H], tm[H];
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        tp[i] = __fadd2_rn(dl[i], e2[i]);
+                        tm[i] = __fadd2_rn(dl[i], make_float2(-e2[i].x, -e2[i].y));
+                        a0 = __ffma2_rn(tp[i], tp[i], a0);
+                        a1 = __ffma2_rn(tm[i], tm[i], a1);
+                    }
+                    const float cb = c.ck + base;
+                    up = M<float>::ex2(fmaf(-c.h, a0.x + a0.y, cb));
+                    um = M<float>::ex2(fmaf(-c.h, a1.x + a1.y, cb));
+                    qp = fmaf(c.w, up, qp);
+                    qm = fmaf(c.w, um, qm);
+                    if constexpr (ANYGRAD) {
+                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                        for (int i = 0; i < H; ++i) {
+                            lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
+                            lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
+                        }
+                    }
+                }
+                if (WGRAD) {
+                    Ucol[k * kUS] = up;
+                    Ucol[(K + k) * kUS] = um;
+                }
+            }
+
+            if (live) hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
+            if constexpr (ANYGRAD) {
+                const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
+                const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm);
+                const float2 Gp2 = make_float2(Gp, Gp), nGm2 = make_float2(-Gm, -Gm);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float2 a = __fmul2_rn(__ffma2_rn(e2[i], Gp2, lp[i]), ip2);   // l+ / q+
+                    const float2 bq = __fmul2_rn(__ffma2_rn(e2[i], nGm2, lm[i]), im2);  // l- / q-
+                    accA[i] = __fadd2_rn(accA[i], __fadd2_rn(a, bq));
+                    accB[i] = __ffma2_rn(e2[i], __fadd2_rn(a, make_float2(-bq.x, -bq.y)), accB[i]);
+                }
+                if (WGRAD) {
+                    // fold this batch's tile: racc_k += sum_c u+[k][c] / q+[c] + u-[k][c] / q-[c]
+                    sIq[tid] = iqp;
+                    sIq[128 + tid] = iqm;
+                    __syncwarp();
+                    const float4 *ip4 = reinterpret_cast<const float4 *>(sIq + wid * 32);
+                    const float4 *im4 = reinterpret_cast<const float4 *>(sIq + 128 + wid * 32);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = lane + 32 * rr;
+                        if (row < K) {
+                            const float4 *up4 = reinterpret_cast<const float4 *>(sU + row * kUS + wid * 32);
+                            const float4 *um4 = reinterpret_cast<const float4 *>(sU + (K + row) * kUS + wid * 32);
+                            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 u = up4[c4], v = um4[c4], p4 = ip4[c4], m4 = im4[c4];
+                                a0 = fmaf(u.x, p4.x, a0), a1 = fmaf(v.x, m4.x, a1);
+                                a0 = fmaf(u.y, p4.y, a0), a1 = fmaf(v.y, m4.y, a1);
+                                a0 = fmaf(u.z, p4.z, a0), a1 = fmaf(v.z, m4.z, a1);
+                                a0 = fmaf(u.w, p4.w, a0), a1 = fmaf(v.w, m4.w, a1);
+                            }
+                            racc[rr] += a0 + a1;
+                        }
+                    }
+                    __syncwarp();  // the next batch overwrites the tile
+                }
+            }
+        }
+
+        // ---- segment record: warp-level fp64 reductions, then one combine across the 4 warps -------
+        double *myrec = sRec + wid * part_stride;
+        const double hs = warp_sum(hacc);
+        if (lane == 0) myrec[0] = hs;
+        if constexpr (ANYGRAD) {
+            // spill the register sums to the warp's tile ([2*DP rows][32 columns]) and sum the rows in fp64
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                Ucol[(2 * i) * kUS] = accA[i].x;
+                Ucol[(2 * i + 1) * kUS] = accA[i].y;
+                Ucol[(DP + 2 * i) * kUS] = accB[i].x;
+                Ucol[(DP + 2 * i + 1) * kUS] = accB[i].y;
+            }
+            __syncwarp();
+            for (int row = lane; row < 2 * DP; row += 32) {
+                const float4 *r4 = reinterpret_cast<const float4 *>(sU + row * kUS + wid * 32);
+                double v = 0.0;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 x = r4[c4];
+                    v += (double)x.x + (double)x.y + (double)x.z + (double)x.w;
+                }
+                myrec[1 + row] = v;
+            }
+            if (WGRAD) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                    if (lane + 32 * rr < K) myrec[1 + 2 * DP + lane + 32 * rr] = (double)racc[rr];
+            }
+        }
+        __syncthreads();
+        double *rec = part + ((size_t)blockIdx.x * maxseg + seg) * (size_t)part_stride;
+        const int nf = ANYGRAD ? (WGRAD ? part_stride : 1 + 2 * DP) : 1;
+        for (int f = tid; f < nf; f += 128) rec[f] = (sRec[f] + sRec[part_stride + f]) + (sRec[2 * part_stride + f] + sRec[3 * part_stride + f]);
+    }
+}
+
+static size_t entmc_smem_w(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    (void)nt;
+    const int urows = std::max(wgrad ? 2 * K : 0, anygrad ? 2 * DP : 0);
+    size_t b = (size_t)K * DP * sizeof(float) + (size_t)K * sizeof(KFast) + (size_t)urows * kUS * sizeof(float) +
+               2 * 128 * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)4 * (1 + 2 * DP + K) * sizeof(double) + (size_t)DP * sizeof(double);
+    return b;
+}
+
 static size_t entmc_smem_ds(int DP, int K, int nt, bool wgrad, bool anygrad) {
     const int DHP = ((DP / 2) + 3) & ~3;
     size_t b = (size_t)K * 2 * DHP * sizeof(float) + (size_t)K * sizeof(KConst<float>);
@@ -906,6 +1192,18 @@ int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan
     } while (0)
     if constexpr (sizeof(T) == 4) {
         switch (plan.variant) {
+            case ENTMC_WARP: {
+                auto kern = entmc_kernel_w<DP, WGRAD, ANYGRAD, PHILOX>;
+                static size_t smem_set = 0;
+                if (plan.smem > smem_set) {
+                    VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+                    smem_set = plan.smem;
+                }
+                kern<<<plan.grid, 128, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob,
+                                                              plan.chunk, plan.maxseg, d_eps, seed, offset, d_part,
+                                                              entpart_stride(DP, lay.K), c->entmc_guard);
+                break;
+            }
             case ENTMC_FAST:
                 VBMC_LAUNCH((entmc_kernel_fast<DP, WGRAD, ANYGRAD, PHILOX>), , c->entmc_guard);
                 break;
@@ -993,6 +1291,8 @@ __global__ void philox_dump_kernel(int D, int K, int64_t half, uint64_t seed, ui
 static size_t entmc_smem_variant(int variant, int precision, int DP, int K, int nt, bool wgrad, bool anygrad) {
     if (precision == VBMC_PREC_F64) return entmc_smem<double>(DP, K, nt, wgrad, anygrad);
     switch (variant) {
+        case ENTMC_WARP:
+            return entmc_smem_w(DP, K, nt, wgrad, anygrad);
         case ENTMC_FAST:
             return entmc_smem_fast(DP, K, nt, wgrad, anygrad);
         case ENTMC_DSPLIT:
@@ -1008,8 +1308,40 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     const int DP = pad_dim(D);
     VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "entmc: D > 32 is not supported");
     VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
-    const int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
+    int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
     const size_t smem_cap = 227 * 1024;
+    if (variant == ENTMC_WARP) {
+        // the warp-autonomous kernel keeps racc rows lane + 32 r (r < 4) in registers and needs its tile in smem
+        const size_t smem = entmc_smem_w(DP, K, 128, wgrad, true);
+        if (K > 128 || smem > smem_cap) {
+            variant = ENTMC_FAST;
+        } else {
+            int per_sm = (int)(smem_cap / (smem + 1024));
+            const int reg_cap = DP <= 20 ? 3 : 2;  // __launch_bounds__ of entmc_kernel_w
+            if (per_sm > reg_cap) per_sm = reg_cap;
+            if (per_sm < 1) per_sm = 1;
+            const int64_t T = (int64_t)K * half_local;
+            const int64_t slots = (int64_t)c->sm_count * per_sm;
+            // one balanced wave; at least two batches per warp (256 pairs) per CTA so the tables amortise
+            int64_t G = std::min<int64_t>(slots, std::max<int64_t>(1, T / 256));
+            int64_t chunk = (T + G - 1) / G;
+            chunk = ((chunk + 127) / 128) * 128;  // whole batches for all four warps
+            if (chunk < 128) chunk = 128;
+            G = std::max<int64_t>(1, (T + chunk - 1) / chunk);
+            plan->variant = variant;
+            plan->threads = 128;
+            plan->pairs_per_thread = (int)(chunk / 128);
+            plan->chunk = chunk;
+            plan->grid = (int)G;
+            plan->maxseg = half_local > 0 ? (int)((chunk - 1) / half_local) + 2 : 1;
+            plan->slabs = plan->grid * plan->maxseg;  // records allocated (not all used)
+            plan->half = half_local;
+            plan->pair0 = 0;
+            plan->half_glob = half_local;
+            plan->smem = smem;
+            return VBMC_OK;
+        }
+    }
     int nt = 128;
     auto smem_of = [&](int t) { return entmc_smem_variant(variant, precision, DP, K, t, wgrad, true); };
     while (nt > 32 && smem_of(nt) > smem_cap) nt >>= 1;
@@ -1037,6 +1369,7 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
         if (slabs <= 1) break;
     }
     plan->variant = variant;
+    plan->chunk = 0, plan->grid = 0, plan->maxseg = 0;
     plan->threads = nt;
     plan->pairs_per_thread = bestR;
     plan->slabs = (int)((half_local + (int64_t)ppi * bestR - 1) / ((int64_t)ppi * bestR));

@@ -24,9 +24,12 @@ struct RawArgs {
     ParamLayout lay;
     RawLayout rl;
     EvalFlags f;
-    // entmc CTA records: component j owns records [j*slabs, (j+1)*slabs), each of ent_stride doubles
+    // entmc records of ent_stride doubles.  chunk == 0: component j owns records [j*slabs, (j+1)*slabs);
+    // chunk > 0 (warp-autonomous kernel): CTA c covers pairs [c*chunk, (c+1)*chunk) of the flattened
+    // (component, pair) space and writes record c*maxseg + (j - first component of c) for component j.
     const double *entpart;
-    int slabs, ent_stride;
+    int slabs, ent_stride, maxseg;
+    long long chunk, half;
     double Ns_glob;      // draws per component over all ranks
     double draws_local;  // draws per component on this rank
     // log joint: gps[s] = [G_s | mu | sigma | lambda | w] per-sample raw block, lamc[s][k][d]
@@ -39,8 +42,18 @@ struct RawArgs {
 
 // sum over the slab records of component j of field f (fixed order)
 __device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
-    const double *rec = a.entpart + (size_t)j * a.slabs * a.ent_stride + f;
     double v = 0.0;
+    if (a.chunk > 0) {
+        const long long lo = (long long)j * a.half, hi = lo + a.half - 1;
+        const int c0 = (int)(lo / a.chunk), c1 = (int)(hi / a.chunk);
+#pragma unroll 4
+        for (int c = c0; c <= c1; ++c) {
+            const int seg = j - (int)(((long long)c * a.chunk) / a.half);
+            v += a.entpart[((size_t)c * a.maxseg + seg) * a.ent_stride + f];
+        }
+        return v;
+    }
+    const double *rec = a.entpart + (size_t)j * a.slabs * a.ent_stride + f;
 #pragma unroll 8
     for (int s = 0; s < a.slabs; ++s) v += rec[(size_t)s * a.ent_stride];
     return v;
@@ -409,6 +422,9 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
     a.ent_stride = entpart_stride(DP, K);
     if (plan) {
         a.slabs = plan->slabs;
+        a.chunk = plan->variant == ENTMC_WARP ? plan->chunk : 0;
+        a.maxseg = plan->maxseg;
+        a.half = plan->half;
         a.Ns_glob = (double)Ns_glob;
         a.draws_local = 2.0 * (double)plan->half;
     }
