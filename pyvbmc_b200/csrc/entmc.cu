@@ -880,6 +880,7 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
                double *__restrict__ part, int part_stride, float guard) {
     constexpr int H = DP / 2;
     constexpr int NW = 4;
+    constexpr int RR = 4;  // rows of the tile per lane: K <= 128 and 2*DP <= 64 rows both fit
     const int D = lay.D, K = lay.K;
     {
         const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
@@ -889,12 +890,14 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
     const int urows = max(WGRAD ? 2 * K : 0, ANYGRAD ? 2 * DP : 0);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *sDl = reinterpret_cast<float *>(smem_raw);             // [K][DP]
-    KFast *sKc = reinterpret_cast<KFast *>(sDl + K * DP);         // [K]
+    float *sDl = reinterpret_cast<float *>(smem_raw);             // [K][DP]   (rows in PERMUTED order, see sPerm)
+    KFast *sKc = reinterpret_cast<KFast *>(sDl + K * DP);         // [K]       (permuted order)
     float *sU = reinterpret_cast<float *>(sKc + K);               // [urows][kUS]: u+ rows [0,K), u- rows [K,2K)
     float *sIq = sU + urows * kUS;                                // [2][128]
     double *sRec = reinterpret_cast<double *>(sIq + 2 * 128);     // [NW][part_stride]
     double *sInvL = sRec + NW * part_stride;                      // [DP]
+    int *sPerm = reinterpret_cast<int *>(sInvL + DP);             // [K] position -> component; [K] = #fast
+    float *sFlag = reinterpret_cast<float *>(sPerm + K + 1);      // [K] scratch of the set-up
 
     const double *mu = prm + lay.mu();
     const double *sigma = prm + lay.sigma();
@@ -915,45 +918,67 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
         const int64_t p_lo = lo - (int64_t)j * half;
         const int n = (int)(hi - lo);
 
-        // ---- component tables --------------------------------------------------------------
+        // ---- component tables ----------------------------------------------------------------------
+        // (1) conditioning flag of every component: h_k (A_k + E_max) > guard => direct path (see _fast)
         __syncthreads();
         const double sig_j = sigma[j];
+        const double hjd = kHalfLog2e / (sig_j * sig_j);
+        const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+        for (int k = tid; k < K; k += 128) {
+            double A = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double t = (mu[j * D + d] - mu[k * D + d]) * sInvL[d];
+                A = fma(t, t, A);
+            }
+            const double hk = kHalfLog2e / (sigma[k] * sigma[k]);
+            sFlag[k] = (hk * (A + Emax) > (double)guard && k != j) ? 1.0f : 0.0f;
+        }
+        __syncthreads();
+        // (2) stable partition: un-flagged components first (branch-free inner loop), flagged ones after
+        if (tid == 0) {
+            int nf = 0;
+            for (int k = 0; k < K; ++k)
+                if (sFlag[k] == 0.0f) sPerm[nf++] = k;
+            sPerm[K] = nf;
+            for (int k = 0; k < K; ++k)
+                if (sFlag[k] != 0.0f) sPerm[nf++] = k;
+        }
+        __syncthreads();
+        const int nfast = sPerm[K];
+        // (3) tables in permuted order
         for (int i = tid; i < K * DP; i += 128) {
-            const int k = i / DP, d = i - k * DP;
+            const int pos = i / DP, d = i - pos * DP, k = sPerm[pos];
             sDl[i] = (d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * sInvL[d]) : 0.0f;
         }
         __syncthreads();
-        for (int k = tid; k < K; k += 128) {
+        for (int pos = tid; pos < K; pos += 128) {
+            const int k = sPerm[pos];
             const double sk = sigma[k];
-            const double hk = kHalfLog2e / (sk * sk), hjd = kHalfLog2e / (sig_j * sig_j);
+            const double hk = kHalfLog2e / (sk * sk);
             const double ck = D * (log2(sig_j) - log2(sk));
             double A = 0.0;  // |Delta_k|^2 of the ROUNDED table entries (what the FFMA2s will see)
-            for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
-            const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+            for (int d = 0; d < D; ++d) A += (double)sDl[pos * DP + d] * (double)sDl[pos * DP + d];
             KFast c;
             c.ck2 = (float)(ck - hk * A);
             c.h2 = (float)(2.0 * hk);
             c.hd = (float)(hjd - hk);
             c.w = (float)w[k];
             c.wis2 = (float)(w[k] / (sk * sk));
-            c.flag = (hk * (A + Emax) > (double)guard && k != j) ? 1.0f : 0.0f;
+            c.flag = sFlag[k];
             c.ck = (float)ck;
             c.h = (float)hk;
-            sKc[k] = c;
+            sKc[pos] = c;
         }
         __syncthreads();
 
-        const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+        const float hj = (float)hjd;
         const double is2j = 1.0 / (sig_j * sig_j);
         const float sj = (float)sig_j;
         double hacc = 0.0;
-        float2 accA[ANYGRAD ? H : 1], accB[ANYGRAD ? H : 1];
-        if constexpr (ANYGRAD) {
-#pragma unroll
-            for (int i = 0; i < H; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
-        }
-        float racc[4] = {0.f, 0.f, 0.f, 0.f};  // rows lane, lane+32, lane+64, lane+96 (K <= 128 in this kernel)
-        float *Ucol = sU + tid;                 // column of this thread inside its warp's tile
+        double rowacc[RR] = {0.0, 0.0, 0.0, 0.0};  // fp64 sums of the gradient rows lane + 32 r  (A | Be)
+        float racc[RR] = {0.f, 0.f, 0.f, 0.f};     // d/dw sums of the (permuted) component rows lane + 32 r
+        float *Ucol = sU + tid;                     // column of this thread inside its warp's tile
+        const float4 *tile4 = reinterpret_cast<const float4 *>(sU + wid * 32);
 
         for (int b = wid; b * 32 < n; b += NW) {
             const int off = b * 32 + lane;
@@ -986,84 +1011,83 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
             }
             float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
 
+            // ---- un-flagged components: expanded form, branch-free, two components in flight ---------
+            float *ust = Ucol;
 #pragma unroll 2
-            for (int k = 0; k < K; ++k) {
+            for (int k = 0; k < nfast; ++k) {
                 const KFast c = sKc[k];
                 const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
                 float2 dl[H];
 #pragma unroll
                 for (int i = 0; i < H; ++i) dl[i] = dl2[i];
-                float up, um;
-                if (c.flag == 0.0f) {
-                    float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+                float2 b0 = make_float2(0.f, 0.f), b1 = b0;
 #pragma unroll
-                    for (int i = 0; i + 1 < H; i += 2) {
-                        b0 = __ffma2_rn(dl[i], e2[i], b0);
-                        b1 = __ffma2_rn(dl[i + 1], e2[i + 1], b1);
-                    }
-                    if (H & 1) b0 = __ffma2_rn(dl[H - 1], e2[H - 1], b0);
-                    const float2 bb = __fadd2_rn(b0, b1);
-                    const float B = bb.x + bb.y;
-                    const float s0 = fmaf(c.hd, E, c.ck2);
-                    up = M<float>::ex2(fmaf(-c.h2, B, s0));
-                    um = M<float>::ex2(fmaf(c.h2, B, s0));
-                    qp = fmaf(c.w, up, qp);
-                    qm = fmaf(c.w, um, qm);
-                    if constexpr (ANYGRAD) {
-                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
-                        Gp += gpv;
-                        Gm += gmv;
-                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
-#pragma unroll
-                        for (int i = 0; i < H; ++i) {
-                            lp[i] = __ffma2_rn(gp2, dl[i], lp[i]);
-                            lm[i] = __ffma2_rn(gm2, dl[i], lm[i]);
-                        }
-                    }
-                } else {
-                    // direct path: differences first, squared term by term (no cancellation)
-                    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-                    float2 tp[H], tm[H];
+                for (int i = 0; i + 1 < H; i += 2) {
+                    b0 = __ffma2_rn(dl[i], e2[i], b0);
+                    b1 = __ffma2_rn(dl[i + 1], e2[i + 1], b1);
+                }
+                if (H & 1) b0 = __ffma2_rn(dl[H - 1], e2[H - 1], b0);
+                const float2 bb = __fadd2_rn(b0, b1);
+                const float B = bb.x + bb.y;
+                const float s0 = fmaf(c.hd, E, c.ck2);
+                const float up = M<float>::ex2(fmaf(-c.h2, B, s0));
+                const float um = M<float>::ex2(fmaf(c.h2, B, s0));
+                if (WGRAD) {
+                    ust[0] = up;
+                    ust[K * kUS] = um;
+                    ust += kUS;
+                }
+                qp = fmaf(c.w, up, qp);
+                qm = fmaf(c.w, um, qm);
+                if constexpr (ANYGRAD) {
+                    const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                    Gp += gpv;
+                    Gm += gmv;
 #pragma unroll
                     for (int i = 0; i < H; ++i) {
-                        tp[i] = __fadd2_rn(dl[i], e2[i]);
-                        tm[i] = __fadd2_rn(dl[i], make_float2(-e2[i].x, -e2[i].y));
-                        a0 = __ffma2_rn(tp[i], tp[i], a0);
-                        a1 = __ffma2_rn(tm[i], tm[i], a1);
-                    }
-                    const float cb = c.ck + base;
-                    up = M<float>::ex2(fmaf(-c.h, a0.x + a0.y, cb));
-                    um = M<float>::ex2(fmaf(-c.h, a1.x + a1.y, cb));
-                    qp = fmaf(c.w, up, qp);
-                    qm = fmaf(c.w, um, qm);
-                    if constexpr (ANYGRAD) {
-                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
-                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
-#pragma unroll
-                        for (int i = 0; i < H; ++i) {
-                            lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
-                            lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
-                        }
+                        lp[i] = __ffma2_rn(make_float2(gpv, gpv), dl[i], lp[i]);
+                        lm[i] = __ffma2_rn(make_float2(gmv, gmv), dl[i], lm[i]);
                     }
                 }
+            }
+            // ---- flagged components: direct differences, squared term by term (no cancellation) -------
+#pragma unroll 1
+            for (int k = nfast; k < K; ++k) {
+                const KFast c = sKc[k];
+                const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float2 tp = __fadd2_rn(dl2[i], e2[i]);
+                    const float2 tm = __fadd2_rn(dl2[i], make_float2(-e2[i].x, -e2[i].y));
+                    a0 = __ffma2_rn(tp, tp, a0);
+                    a1 = __ffma2_rn(tm, tm, a1);
+                }
+                const float cb = c.ck + base;
+                const float up = M<float>::ex2(fmaf(-c.h, a0.x + a0.y, cb));
+                const float um = M<float>::ex2(fmaf(-c.h, a1.x + a1.y, cb));
                 if (WGRAD) {
-                    Ucol[k * kUS] = up;
-                    Ucol[(K + k) * kUS] = um;
+                    ust[0] = up;
+                    ust[K * kUS] = um;
+                    ust += kUS;
+                }
+                qp = fmaf(c.w, up, qp);
+                qm = fmaf(c.w, um, qm);
+                if constexpr (ANYGRAD) {
+                    const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {  // t recomputed: this loop is rare, registers are not
+                        const float2 tp = __fadd2_rn(dl2[i], e2[i]);
+                        const float2 tm = __fadd2_rn(dl2[i], make_float2(-e2[i].x, -e2[i].y));
+                        lp[i] = __ffma2_rn(make_float2(gpv, gpv), tp, lp[i]);
+                        lm[i] = __ffma2_rn(make_float2(gmv, gmv), tm, lm[i]);
+                    }
                 }
             }
 
             if (live) hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
             if constexpr (ANYGRAD) {
                 const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
-                const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm);
-                const float2 Gp2 = make_float2(Gp, Gp), nGm2 = make_float2(-Gm, -Gm);
-#pragma unroll
-                for (int i = 0; i < H; ++i) {
-                    const float2 a = __fmul2_rn(__ffma2_rn(e2[i], Gp2, lp[i]), ip2);   // l+ / q+
-                    const float2 bq = __fmul2_rn(__ffma2_rn(e2[i], nGm2, lm[i]), im2);  // l- / q-
-                    accA[i] = __fadd2_rn(accA[i], __fadd2_rn(a, bq));
-                    accB[i] = __ffma2_rn(e2[i], __fadd2_rn(a, make_float2(-bq.x, -bq.y)), accB[i]);
-                }
                 if (WGRAD) {
                     // fold this batch's tile: racc_k += sum_c u+[k][c] / q+[c] + u-[k][c] / q-[c]
                     sIq[tid] = iqp;
@@ -1072,11 +1096,11 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
                     const float4 *ip4 = reinterpret_cast<const float4 *>(sIq + wid * 32);
                     const float4 *im4 = reinterpret_cast<const float4 *>(sIq + 128 + wid * 32);
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
+                    for (int rr = 0; rr < RR; ++rr) {
                         const int row = lane + 32 * rr;
                         if (row < K) {
-                            const float4 *up4 = reinterpret_cast<const float4 *>(sU + row * kUS + wid * 32);
-                            const float4 *um4 = reinterpret_cast<const float4 *>(sU + (K + row) * kUS + wid * 32);
+                            const float4 *up4 = tile4 + row * (kUS / 4);
+                            const float4 *um4 = tile4 + (K + row) * (kUS / 4);
                             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                             for (int c4 = 0; c4 < 8; ++c4) {
@@ -1089,46 +1113,60 @@ entmc_kernel_w(const double *__restrict__ prm, ParamLayout lay, int64_t half, in
                             racc[rr] += a0 + a1;
                         }
                     }
-                    __syncwarp();  // the next batch overwrites the tile
+                    __syncwarp();  // the tile is about to be reused
                 }
+                // gradient rows of this batch through the tile: row d = l+_d/q+ + l-_d/q-, row DP+d = e_d (..-..);
+                // lane r sums row r over the 32 pairs in fp64 (cross-thread accumulation never sees fp32)
+                const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm);
+                const float2 Gp2 = make_float2(Gp, Gp), nGm2 = make_float2(-Gm, -Gm);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float2 a = __fmul2_rn(__ffma2_rn(e2[i], Gp2, lp[i]), ip2);    // l+ / q+
+                    const float2 bq = __fmul2_rn(__ffma2_rn(e2[i], nGm2, lm[i]), im2);  // l- / q-
+                    const float2 sa = __fadd2_rn(a, bq);
+                    const float2 sb = __fmul2_rn(e2[i], __fadd2_rn(a, make_float2(-bq.x, -bq.y)));
+                    Ucol[(2 * i) * kUS] = sa.x;
+                    Ucol[(2 * i + 1) * kUS] = sa.y;
+                    Ucol[(DP + 2 * i) * kUS] = sb.x;
+                    Ucol[(DP + 2 * i + 1) * kUS] = sb.y;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < RR; ++rr) {
+                    const int row = lane + 32 * rr;
+                    if (row < 2 * DP) {
+                        const float4 *r4 = tile4 + row * (kUS / 4);
+                        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 x = r4[c4];
+                            v0 += x.x + x.y;
+                            v1 += x.z + x.w;
+                        }
+                        rowacc[rr] += (double)v0 + (double)v1;
+                    }
+                }
+                __syncwarp();
             }
         }
 
-        // ---- segment record: warp-level fp64 reductions, then one combine across the 4 warps -------
+        // ---- segment record: each warp contributes its sums, one combine across the 4 warps -----------
         double *myrec = sRec + wid * part_stride;
         const double hs = warp_sum(hacc);
         if (lane == 0) myrec[0] = hs;
         if constexpr (ANYGRAD) {
-            // spill the register sums to the warp's tile ([2*DP rows][32 columns]) and sum the rows in fp64
-            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < H; ++i) {
-                Ucol[(2 * i) * kUS] = accA[i].x;
-                Ucol[(2 * i + 1) * kUS] = accA[i].y;
-                Ucol[(DP + 2 * i) * kUS] = accB[i].x;
-                Ucol[(DP + 2 * i + 1) * kUS] = accB[i].y;
-            }
-            __syncwarp();
-            for (int row = lane; row < 2 * DP; row += 32) {
-                const float4 *r4 = reinterpret_cast<const float4 *>(sU + row * kUS + wid * 32);
-                double v = 0.0;
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 x = r4[c4];
-                    v += (double)x.x + (double)x.y + (double)x.z + (double)x.w;
-                }
-                myrec[1 + row] = v;
-            }
-            if (WGRAD) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
-                    if (lane + 32 * rr < K) myrec[1 + 2 * DP + lane + 32 * rr] = (double)racc[rr];
+            for (int rr = 0; rr < RR; ++rr) {
+                const int row = lane + 32 * rr;
+                if (row < 2 * DP) myrec[1 + row] = rowacc[rr];
+                if (WGRAD && row < K) myrec[1 + 2 * DP + sPerm[row]] = (double)racc[rr];  // un-permute
             }
         }
         __syncthreads();
         double *rec = part + ((size_t)blockIdx.x * maxseg + seg) * (size_t)part_stride;
         const int nf = ANYGRAD ? (WGRAD ? part_stride : 1 + 2 * DP) : 1;
-        for (int f = tid; f < nf; f += 128) rec[f] = (sRec[f] + sRec[part_stride + f]) + (sRec[2 * part_stride + f] + sRec[3 * part_stride + f]);
+        for (int f = tid; f < nf; f += 128)
+            rec[f] = (sRec[f] + sRec[part_stride + f]) + (sRec[2 * part_stride + f] + sRec[3 * part_stride + f]);
     }
 }
 
@@ -1139,6 +1177,7 @@ static size_t entmc_smem_w(int DP, int K, int nt, bool wgrad, bool anygrad) {
                2 * 128 * sizeof(float);
     b = (b + 15) & ~(size_t)15;
     b += (size_t)4 * (1 + 2 * DP + K) * sizeof(double) + (size_t)DP * sizeof(double);
+    b += (size_t)(K + 1) * sizeof(int) + (size_t)K * sizeof(float) + 16;
     return b;
 }
 
