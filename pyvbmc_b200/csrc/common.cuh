@@ -164,7 +164,7 @@ struct Ctx {
 
     // fp32 entropy kernel selection (VBMC_ENTMC_VARIANT / VBMC_ENTMC_GUARD environment overrides)
     int entmc_variant = 4;  // ENTMC_WARP
-    float entmc_guard = 128.0f;
+    float entmc_guard = 1024.0f;  // worst-case per-term relative error of the expanded form ~ 8e-8 * guard
 
     // optional per-stage timeline (VBMC_STAGE_TIMING=1): events on the main stream
     bool stage_timing = false;

@@ -1361,12 +1361,13 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
             if (per_sm < 1) per_sm = 1;
             const int64_t T = (int64_t)K * half_local;
             const int64_t slots = (int64_t)c->sm_count * per_sm;
-            // one balanced wave; at least two batches per warp (256 pairs) per CTA so the tables amortise
-            int64_t G = std::min<int64_t>(slots, std::max<int64_t>(1, T / 256));
-            int64_t chunk = (T + G - 1) / G;
-            chunk = ((chunk + 127) / 128) * 128;  // whole batches for all four warps
+            // one wave over all resident slots; whole batches for all four warps (chunk multiple of 128).
+            // Small problems still get one batch per warp and as many CTAs as that allows: resident warps
+            // matter more than amortising the table set-up.
+            int64_t chunk = (T + slots - 1) / slots;
+            chunk = ((chunk + 127) / 128) * 128;
             if (chunk < 128) chunk = 128;
-            G = std::max<int64_t>(1, (T + chunk - 1) / chunk);
+            const int64_t G = std::max<int64_t>(1, (T + chunk - 1) / chunk);
             plan->variant = variant;
             plan->threads = 128;
             plan->pairs_per_thread = (int)(chunk / 128);
