@@ -300,7 +300,7 @@ def run_b200(args):
         achieved_gbs = b_alg / k_s / 1e9
         roofline = {
             "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-            "traffic": None, "kernel": "entmc_kernel_f32x2<20,WGRAD,ANYGRAD,PHILOX>", "kernel_ms": k_ms,
+            "traffic": None, "kernel": "entmc_kernel_w<20,WGRAD,ANYGRAD,PHILOX>", "kernel_ms": k_ms,
             "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": b_alg, "peak_source": hbm_src,
             "note": ("entmc is bound by the FP32 FMA pipe, not HBM (arithmetic intensity >> ridge; with device "
                      "Philox draws its only HBM traffic is the parameter block and one record per CTA), so the "

@@ -163,7 +163,7 @@ struct Ctx {
     int ent_grid_slabs = 0;
 
     // fp32 entropy kernel selection (VBMC_ENTMC_VARIANT / VBMC_ENTMC_GUARD environment overrides)
-    int entmc_variant = 4;  // ENTMC_WARP
+    int entmc_variant = -1;  // auto (ENTMC_WARP for large draw counts, ENTMC_FAST otherwise)
     float entmc_guard = 1024.0f;  // worst-case per-term relative error of the expanded form ~ 8e-8 * guard
 
     // optional per-stage timeline (VBMC_STAGE_TIMING=1): events on the main stream

@@ -1348,6 +1348,8 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "entmc: D > 32 is not supported");
     VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
     int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
+    if (variant < 0)  // auto: the warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
+        variant = (int64_t)K * half_local >= 65536 ? ENTMC_WARP : ENTMC_FAST;
     const size_t smem_cap = 227 * 1024;
     if (variant == ENTMC_WARP) {
         // the warp-autonomous kernel keeps racc rows lane + 32 r (r < 4) in registers and needs its tile in smem
