@@ -333,3 +333,122 @@ def test_full_size_against_oracle(pv, name):
     # bitwise determinism of the whole evaluation
     F2, dF2, *_ = pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd, eps=eps)
     assert F2 == F and np.array_equal(dF, dF2)
+
+
+# ------------------------------------------------------------------ randomized shapes / edge cases vs the oracle
+def _random_problem(rng, D, K, N, S, mean_kind="negquad", scale_spread=0.3):
+    X = rng.normal(size=(N, D))
+    y = -0.5 * np.sum(X**2, axis=1) + 0.1 * rng.normal(size=N)
+    lay = gpp.hyp_layout(D, 1, mean_kind)
+    hyps = np.zeros((S, lay["H"]))
+    for s in range(S):
+        h = hyps[s]
+        h[:D] = rng.normal(0.0, 0.3, size=D)
+        h[D] = rng.normal(0.5, 0.2)
+        h[D + 1] = np.log(1e-2)
+        b = lay["mean_start"]
+        if mean_kind != "zero":
+            h[b] = y.max()
+        if mean_kind == "negquad":
+            h[b + 1 : b + 1 + D] = 0.1 * rng.normal(size=D)
+            h[b + 1 + D : b + 1 + 2 * D] = np.log(2.0) + 0.1 * rng.normal(size=D)
+    posts = gpp.posteriors(X, y, hyps, mean_kind=mean_kind)
+    gp = eo.make_gp(X, posts, mean_kind=mean_kind)
+    mu = rng.normal(size=(D, K))
+    sigma = np.exp(scale_spread * rng.normal(size=K))
+    lambd = np.exp(0.3 * rng.normal(size=D))
+    eta = rng.normal(size=K)
+    w = np.exp(eta - eta.max())
+    w /= w.sum()
+    return gp, X, (mu, sigma, lambd, w, eta - eta.max())
+
+
+SHAPES = [  # D, K, N, S, Ns_K
+    (1, 1, 5, 1, 6), (1, 3, 9, 2, 7), (2, 2, 10, 8, 80), (3, 1, 12, 3, 33), (4, 7, 20, 2, 64), (5, 33, 40, 3, 20),
+    (7, 5, 31, 1, 130), (12, 64, 50, 2, 10), (13, 17, 64, 5, 258), (20, 50, 97, 4, 100), (21, 9, 40, 2, 50),
+    (24, 40, 33, 1, 40), (29, 3, 35, 2, 66), (32, 12, 64, 3, 34), (8, 130, 30, 1, 8), (6, 200, 25, 2, 4),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_random_shapes_against_oracle(pv, shape):
+    D, K, N, S, Ns_K = shape
+    rng = np.random.default_rng(1000 + D * 31 + K)
+    for mean_kind, opt in (("negquad", (True,) * 4), ("const", (True, True, True, False)), ("zero", (True, True, False, True))):
+        gp, X, (mu, sigma, lambd, w, eta) = _random_problem(rng, D, K, N, S, mean_kind)
+        vo = eo.OracleVP.create(D, K, mu, sigma, lambd, w, eta, opt)
+        theta = eo.get_parameters(vo)
+        bnd = eo.get_bounds(vo, X, syn.OPTIONS, K)
+        theta = theta + 0.05 * rng.normal(size=theta.size)
+        Ns_even = eo.even_ns(Ns_K)
+        eps = rng.normal(size=(K, Ns_even // 2, D))
+        Fo, dFo, Go, Ho, _ = eo.neg_elcbo(theta, gp, vo.copy(), 0.0, Ns_K, True, False, bnd, eps_half=eps)
+        for prec, tv, tg in (("f32", TOL_F32_VAL, TOL_F32_GRAD), ("f64", TOL_F64, TOL_F64)):
+            pv.config.precision = prec
+            try:
+                vp = make_vp(pv, D, K, mu, sigma, lambd, w, eta, opt)
+                F, dF, G, H, _ = pv._neg_elcbo(theta, gp, vp, 0.0, Ns_K, True, False, bnd, eps=eps)
+            finally:
+                pv.config.precision = "f32"
+            assert dF.shape == dFo.shape
+            assert relerr(G, Go) < TOL_F64, (shape, mean_kind)
+            assert abs(H - Ho) <= tv * max(abs(Ho), 1.0), (shape, mean_kind, prec, H, Ho)
+            assert abs(F - Fo) <= tv * max(abs(Fo), 1.0), (shape, mean_kind, prec)
+            assert relmax(dF, dFo) < tg, (shape, mean_kind, prec)
+        # deterministic entropy + value-only + Philox smoke on the same shapes
+        Fl, dFl, Gl, Hl, _ = eo.neg_elcbo(theta, gp, vo.copy(), 0.0, 0, True, False, bnd)
+        F, dF, G, H, _ = pv._neg_elcbo(theta, gp, make_vp(pv, D, K, mu, sigma, lambd, w, eta, opt), 0.0, 0, True, False, bnd)
+        assert relerr(F, Fl) < TOL_F64 and relmax(dF, dFl) < TOL_F64, (shape, mean_kind)
+        F, dF, *_ = pv._neg_elcbo(theta, gp, make_vp(pv, D, K, mu, sigma, lambd, w, eta, opt), 0.0, Ns_K, False, False, bnd, eps=eps)
+        assert dF is None and abs(F - Fo) <= TOL_F32_VAL * max(abs(Fo), 1.0)
+        F, dF, *_ = pv._neg_elcbo(theta, gp, make_vp(pv, D, K, mu, sigma, lambd, w, eta, opt), 0.0, Ns_K, True, False, bnd, seed=5)
+        assert np.isfinite(F) and np.all(np.isfinite(dF))
+
+
+def test_disparate_scales_take_the_direct_path(pv):
+    """Narrow components inside wide ones: the expanded distance would cancel, the conditioning guard must
+    route those components through the direct-difference path and keep fp32 parity."""
+    rng = np.random.default_rng(7)
+    D, K = 6, 12
+    mu = 0.3 * rng.normal(size=(D, K))
+    sigma = np.array([1.0, 0.8, 1.2, 1e-2, 2e-2, 5e-3, 0.5, 1e-3, 0.3, 2.0, 1e-2, 0.7])
+    lambd = np.exp(0.2 * rng.normal(size=D))
+    eta = rng.normal(size=K)
+    w = np.exp(eta - eta.max())
+    w /= w.sum()
+    vo = eo.OracleVP.create(D, K, mu, sigma, lambd, w, eta - eta.max())
+    vp = make_vp(pv, D, K, mu, sigma, lambd, w, eta - eta.max())
+    for Ns in (400, 70000):  # both fp32 kernels (small: fast, large: warp-autonomous)
+        eps = np.random.default_rng(3).normal(size=(K, Ns // 2, D))
+        Ho, dHo = eo.entmc(vo, eps, (True,) * 4, True)
+        H, dH = pv.entmc_vbmc(vp, Ns, eps=eps)
+        assert relerr(H, Ho) < TOL_F32_VAL and relmax(dH, dHo) < TOL_F32_GRAD, Ns
+        H64, dH64 = pv.entropy_context().entmc(vp, Ns, eps=eps, precision="f64")
+        assert relerr(H64, Ho) < TOL_F64 and relmax(dH64, dHo) < TOL_F64
+
+
+def test_finite_difference_gradients(pv):
+    """The reference's second kind of test (pyvbmc/testing/_check_grad.py): analytic gradient vs central
+    differences of the value, with the Monte-Carlo noise frozen (fixed Philox seed)."""
+    c = load_case("c2")
+    g = c.g
+    theta0 = g["theta2"].copy()
+    Ns = 400
+
+    def f(th):
+        return pv._neg_elcbo(th, c.gp, case_vp(pv, c), 0.0, Ns, False, False, c.theta_bnd, seed=21)[0]
+
+    pv.config.precision = "f64"
+    try:
+        F, dF, *_ = pv._neg_elcbo(theta0, c.gp, case_vp(pv, c), 0.0, Ns, True, False, c.theta_bnd, seed=21)
+        rng = np.random.default_rng(0)
+        idx = rng.choice(theta0.size, size=25, replace=False)
+        for i in idx:
+            h = 1e-5 * max(1.0, abs(theta0[i]))
+            tp, tm = theta0.copy(), theta0.copy()
+            tp[i] += h
+            tm[i] -= h
+            fd = (f(tp) - f(tm)) / (2 * h)
+            assert abs(fd - dF[i]) <= 1e-5 * max(1.0, abs(dF[i])) + 1e-6 * np.abs(dF).max(), (i, fd, dF[i])
+    finally:
+        pv.config.precision = "f32"
