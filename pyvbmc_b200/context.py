@@ -221,11 +221,18 @@ class Context:
             return False
         # fast path: the very same dict / arrays as last time (get_bounds builds fresh arrays per call,
         # variational_posterior.py:213-228, and nothing in the reference mutates them afterwards)
-        ids = (id(theta_bnd), id(theta_bnd["lb"]), id(theta_bnd["ub"]), theta_bnd["tol_con"],
-               theta_bnd.get("weight_threshold"), theta_bnd.get("weight_penalty"))
-        if ids == self._bnd_ids:
+        # (held references compared with `is`: a bare id() is recycled once the object dies)
+        held = self._bnd_ids
+        if (
+            held is not None
+            and held[0] is theta_bnd
+            and held[1] is theta_bnd["lb"]
+            and held[2] is theta_bnd["ub"]
+            and held[3:] == (theta_bnd["tol_con"], theta_bnd.get("weight_threshold"), theta_bnd.get("weight_penalty"))
+        ):
             return True
-        self._bnd_ids = ids
+        self._bnd_ids = (theta_bnd, theta_bnd["lb"], theta_bnd["ub"], theta_bnd["tol_con"],
+                         theta_bnd.get("weight_threshold"), theta_bnd.get("weight_penalty"))
         lb = _arr(theta_bnd["lb"]).reshape(-1)
         ub = _arr(theta_bnd["ub"]).reshape(-1)
         tol = float(theta_bnd["tol_con"])
@@ -439,26 +446,40 @@ def entropy_context(device=None) -> Context:
     return _entropy_ctx[dev]
 
 
+def _hold(gp):
+    """Keeps a cached GP identifiable: a weak reference where the type allows one, else the object itself
+    (a strong reference, so that its ``id`` cannot be recycled while the cache entry lives), plus the first
+    and last posterior ``alpha`` arrays (small; their identity changes with every ``gp.update`` / ``gp.fit``)."""
+    posts = gp.posteriors
+    try:
+        ref = weakref.ref(gp)
+    except TypeError:
+        ref = lambda gp=gp: gp  # noqa: E731
+    return (ref, len(posts), posts[0].alpha, posts[-1].alpha)
+
+
+def _held_is(hold, gp) -> bool:
+    ref, n, a0, a1 = hold
+    if ref() is not gp:
+        return False
+    posts = gp.posteriors
+    return len(posts) == n and posts[0].alpha is a0 and posts[-1].alpha is a1
+
+
 def context_for_gp(gp, need_L=False, device=None) -> Context:
     """Context holding ``gp`` on the device (packed once per trained GP, small LRU).
 
-    Keyed by the identity of the posterior arrays: ``gp.update`` / ``gp.fit`` create new
-    posterior records, which invalidates the entry.  Nothing is attached to ``gp`` itself.
-    """
+    Keyed by the identity of the GP object and of its posterior arrays: ``gp.update`` / ``gp.fit`` create
+    new posterior records, which invalidates the entry.  Identity is checked against held references
+    (never a bare ``id``, which CPython recycles once an object dies).  Nothing is attached to ``gp``."""
     dev = config.device if device is None else int(device)
     global _last_gp
-    posts = gp.posteriors
-    quick = (dev, id(gp), id(posts), len(posts), id(posts[0].alpha), id(posts[-1].alpha))
-    if _last_gp is not None and _last_gp[0] == quick and (_last_gp[2] is None or _last_gp[2]() is gp):
+    if _last_gp is not None and _last_gp[0] == dev and _held_is(_last_gp[2], gp):
         ctx = _last_gp[1]
         if ctx._h and (not need_L or ctx._gp_has_L):
             return ctx
     ctx = _context_for_gp_slow(gp, need_L, dev)
-    try:
-        ref = weakref.ref(gp)
-    except TypeError:
-        ref = None
-    _last_gp = (quick, ctx, ref)
+    _last_gp = (dev, ctx, _hold(gp))
     return ctx
 
 
@@ -466,21 +487,17 @@ def _context_for_gp_slow(gp, need_L, dev) -> Context:
     tok = (dev,) + Context.gp_token(gp, False)
     hit = _gp_ctx.get(tok)
     if hit is not None:
-        ctx, ref = hit
-        alive = ref is None or ref() is gp
-        if alive:
+        ctx, hold = hit
+        if ctx._h and _held_is(hold, gp):
             _gp_ctx.move_to_end(tok)
             if need_L and not ctx._gp_has_L:
                 ctx.pack_gp(gp, need_L=True)
             return ctx
         del _gp_ctx[tok]
+        ctx.close()
     ctx = Context(dev)
     ctx.pack_gp(gp, need_L=need_L)
-    try:
-        ref = weakref.ref(gp)
-    except TypeError:
-        ref = None
-    _gp_ctx[tok] = (ctx, ref)
+    _gp_ctx[tok] = (ctx, _hold(gp))
     while len(_gp_ctx) > _GP_CTX_MAX:
         _, (old, _r) = _gp_ctx.popitem(last=False)
         old.close()
