@@ -211,7 +211,7 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
             VBMC_TRY(entmc_plan(c, D, K, p1 - p0, s.grad[3] != 0, s.precision, &st.plan));
             st.plan.pair0 = p0;
             st.plan.half_glob = half_glob;
-            const size_t n_rec = st.plan.variant == ENTMC_WARP ? (size_t)st.plan.grid * st.plan.maxseg
+            const size_t n_rec = (st.plan.variant == ENTMC_WARP || st.plan.variant == ENTMC_TC) ? (size_t)st.plan.grid * st.plan.maxseg
                                                                 : (size_t)K * st.plan.slabs;
             VBMC_TRY(ensure(&c->d_entpart, &c->entpart_cap, n_rec * entpart_stride(DP, K)));
             VBMC_TRY(entmc_launch(c, c->d_in, D, K, st.plan, anyg, s.grad[3] != 0, s.precision, s.rng_mode, c->d_eps,

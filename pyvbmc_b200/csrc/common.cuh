@@ -186,10 +186,10 @@ int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
 // ----------------------------------------------------------------------------- launchers
 // entmc.cu
-enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENTMC_WARP = 4 };
+enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENTMC_WARP = 4, ENTMC_TC = 5 };
 struct EntmcPlan {
     int variant;
-    int64_t chunk;    // ENTMC_WARP: pairs of the flattened (component, pair) space per CTA
+    int64_t chunk;    // ENTMC_WARP / ENTMC_TC: pairs of the flattened (component, pair) space per CTA
     int grid, maxseg; // ENTMC_WARP: CTAs, records reserved per CTA
     int threads, slabs, pairs_per_thread;
     int64_t half;      // pairs per component handled by THIS rank
@@ -202,6 +202,11 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
                  bool wgrad, int precision, int rng_mode, const double *d_eps, uint64_t seed,
                  uint64_t offset, double *d_part);
 int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
+// entmc_tc.cu (tcgen05 / TMEM kernel)
+bool entmc_tc_supported(int DP, int K);
+int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *plan);
+int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
+                    const double *d_eps, double *d_part);
 
 // gplj.cu
 int gplj_launch(Ctx *c, const double *d_params, int K, int s_begin, int s_step, bool anygrad, cudaStream_t stream,

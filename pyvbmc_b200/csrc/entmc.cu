@@ -1351,6 +1351,10 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     if (variant < 0)  // auto: the warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
         variant = (int64_t)K * half_local >= 65536 ? ENTMC_WARP : ENTMC_FAST;
     const size_t smem_cap = 227 * 1024;
+    if (variant == ENTMC_TC) {
+        if (entmc_tc_supported(DP, K)) return entmc_tc_plan(c, D, K, half_local, plan);
+        variant = ENTMC_WARP;
+    }
     if (variant == ENTMC_WARP) {
         // the warp-autonomous kernel keeps racc rows lane + 32 r (r < 4) in registers and needs its tile in smem
         const size_t smem = entmc_smem_w(DP, K, 128, wgrad, true);
@@ -1434,6 +1438,21 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
     p.smem = entmc_smem_variant(plan.variant, precision, lay.DP, K, plan.threads, wgrad, anygrad);
     if (precision == VBMC_PREC_F64)
         return launch_t<double>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
+    if (plan.variant == ENTMC_TC) {
+        if (c->time_entmc) VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+        VBMC_TRY(entmc_tc_launch(c, d_params, lay, plan, anygrad, philox, d_eps, d_part));
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
+        if (c->time_entmc) {
+            VBMC_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+            VBMC_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+            float ms = 0;
+            VBMC_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->entmc_ms_sum += ms;
+            c->entmc_ms_n++;
+        }
+        return VBMC_OK;
+    }
     return launch_t<float>(c, d_params, lay, p, anygrad, wgrad, philox, d_eps, seed, offset, d_part);
 }
 

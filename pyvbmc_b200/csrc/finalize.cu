@@ -422,7 +422,7 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
     a.ent_stride = entpart_stride(DP, K);
     if (plan) {
         a.slabs = plan->slabs;
-        a.chunk = plan->variant == ENTMC_WARP ? plan->chunk : 0;
+        a.chunk = (plan->variant == ENTMC_WARP || plan->variant == ENTMC_TC) ? plan->chunk : 0;
         a.maxseg = plan->maxseg;
         a.half = plan->half;
         a.Ns_glob = (double)Ns_glob;

@@ -13,9 +13,10 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 pr = syn.make_problem(cfg)
 vp = pv.VariationalPosterior(pr.D, pr.K)
 vp.mu, vp.sigma, vp.lambd, vp.w, vp.eta = pr.mu, pr.sigma.reshape(1, -1), pr.lambd.reshape(-1, 1), pr.w.reshape(1, -1), pr.eta.reshape(1, -1)
-names = {0: "fast(expanded)", 1: "dsplit", 2: "packed", 3: "scalar", 4: "warp-autonomous"}
+names = {0: "fast(expanded)", 1: "dsplit", 2: "packed", 3: "scalar", 4: "warp-autonomous", 5: "tensor-core"}
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else (3, 2, 1, 0, 4, 5)
 ref = None
-for variant in (3, 2, 1, 0, 4):
+for variant in variants:
     os.environ["VBMC_ENTMC_VARIANT"] = str(variant)
     ctx = pv.Context(0)
     if ref is None:
