@@ -15,7 +15,7 @@ hi = next(i for i, r in enumerate(rows) if "Source" in r)
 h = rows[hi]
 c_src = h.index("Source")
 c_samp = h.index("# Samples") if "# Samples" in h else h.index("Warp Stall Sampling (All Samples)")
-c_exec = h.index("# Instructions Executed") if "# Instructions Executed" in h else None
+c_exec = next((h.index(n) for n in ("# Instructions Executed", "Instructions Executed") if n in h), None)
 data = []
 for r in rows[hi + 1:]:
     try:
