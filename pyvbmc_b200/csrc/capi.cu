@@ -77,6 +77,7 @@ struct Spec {
     int precision = VBMC_PREC_F32;
     bool compute_var = false;
     int avg = 1;
+    bool parts = true;  // dH / dG wanted besides dF
 };
 
 struct Staged {
@@ -170,6 +171,7 @@ int stage(CtxEx *x, const Spec &s) {
     f.have_ent = s.have_ent, f.have_gp = s.have_gp;
     f.use_bounds = s.use_bounds;
     f.avg = 1;
+    f.parts = s.parts;
     st.planned = false;
     c->staged = true;
     return VBMC_OK;
@@ -227,7 +229,8 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     stage_mark(c, 3);
     st.f_partials = f;
-    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev));
+    // single GPU: the raw phases are fused into the finalize launch (one cluster kernel for the whole tail)
+    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, world == 1));
     return VBMC_OK;
 }
 
@@ -285,7 +288,7 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     k.D = s.vp.D, k.K = s.vp.K, k.Ns = s.Ns, k.n_bnd = s.use_bounds ? c->n_bnd : 0, k.precision = s.precision;
     k.variant = c->entmc_variant, k.S = c->S, k.N = c->N, k.gen = x->gen;
     for (int i = 0; i < 4; ++i) k.flags |= (s.grad[i] ? 1 : 0) << i | (s.optimize[i] ? 1 : 0) << (4 + i);
-    k.flags |= (s.use_bounds ? 1 : 0) << 8 | (s.have_gp ? 1 : 0) << 9 | (s.have_ent ? 1 : 0) << 10;
+    k.flags |= (s.use_bounds ? 1 : 0) << 8 | (s.have_gp ? 1 : 0) << 9 | (s.have_ent ? 1 : 0) << 10 | (s.parts ? 1 : 0) << 11;
     if (x->gexec && k == x->gkey) {
         const ParamLayout lay{k.D, pad_dim(k.D), k.K};
         memcpy(c->h_in, s.flat, sizeof(double) * lay.total());
@@ -388,7 +391,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     cudaStreamSynchronize(c->stream);
     drop_graph(x);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
-                     c->d_entpart, c->d_gps, c->d_raw, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -716,6 +719,7 @@ int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const in
     s.Ns = Ns;
     s.use_bounds = use_bounds != 0;
     s.rng_mode = rng_mode, s.eps = eps, s.seed = seed, s.offset = offset, s.precision = precision;
+    s.parts = want_dH != 0;
     const int P = packed_len(D, K, s.grad);
     const size_t Pfull = RawLayout{D, K}.block();
     const size_t n_dev = kOutHead + (compute_grad ? (want_dH ? 2 * Pfull : (size_t)P) : 0);

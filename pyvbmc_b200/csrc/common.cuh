@@ -103,6 +103,7 @@ struct EvalFlags {
     int use_bounds;
     int optimize[4];
     int avg;
+    int parts;  // also write dH and dG (the out vector may live in pinned HOST memory: every byte crosses PCIe)
 };
 
 // ----------------------------------------------------------------------------- context
@@ -145,6 +146,10 @@ struct Ctx {
     double red_Ns_glob = 0, red_draws_local = 0;
     double *d_raw = nullptr;
     size_t raw_cap = 0;
+    double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
+    size_t csum_cap = 0;
+    bool raw_pending = false;  // reduce stage deferred into the next finalize launch (single GPU)
+    alignas(8) unsigned char raw_pending_blob[320];
     double *d_out = nullptr, *h_out = nullptr;
     size_t out_cap = 0;
     double *d_eps = nullptr;
@@ -224,7 +229,7 @@ int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4]
 
 // finalize.cu
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw);
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool defer);
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
                     double *d_out);
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s);

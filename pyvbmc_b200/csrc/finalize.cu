@@ -13,6 +13,9 @@
 // per thread (element-wise entries) or per warp (entries that are sums over components / samples / slabs:
 // lanes stride over the summed index, butterfly tree => fixed summation order, bitwise reproducible).
 // Small global scalars (softmax sums, penalty) are recomputed by every CTA instead of being exchanged.
+#include <cooperative_groups.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vbmc {
@@ -36,20 +39,37 @@ struct RawArgs {
     double *gps;
     const double *lamc;
     int gps_stride, s_begin, s_step, S, S_glob, S_local;
-    double *raw;  // global raw vector (the entlb kernels may already have written H and the ent block)
-    int n_warp_entries, n_thread_entries;
+    double *raw;   // global raw vector (the entlb kernels may already have written H and the ent block)
+    double *csum;  // [K][ent_stride] per-component sums of the entmc records (scratch between the two raw phases)
 };
 
 // sum over the slab records of component j of field f (fixed order)
 __device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
     double v = 0.0;
     if (a.chunk > 0) {
+        // CTA c covers pairs [c*chunk, (c+1)*chunk) of the flattened space; component j spans CTAs c0..c1.  Every
+        // CTA after c0 STARTS inside component j (c*chunk > j*half), so j is its segment 0; only c0 needs a division.
         const long long lo = (long long)j * a.half, hi = lo + a.half - 1;
-        const int c0 = (int)(lo / a.chunk), c1 = (int)(hi / a.chunk);
-#pragma unroll 4
-        for (int c = c0; c <= c1; ++c) {
-            const int seg = j - (int)(((long long)c * a.chunk) / a.half);
-            v += a.entpart[((size_t)c * a.maxseg + seg) * a.ent_stride + f];
+        int c0, c1, seg0;
+        if (hi < 0x7fffffffLL && a.chunk < 0x7fffffffLL) {
+            const unsigned ch = (unsigned)a.chunk;
+            c0 = (int)((unsigned)lo / ch), c1 = (int)((unsigned)hi / ch);
+            seg0 = j - (int)(((unsigned)c0 * ch) / (unsigned)a.half);
+        } else {
+            c0 = (int)(lo / a.chunk), c1 = (int)(hi / a.chunk);
+            seg0 = j - (int)(((long long)c0 * a.chunk) / a.half);
+        }
+        const double *rec = a.entpart + f;
+        v = rec[((size_t)c0 * a.maxseg + seg0) * a.ent_stride];
+        const size_t step = (size_t)a.maxseg * a.ent_stride;
+        rec += (size_t)(c0 + 1) * step;
+        // batches of 8 independent (predicated) loads: one L2 round trip per batch, fixed summation order
+        for (int c = c0 + 1; c <= c1; c += 8, rec += 8 * step) {
+            double t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = (c + i <= c1) ? rec[(size_t)i * step] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v += t[i];
         }
         return v;
     }
@@ -59,10 +79,12 @@ __device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) raw_kernel(const double *__restrict__ prm, RawArgs a) {
+// ---- phase 1: everything that reads producer outputs (entmc records, per-(s,k) log-joint terms) ---------
+// gtid / GT: index and number of the threads of the whole cluster
+__device__ __forceinline__ void raw_phase1(const double *__restrict__ prm, const RawArgs &a, int gtid, int GT) {
     const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K;
-    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
+    const int lane = gtid & 31, gw = gtid >> 5, GW = GT >> 5;
+    const double *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
     const RawLayout rl = a.rl;
     double *raw = a.raw;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
@@ -72,97 +94,43 @@ __global__ void __launch_bounds__(256) raw_kernel(const double *__restrict__ prm
     const int st = a.ent_stride;
     double *ent = raw + rl.ent(), *gpb = raw + rl.gp();
 
-    if (gw < a.n_warp_entries) {
-        // ------------------------------------------------------------ one WARP per summed entry
-        // order: [H | ent sigma (K) | ent lambda (D) | ent w (K) | G | gp lambda (D) | per-sample (S_local x (D+1))]
-        int idx = gw;
-        if (idx == 0) {  // H = -sum_j w_j mean log q  (entmc_vbmc.py:80)
-            if (ent_mc) {
-                double sl = 0.0;
-                for (int d = lane; d < D; d += 32) sl += log(lambd[d]);
-                sl = warp_sum(sl);
-                double h = 0.0;
-                for (int j = lane; j < K; j += 32) {
-                    const double hs = slab_sum(a, j, 0) + a.draws_local * (-0.5 * D * kLog2Pi - sl - D * log(sigma[j]));
-                    h -= w[j] * hs;
-                }
-                h = warp_sum(h);
-                if (lane == 0) raw[0] = h * inv_ns;
-            } else if (!ent_lb && lane == 0) {
-                raw[0] = 0.0;
-            }
-            if (lane == 0) raw[2] = raw[3] = 0.0;
-            return;
+    // (a) per-component sums of the entmc records: csum[j][f]; the mu block of the entropy gradient (:98)
+    //     needs nothing else and is finished here.  Threads run over f fastest => coalesced record reads.
+    if (ent_mc) {
+        const int nf = anyg ? st : 1;
+        for (int e = gtid; e < K * nf; e += GT) {
+            const int j = e / nf, f = e - j * nf;
+            double v = slab_sum(a, j, f);
+            // f = 0: complete sum_i log q(x_i) of component j up to the shared sum_d ln lambda_d term (phase 2)
+            if (f == 0) v += a.draws_local * (-0.5 * D * kLog2Pi - D * log(prm[a.lay.sigma() + j]));
+            a.csum[j * st + f] = v;
+            if (f >= 1 && f < 1 + D) ent[rl.o_mu() + j * D + (f - 1)] = w[j] * v * inv_ns / lambd[f - 1];
         }
-        idx -= 1;
-        if (idx < K) {  // d/dsigma_j (:102-103): sum over dimensions of Be
-            if (ent_mc && anyg) {
-                double v = 0.0;
-                for (int d = lane; d < D; d += 32) v += slab_sum(a, idx, 1 + DP + d);
-                v = warp_sum(v);
-                if (lane == 0) ent[rl.o_sig() + idx] = w[idx] * v * inv_ns / sigma[idx];
-            } else if (!ent_lb && lane == 0) {
-                ent[rl.o_sig() + idx] = 0.0;
-            }
-            return;
+    }
+    if (!ent_lb && !(ent_mc && anyg)) {  // no entropy gradient from this evaluation: keep the block defined
+        for (int e = gtid; e < rl.block(); e += GT) ent[e] = 0.0;
+        if (!ent_mc && gtid == 0) raw[0] = 0.0;
+    }
+    if (gtid == 0) raw[2] = raw[3] = 0.0;
+
+    // (b) log joint, element-wise entries [gp mu (K*D) | gp sigma (K) | gp w (K)]: average over this
+    //     rank's hyper-samples (:1578-1596)
+    const int n_cs = (a.f.have_ent && a.f.use_ent_mc) ? K * (anyg ? st : 1) : 0;
+    for (int e = (gtid + GT - n_cs % GT) % GT; e < K * D + 2 * K; e += GT) {
+        const int off = e < K * D ? rl.o_mu() + e : (e < K * D + K ? rl.o_sig() + (e - K * D) : rl.o_w() + (e - K * D - K));
+        double v = 0.0;
+        if (a.f.have_gp && anyg) {
+#pragma unroll 8
+            for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * a.gps_stride + 1 + off];
         }
-        idx -= K;
-        if (idx < D) {  // d/dlambda_d (:106-108): sum over components
-            if (ent_mc && anyg) {
-                double v = 0.0;
-                for (int j = lane; j < K; j += 32) v += w[j] * slab_sum(a, j, 1 + DP + idx);
-                v = warp_sum(v);
-                if (lane == 0) ent[rl.o_lam() + idx] = v * inv_ns / lambd[idx];
-            } else if (!ent_lb && lane == 0) {
-                ent[rl.o_lam() + idx] = 0.0;
-            }
-            return;
-        }
-        idx -= D;
-        if (idx < K) {  // d/dw_k (:111-112): -E_k[log q] - sum_j w_j E_j[N_k / q]
-            if (ent_mc && anyg) {
-                double v = 0.0;
-                if (a.f.grad[3])
-                    for (int j = lane; j < K; j += 32) v += w[j] * slab_sum(a, j, 1 + 2 * DP + idx);
-                double sl = 0.0;
-                for (int d = lane; d < D; d += 32) sl += log(lambd[d]);
-                sl = warp_sum(sl);
-                v = warp_sum(v);
-                if (lane == 0) {
-                    const double hs = slab_sum(a, idx, 0) + a.draws_local * (-0.5 * D * kLog2Pi - sl - D * log(sigma[idx]));
-                    ent[rl.o_w() + idx] = -(hs + v) * inv_ns;
-                }
-            } else if (!ent_lb && lane == 0) {
-                ent[rl.o_w() + idx] = 0.0;
-            }
-            return;
-        }
-        idx -= K;
-        if (idx == 0) {  // G = mean_s sum_k w_k I_sk  (:1425, :1581)
-            double v = 0.0;
-            if (a.f.have_gp)
-                for (int i = lane; i < a.S_local * K; i += 32) {
-                    const int s = a.s_begin + (i / K) * a.s_step, k = i % K;
-                    v += w[k] * a.gps[(size_t)s * a.gps_stride + 1 + rl.o_w() + k];
-                }
-            v = warp_sum(v);
-            if (lane == 0) raw[1] = v * inv_S;
-            return;
-        }
-        idx -= 1;
-        if (idx < D) {  // gp d/dlambda_d: mean_s sum_k lamc  (:1452-1462, :1596)
-            double v = 0.0;
-            if (a.f.have_gp && anyg)
-                for (int i = lane; i < a.S_local * K; i += 32) {
-                    const int s = a.s_begin + (i / K) * a.s_step, k = i % K;
-                    v += a.lamc[((size_t)s * K + k) * D + idx];
-                }
-            v = warp_sum(v);
-            if (lane == 0) gpb[rl.o_lam() + idx] = v * inv_S;
-            return;
-        }
-        idx -= D;
-        if (a.f.have_gp) {  // per-sample G_s and lambda block (consumers: variance path, avg_flag = 0, I_sk)
+        gpb[off] = v * inv_S;
+    }
+
+    // (c) log joint, one WARP per summed entry: per-sample G_s and lambda block, S_local x (D + 1) sums over the
+    //     components (consumers: phase 2 for G and the lambda gradient; variance path, avg_flag = 0, I_sk)
+    const int n_we = a.f.have_gp ? a.S_local * (D + 1) : 0;
+    for (int idx = GW - 1 - gw; idx < n_we; idx += GW) {
+        {
             const int si = idx / (D + 1), col = idx - si * (D + 1), s = a.s_begin + si * a.s_step;
             double *gs = a.gps + (size_t)s * a.gps_stride;
             double v = 0.0;
@@ -173,30 +141,83 @@ __global__ void __launch_bounds__(256) raw_kernel(const double *__restrict__ prm
             v = warp_sum(v);
             if (lane == 0) gs[col == 0 ? 0 : 1 + rl.o_lam() + col - 1] = v;
         }
-        return;
     }
-    // ---------------------------------------------------------------- one THREAD per element-wise entry
-    // order: [ent mu (K*D) | gp mu (K*D) | gp sigma (K) | gp w (K)]
-    int e = (gw - a.n_warp_entries) * 32 + lane;
-    if (e >= a.n_thread_entries) return;
-    if (e < K * D) {  // d/dmu_j (:98)
-        if (ent_mc && anyg) {
-            const int j = e / D, d = e - j * D;
-            ent[rl.o_mu() + e] = w[j] * slab_sum(a, j, 1 + d) * inv_ns / lambd[d];
-        } else if (!ent_lb) {
-            ent[rl.o_mu() + e] = 0.0;
+    (void)DP;
+}
+
+// ---- phase 2: entropy entries that are sums over components / dimensions of csum (one warp each) ---------
+__device__ __forceinline__ void raw_phase2(const double *__restrict__ prm, const RawArgs &a, int gtid, int GT) {
+    const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
+    const int D = a.lay.D, DP = a.lay.DP, K = a.lay.K;
+    const int lane = gtid & 31, gw = gtid >> 5, GW = GT >> 5;
+    {  // G = mean_s G_s (:1425, :1581) and gp d/dlambda_d = mean_s sum_k lamc (:1452-1462, :1596): last threads
+        const int e = GT - 1 - gtid;
+        if (e < 1 + D) {
+            double v = 0.0;
+            if (a.f.have_gp && (e == 0 || anyg)) {
+                const int off = e == 0 ? 0 : 1 + a.rl.o_lam() + e - 1;
+#pragma unroll 8
+                for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * a.gps_stride + off];
+            }
+            v *= 1.0 / (double)a.S_glob;
+            if (e == 0)
+                a.raw[1] = v;
+            else
+                a.raw[a.rl.gp() + a.rl.o_lam() + e - 1] = v;
         }
-        return;
     }
-    e -= K * D;
-    // gp blocks: average over this rank's hyper-samples (:1578-1596)
-    const int off = e < K * D ? rl.o_mu() + e : (e < K * D + K ? rl.o_sig() + (e - K * D) : rl.o_w() + (e - K * D - K));
-    double v = 0.0;
-    if (a.f.have_gp && anyg) {
-#pragma unroll 4
-        for (int s = a.s_begin; s < a.S; s += a.s_step) v += a.gps[(size_t)s * a.gps_stride + 1 + off];
+    if (!(a.f.have_ent && a.f.use_ent_mc)) return;
+    const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd(), *w = prm + a.lay.w();
+    const RawLayout rl = a.rl;
+    const double inv_ns = 1.0 / a.Ns_glob;
+    const int st = a.ent_stride;
+    const double *cs = a.csum;
+    double *ent = a.raw + rl.ent();
+    const int n_we = anyg ? 1 + K + D + K : 1;
+    for (int idx0 = gw; idx0 < n_we; idx0 += GW) {
+        int idx = idx0;
+        double sl = 0.0;  // sum_d ln lambda_d (normalisation of the own-component density)
+        if (idx == 0 || idx >= 1 + K + D) {
+            for (int d = lane; d < D; d += 32) sl += log(lambd[d]);
+            sl = warp_sum(sl);
+        }
+        if (idx == 0) {  // H = -sum_j w_j mean log q  (entmc_vbmc.py:80)
+            double h = 0.0;
+            for (int j = lane; j < K; j += 32) {
+                h -= w[j] * (cs[j * st] - a.draws_local * sl);
+            }
+            h = warp_sum(h);
+            if (lane == 0) a.raw[0] = h * inv_ns;
+            continue;
+        }
+        idx -= 1;
+        if (idx < K) {  // d/dsigma_j (:102-103): sum over dimensions of Be
+            double v = 0.0;
+            for (int d = lane; d < D; d += 32) v += cs[idx * st + 1 + DP + d];
+            v = warp_sum(v);
+            if (lane == 0) ent[rl.o_sig() + idx] = w[idx] * v * inv_ns / sigma[idx];
+            continue;
+        }
+        idx -= K;
+        if (idx < D) {  // d/dlambda_d (:106-108): sum over components
+            double v = 0.0;
+            for (int j = lane; j < K; j += 32) v += w[j] * cs[j * st + 1 + DP + idx];
+            v = warp_sum(v);
+            if (lane == 0) ent[rl.o_lam() + idx] = v * inv_ns / lambd[idx];
+            continue;
+        }
+        idx -= D;
+        {  // d/dw_k (:111-112): -E_k[log q] - sum_j w_j E_j[N_k / q]
+            double v = 0.0;
+            if (a.f.grad[3])
+                for (int j = lane; j < K; j += 32) v += w[j] * cs[j * st + 1 + 2 * DP + idx];
+            v = warp_sum(v);
+            if (lane == 0) {
+                const double hs = cs[idx * st] - a.draws_local * sl;
+                ent[rl.o_w() + idx] = -(hs + v) * inv_ns;
+            }
+        }
     }
-    gpb[off] = v * inv_S;
 }
 
 // Apply the reparameterisation Jacobians to one raw block and scatter it into theta order.
@@ -253,6 +274,7 @@ struct FinalArgs {
     double tol_con, w_thr, w_pen;
     double *out;
     int Pfull;
+    double *lpart;  // [cluster size] per-CTA shares of the bound loss (scratch behind csum)
 };
 
 // violation derivative of extended-theta entry e (and its loss), variational_optimization.py:639-653
@@ -275,14 +297,37 @@ __device__ __forceinline__ double bound_dy(const FinalArgs &a, const double *prm
     return r / ell;
 }
 
-__global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ prm, FinalArgs a) {
+// ---- phase 0 (needs only the parameter block, so it runs BEFORE the first cluster barrier and hides behind the
+// record loads of phase 1): bound-loss derivative of the ln-scale entries (tmp, every CTA that finishes entries),
+// exp(eta) (sek), and this CTA's share of the bound loss itself -> a.lpart[cluster rank].
+__device__ __forceinline__ void final_prep(const double *__restrict__ prm, const FinalArgs &a, bool has_entries,
+                                           int crank, int gtid, int GT, double *scratch, double *sek, double *tmp) {
     const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
-    __shared__ double scratch[40];
-    __shared__ double ssm[5];  // es, dote, dotg, dotp, Lp
-    extern __shared__ double tmp[];  // [K*D] d(bound loss)/d(ln-scale entry), recomputed by every CTA
+    const bool bounds = a.f.use_bounds && a.n_bnd > 0;
+    const int n_mu = a.f.optimize[0] ? K * D : 0, n_sc = K * D, n_eta = a.f.optimize[3] ? K : 0;
+    if (has_entries)
+        for (int k = tid; k < K; k += nt) sek[k] = exp(prm[a.lay.eta() + k]);
+    double Lb = 0.0;
+    if (bounds) {
+        if (has_entries) {
+#pragma unroll 2
+            for (int i = tid; i < n_sc; i += nt) tmp[i] = bound_dy(a, prm, n_mu + i, n_mu, n_sc, nullptr);
+        }
+#pragma unroll 2
+        for (int e = gtid; e < n_mu + n_sc + n_eta; e += GT) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
+    }
+    Lb = block_sum(Lb, scratch);  // (also the barrier that publishes tmp / sek inside the CTA)
+    if (tid == 0) a.lpart[crank] = Lb;
+}
+
+// ---- phase 3: raw -> out.  `vb` is the (virtual) block index: block vb finishes entries [vb*nt, (vb+1)*nt) ----
+__device__ __forceinline__ void final_phase(const double *__restrict__ prm, const FinalArgs &a, int vb, int nblk,
+                                            double *ssm /*[5]: es, dote, dotg, dotp, Lp*/, const double *sek,
+                                            const double *tmp /*[K*D] d(bound loss)/d(ln-scale entry), per CTA*/) {
+    const int D = a.lay.D, K = a.lay.K, tid = threadIdx.x, nt = blockDim.x;
     const RawLayout rl = a.rl;
     const double *raw = a.raw;
-    const double *eta = prm + a.lay.eta(), *w = prm + a.lay.w();
+    const double *w = prm + a.lay.w();
     double *out = a.out;
     double *dF = out + kOutHead, *dH = dF + a.Pfull, *dG = dH + a.Pfull;
     const bool anyg = a.f.grad[0] || a.f.grad[1] || a.f.grad[2] || a.f.grad[3];
@@ -295,7 +340,7 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
     if (tid < 32 && need_sm) {
         double es = 0.0, dote = 0.0, dotg = 0.0, dotp = 0.0, Lp = 0.0;
         for (int k = tid; k < K; k += 32) {
-            const double ek = exp(eta[k]);
+            const double ek = sek[k];
             es += ek;
             dote += ek * raw[rl.ent() + rl.o_w() + k];
             dotg += ek * raw[rl.gp() + rl.o_w() + k];
@@ -308,82 +353,131 @@ __global__ void __launch_bounds__(256) final_kernel(const double *__restrict__ p
         es = warp_sum(es), dote = warp_sum(dote), dotg = warp_sum(dotg), dotp = warp_sum(dotp), Lp = warp_sum(Lp);
         if (tid == 0) ssm[0] = es, ssm[1] = dote, ssm[2] = dotg, ssm[3] = dotp, ssm[4] = Lp;
     }
-    // ln-scale block of the bound loss: all K*D entries in one parallel pass (independent loads), the
-    // row / column sums below then run out of shared memory.  CTA 0 also collects the loss itself.
-    double Lb = 0.0;
-    if (bounds) {
-        for (int i = tid; i < n_sc; i += nt) tmp[i] = bound_dy(a, prm, n_mu + i, n_mu, n_sc, &Lb);
-        if (blockIdx.x == 0) {
-            for (int e = tid; e < n_mu; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
-            for (int e = n_mu + n_sc + tid; e < n_mu + n_sc + n_eta; e += nt) bound_dy(a, prm, e, n_mu, n_sc, &Lb);
-        }
-    }
-    __syncthreads();
-    const double es = ssm[0], dote = ssm[1], dotg = ssm[2], dotp = ssm[3];
-
     // ---- one output entry per thread: Jacobians, bound-loss and penalty gradients, dF ---------------
-    if (anyg) {
+    // (loads first, the softmax sums are only needed by the weight entries after the barrier)
+    const int n0 = a.f.grad[0] ? K * D : 0, n1 = a.f.grad[1] ? K : 0, n2 = a.f.grad[2] ? D : 0, n3 = a.f.grad[3] ? K : 0;
+    const int e = vb * nt + tid;
+    const bool live = anyg && e < n0 + n1 + n2 + n3;
+    double gh = 0.0, gg = 0.0, add = 0.0;
+    int kw = -1;
+    if (live) {
         const double *be = raw + rl.ent(), *bg = raw + rl.gp();
         const double *sigma = prm + a.lay.sigma(), *lambd = prm + a.lay.lambd();
         const int jac = a.f.jacobian;
-        const int n0 = a.f.grad[0] ? K * D : 0, n1 = a.f.grad[1] ? K : 0, n2 = a.f.grad[2] ? D : 0,
-                  n3 = a.f.grad[3] ? K : 0;
-        const int e = blockIdx.x * nt + tid;
-        if (e < n0 + n1 + n2 + n3) {
-            double gh, gg, add = 0.0;
-            if (e < n0) {
-                gh = be[rl.o_mu() + e], gg = bg[rl.o_mu() + e];
-                if (bounds && n_mu) add = bound_dy(a, prm, e, n_mu, n_sc, nullptr);
-            } else if (e < n0 + n1) {
-                const int k = e - n0;
-                const double sc = jac ? sigma[k] : 1.0;
-                gh = be[rl.o_sig() + k] * sc, gg = bg[rl.o_sig() + k] * sc;
-                // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = dy[r*K + b]
-                // (:584-586); sigma_b gets the column sum over r
-                if (bounds)
-                    for (int r = 0; r < D; ++r) add += tmp[r * K + k];
-            } else if (e < n0 + n1 + n2) {
-                const int d = e - n0 - n1;
-                const double sc = jac ? lambd[d] : 1.0;
-                gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
-                if (bounds)  // ... and lambda_r the row sum over b
-                    for (int b = 0; b < K; ++b) add += tmp[d * K + b];
-            } else {
-                const int k = e - n0 - n1 - n2;
-                gh = be[rl.o_w() + k], gg = bg[rl.o_w() + k];
-                const double ek = (jac || pen) ? exp(eta[k]) : 0.0;
-                if (jac) {  // row k of J_w @ g
-                    gh = ek / es * gh - ek / (es * es) * dote;
-                    gg = ek / es * gg - ek / (es * es) * dotg;
-                }
-                if (bounds && n_eta) add = bound_dy(a, prm, n_mu + n_sc + k, n_mu, n_sc, nullptr);
-                if (pen) {  // weight penalty through the softmax Jacobian (:1221-1229)
-                    const double g = w[k] < a.w_thr ? a.w_pen : 0.0;
-                    add += ek / es * g - ek / (es * es) * dotp;
-                }
-            }
-            dH[e] = gh;
-            dG[e] = gg;
-            dF[e] = -gg - gh + add;  // :1171-1173, :1200, :1227-1229
+        if (e < n0) {
+            gh = be[rl.o_mu() + e], gg = bg[rl.o_mu() + e];
+            if (bounds && n_mu) add = bound_dy(a, prm, e, n_mu, n_sc, nullptr);
+        } else if (e < n0 + n1) {
+            const int k = e - n0;
+            const double sc = jac ? sigma[k] : 1.0;
+            gh = be[rl.o_sig() + k] * sc, gg = bg[rl.o_sig() + k] * sc;
+            // the reference reshapes the ln-scale gradient ROW-major to (D, K): dls[r][b] = dy[r*K + b]
+            // (:584-586); sigma_b gets the column sum over r
+            if (bounds)
+                for (int r = 0; r < D; ++r) add += tmp[r * K + k];
+        } else if (e < n0 + n1 + n2) {
+            const int d = e - n0 - n1;
+            const double sc = jac ? lambd[d] : 1.0;
+            gh = be[rl.o_lam() + d] * sc, gg = bg[rl.o_lam() + d] * sc;
+            if (bounds)  // ... and lambda_r the row sum over b
+                for (int b = 0; b < K; ++b) add += tmp[d * K + b];
+        } else {
+            kw = e - n0 - n1 - n2;
+            gh = be[rl.o_w() + kw], gg = bg[rl.o_w() + kw];
+            if (bounds && n_eta) add = bound_dy(a, prm, n_mu + n_sc + kw, n_mu, n_sc, nullptr);
         }
+    }
+    __syncthreads();
+    if (live) {
+        if (kw >= 0) {
+            const double es = ssm[0], dote = ssm[1], dotg = ssm[2], dotp = ssm[3];
+            const double ek = sek[kw];
+            if (a.f.jacobian) {  // row k of J_w @ g
+                gh = ek / es * gh - ek / (es * es) * dote;
+                gg = ek / es * gg - ek / (es * es) * dotg;
+            }
+            if (pen) {  // weight penalty through the softmax Jacobian (:1221-1229)
+                const double g = w[kw] < a.w_thr ? a.w_pen : 0.0;
+                add += ek / es * g - ek / (es * es) * dotp;
+            }
+        }
+        if (a.f.parts) dH[e] = gh, dG[e] = gg;
+        dF[e] = -gg - gh + add;  // :1171-1173, :1200, :1227-1229
     }
 
-    // ---- CTA 0: the scalars ----------------------------------------------------------------------------
-    if (blockIdx.x == 0) {
-        Lb = block_sum(Lb, scratch);
-        if (tid == 0) {
-            const double H = raw[0], G = raw[1], Lp = pen ? ssm[4] : 0.0;
-            const double F = -G - H + Lb + Lp;
-            out[0] = F;
-            out[1] = G;
-            out[2] = H;
-            out[3] = 0.0;
-            out[4] = 0.0;
-            out[5] = Lb;
-            out[6] = Lp;
-            out[7] = isfinite(F) ? 0.0 : 1.0;
+    // ---- block 0: the scalars ----------------------------------------------------------------------------
+    if (vb == 0 && tid == 0) {
+        double Lb = 0.0;
+        if (bounds)
+            for (int r = 0; r < nblk; ++r) Lb += a.lpart[r];  // fixed order
+        const double H = raw[0], G = raw[1], Lp = pen ? ssm[4] : 0.0;
+        const double F = -G - H + Lb + Lp;
+        out[0] = F;
+        out[1] = G;
+        out[2] = H;
+        out[3] = 0.0;
+        out[4] = 0.0;
+        out[5] = Lb;
+        out[6] = Lp;
+        out[7] = isfinite(F) ? 0.0 : 1.0;
+    }
+}
+
+constexpr int kTailThreads = 1024, kTailCluster = 8;
+enum { PH_RAW = 1, PH_FINAL = 2 };
+
+// One launch for everything behind the producers: a cluster of 8 CTAs; the phases are separated by cluster
+// barriers (release/acquire at cluster scope, so plain global stores of one phase are visible to the next).
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const double *__restrict__ prm, RawArgs ra, FinalArgs fa,
+                                                           int phases) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double scratch[40];
+    __shared__ double ssm[5];
+    extern __shared__ double tmp[];  // [K*D] bound-loss derivatives of the ln-scale entries | [K] exp(eta)
+    const int nblk = (int)gridDim.x, gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), GT = nblk * (int)blockDim.x;
+    int nvb = 0;
+    double *sek = nullptr;
+#ifdef VBMC_TAIL_DEBUG
+    unsigned long long ts[7];
+#define TS(i) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])::"memory")
+#else
+#define TS(i)
+#endif
+    TS(0);
+    if (phases & PH_FINAL) {
+        const bool anyg = fa.f.grad[0] || fa.f.grad[1] || fa.f.grad[2] || fa.f.grad[3];
+        const int P = anyg ? (fa.f.grad[0] ? fa.lay.K * fa.lay.D : 0) + (fa.f.grad[1] ? fa.lay.K : 0) +
+                                 (fa.f.grad[2] ? fa.lay.D : 0) + (fa.f.grad[3] ? fa.lay.K : 0)
+                           : 0;
+        nvb = P > 0 ? (P + (int)blockDim.x - 1) / (int)blockDim.x : 1;
+        sek = tmp + fa.lay.K * fa.lay.D;
+        final_prep(prm, fa, (int)blockIdx.x < nvb, (int)blockIdx.x, gtid, GT, scratch, sek, tmp);
+    }
+    TS(1);
+    if (phases & PH_RAW) {
+        raw_phase1(prm, ra, gtid, GT);
+        TS(2);
+        cluster.sync();
+        TS(3);
+        raw_phase2(prm, ra, gtid, GT);
+    }
+    TS(4);
+    if (phases & PH_FINAL) {
+        cluster.sync();  // raw vector (fused launch) and the bound-loss shares are complete
+        TS(5);
+        for (int vb = blockIdx.x; vb < nvb; vb += nblk) {
+            final_phase(prm, fa, vb, nblk, ssm, sek, tmp);
+            __syncthreads();
         }
     }
+    TS(6);
+#ifdef VBMC_TAIL_DEBUG
+    if (threadIdx.x == 0 && phases == (PH_RAW | PH_FINAL))
+        printf("tail cta %d: prep %llu p1 %llu sync %llu p2 %llu sync %llu final %llu ns\n", (int)blockIdx.x, ts[1] - ts[0],
+               ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5]);
+#endif
+#undef TS
 }
 
 // per-hyper-sample Jacobians for avg_flag == 0: CTA s -> out_s[s] = [G_s | dG_s (P)]
@@ -408,11 +502,8 @@ gps_finalize_kernel(const double *__restrict__ prm, ParamLayout lay, RawLayout r
     pack_block(blk, rl, prm, lay, f.grad, f.jacobian, es, dot, 1.0, dst + 1, false);
 }
 
-}  // namespace
-
-// records / per-sample terms -> raw vector (device pointer d_raw)
-int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
-                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw) {
+int fill_raw_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *plan, int64_t Ns_glob, int s_begin,
+                  int s_step, int S_glob, double *d_raw, RawArgs *out) {
     RawArgs a{};
     const int DP = pad_dim(D);
     a.lay = ParamLayout{D, DP, K};
@@ -435,18 +526,16 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
     a.S_local = f.have_gp ? (c->S - s_begin + s_step - 1) / s_step : 0;
     if (a.S_local < 0) a.S_local = 0;
     a.raw = d_raw;
-    a.n_warp_entries = 1 + K + D + K + 1 + D + a.S_local * (D + 1);
-    a.n_thread_entries = 2 * K * D + 2 * K;
-    const int warps = a.n_warp_entries + (a.n_thread_entries + 31) / 32;
-    raw_kernel<<<(warps + 7) / 8, 256, 0, c->stream>>>(d_params, a);
-    VBMC_CUDA_CHECK(cudaGetLastError());
-    c->launches++;
+    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * a.ent_stride + 16));
+    a.csum = c->d_csum + 16;
+    *out = a;
     return VBMC_OK;
 }
 
-int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
-                    double *d_out) {
+int fill_final_args(Ctx *c, int D, int K, const EvalFlags &f, const double *d_raw, double *d_out, FinalArgs *out) {
     FinalArgs a{};
+    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * entpart_stride(pad_dim(D), K) + 16));
+    a.lpart = c->d_csum;
     a.lay = ParamLayout{D, pad_dim(D), K};
     a.rl = RawLayout{D, K};
     a.f = f;
@@ -459,18 +548,62 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
     a.w_pen = c->w_pen;
     a.out = d_out;
     a.Pfull = a.rl.block();
-    const int P = (f.grad[0] ? K * D : 0) + (f.grad[1] ? K : 0) + (f.grad[2] ? D : 0) + (f.grad[3] ? K : 0);
-    const int grid = P > 0 ? (P + 255) / 256 : 1;
-    const size_t smem = (size_t)K * D * sizeof(double);
+    *out = a;
+    return VBMC_OK;
+}
+
+// raw phase deferred by reduce_launch(defer = true), consumed by the next finalize_launch of the same context
+static_assert(sizeof(RawArgs) <= sizeof(Ctx::raw_pending_blob), "Ctx::raw_pending_blob is too small");
+
+int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalArgs &fa, int phases, int D, int K) {
+    const size_t smem = (phases & PH_FINAL) ? (size_t)(K * D + K) * sizeof(double) : 0;
     VBMC_REQUIRE(smem <= 200 * 1024, VBMC_ERR_UNSUPPORTED, "finalize: D*K too large");
     if (smem > c->finalize_smem_set && smem > 48 * 1024) {
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VBMC_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->finalize_smem_set = smem;
     }
-    final_kernel<<<grid, 256, smem, c->stream>>>(d_params, a);
-    VBMC_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kTailCluster), cfg.blockDim = dim3(kTailThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTailCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases));
     c->launches++;
     return VBMC_OK;
+}
+
+}  // namespace
+
+// records / per-sample terms -> raw vector (device pointer d_raw).  defer = true (single GPU): nothing is
+// launched; the raw phases run fused with the next finalize_launch on the same raw vector (one launch).
+int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
+                  int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool defer) {
+    RawArgs ra;
+    VBMC_TRY(fill_raw_args(c, D, K, f, plan, Ns_glob, s_begin, s_step, S_glob, d_raw, &ra));
+    if (defer) {
+        memcpy(c->raw_pending_blob, &ra, sizeof(RawArgs));
+        c->raw_pending = true;
+        return VBMC_OK;
+    }
+    c->raw_pending = false;
+    return tail_launch(c, d_params, ra, FinalArgs{}, PH_RAW, D, K);
+}
+
+int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,
+                    double *d_out) {
+    FinalArgs fa;
+    VBMC_TRY(fill_final_args(c, D, K, f, d_raw, d_out, &fa));
+    if (c->raw_pending) {
+        c->raw_pending = false;
+        RawArgs ra;
+        memcpy(&ra, c->raw_pending_blob, sizeof(RawArgs));
+        VBMC_REQUIRE(ra.raw == d_raw, VBMC_ERR_STATE, "finalize: raw vector differs from the one given to partials");
+        return tail_launch(c, d_params, ra, fa, PH_RAW | PH_FINAL, D, K);
+    }
+    return tail_launch(c, d_params, RawArgs{}, fa, PH_FINAL, D, K);
 }
 
 int gps_finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, double *d_out_s) {
