@@ -146,6 +146,8 @@ struct Ctx {
     double red_Ns_glob = 0, red_draws_local = 0;
     double *d_raw = nullptr;
     size_t raw_cap = 0;
+    double *d_tctab = nullptr;  // per-component table images of the tensor-core entmc kernel
+    size_t tctab_cap = 0;
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
     size_t csum_cap = 0;
     bool raw_pending = false;  // reduce stage deferred into the next finalize launch (single GPU)

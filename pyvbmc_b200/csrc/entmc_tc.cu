@@ -8,17 +8,26 @@
 // and the reparameterisation gradient (entmc_vbmc.py:84-112) needs, per antithetic pair,
 //     racc_k  += u+_k / q+ + u-_k / q-                                          (d/dw, and d/dmu through Delta)
 //     v_d      = sum_k Delta_kd c_k ,   c_k = (w_k / sigma_k^2) (u+_k / q+ - u-_k / q-)
-// B = E Delta^T  ([pairs x D] x [D x K])  and  V = C Delta  ([pairs x K] x [K x D])  are GEMMs.  A CTA owns tiles of
-// 128 antithetic pairs (thread t <-> pair t <-> TMEM lane t):
-//   GEMM1  B[128 x KP]  = E[128 x D8] Delta^T      tcgen05.mma kind::tf32, A and B from shared memory (K-major,
-//                                                  no-swizzle canonical layout), 3xTF32 split (hi*hi + hi*lo + lo*hi)
-//   pass 1 tcgen05.ld B rows -> u(+-) (2 MUFU.EX2 per (pair, k)), q(+-), G(+-); u(+-) parked in TMEM (tcgen05.st)
-//   pass 2 u(+-) -> racc_k (accumulated in TMEM across the tiles of a segment), c_k split hi/lo -> TMEM
-//   GEMM2  V[128 x N2]  = C[128 x KP] Delta        A operand straight from TMEM, B from shared memory, 3xTF32
-//   epilogue: per-thread sums of e_d (v_d + e_d (G+/q+ + G-/q-)) and e_d (G+/q+ - G-/q-)
-// which leaves ~20 CUDA-core instructions per (pair, component) instead of ~50 (30 of them packed FFMA2) in the
-// CUDA-core kernels of entmc.cu.  Components whose expanded distance is badly conditioned (same guard as
-// entmc_kernel_w) have their u(+-) recomputed with direct differences on the CUDA cores.
+// X = E (h2 Delta)^T  ([pairs x D] x [D x K])  and  V = C' (wis Delta)  ([pairs x K] x [K x D]) are GEMMs.
+//
+// Two kernels per evaluation:
+//   entmc_tc_prep_kernel  one CTA per component j: every j-dependent table in its final shared-memory image
+//                         (GEMM operand tiles split hi/lo for 3xTF32, per-component constants, guard mask),
+//                         written once to global memory (L2 resident), so a segment switch in the main kernel
+//                         is a 30 KB copy instead of fp64 table arithmetic in every CTA.
+//   entmc_kernel_tc       a CTA owns tiles of 128 antithetic pairs (2 threads per pair; thread <-> TMEM lane):
+//     RNG     Philox + Box-Muller (or eps input) -> noise tile in shared memory (tf32 hi/lo split)
+//     GEMM1   X[128 x KP]  = E[128 x D8] (h2 Delta)^T   tcgen05.mma kind::tf32, operands from shared memory
+//                                                       (K-major, no swizzle), 3xTF32 (hi*hi + hi*lo + lo*hi)
+//     pass 1  tcgen05.ld X rows -> u(+-) (2 MUFU.EX2 per (pair, k)), q(+-), G(+-); u(+-) parked in TMEM
+//     pass 2  u(+-) -> racc_k (registers), c'_k = u+/q+ - u-/q- split hi/lo -> TMEM
+//     GEMM2   V[128 x N2]  = C'[128 x KP] (wis Delta)   A operand straight from TMEM, 3xTF32
+//     epilogue per-thread sums of e_d (v_d + e_d (G+/q+ + G-/q-)) and e_d (G+/q+ - G-/q-)
+//   The tile loop is software-pipelined: X is double-buffered in TMEM and the noise tile in shared memory, so
+//   the RNG of tile t+1 runs under GEMM2(t) and GEMM1(t+1) runs under the epilogue of tile t; two CTAs per SM
+//   cover each other's barriers.  ~19 CUDA-core instructions per (pair, component) instead of ~50.
+// Components whose expanded distance is badly conditioned (same guard as entmc_kernel_w) have their u(+-)
+// recomputed with direct differences on the CUDA cores.
 // Work distribution, records and determinism are those of entmc_kernel_w: the K * half pairs are one index space
 // cut into equal chunks (one per CTA, a multiple of 128 pairs), a chunk that straddles components is processed
 // segment by segment, ONE fp64 record [hacc | A_d | Be_d | racc_k] per (CTA, segment), no atomics.
@@ -29,7 +38,7 @@ namespace vbmc {
 namespace {
 
 struct alignas(16) KTc {
-    float ck2, h2, hd, w;  // s0_k = hd E + ck2 ;  log2 u(+-) = s0_k -+ h2 B_k
+    float ck2, hd, w, wis;  // s0_k = hd E + ck2 ;  log2 u(+-) = s0_k -+ X_k ;  wis = w / sigma^2
 };
 struct alignas(8) KDir {
     float ck, h;  // direct path: log2 u = ck + hj E - h |t|^2
@@ -120,27 +129,21 @@ __device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tm_ld16x2(uint32_t ta, uint32_t (&a)[16], uint32_t tb, uint32_t (&b)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : TM_R16(a), TM_R16(b)
+        : "r"(ta), "r"(tb)
+        : "memory");
+}
 __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
         ::"r"(taddr), TM_W16(v)
         : "memory");
-}
-#define TM_R8(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-#define TM_W8(v) "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-__device__ __forceinline__ void tm_ld8x3(uint32_t ta, uint32_t (&a)[8], uint32_t tb, uint32_t (&b)[8], uint32_t tc,
-                                         uint32_t (&c)[8]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : TM_R8(a), TM_R8(b), TM_R8(c)
-        : "r"(ta), "r"(tb), "r"(tc)
-        : "memory");
-}
-__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), TM_W8(v) : "memory");
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -152,13 +155,46 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 constexpr int kTile = 128;     // antithetic pairs per tile = TMEM lanes
 constexpr int kThreads = 256;  // two threads per pair: each owns half of the dimensions and half of the components
+constexpr int kMaxChunks = 2;  // 16-column component chunks per thread (K <= 64): racc lives in registers
+
+__host__ __device__ inline int tc_d8(int DP) { return (DP + 7) / 8 * 8; }
+__host__ __device__ inline int tc_n2(int DP) { return tc_d8(DP) <= 16 ? 16 : 32; }
+__host__ __device__ inline int tc_kp(int K) { return (K + 15) / 16 * 16; }
+
+// Per-component table block (byte offsets): the image entmc_tc_prep_kernel writes to global memory and the main
+// kernel copies verbatim into shared memory at a segment start.  Dl (plain Delta, fp32) is only read by the rare
+// direct-difference path and stays in global memory (it sits behind `smem_bytes`).
+struct TcTab {
+    uint32_t B1h, B1l, B2h, B2l, Kc, Dir, Mask, Scal, smem_bytes, Dl, total;
+};
+__host__ __device__ inline TcTab tc_tab_layout(int DP, int K) {
+    const int D8 = tc_d8(DP), NC1 = D8 / 4, N2 = tc_n2(DP), KP = tc_kp(K);
+    TcTab s;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        const uint32_t at = o;
+        o += (bytes + 127u) & ~127u;
+        return at;
+    };
+    s.B1h = take(NC1 * KP * 16);
+    s.B1l = take(NC1 * KP * 16);
+    s.B2h = take((KP / 4) * N2 * 16);
+    s.B2l = take((KP / 4) * N2 * 16);
+    s.Kc = take(KP * sizeof(KTc));
+    s.Dir = take(KP * sizeof(KDir));
+    s.Mask = take(16 * 4);
+    s.Scal = take(64);  // float sj, hj ; double is2j
+    s.smem_bytes = o;
+    s.Dl = take(KP * DP * 4);
+    s.total = o;
+    return s;
+}
 
 struct TcSmem {  // byte offsets inside the dynamic shared memory of entmc_kernel_tc
-    uint32_t Ah, Al, B1h, B1l, B2h, B2l, Dl, Mu, Kc, Wis, Dir, Mask, E, Q, Rec, Tot, InvL, Bar, total;
+    uint32_t Tab, A, E, Q, Rec, Tot, Bar, total;
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int DP, int D, int K, int part_stride) {
-    const int D8 = (DP + 7) / 8 * 8, NC1 = D8 / 4, N2 = D8 <= 16 ? 16 : 32;
-    const int KP = (K + 15) / 16 * 16;
+__host__ __device__ inline uint32_t tc_a_bytes(int DP) { return (uint32_t)(tc_d8(DP) / 4) * kTile * 16; }  // one of hi / lo
+__host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride) {
     TcSmem s;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -166,26 +202,115 @@ __host__ __device__ inline TcSmem tc_smem_layout(int DP, int D, int K, int part_
         o += (bytes + 127u) & ~127u;
         return at;
     };
-    s.Ah = take(NC1 * kTile * 16);
-    s.Al = take(NC1 * kTile * 16);
-    s.B1h = take(NC1 * KP * 16);
-    s.B1l = take(NC1 * KP * 16);
-    s.B2h = take((KP / 4) * N2 * 16);
-    s.B2l = take((KP / 4) * N2 * 16);
-    s.Dl = take(K * DP * 4);
-    s.Mu = take(K * D * 8);
-    s.Kc = take(KP * sizeof(KTc));
-    s.Wis = take(KP * 4);
-    s.Dir = take(KP * sizeof(KDir));
-    s.Mask = take(16 * 4);
-    s.E = take(2 * kTile * 4);
-    s.Q = take(2 * 4 * kTile * 4);
+    s.Tab = take(tc_tab_layout(DP, K).smem_bytes);
+    s.A = take(4 * tc_a_bytes(DP));  // [buffer 0: hi | lo][buffer 1: hi | lo]
+    s.E = take(2 * 2 * kTile * 4);   // [buffer][half][row] partial |e|^2
+    s.Q = take(2 * 4 * kTile * 4);   // [half][q+, q-, G+, G-][row]
     s.Rec = take(8 * part_stride * 8);
     s.Tot = take(part_stride * 8);
-    s.InvL = take(DP * 8);
     s.Bar = take(64);
     s.total = o;
     return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tables of component j = blockIdx.x
+__global__ void __launch_bounds__(256)
+entmc_tc_prep_kernel(const double *__restrict__ prm, ParamLayout lay, float guard, unsigned char *__restrict__ tab) {
+    const int D = lay.D, DP = lay.DP, K = lay.K, j = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int D8 = tc_d8(DP), N2 = tc_n2(DP), KP = tc_kp(K);
+    const TcTab L = tc_tab_layout(DP, K);
+    unsigned char *base = tab + (size_t)j * L.total;
+    float *gB1h = reinterpret_cast<float *>(base + L.B1h), *gB1l = reinterpret_cast<float *>(base + L.B1l);
+    float *gB2h = reinterpret_cast<float *>(base + L.B2h), *gB2l = reinterpret_cast<float *>(base + L.B2l);
+    KTc *gKc = reinterpret_cast<KTc *>(base + L.Kc);
+    KDir *gDir = reinterpret_cast<KDir *>(base + L.Dir);
+    uint32_t *gMask = reinterpret_cast<uint32_t *>(base + L.Mask);
+    float *gDl = reinterpret_cast<float *>(base + L.Dl);
+    extern __shared__ __align__(16) unsigned char psm[];
+    float *sDl = reinterpret_cast<float *>(psm);            // [KP][DP] Delta (fp32-rounded)
+    double *sH2 = reinterpret_cast<double *>(sDl + KP * DP);  // [KP] 2 h_k (0: padded / guarded component)
+    double *sWis = sH2 + KP;                                  // [KP] w_k / sigma_k^2
+    __shared__ uint32_t sMask[16];
+
+    const double *mu = prm + lay.mu(), *sigma = prm + lay.sigma(), *lambd = prm + lay.lambd(), *w = prm + lay.w();
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+    const double sig_j = sigma[j];
+    const double hjd = kHalfLog2e / (sig_j * sig_j);
+    const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+    if (tid < 16) sMask[tid] = 0u;
+    for (int i = tid; i < KP * DP; i += nt) {
+        const int k = i / DP, d = i - k * DP;
+        const float v = (k < K && d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * (1.0 / lambd[d])) : 0.0f;
+        sDl[i] = v;
+        gDl[i] = v;
+    }
+    __syncthreads();
+    for (int k = tid; k < KP; k += nt) {
+        KTc c;
+        KDir dr;
+        c.ck2 = -200.0f, c.hd = 0.f, c.w = 0.f, c.wis = 0.f;  // padding / guarded: expanded-form u = 2^-200 = 0
+        dr.ck = -200.0f, dr.h = 0.f;
+        double h2 = 0.0, wis = 0.0;
+        if (k < K) {
+            const double sk = sigma[k];
+            const double hk = kHalfLog2e / (sk * sk);
+            const double ck = D * (log2(sig_j) - log2(sk));
+            double A = 0.0;  // |Delta_k|^2 of the rounded table entries
+            for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
+            c.w = (float)w[k];
+            wis = w[k] / (sk * sk);
+            c.wis = (float)wis;
+            dr.ck = (float)ck;
+            dr.h = (float)hk;
+            // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
+            if (k != j && hk * (A + Emax) > (double)guard) {
+                atomicOr(&sMask[k >> 4], 1u << (k & 15));
+            } else {
+                c.ck2 = (float)(ck - hk * A);
+                c.hd = (float)(hjd - hk);
+                h2 = 2.0 * hk;
+            }
+        }
+        gKc[k] = c;
+        gDir[k] = dr;
+        sH2[k] = h2;
+        sWis[k] = wis;
+    }
+    __syncthreads();
+    if (tid < 16) gMask[tid] = sMask[tid];
+    if (tid == 0) {
+        float *sc = reinterpret_cast<float *>(base + L.Scal);
+        sc[0] = (float)sig_j;
+        sc[1] = (float)hjd;
+        *reinterpret_cast<double *>(sc + 2) = 1.0 / (sig_j * sig_j);
+    }
+    // operand tables of the two GEMMs (hi = upper 19 bits = exact tf32, lo = remainder); the per-component scales
+    // are folded in: GEMM1 yields X_k = 2 h_k B_k directly, GEMM2 contracts (u+/q+ - u-/q-) with wis_k Delta_k
+    for (int i = tid; i < KP * D8; i += nt) {
+        const int k = i / D8, d = i - k * D8;
+        const double dl = (k < K && d < DP) ? (double)sDl[k * DP + d] : 0.0;
+        {
+            const float v = (float)(sH2[k] * dl);
+            const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u), vl = v - vh;
+            const int o1 = (d >> 2) * (KP * 4) + k * 4 + (d & 3);  // GEMM1 B operand: rows = components, K dim = d
+            gB1h[o1] = vh, gB1l[o1] = vl;
+        }
+        {
+            const float v = (float)(sWis[k] * dl);
+            const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u), vl = v - vh;
+            const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);  // GEMM2 B operand: rows = d, K dim = components
+            gB2h[o2] = vh, gB2l[o2] = vl;
+        }
+    }
+    if (N2 > D8) {
+        const int NZ = N2 - D8;
+        for (int i = tid; i < KP * NZ; i += nt) {
+            const int k = i / NZ, d = D8 + (i - k * NZ);
+            const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);
+            gB2h[o2] = 0.f, gB2l[o2] = 0.f;
+        }
+    }
 }
 
 template <int N>
@@ -210,12 +335,13 @@ template <int DP, bool ANYGRAD, bool PHILOX>
 __global__ void __launch_bounds__(kThreads, 2)
 entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
                 int64_t chunk, int maxseg, const double *__restrict__ eps, double *__restrict__ part, int part_stride,
-                float guard, uint32_t tmem_cols, int desc_swap) {
-    constexpr int DH = DP / 2;              // dimensions per thread
-    constexpr int D8 = (DP + 7) / 8 * 8;    // GEMM1 reduction length (tf32 MMAs consume 8 per instruction)
-    constexpr int NC1 = D8 / 4;             // 16-byte chunks along D
+                const unsigned char *__restrict__ tab, uint32_t tmem_cols) {
+    constexpr int DH = DP / 2;            // dimensions per thread
+    constexpr int D8 = (DP + 7) / 8 * 8;  // GEMM1 reduction length (tf32 MMAs consume 8 per instruction)
+    constexpr int NC1 = D8 / 4;           // 16-byte chunks along D
     constexpr int N2 = D8 <= 16 ? 16 : 32;  // GEMM2 output columns (M = 128 needs N % 16 == 0)
     constexpr int LW = DH <= 8 ? 8 : 16;    // columns of V loaded per thread in the epilogue (DH + LW <= N2)
+    constexpr uint32_t ABYTES = (uint32_t)NC1 * kTile * 16;
     const int D = lay.D, K = lay.K;
     const int nch = (K + 15) >> 4, KP = nch * 16;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -229,34 +355,28 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
     }
 
     extern __shared__ __align__(128) unsigned char smem[];
-    const TcSmem L = tc_smem_layout(DP, D, K, part_stride);
-    float *sAh = reinterpret_cast<float *>(smem + L.Ah), *sAl = reinterpret_cast<float *>(smem + L.Al);
-    float *sB1h = reinterpret_cast<float *>(smem + L.B1h), *sB1l = reinterpret_cast<float *>(smem + L.B1l);
-    float *sB2h = reinterpret_cast<float *>(smem + L.B2h), *sB2l = reinterpret_cast<float *>(smem + L.B2l);
-    float *sDl = reinterpret_cast<float *>(smem + L.Dl);
-    double *sMu = reinterpret_cast<double *>(smem + L.Mu);
-    KTc *sKc = reinterpret_cast<KTc *>(smem + L.Kc);
-    float *sWis = reinterpret_cast<float *>(smem + L.Wis);
-    KDir *sDir = reinterpret_cast<KDir *>(smem + L.Dir);
-    uint32_t *sMask = reinterpret_cast<uint32_t *>(smem + L.Mask);
-    float *sE = reinterpret_cast<float *>(smem + L.E);  // [2][128] partial |e|^2
-    float *sQ = reinterpret_cast<float *>(smem + L.Q);  // [2][4][128] partial q+, q-, G+, G-
+    const TcTab T = tc_tab_layout(DP, K);
+    const TcSmem L = tc_smem_layout(DP, K, part_stride);
+    unsigned char *sTab = smem + L.Tab;
+    const float *sB1h = reinterpret_cast<const float *>(sTab + T.B1h), *sB1l = reinterpret_cast<const float *>(sTab + T.B1l);
+    const float *sB2h = reinterpret_cast<const float *>(sTab + T.B2h), *sB2l = reinterpret_cast<const float *>(sTab + T.B2l);
+    const KTc *sKc = reinterpret_cast<const KTc *>(sTab + T.Kc);
+    const KDir *sDir = reinterpret_cast<const KDir *>(sTab + T.Dir);
+    const uint32_t *sMask = reinterpret_cast<const uint32_t *>(sTab + T.Mask);
+    const float *sScal = reinterpret_cast<const float *>(sTab + T.Scal);
+    float *sA = reinterpret_cast<float *>(smem + L.A);  // [buf][hi | lo][NC1][128][4]
+    float *sE = reinterpret_cast<float *>(smem + L.E);  // [buf][half][128] partial |e|^2
+    float *sQ = reinterpret_cast<float *>(smem + L.Q);  // [half][4][128] partial q+, q-, G+, G-
     double *sRec = reinterpret_cast<double *>(smem + L.Rec);
     double *sTot = reinterpret_cast<double *>(smem + L.Tot);
-    double *sInvL = reinterpret_cast<double *>(smem + L.InvL);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.Bar);
     uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2);
 
-    const double *sigma = prm + lay.sigma();
-    const double *lambd = prm + lay.lambd();
-    const double *w = prm + lay.w();
-    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+    const int64_t Tn = (int64_t)K * half;
+    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, Tn);
+    if (g0 >= Tn) return;
 
-    const int64_t T = (int64_t)K * half;
-    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, T);
-    if (g0 >= T) return;
-
-    // ---- one-time set-up: barriers, tensor memory, component means, zeroed operand tile --------------------
+    // ---- one-time set-up: barriers, tensor memory, zeroed noise tiles (padding dims stay 0) ---------------------
     const uint32_t bar0 = smem_u32(sBar), bar1 = smem_u32(sBar + 1);
     if (tid == 0) {
         mbar_init(bar0, 1);
@@ -270,25 +390,61 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < DP) sInvL[tid] = tid < D ? 1.0 / lambd[tid] : 0.0;
-    {
-        const double *mu = prm + lay.mu();
-        for (int i = tid; i < K * D; i += kThreads) sMu[i] = mu[i];
-        for (int i = tid; i < NC1 * kTile * 4; i += kThreads) sAh[i] = 0.f, sAl[i] = 0.f;  // padding dims stay 0
-    }
+    for (int i = tid; i < (int)(4 * ABYTES / 16); i += kThreads) reinterpret_cast<float4 *>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
-    // TMEM columns: R0 = B -> u+ -> c_hi, R1 = u- -> c_lo, R2 = racc, D2 = V
-    const uint32_t cR0 = 0, cR1 = KP, cR2 = 2 * KP, cD2 = 3 * KP;
+    // TMEM columns: X0 / X1 = GEMM1 output of even / odd tiles -> u+ -> c_hi (in place), U = u- -> c_lo, V = GEMM2 output
+    const uint32_t cX0 = 0, cU = 2 * KP, cV = 3 * KP;
     uint32_t ph0 = 0, ph1 = 0;
 
     const uint32_t idesc1 = umma_idesc_tf32(KP), idesc2 = umma_idesc_tf32(N2);
     // operand strides: rows 16 B apart, 8-row groups 128 B apart, K chunks one whole row-block apart
     const uint32_t lboA = kTile * 16, lboB1 = KP * 16, lboB2 = N2 * 16, sbo = 128;
-    (void)desc_swap;
+
+    // noise of tile `t0 / 128` of the current segment -> buffer b (this thread: its half of the dims of pair `row`)
+    auto rng_tile = [&](int b, int j, int64_t p_lo, int n, int t0, float sj) {
+        const int off = t0 + row;
+        const bool live = off < n;
+        const int64_t gpair = pair0 + p_lo + (live ? off : 0);
+        float z[DH];
+        if (PHILOX) {
+            philox_normals_half<DH>(seed, offset, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
+        } else {
+            const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+            for (int i = 0; i < DH; ++i) z[i] = (hsel * DH + i < D) ? (float)__ldg(ep + hsel * DH + i) : 0.0f;
+        }
+        float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
+        float Eh = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) {
+            const float e = live ? sj * z[i] : 0.0f;
+            Eh = fmaf(e, e, Eh);
+            const int d = hsel * DH + i;
+            const float vh = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
+            const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
+            aH[o] = vh, aL[o] = e - vh;
+        }
+        sE[(b * 2 + hsel) * kTile + row] = Eh;
+    };
+    // X[b] = E[b] (h2 Delta)^T, 3xTF32 (one elected thread)
+    auto issue_gemm1 = [&](int b) {
+        const uint32_t aH = smem_u32(sA) + (uint32_t)b * 2 * ABYTES, aL = aH + ABYTES;
+        const uint32_t bH = smem_u32(sB1h), bL = smem_u32(sB1l);
+        const uint32_t dcol = tmem + cX0 + (uint32_t)b * KP;
+#pragma unroll
+        for (int s = 0; s < D8 / 8; ++s) {
+            const uint64_t dAh = umma_desc(aH + s * 2 * lboA, lboA, sbo), dAl = umma_desc(aL + s * 2 * lboA, lboA, sbo);
+            const uint64_t dBh = umma_desc(bH + s * 2 * lboB1, lboB1, sbo), dBl = umma_desc(bL + s * 2 * lboB1, lboB1, sbo);
+            mma_ss(dcol, dAh, dBh, idesc1, s > 0 ? 1u : 0u);
+            mma_ss(dcol, dAh, dBl, idesc1, 1u);
+            mma_ss(dcol, dAl, dBh, idesc1, 1u);
+        }
+        tc_commit(bar0);
+    };
 
     const int j_first = (int)(g0 / half);
     for (int seg = 0;; ++seg) {
@@ -298,185 +454,97 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
         const int64_t p_lo = lo - (int64_t)j * half;
         const int n = (int)(hi - lo);
 
-        // ---- component tables ------------------------------------------------------------------------
+        // ---- component tables: verbatim copy of the prepared image ------------------------------------------------
         __syncthreads();
-        const double sig_j = sigma[j];
-        const double hjd = kHalfLog2e / (sig_j * sig_j);
-        const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
-        if (tid < 16) sMask[tid] = 0u;
-        for (int i = tid; i < K * DP; i += kThreads) {
-            const int k = i / DP, d = i - k * DP;
-            sDl[i] = (d < D) ? (float)((sMu[j * D + d] - sMu[k * D + d]) * sInvL[d]) : 0.0f;
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(tab + (size_t)j * T.total);
+            uint4 *dst = reinterpret_cast<uint4 *>(sTab);
+            for (int i = tid; i < (int)(T.smem_bytes / 16); i += kThreads) dst[i] = __ldg(src + i);
         }
         __syncthreads();
-        for (int k = tid; k < KP; k += kThreads) {
-            KTc c;
-            KDir dr;
-            float wis = 0.f;
-            c.ck2 = -200.0f, c.h2 = 0.f, c.hd = 0.f, c.w = 0.f;  // padding / flagged: expanded-form u = 2^-200 = 0
-            dr.ck = -200.0f, dr.h = 0.f;
-            if (k < K) {
-                const double sk = sigma[k];
-                const double hk = kHalfLog2e / (sk * sk);
-                const double ck = D * (log2(sig_j) - log2(sk));
-                double A = 0.0;  // |Delta_k|^2 of the rounded table entries
-                for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
-                c.w = (float)w[k];
-                wis = (float)(w[k] / (sk * sk));
-                dr.ck = (float)ck;
-                dr.h = (float)hk;
-                // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
-                if (k != j && hk * (A + Emax) > (double)guard) {
-                    atomicOr(&sMask[k >> 4], 1u << (k & 15));
-                } else {
-                    c.ck2 = (float)(ck - hk * A);
-                    c.h2 = (float)(2.0 * hk);
-                    c.hd = (float)(hjd - hk);
-                }
-            }
-            sKc[k] = c;
-            sWis[k] = wis;
-            sDir[k] = dr;
-        }
-        // operand tables of the two GEMMs (hi = upper 19 bits = exact tf32, lo = remainder)
-        for (int i = tid; i < KP * D8; i += kThreads) {
-            const int k = i / D8, d = i - k * D8;
-            const float v = (k < K && d < DP) ? sDl[k * DP + d] : 0.0f;
-            const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u), vl = v - vh;
-            const int o1 = (d >> 2) * (KP * 4) + k * 4 + (d & 3);  // GEMM1 B operand: rows = components, K dim = d
-            sB1h[o1] = vh, sB1l[o1] = vl;
-            if (ANYGRAD) {
-                const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);  // GEMM2 B operand: rows = d, K dim = components
-                sB2h[o2] = vh, sB2l[o2] = vl;
-            }
-        }
-        if constexpr (ANYGRAD && N2 > D8) {
-            constexpr int NZ = N2 - D8;
-            for (int i = tid; i < KP * NZ; i += kThreads) {
-                const int k = i / NZ, d = D8 + (i - k * NZ);
-                const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);
-                sB2h[o2] = 0.f, sB2l[o2] = 0.f;
-            }
-        }
-        if (ANYGRAD) {  // racc = 0 in TMEM (own chunks)
-            uint32_t z[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = 0u;
-            for (int ci = c_begin; ci < c_end; ++ci) tm_st16(trow + cR2 + 16 * ci, z);
-            tm_wait_st();
-        }
-        __syncthreads();
+        const float sj = sScal[0], hj = sScal[1];
+        const double is2j = *reinterpret_cast<const double *>(sScal + 2);
+        const float *gDl = reinterpret_cast<const float *>(tab + (size_t)j * T.total + T.Dl);
 
-        const float hj = (float)hjd;
-        const double is2j = 1.0 / (sig_j * sig_j);
-        const float sj = (float)sig_j;
         double hacc = 0.0;
+        float racc[ANYGRAD ? kMaxChunks * 16 : 1];
         float ae[ANYGRAD ? DH : 1], be[ANYGRAD ? DH : 1];
         if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < kMaxChunks * 16; ++i) racc[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < DH; ++i) ae[i] = be[i] = 0.f;
         }
 
-        for (int t0 = 0; t0 < n; t0 += kTile) {
-            const int off = t0 + row;
-            const bool live = off < n;
-            const int64_t gpair = pair0 + p_lo + (live ? off : 0);
+        // ---- prologue: noise and GEMM1 of the first tile --------------------------------------------------------
+        rng_tile(0, j, p_lo, n, 0, sj);
+        fence_async_smem();  // generic-proxy writes (noise tile, tables) -> async proxy
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm1(0);
+        }
 
-            // ---- 1. this thread's half of the noise of pair `row`, operand tile of GEMM1 ---------------------
-            float e[DH];
-            {
-                float z[DH];
-                if (PHILOX) {
-                    philox_normals_half<DH>(seed, offset, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
-                } else {
-                    const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
-#pragma unroll
-                    for (int i = 0; i < DH; ++i) z[i] = (hsel * DH + i < D) ? (float)__ldg(ep + hsel * DH + i) : 0.0f;
-                }
-#pragma unroll
-                for (int i = 0; i < DH; ++i) e[i] = live ? sj * z[i] : 0.0f;
-            }
-            {
-                float Eh = 0.f;
-#pragma unroll
-                for (int i = 0; i < DH; ++i) {
-                    Eh = fmaf(e[i], e[i], Eh);
-                    const int d = hsel * DH + i;
-                    const float vh = __uint_as_float(__float_as_uint(e[i]) & 0xffffe000u);
-                    const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-                    sAh[o] = vh, sAl[o] = e[i] - vh;
-                }
-                sE[hsel * kTile + row] = Eh;
-            }
-            fence_async_smem();  // generic-proxy writes (tile, and the tables at a segment start) -> async proxy
-            tc_fence_before();
-            __syncthreads();
-
-            // ---- 2. GEMM1: B = E Delta^T (3xTF32) -----------------------------------------------------------
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t aH = smem_u32(sAh), aL = smem_u32(sAl), bH = smem_u32(sB1h), bL = smem_u32(sB1l);
-#pragma unroll
-                for (int s = 0; s < D8 / 8; ++s) {
-                    const uint64_t dAh = umma_desc(aH + s * 2 * lboA, lboA, sbo), dAl = umma_desc(aL + s * 2 * lboA, lboA, sbo);
-                    const uint64_t dBh = umma_desc(bH + s * 2 * lboB1, lboB1, sbo), dBl = umma_desc(bL + s * 2 * lboB1, lboB1, sbo);
-                    mma_ss(tmem + cR0, dAh, dBh, idesc1, s > 0 ? 1u : 0u);
-                    mma_ss(tmem + cR0, dAh, dBl, idesc1, 1u);
-                    mma_ss(tmem + cR0, dAl, dBh, idesc1, 1u);
-                }
-                tc_commit(bar0);
-            }
-            const float E = sE[row] + sE[kTile + row];
+        int b = 0;
+        for (int t0 = 0; t0 < n; t0 += kTile, b ^= 1) {
+            const bool live = t0 + row < n;
+            const uint32_t cX = cX0 + (uint32_t)b * KP;
+            const float E = sE[(b * 2) * kTile + row] + sE[(b * 2 + 1) * kTile + row];
             mbar_wait(bar0, ph0);
             ph0 ^= 1u;
             tc_fence_after();
 
-            // ---- 3. pass 1: density ratios u(+-) of this thread's components, partial mixture sums --------
+            // ---- pass 1: density ratios u(+-) of this thread's components, partial mixture sums ----------------
             float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
-            for (int ci = c_begin; ci < c_end; ++ci) {
-                uint32_t b[16], um[16];
-                tm_ld16(trow + cR0 + 16 * ci, b);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = 16 * ci + i;
-                    const KTc c = sKc[k];
-                    const float wis = sWis[k];
-                    const float s0 = fmaf(c.hd, E, c.ck2);
-                    const float x = c.h2 * __uint_as_float(b[i]);
-                    const float vp = ex2f(s0 - x), vm = ex2f(s0 + x);
-                    qp = fmaf(c.w, vp, qp), qm = fmaf(c.w, vm, qm);
-                    Gp = fmaf(wis, vp, Gp), Gm = fmaf(wis, vm, Gm);
-                    b[i] = __float_as_uint(vp), um[i] = __float_as_uint(vm);
-                }
-                const uint32_t fm = sMask[ci];
-                if (fm != 0u) {  // CTA-uniform, rare: badly conditioned components, direct differences
-                    const float base = hj * E;
+            for (int cc = 0; cc < kMaxChunks; ++cc) {
+                const int ci = c_begin + cc;
+                if (ci < c_end) {
+                    uint32_t x[16], um[16];
+                    tm_ld16(trow + cX + 16 * ci, x);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        if ((fm >> i) & 1u) {
-                            const int k = 16 * ci + i;
-                            const KDir dr = sDir[k];
-                            const float *dl = sDl + k * DP;
-                            float a0 = 0.f, a1 = 0.f;
+                        const KTc c = sKc[16 * ci + i];
+                        const float s0 = fmaf(c.hd, E, c.ck2);
+                        const float xx = __uint_as_float(x[i]);
+                        const float vp = ex2f(s0 - xx), vm = ex2f(s0 + xx);
+                        qp = fmaf(c.w, vp, qp), qm = fmaf(c.w, vm, qm);
+                        if constexpr (ANYGRAD) Gp = fmaf(c.wis, vp, Gp), Gm = fmaf(c.wis, vm, Gm);
+                        x[i] = __float_as_uint(vp), um[i] = __float_as_uint(vm);
+                    }
+                    const uint32_t fm = sMask[ci];
+                    if (fm != 0u) {  // CTA-uniform, rare: badly conditioned components, direct differences
+                        const float base = hj * E;
+                        const float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if ((fm >> i) & 1u) {
+                                const int k = 16 * ci + i;
+                                const KDir dr = sDir[k];
+                                const float *dl = gDl + k * DP;
+                                float a0 = 0.f, a1 = 0.f;
 #pragma unroll 1
-                            for (int d = 0; d < DP; ++d) {
-                                const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-                                const float ed = sAh[o] + sAl[o];
-                                const float tp = dl[d] + ed, tm = dl[d] - ed;
-                                a0 = fmaf(tp, tp, a0), a1 = fmaf(tm, tm, a1);
+                                for (int d = 0; d < DP; ++d) {
+                                    const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
+                                    const float ed = aH[o] + aL[o], dd = __ldg(dl + d);
+                                    const float tp = dd + ed, tm = dd - ed;
+                                    a0 = fmaf(tp, tp, a0), a1 = fmaf(tm, tm, a1);
+                                }
+                                const float vp = ex2f(fmaf(-dr.h, a0, dr.ck + base));
+                                const float vm = ex2f(fmaf(-dr.h, a1, dr.ck + base));
+                                // (the expanded-form value of a guarded component above is exactly 0: ck2 = -200)
+                                const float wk = sKc[k].w, wis = sKc[k].wis;
+                                qp = fmaf(wk, vp, qp), qm = fmaf(wk, vm, qm);
+                                if constexpr (ANYGRAD) Gp = fmaf(wis, vp, Gp), Gm = fmaf(wis, vm, Gm);
+                                x[i] = __float_as_uint(vp), um[i] = __float_as_uint(vm);
                             }
-                            const float vp = ex2f(fmaf(-dr.h, a0, dr.ck + base));
-                            const float vm = ex2f(fmaf(-dr.h, a1, dr.ck + base));
-                            const float wk = sKc[k].w, wis = sWis[k];
-                            qp = fmaf(wk, vp, qp), qm = fmaf(wk, vm, qm);
-                            Gp = fmaf(wis, vp, Gp), Gm = fmaf(wis, vm, Gm);
-                            b[i] = __float_as_uint(vp), um[i] = __float_as_uint(vm);
                         }
                     }
-                }
-                if constexpr (ANYGRAD) {
-                    tm_st16(trow + cR0 + 16 * ci, b);
-                    tm_st16(trow + cR1 + 16 * ci, um);
+                    if constexpr (ANYGRAD) {
+                        tm_st16(trow + cX + 16 * ci, x);
+                        tm_st16(trow + cU + 16 * ci, um);
+                    }
                 }
             }
             // exchange the partial sums of the two threads of a pair
@@ -491,57 +559,79 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
             if (live && hsel == 0)
                 hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
 
+            float gs = 0.f, gd = 0.f;
             if constexpr (ANYGRAD) {
                 Gp = sQ[2 * kTile + row] + sQ[6 * kTile + row];
                 Gm = sQ[3 * kTile + row] + sQ[7 * kTile + row];
                 const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
-                // ---- 4. pass 2: racc_k += u+/q+ + u-/q- ;  c_k = wis2_k (u+/q+ - u-/q-) split hi/lo --------------
-                for (int c8 = 2 * c_begin; c8 < 2 * c_end; ++c8) {  // 8 components at a time (register pressure)
-                    uint32_t up[8], um[8], ra[8];
-                    tm_ld8x3(trow + cR0 + 8 * c8, up, trow + cR1 + 8 * c8, um, trow + cR2 + 8 * c8, ra);
+                gs = fmaf(Gp, iqp, Gm * iqm), gd = fmaf(Gp, iqp, -(Gm * iqm));
+                // ---- pass 2: racc_k += u+/q+ + u-/q- ;  c'_k = u+/q+ - u-/q- split hi/lo -------------------------
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a = __uint_as_float(up[i]) * iqp, bq = __uint_as_float(um[i]) * iqm;
-                        ra[i] = __float_as_uint(__uint_as_float(ra[i]) + (a + bq));
-                        const float c = sWis[8 * c8 + i] * (a - bq);
-                        const uint32_t ch = __float_as_uint(c) & 0xffffe000u;
-                        up[i] = ch;
-                        um[i] = __float_as_uint(c - __uint_as_float(ch));
+                for (int cc = 0; cc < kMaxChunks; ++cc) {
+                    const int ci = c_begin + cc;
+                    if (ci < c_end) {
+                        uint32_t up[16], um[16];
+                        tm_ld16x2(trow + cX + 16 * ci, up, trow + cU + 16 * ci, um);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float a = __uint_as_float(up[i]) * iqp, bq = __uint_as_float(um[i]) * iqm;
+                            racc[cc * 16 + i] += a + bq;
+                            const float c = a - bq;
+                            const uint32_t ch = __float_as_uint(c) & 0xffffe000u;
+                            up[i] = ch;
+                            um[i] = __float_as_uint(c - __uint_as_float(ch));
+                        }
+                        tm_st16(trow + cX + 16 * ci, up);
+                        tm_st16(trow + cU + 16 * ci, um);
                     }
-                    tm_st8(trow + cR0 + 8 * c8, up);
-                    tm_st8(trow + cR1 + 8 * c8, um);
-                    tm_st8(trow + cR2 + 8 * c8, ra);
                 }
                 tm_wait_st();
                 tc_fence_before();
                 __syncthreads();
 
-                // ---- 5. GEMM2: V = C Delta (A from TMEM, 3xTF32) ---------------------------------------------
+                // ---- GEMM2: V = C' (wis Delta) (A from TMEM, 3xTF32) ---------------------------------------------
                 if (tid == 0) {
                     tc_fence_after();
                     const uint32_t bH = smem_u32(sB2h), bL = smem_u32(sB2l);
                     for (int s = 0; s < KP / 8; ++s) {
                         const uint64_t dBh = umma_desc(bH + s * 2 * lboB2, lboB2, sbo), dBl = umma_desc(bL + s * 2 * lboB2, lboB2, sbo);
-                        mma_ts(tmem + cD2, tmem + cR0 + 8 * s, dBh, idesc2, s > 0 ? 1u : 0u);
-                        mma_ts(tmem + cD2, tmem + cR0 + 8 * s, dBl, idesc2, 1u);
-                        mma_ts(tmem + cD2, tmem + cR1 + 8 * s, dBh, idesc2, 1u);
+                        mma_ts(tmem + cV, tmem + cX + 8 * s, dBh, idesc2, s > 0 ? 1u : 0u);
+                        mma_ts(tmem + cV, tmem + cX + 8 * s, dBl, idesc2, 1u);
+                        mma_ts(tmem + cV, tmem + cU + 8 * s, dBh, idesc2, 1u);
                     }
                     tc_commit(bar1);
                 }
-                const float sgp = Gp * iqp, sgm = Gm * iqm;
-                const float gs = sgp + sgm, gd = sgp - sgm;
+            }
+
+            // ---- noise + GEMM1 of the NEXT tile run under GEMM2 of this one ---------------------------------------
+            if (t0 + kTile < n) {
+                rng_tile(b ^ 1, j, p_lo, n, t0 + kTile, sj);
+                fence_async_smem();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_gemm1(b ^ 1);
+                }
+            }
+
+            if constexpr (ANYGRAD) {
                 mbar_wait(bar1, ph1);
                 ph1 ^= 1u;
                 tc_fence_after();
-
-                // ---- 6. epilogue: per-thread gradient sums over this thread's dimensions -------------------------
+                // ---- epilogue: per-thread gradient sums over this thread's dimensions -------------------------------
                 uint32_t v[LW];
-                TmLd<LW>::go(trow + cD2 + hsel * DH, v);
+                TmLd<LW>::go(trow + cV + hsel * DH, v);
+                const float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
 #pragma unroll
                 for (int i = 0; i < DH; ++i) {
-                    be[i] = fmaf(e[i], fmaf(e[i], gs, __uint_as_float(v[i])), be[i]);
-                    ae[i] = fmaf(e[i], gd, ae[i]);
+                    const int d = hsel * DH + i;
+                    const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
+                    const float e = aH[o] + aL[o];  // exact: hi + lo is the fp32 noise value
+                    be[i] = fmaf(e, fmaf(e, gs, __uint_as_float(v[i])), be[i]);
+                    ae[i] = fmaf(e, gd, ae[i]);
                 }
+                tc_fence_before();  // the next tile's MMAs overwrite V / X after the next barrier
             }
         }
 
@@ -553,19 +643,20 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
         if constexpr (ANYGRAD) {
 #pragma unroll
             for (int i = 0; i < DH; ++i) {
-                const float a = warp_sum_f(ae[i]), b = warp_sum_f(be[i]);
-                if (lane == 0) myrec[1 + hsel * DH + i] = (double)a, myrec[1 + DP + hsel * DH + i] = (double)b;
+                const float a = warp_sum_f(ae[i]), bb = warp_sum_f(be[i]);
+                if (lane == 0) myrec[1 + hsel * DH + i] = (double)a, myrec[1 + DP + hsel * DH + i] = (double)bb;
             }
-            for (int ci = c_begin; ci < c_end; ++ci) {
-                uint32_t ra[16];
-                tm_ld16(trow + cR2 + 16 * ci, ra);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float r = warp_sum_f(__uint_as_float(ra[i]));
-                    if (lane == 0 && 16 * ci + i < K) myrec[1 + 2 * DP + 16 * ci + i] = (double)r;
+            for (int cc = 0; cc < kMaxChunks; ++cc) {
+                const int ci = c_begin + cc;
+                if (ci < c_end) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float r = warp_sum_f(racc[cc * 16 + i]);
+                        if (lane == 0 && 16 * ci + i < K) myrec[1 + 2 * DP + 16 * ci + i] = (double)r;
+                    }
                 }
             }
-            tc_fence_before();
         }
         __syncthreads();
         const int nf = ANYGRAD ? part_stride : 1;
@@ -579,15 +670,19 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
         }
         __syncthreads();
         double *rec = part + ((size_t)blockIdx.x * maxseg + seg) * (size_t)part_stride;
-        for (int f = tid; f < nf; f += kThreads) {
-            double v = sTot[f];
-            if (ANYGRAD && f >= 1 && f < 1 + DP) {  // A_d += sum_k Delta_kd (w_k / sigma_k^2) racc_k
-                const int d = f - 1;
+        for (int f = tid; f < nf; f += kThreads)
+            if (!(ANYGRAD && f >= 1 && f < 1 + D)) rec[f] = sTot[f];
+        if constexpr (ANYGRAD) {
+            // A_d += sum_k Delta_kd (w_k / sigma_k^2) racc_k : one warp per dimension, lanes over the components
+            for (int d = wid; d < D; d += kThreads / 32) {
                 double s = 0.0;
-                for (int k = 0; k < K; ++k) s += (double)sDl[k * DP + d] * (double)sWis[k] * sTot[1 + 2 * DP + k];
-                v += s;
+                for (int k = lane; k < K; k += 32) {
+                    const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);
+                    s += ((double)sB2h[o2] + (double)sB2l[o2]) * sTot[1 + 2 * DP + k];  // (wis Delta) is folded in the table
+                }
+                s = warp_sum(s);
+                if (lane == 0) rec[1 + d] = sTot[1 + d] + s;
             }
-            rec[f] = v;
         }
     }
 
@@ -600,8 +695,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
 }
 
 uint32_t tc_tmem_cols(int DP, int K) {
-    const int D8 = (DP + 7) / 8 * 8, N2 = D8 <= 16 ? 16 : 32, KP = (K + 15) / 16 * 16;
-    const int need = 3 * KP + N2;
+    const int need = 3 * tc_kp(K) + tc_n2(DP);
     uint32_t c = 32;
     while ((int)c < need) c <<= 1;
     return c;
@@ -609,45 +703,43 @@ uint32_t tc_tmem_cols(int DP, int K) {
 
 template <int DP, bool ANYGRAD, bool PHILOX>
 int tc_launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, const double *d_eps,
-                   double *d_part) {
+                   double *d_part, const unsigned char *d_tab) {
     auto kern = entmc_kernel_tc<DP, ANYGRAD, PHILOX>;
     static size_t smem_set = 0;
     if (plan.smem > smem_set) {
         VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
         smem_set = plan.smem;
     }
-    static int desc_swap = -1;
-    if (desc_swap < 0) {
-        const char *e = getenv("VBMC_TC_DESC_SWAP");
-        desc_swap = e ? atoi(e) : 0;
-    }
     kern<<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob, plan.chunk,
-                                                     plan.maxseg, d_eps, d_part, entpart_stride(DP, lay.K),
-                                                     c->entmc_guard, tc_tmem_cols(DP, lay.K), desc_swap);
+                                                     plan.maxseg, d_eps, d_part, entpart_stride(DP, lay.K), d_tab,
+                                                     tc_tmem_cols(DP, lay.K));
     return VBMC_OK;
 }
 
 template <int DP>
 int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
-                 const double *d_eps, double *d_part) {
+                 const double *d_eps, double *d_part, const unsigned char *d_tab) {
     if (anygrad) {
-        if (philox) return tc_launch_inst<DP, true, true>(c, d_params, lay, plan, d_eps, d_part);
-        return tc_launch_inst<DP, true, false>(c, d_params, lay, plan, d_eps, d_part);
+        if (philox) return tc_launch_inst<DP, true, true>(c, d_params, lay, plan, d_eps, d_part, d_tab);
+        return tc_launch_inst<DP, true, false>(c, d_params, lay, plan, d_eps, d_part, d_tab);
     }
-    if (philox) return tc_launch_inst<DP, false, true>(c, d_params, lay, plan, d_eps, d_part);
-    return tc_launch_inst<DP, false, false>(c, d_params, lay, plan, d_eps, d_part);
+    if (philox) return tc_launch_inst<DP, false, true>(c, d_params, lay, plan, d_eps, d_part, d_tab);
+    return tc_launch_inst<DP, false, false>(c, d_params, lay, plan, d_eps, d_part, d_tab);
 }
 
 }  // namespace
 
-bool entmc_tc_supported(int DP, int K) { return DP > 0 && K >= 1 && K <= 160 && tc_tmem_cols(DP, K) <= 512; }
+bool entmc_tc_supported(int DP, int K) {
+    return DP > 0 && K >= 1 && tc_kp(K) <= 16 * 2 * kMaxChunks && tc_tmem_cols(DP, K) <= 512;
+}
 
 // chunk (multiple of 128 pairs), grid and shared memory of the tensor-core kernel
 int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *plan) {
     const int DP = pad_dim(D);
     const uint32_t cols = tc_tmem_cols(DP, K);
-    const int per_sm = (int)(512 / cols);  // tensor memory: 512 columns per SM
-    size_t smem = tc_smem_layout(DP, D, K, entpart_stride(DP, K)).total;
+    int per_sm = (int)(512 / cols);  // tensor memory: 512 columns per SM
+    if (per_sm > 2) per_sm = 2;      // __launch_bounds__(256, 2)
+    size_t smem = tc_smem_layout(DP, K, entpart_stride(DP, K)).total;
     VBMC_REQUIRE(smem <= 227 * 1024, VBMC_ERR_UNSUPPORTED, "entmc (tensor-core): tables do not fit in shared memory");
     // never let more CTAs become resident than tensor memory can serve (tcgen05.alloc would spin): pad the
     // shared-memory request so that exactly per_sm CTAs fit
@@ -674,10 +766,21 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
 
 int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
                     const double *d_eps, double *d_part) {
+    // per-component tables (one small launch; its result stays in L2 for the main kernel)
+    const TcTab T = tc_tab_layout(lay.DP, lay.K);
+    VBMC_TRY(ensure(&c->d_tctab, &c->tctab_cap, ((size_t)lay.K * T.total + 7) / 8));
+    unsigned char *d_tab = reinterpret_cast<unsigned char *>(c->d_tctab);
+    {
+        const int KP = tc_kp(lay.K);
+        const size_t psm = (size_t)KP * lay.DP * 4 + (size_t)KP * 16;
+        entmc_tc_prep_kernel<<<lay.K, 256, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
+    }
     switch (lay.DP) {
 #define VBMC_CASE(N) \
     case N:          \
-        return tc_launch_dp<N>(c, d_params, lay, plan, anygrad, philox, d_eps, d_part)
+        return tc_launch_dp<N>(c, d_params, lay, plan, anygrad, philox, d_eps, d_part, d_tab)
         VBMC_CASE(4);
         VBMC_CASE(8);
         VBMC_CASE(12);

@@ -11,6 +11,16 @@ rep = sys.argv[1]
 blk = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+# several kernels in one report: sections start with a "Kernel Name" row; pick the one matching argv[3] (default: last)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if starts:
+    want = sys.argv[3] if len(sys.argv) > 3 else None
+    pick = starts[-1]
+    if want:
+        pick = next((i for i in starts if want in rows[i][1]), pick)
+    end = next((i for i in starts if i > pick), len(rows))
+    print("kernel:", rows[pick][1][:100])
+    rows = rows[pick:end]
 hi = next(i for i, r in enumerate(rows) if "Source" in r)
 h = rows[hi]
 c_src = h.index("Source")
