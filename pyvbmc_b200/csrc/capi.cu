@@ -391,7 +391,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     cudaStreamSynchronize(c->stream);
     drop_graph(x);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
-                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);

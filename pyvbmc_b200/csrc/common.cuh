@@ -148,6 +148,8 @@ struct Ctx {
     size_t raw_cap = 0;
     double *d_tctab = nullptr;  // per-component table images of the tensor-core entmc kernel
     size_t tctab_cap = 0;
+    double *d_tctiles = nullptr;  // noise-tile images of the tensor-core entmc kernel
+    size_t tctiles_cap = 0;
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
     size_t csum_cap = 0;
     bool raw_pending = false;  // reduce stage deferred into the next finalize launch (single GPU)

@@ -11,21 +11,24 @@
 // X = E (h2 Delta)^T  ([pairs x D] x [D x K])  and  V = C' (wis Delta)  ([pairs x K] x [K x D]) are GEMMs.
 //
 // Two kernels per evaluation:
-//   entmc_tc_prep_kernel  one CTA per component j: every j-dependent table in its final shared-memory image
-//                         (GEMM operand tiles split hi/lo for 3xTF32, per-component constants, guard mask),
-//                         written once to global memory (L2 resident), so a segment switch in the main kernel
-//                         is a 30 KB copy instead of fp64 table arithmetic in every CTA.
-//   entmc_kernel_tc       a CTA owns tiles of 128 antithetic pairs (2 threads per pair; thread <-> TMEM lane):
-//     RNG     Philox + Box-Muller (or eps input) -> noise tile in shared memory (tf32 hi/lo split)
+//   entmc_tc_gen_kernel   (a) CTAs [0, K): every j-dependent table of component j in its final shared-memory image
+//                         (GEMM operand tiles split hi/lo for 3xTF32, per-component constants, guard mask);
+//                         (b) one CTA per tile of 128 antithetic pairs: the noise tile (Philox + Box-Muller, or the
+//                         eps input of parity mode) scaled by sigma_j, split hi/lo, in the K-major operand layout
+//                         GEMM1 reads, plus |e|^2 per pair.  Both go to global memory and stay L2 resident.
+//   entmc_kernel_tc       a CTA owns a chunk of the flattened (component, pair) space, tile by tile (2 threads per
+//                         pair; thread <-> TMEM lane):
+//     tile    cp.async.bulk (TMA, 1-D) of the prepared 25 KB image into a 3-deep shared-memory ring
 //     GEMM1   X[128 x KP]  = E[128 x D8] (h2 Delta)^T   tcgen05.mma kind::tf32, operands from shared memory
 //                                                       (K-major, no swizzle), 3xTF32 (hi*hi + hi*lo + lo*hi)
 //     pass 1  tcgen05.ld X rows -> u(+-) (2 MUFU.EX2 per (pair, k)), q(+-), G(+-); u(+-) parked in TMEM
 //     pass 2  u(+-) -> racc_k (registers), c'_k = u+/q+ - u-/q- split hi/lo -> TMEM
 //     GEMM2   V[128 x N2]  = C'[128 x KP] (wis Delta)   A operand straight from TMEM, 3xTF32
 //     epilogue per-thread sums of e_d (v_d + e_d (G+/q+ + G-/q-)) and e_d (G+/q+ - G-/q-)
-//   The tile loop is software-pipelined: X is double-buffered in TMEM and the noise tile in shared memory, so
-//   the RNG of tile t+1 runs under GEMM2(t) and GEMM1(t+1) runs under the epilogue of tile t; two CTAs per SM
-//   cover each other's barriers.  ~19 CUDA-core instructions per (pair, component) instead of ~50.
+//   X is double-buffered in TMEM; there is NO CTA-wide barrier in the tile loop: the two threads of a pair meet on
+//   a 64-thread named barrier, everything else is mbarriers (tile landed / X ready / V ready / warps done), so
+//   warps drift apart and cover each other's TMEM and MUFU latencies; two CTAs per SM.
+//   ~19 CUDA-core instructions per (pair, component) instead of ~50 in the CUDA-core kernels of entmc.cu.
 // Components whose expanded distance is badly conditioned (same guard as entmc_kernel_w) have their u(+-)
 // recomputed with direct differences on the CUDA cores.
 // Work distribution, records and determinism are those of entmc_kernel_w: the K * half pairs are one index space
@@ -55,9 +58,29 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int quad) {  // the two warps that share a TMEM lane quadrant
+    switch (quad) {  // immediate barrier ids: a register operand would reserve all 16 hardware barriers
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    const long long t0 = clock64();
+    long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -67,7 +90,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > 2000000000LL) __trap();  // ~1 s: a lost MMA completion must not hang the GPU
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 2000000000LL) __trap();  // ~1 s: a lost completion must not hang the GPU
     }
 }
 
@@ -147,21 +171,32 @@ __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16])
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float warp_sum_f(float v) {
+// sums over the 32 lanes of 32 per-lane values at once: afterwards lane l holds sum_lanes v[l] in v[0]
+// (31 shuffles instead of 32 x 5: at every step a lane keeps one half of its values and trades the other)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int s = 16, n = 16; s >= 1; s >>= 1, n >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = upper ? v[i] : v[i + n];
+            const float keep = upper ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
 }
 
 constexpr int kTile = 128;     // antithetic pairs per tile = TMEM lanes
 constexpr int kThreads = 256;  // two threads per pair: each owns half of the dimensions and half of the components
 constexpr int kMaxChunks = 2;  // 16-column component chunks per thread (K <= 64): racc lives in registers
+constexpr int kRing = 3;       // noise-tile buffers in shared memory
 
 __host__ __device__ inline int tc_d8(int DP) { return (DP + 7) / 8 * 8; }
 __host__ __device__ inline int tc_n2(int DP) { return tc_d8(DP) <= 16 ? 16 : 32; }
 __host__ __device__ inline int tc_kp(int K) { return (K + 15) / 16 * 16; }
 
-// Per-component table block (byte offsets): the image entmc_tc_prep_kernel writes to global memory and the main
+// Per-component table block (byte offsets): the image entmc_tc_gen_kernel writes to global memory and the main
 // kernel copies verbatim into shared memory at a segment start.  Dl (plain Delta, fp32) is only read by the rare
 // direct-difference path and stays in global memory (it sits behind `smem_bytes`).
 struct TcTab {
@@ -190,10 +225,14 @@ __host__ __device__ inline TcTab tc_tab_layout(int DP, int K) {
     return s;
 }
 
-struct TcSmem {  // byte offsets inside the dynamic shared memory of entmc_kernel_tc
-    uint32_t Tab, A, E, Q, Rec, Tot, Bar, total;
-};
+// noise-tile image: [hi (NC1 x 128 x 16 B) | lo (same) | partial |e|^2 (2 halves x 128 floats)], K-major
+// no-swizzle operand layout
 __host__ __device__ inline uint32_t tc_a_bytes(int DP) { return (uint32_t)(tc_d8(DP) / 4) * kTile * 16; }  // one of hi / lo
+__host__ __device__ inline uint32_t tc_tile_bytes(int DP) { return 2 * tc_a_bytes(DP) + 2 * kTile * 4; }
+
+struct TcSmem {  // byte offsets inside the dynamic shared memory of entmc_kernel_tc
+    uint32_t Tab, A, Q, Rec, Tot, Bar, total;
+};
 __host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride) {
     TcSmem s;
     uint32_t o = 0;
@@ -203,22 +242,120 @@ __host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride)
         return at;
     };
     s.Tab = take(tc_tab_layout(DP, K).smem_bytes);
-    s.A = take(4 * tc_a_bytes(DP));  // [buffer 0: hi | lo][buffer 1: hi | lo]
-    s.E = take(2 * 2 * kTile * 4);   // [buffer][half][row] partial |e|^2
-    s.Q = take(2 * 4 * kTile * 4);   // [half][q+, q-, G+, G-][row]
-    s.Rec = take(8 * part_stride * 8);
-    s.Tot = take(part_stride * 8);
-    s.Bar = take(64);
+    s.A = take(kRing * tc_tile_bytes(DP));
+    s.Q = take(2 * 4 * kTile * 4);  // [half][q+, q-, G+, G-][row]
+    s.Bar = take(128);
     s.total = o;
+    // the record scratch is only used between segments, when the ring is idle: it aliases the first slots
+    s.Rec = s.A;
+    s.Tot = s.A + (((uint32_t)(8 * part_stride * 8) + 127u) & ~127u);
     return s;
 }
 
+// tiles of one CTA's chunk, in processing order: segment after segment, each segment's pairs in tiles of 128.
+// Both kernels enumerate them with this walk; `tpc` images are reserved per CTA.
+struct TcWork {
+    int64_t half, pair0, half_glob, chunk;
+    int K, tpc;
+};
+
 // ------------------------------------------------------------------------------------------------------------
-// tables of component j = blockIdx.x
-__global__ void __launch_bounds__(256)
-entmc_tc_prep_kernel(const double *__restrict__ prm, ParamLayout lay, float guard, unsigned char *__restrict__ tab) {
-    const int D = lay.D, DP = lay.DP, K = lay.K, j = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int D8 = tc_d8(DP), N2 = tc_n2(DP), KP = tc_kp(K);
+// CTAs [0, K): tables of component j = blockIdx.x.  CTAs K + g: noise-tile image g.
+// dims [D0, D0 + DH) of one row -> operand layout in global memory, in 16-byte pieces where the alignment allows
+template <int DH, int D0>
+__device__ __forceinline__ void store_half(const float (&eh)[DH], const float (&el)[DH], float *aH, float *aL, int row) {
+    static_assert(DH % 2 == 0 && D0 % 2 == 0, "dimension halves are stored in 8- or 16-byte pieces");
+#pragma unroll
+    for (int i = 0; i < DH; i += 2) {
+        const int d = D0 + i;
+        const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
+        if ((d & 3) == 0 && i + 4 <= DH) {
+            *reinterpret_cast<float4 *>(aH + o) = make_float4(eh[i], eh[i + 1], eh[i + 2 < DH ? i + 2 : i], eh[i + 3 < DH ? i + 3 : i]);
+            *reinterpret_cast<float4 *>(aL + o) = make_float4(el[i], el[i + 1], el[i + 2 < DH ? i + 2 : i], el[i + 3 < DH ? i + 3 : i]);
+        } else if ((d & 3) == 2 && i >= 2 && i + 2 <= DH) {
+            // second half of the 16-byte piece stored in the previous step
+        } else {
+            *reinterpret_cast<float2 *>(aH + o) = make_float2(eh[i], eh[i + 1]);
+            *reinterpret_cast<float2 *>(aL + o) = make_float2(el[i], el[i + 1]);
+        }
+    }
+}
+
+template <int DP, bool PHILOX>
+__global__ void __launch_bounds__(kThreads)
+entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard, unsigned char *__restrict__ tab,
+                    TcWork wk, const double *__restrict__ eps, unsigned char *__restrict__ tiles) {
+    const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
+    constexpr int DH = DP / 2, D8 = (DP + 7) / 8 * 8, N2 = D8 <= 16 ? 16 : 32;
+    extern __shared__ __align__(16) unsigned char psm[];
+    if ((int)blockIdx.x >= K) {
+        // ---- (b) noise tile -------------------------------------------------------------------------------
+        const int g = (int)blockIdx.x - K;
+        const int cta = g / wk.tpc, l = g - cta * wk.tpc;
+        const int64_t Tn = (int64_t)K * wk.half;
+        const int64_t g0 = (int64_t)cta * wk.chunk, g1 = min(g0 + wk.chunk, Tn);
+        if (g0 >= Tn) return;
+        int j = (int)(g0 / wk.half), cnt = 0, n = 0, t0 = 0;
+        int64_t p_lo = 0;
+        for (;; ++j) {
+            const int64_t lo = max(g0, (int64_t)j * wk.half), hi = min(g1, (int64_t)(j + 1) * wk.half);
+            if (j >= K || lo >= hi) return;  // image not used by this chunk
+            n = (int)(hi - lo);
+            const int ntile = (n + kTile - 1) / kTile;
+            if (l < cnt + ntile) {
+                t0 = (l - cnt) * kTile;
+                p_lo = lo - (int64_t)j * wk.half;
+                break;
+            }
+            cnt += ntile;
+        }
+        constexpr uint32_t ABYTES = (uint32_t)(D8 / 4) * kTile * 16, TB = 2 * ABYTES + 2 * kTile * 4;
+        unsigned char *img = tiles + (size_t)g * TB;
+        float *aH = reinterpret_cast<float *>(img), *aL = reinterpret_cast<float *>(img + ABYTES);
+        float *gE = reinterpret_cast<float *>(img + 2 * ABYTES);
+        const int row = tid & (kTile - 1), hsel = tid >> 7;
+        const float sj = (float)prm[lay.sigma() + j];
+        const int off = t0 + row;
+        const bool live = off < n;
+        const int64_t gpair = wk.pair0 + p_lo + (live ? off : 0);
+        float z[DH];
+        if (PHILOX) {
+            const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+            philox_normals_half<DH>(rngp[0], rngp[1], (uint32_t)j, (uint64_t)gpair, hsel, D, z);
+        } else {
+            const double *ep = eps + ((size_t)j * (size_t)wk.half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+            for (int i = 0; i < DH; ++i) z[i] = (hsel * DH + i < D) ? (float)__ldg(ep + hsel * DH + i) : 0.0f;
+        }
+        // straight to global memory in the operand layout: element (row, d) sits at (d / 4) * 2048 + row * 16 + (d % 4) * 4
+        // bytes, so the lanes of a warp write 32 consecutive 16-byte (or 8-byte: DH % 4 == 2) pieces per store
+        float Eh = 0.f, eh[DH], el[DH];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) {
+            const float e = live ? sj * z[i] : 0.0f;
+            Eh = fmaf(e, e, Eh);
+            eh[i] = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
+            el[i] = e - eh[i];
+        }
+        gE[hsel * kTile + row] = Eh;
+        if (hsel == 0)
+            store_half<DH, 0>(eh, el, aH, aL, row);
+        else
+            store_half<DH, DH>(eh, el, aH, aL, row);
+        if constexpr (D8 > DP) {  // padded dimensions of the operand tile are zero (DP % 4 == 0: whole 16-byte pieces)
+            if (hsel == 1) {
+#pragma unroll
+                for (int d = DP; d < D8; d += 4) {
+                    const int o = (d >> 2) * (kTile * 4) + row * 4;
+                    *reinterpret_cast<float4 *>(aH + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(aL + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        return;
+    }
+    // ---- (a) tables of component j ------------------------------------------------------------------------
+    const int j = blockIdx.x, KP = tc_kp(K);
     const TcTab L = tc_tab_layout(DP, K);
     unsigned char *base = tab + (size_t)j * L.total;
     float *gB1h = reinterpret_cast<float *>(base + L.B1h), *gB1l = reinterpret_cast<float *>(base + L.B1l);
@@ -227,8 +364,7 @@ entmc_tc_prep_kernel(const double *__restrict__ prm, ParamLayout lay, float guar
     KDir *gDir = reinterpret_cast<KDir *>(base + L.Dir);
     uint32_t *gMask = reinterpret_cast<uint32_t *>(base + L.Mask);
     float *gDl = reinterpret_cast<float *>(base + L.Dl);
-    extern __shared__ __align__(16) unsigned char psm[];
-    float *sDl = reinterpret_cast<float *>(psm);            // [KP][DP] Delta (fp32-rounded)
+    float *sDl = reinterpret_cast<float *>(psm);              // [KP][DP] Delta (fp32-rounded)
     double *sH2 = reinterpret_cast<double *>(sDl + KP * DP);  // [KP] 2 h_k (0: padded / guarded component)
     double *sWis = sH2 + KP;                                  // [KP] w_k / sigma_k^2
     __shared__ uint32_t sMask[16];
@@ -246,36 +382,44 @@ entmc_tc_prep_kernel(const double *__restrict__ prm, ParamLayout lay, float guar
         gDl[i] = v;
     }
     __syncthreads();
-    for (int k = tid; k < KP; k += nt) {
-        KTc c;
-        KDir dr;
-        c.ck2 = -200.0f, c.hd = 0.f, c.w = 0.f, c.wis = 0.f;  // padding / guarded: expanded-form u = 2^-200 = 0
-        dr.ck = -200.0f, dr.h = 0.f;
-        double h2 = 0.0, wis = 0.0;
-        if (k < K) {
-            const double sk = sigma[k];
-            const double hk = kHalfLog2e / (sk * sk);
-            const double ck = D * (log2(sig_j) - log2(sk));
+    {
+        // one warp per component: lanes over the dimensions for |Delta_k|^2, lane 0 finishes the constants
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int k = wid; k < KP; k += nt / 32) {
             double A = 0.0;  // |Delta_k|^2 of the rounded table entries
-            for (int d = 0; d < D; ++d) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
-            c.w = (float)w[k];
-            wis = w[k] / (sk * sk);
-            c.wis = (float)wis;
-            dr.ck = (float)ck;
-            dr.h = (float)hk;
-            // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
-            if (k != j && hk * (A + Emax) > (double)guard) {
-                atomicOr(&sMask[k >> 4], 1u << (k & 15));
-            } else {
-                c.ck2 = (float)(ck - hk * A);
-                c.hd = (float)(hjd - hk);
-                h2 = 2.0 * hk;
+            if (k < K)
+                for (int d = lane; d < D; d += 32) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
+            A = warp_sum(A);
+            if (lane == 0) {
+                KTc c;
+                KDir dr;
+                c.ck2 = -200.0f, c.hd = 0.f, c.w = 0.f, c.wis = 0.f;  // padding / guarded: expanded-form u = 2^-200 = 0
+                dr.ck = -200.0f, dr.h = 0.f;
+                double h2 = 0.0, wis = 0.0;
+                if (k < K) {
+                    const double sk = sigma[k];
+                    const double hk = kHalfLog2e / (sk * sk);
+                    const double ck = D * (log2(sig_j) - log2(sk));
+                    c.w = (float)w[k];
+                    wis = w[k] / (sk * sk);
+                    c.wis = (float)wis;
+                    dr.ck = (float)ck;
+                    dr.h = (float)hk;
+                    // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
+                    if (k != j && hk * (A + Emax) > (double)guard) {
+                        atomicOr(&sMask[k >> 4], 1u << (k & 15));
+                    } else {
+                        c.ck2 = (float)(ck - hk * A);
+                        c.hd = (float)(hjd - hk);
+                        h2 = 2.0 * hk;
+                    }
+                }
+                gKc[k] = c;
+                gDir[k] = dr;
+                sH2[k] = h2;
+                sWis[k] = wis;
             }
         }
-        gKc[k] = c;
-        gDir[k] = dr;
-        sH2[k] = h2;
-        sWis[k] = wis;
     }
     __syncthreads();
     if (tid < 16) gMask[tid] = sMask[tid];
@@ -303,8 +447,8 @@ entmc_tc_prep_kernel(const double *__restrict__ prm, ParamLayout lay, float guar
             gB2h[o2] = vh, gB2l[o2] = vl;
         }
     }
-    if (N2 > D8) {
-        const int NZ = N2 - D8;
+    if constexpr (N2 > D8) {
+        constexpr int NZ = N2 - D8;
         for (int i = tid; i < KP * NZ; i += nt) {
             const int k = i / NZ, d = D8 + (i - k * NZ);
             const int o2 = (k >> 2) * (N2 * 4) + d * 4 + (k & 3);
@@ -331,56 +475,53 @@ struct TmLd<8> {
     }
 };
 
-template <int DP, bool ANYGRAD, bool PHILOX>
+template <int DP, bool ANYGRAD>
 __global__ void __launch_bounds__(kThreads, 2)
-entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
-                int64_t chunk, int maxseg, const double *__restrict__ eps, double *__restrict__ part, int part_stride,
-                const unsigned char *__restrict__ tab, uint32_t tmem_cols) {
+entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int maxseg, double *__restrict__ part,
+                int part_stride, const unsigned char *__restrict__ tab, const unsigned char *__restrict__ tiles,
+                uint32_t tmem_cols) {
     constexpr int DH = DP / 2;            // dimensions per thread
     constexpr int D8 = (DP + 7) / 8 * 8;  // GEMM1 reduction length (tf32 MMAs consume 8 per instruction)
     constexpr int NC1 = D8 / 4;           // 16-byte chunks along D
     constexpr int N2 = D8 <= 16 ? 16 : 32;  // GEMM2 output columns (M = 128 needs N % 16 == 0)
     constexpr int LW = DH <= 8 ? 8 : 16;    // columns of V loaded per thread in the epilogue (DH + LW <= N2)
-    constexpr uint32_t ABYTES = (uint32_t)NC1 * kTile * 16;
+    constexpr uint32_t ABYTES = (uint32_t)NC1 * kTile * 16, TB = 2 * ABYTES + 2 * kTile * 4;
     const int D = lay.D, K = lay.K;
+    const int64_t half = wk.half, chunk = wk.chunk;
     const int nch = (K + 15) >> 4, KP = nch * 16;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int row = tid & (kTile - 1), hsel = tid >> 7, quad = wid & 3;
     // components (16-column chunks) of this thread: the first half of the chunks for hsel = 0, the rest for 1
     const int c_begin = hsel ? (nch + 1) / 2 : 0, c_end = hsel ? nch : (nch + 1) / 2;
-    uint64_t seed, offset;
-    {
-        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
-        seed = rngp[0], offset = rngp[1];
-    }
 
     extern __shared__ __align__(128) unsigned char smem[];
     const TcTab T = tc_tab_layout(DP, K);
     const TcSmem L = tc_smem_layout(DP, K, part_stride);
     unsigned char *sTab = smem + L.Tab;
-    const float *sB1h = reinterpret_cast<const float *>(sTab + T.B1h), *sB1l = reinterpret_cast<const float *>(sTab + T.B1l);
     const float *sB2h = reinterpret_cast<const float *>(sTab + T.B2h), *sB2l = reinterpret_cast<const float *>(sTab + T.B2l);
     const KTc *sKc = reinterpret_cast<const KTc *>(sTab + T.Kc);
     const KDir *sDir = reinterpret_cast<const KDir *>(sTab + T.Dir);
     const uint32_t *sMask = reinterpret_cast<const uint32_t *>(sTab + T.Mask);
     const float *sScal = reinterpret_cast<const float *>(sTab + T.Scal);
-    float *sA = reinterpret_cast<float *>(smem + L.A);  // [buf][hi | lo][NC1][128][4]
-    float *sE = reinterpret_cast<float *>(smem + L.E);  // [buf][half][128] partial |e|^2
+    unsigned char *sA = smem + L.A;                     // ring of tile images [hi | lo | E]
     float *sQ = reinterpret_cast<float *>(smem + L.Q);  // [half][4][128] partial q+, q-, G+, G-
     double *sRec = reinterpret_cast<double *>(smem + L.Rec);
     double *sTot = reinterpret_cast<double *>(smem + L.Tot);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.Bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 8);
 
     const int64_t Tn = (int64_t)K * half;
     const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, Tn);
     if (g0 >= Tn) return;
 
-    // ---- one-time set-up: barriers, tensor memory, zeroed noise tiles (padding dims stay 0) ---------------------
-    const uint32_t bar0 = smem_u32(sBar), bar1 = smem_u32(sBar + 1);
+    // ---- one-time set-up: barriers, tensor memory ---------------------------------------------------------------
+    // sBar: [0..2] tile landed (tx) | [3] X ready (GEMM1 commit) | [4] V ready (GEMM2 commit) | [5] warps done (8)
+    const uint32_t barF = smem_u32(sBar), bar0 = smem_u32(sBar + 3), bar1 = smem_u32(sBar + 4), barC = smem_u32(sBar + 5);
     if (tid == 0) {
+        for (int i = 0; i < kRing; ++i) mbar_init(barF + 8 * i, 1);
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
+        mbar_init(barC, kThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (wid == 0) {
@@ -390,51 +531,31 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < (int)(4 * ABYTES / 16); i += kThreads) reinterpret_cast<float4 *>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
     // TMEM columns: X0 / X1 = GEMM1 output of even / odd tiles -> u+ -> c_hi (in place), U = u- -> c_lo, V = GEMM2 output
-    const uint32_t cX0 = 0, cU = 2 * KP, cV = 3 * KP;
-    uint32_t ph0 = 0, ph1 = 0;
+    const uint32_t cU = 2 * KP, cV = 3 * KP;
+    uint32_t ph0 = 0, ph1 = 0, phC = 0;
 
     const uint32_t idesc1 = umma_idesc_tf32(KP), idesc2 = umma_idesc_tf32(N2);
     // operand strides: rows 16 B apart, 8-row groups 128 B apart, K chunks one whole row-block apart
     const uint32_t lboA = kTile * 16, lboB1 = KP * 16, lboB2 = N2 * 16, sbo = 128;
+    const unsigned char *my_tiles = tiles + (size_t)blockIdx.x * wk.tpc * TB;
 
-    // noise of tile `t0 / 128` of the current segment -> buffer b (this thread: its half of the dims of pair `row`)
-    auto rng_tile = [&](int b, int j, int64_t p_lo, int n, int t0, float sj) {
-        const int off = t0 + row;
-        const bool live = off < n;
-        const int64_t gpair = pair0 + p_lo + (live ? off : 0);
-        float z[DH];
-        if (PHILOX) {
-            philox_normals_half<DH>(seed, offset, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
-        } else {
-            const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
-#pragma unroll
-            for (int i = 0; i < DH; ++i) z[i] = (hsel * DH + i < D) ? (float)__ldg(ep + hsel * DH + i) : 0.0f;
-        }
-        float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
-        float Eh = 0.f;
-#pragma unroll
-        for (int i = 0; i < DH; ++i) {
-            const float e = live ? sj * z[i] : 0.0f;
-            Eh = fmaf(e, e, Eh);
-            const int d = hsel * DH + i;
-            const float vh = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
-            const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-            aH[o] = vh, aL[o] = e - vh;
-        }
-        sE[(b * 2 + hsel) * kTile + row] = Eh;
+    // (elected thread) tile image r of this CTA -> ring slot r % kRing
+    auto issue_load = [&](int r) {
+        const uint32_t bar = barF + 8 * (r % kRing);
+        mbar_expect_tx(bar, TB);
+        bulk_g2s(smem_u32(sA) + (uint32_t)(r % kRing) * TB, my_tiles + (size_t)r * TB, TB, bar);
     };
-    // X[b] = E[b] (h2 Delta)^T, 3xTF32 (one elected thread)
-    auto issue_gemm1 = [&](int b) {
-        const uint32_t aH = smem_u32(sA) + (uint32_t)b * 2 * ABYTES, aL = aH + ABYTES;
-        const uint32_t bH = smem_u32(sB1h), bL = smem_u32(sB1l);
-        const uint32_t dcol = tmem + cX0 + (uint32_t)b * KP;
+    // (elected thread) X[r & 1] = E[r] (h2 Delta)^T, 3xTF32
+    auto issue_gemm1 = [&](int r) {
+        const uint32_t aH = smem_u32(sA) + (uint32_t)(r % kRing) * TB, aL = aH + ABYTES;
+        const uint32_t bH = smem_u32(sTab + T.B1h), bL = smem_u32(sTab + T.B1l);
+        const uint32_t dcol = tmem + (uint32_t)(r & 1) * KP;
 #pragma unroll
         for (int s = 0; s < D8 / 8; ++s) {
             const uint64_t dAh = umma_desc(aH + s * 2 * lboA, lboA, sbo), dAl = umma_desc(aL + s * 2 * lboA, lboA, sbo);
@@ -446,25 +567,36 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
         tc_commit(bar0);
     };
 
+    int r0 = 0;  // tiles of this CTA processed so far (ring slots and barrier parities run on across segments)
     const int j_first = (int)(g0 / half);
     for (int seg = 0;; ++seg) {
         const int j = j_first + seg;
         const int64_t lo = max(g0, (int64_t)j * half), hi = min(g1, (int64_t)(j + 1) * half);
         if (j >= K || lo >= hi) break;
-        const int64_t p_lo = lo - (int64_t)j * half;
         const int n = (int)(hi - lo);
+        const int ntile = (n + kTile - 1) / kTile;
 
-        // ---- component tables: verbatim copy of the prepared image ------------------------------------------------
+        // ---- component tables: verbatim copy of the prepared image; first two noise tiles in flight ----------------
         __syncthreads();
+        if (tid == 0) {
+            issue_load(r0);
+            if (ntile > 1) issue_load(r0 + 1);
+        }
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(tab + (size_t)j * T.total);
             uint4 *dst = reinterpret_cast<uint4 *>(sTab);
             for (int i = tid; i < (int)(T.smem_bytes / 16); i += kThreads) dst[i] = __ldg(src + i);
         }
+        fence_async_smem();  // generic-proxy writes (tables) -> async proxy (MMA operand reads)
         __syncthreads();
-        const float sj = sScal[0], hj = sScal[1];
+        const float hj = sScal[1];
         const double is2j = *reinterpret_cast<const double *>(sScal + 2);
         const float *gDl = reinterpret_cast<const float *>(tab + (size_t)j * T.total + T.Dl);
+        if (tid == 0) {
+            mbar_wait(barF + 8 * (r0 % kRing), (uint32_t)(r0 / kRing) & 1u);
+            tc_fence_after();
+            issue_gemm1(r0);
+        }
 
         double hacc = 0.0;
         float racc[ANYGRAD ? kMaxChunks * 16 : 1];
@@ -476,21 +608,14 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
             for (int i = 0; i < DH; ++i) ae[i] = be[i] = 0.f;
         }
 
-        // ---- prologue: noise and GEMM1 of the first tile --------------------------------------------------------
-        rng_tile(0, j, p_lo, n, 0, sj);
-        fence_async_smem();  // generic-proxy writes (noise tile, tables) -> async proxy
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue_gemm1(0);
-        }
-
-        int b = 0;
-        for (int t0 = 0; t0 < n; t0 += kTile, b ^= 1) {
-            const bool live = t0 + row < n;
-            const uint32_t cX = cX0 + (uint32_t)b * KP;
-            const float E = sE[(b * 2) * kTile + row] + sE[(b * 2 + 1) * kTile + row];
+        for (int t = 0; t < ntile; ++t) {
+            const int r = r0 + t;
+            const bool live = t * kTile + row < n;
+            const uint32_t cX = (uint32_t)(r & 1) * KP;
+            const unsigned char *img = sA + (size_t)(r % kRing) * TB;
+            const float *aH = reinterpret_cast<const float *>(img), *aL = reinterpret_cast<const float *>(img + ABYTES);
+            mbar_wait(barF + 8 * (r % kRing), (uint32_t)(r / kRing) & 1u);  // (long since complete: makes the image visible)
+            const float E = reinterpret_cast<const float *>(img + 2 * ABYTES)[row] + reinterpret_cast<const float *>(img + 2 * ABYTES)[kTile + row];
             mbar_wait(bar0, ph0);
             ph0 ^= 1u;
             tc_fence_after();
@@ -516,7 +641,6 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                     const uint32_t fm = sMask[ci];
                     if (fm != 0u) {  // CTA-uniform, rare: badly conditioned components, direct differences
                         const float base = hj * E;
-                        const float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             if ((fm >> i) & 1u) {
@@ -534,8 +658,8 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                                 const float vp = ex2f(fmaf(-dr.h, a0, dr.ck + base));
                                 const float vm = ex2f(fmaf(-dr.h, a1, dr.ck + base));
                                 // (the expanded-form value of a guarded component above is exactly 0: ck2 = -200)
-                                const float wk = sKc[k].w, wis = sKc[k].wis;
-                                qp = fmaf(wk, vp, qp), qm = fmaf(wk, vm, qm);
+                                const float wk_ = sKc[k].w, wis = sKc[k].wis;
+                                qp = fmaf(wk_, vp, qp), qm = fmaf(wk_, vm, qm);
                                 if constexpr (ANYGRAD) Gp = fmaf(wis, vp, Gp), Gm = fmaf(wis, vm, Gm);
                                 x[i] = __float_as_uint(vp), um[i] = __float_as_uint(vm);
                             }
@@ -547,13 +671,10 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                     }
                 }
             }
-            // exchange the partial sums of the two threads of a pair
+            // exchange the partial sums of the two threads of a pair (they sit in the two warps of one quadrant)
             sQ[(hsel * 4 + 0) * kTile + row] = qp, sQ[(hsel * 4 + 1) * kTile + row] = qm;
-            if constexpr (ANYGRAD) {
-                sQ[(hsel * 4 + 2) * kTile + row] = Gp, sQ[(hsel * 4 + 3) * kTile + row] = Gm;
-                tm_wait_st();
-            }
-            __syncthreads();
+            if constexpr (ANYGRAD) sQ[(hsel * 4 + 2) * kTile + row] = Gp, sQ[(hsel * 4 + 3) * kTile + row] = Gm;
+            pair_barrier(quad);
             qp = sQ[0 * kTile + row] + sQ[4 * kTile + row];
             qm = sQ[1 * kTile + row] + sQ[5 * kTile + row];
             if (live && hsel == 0)
@@ -565,6 +686,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                 Gm = sQ[3 * kTile + row] + sQ[7 * kTile + row];
                 const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
                 gs = fmaf(Gp, iqp, Gm * iqm), gd = fmaf(Gp, iqp, -(Gm * iqm));
+                tm_wait_st();  // own u(+-) stores of pass 1
                 // ---- pass 2: racc_k += u+/q+ + u-/q- ;  c'_k = u+/q+ - u-/q- split hi/lo -------------------------
 #pragma unroll
                 for (int cc = 0; cc < kMaxChunks; ++cc) {
@@ -586,12 +708,17 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                     }
                 }
                 tm_wait_st();
-                tc_fence_before();
-                __syncthreads();
-
-                // ---- GEMM2: V = C' (wis Delta) (A from TMEM, 3xTF32) ---------------------------------------------
-                if (tid == 0) {
-                    tc_fence_after();
+            }
+            // ---- this warp is done with X[r & 1] / U (and with the ring slot of tile r - 1) ------------------------
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barC);
+            if (tid == 0) {
+                // elected thread: once ALL warps are there, GEMM2 of this tile, the load of tile r + 2 (its ring slot
+                // was tile r - 1's, whose epilogue every warp finished before arriving) and GEMM1 of tile r + 1
+                mbar_wait(barC, phC);
+                tc_fence_after();
+                if constexpr (ANYGRAD) {
                     const uint32_t bH = smem_u32(sB2h), bL = smem_u32(sB2l);
                     for (int s = 0; s < KP / 8; ++s) {
                         const uint64_t dBh = umma_desc(bH + s * 2 * lboB2, lboB2, sbo), dBl = umma_desc(bL + s * 2 * lboB2, lboB2, sbo);
@@ -601,19 +728,14 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                     }
                     tc_commit(bar1);
                 }
-            }
-
-            // ---- noise + GEMM1 of the NEXT tile run under GEMM2 of this one ---------------------------------------
-            if (t0 + kTile < n) {
-                rng_tile(b ^ 1, j, p_lo, n, t0 + kTile, sj);
-                fence_async_smem();
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_gemm1(b ^ 1);
+                if (t + 2 < ntile) issue_load(r + 2);
+                if (t + 1 < ntile) {
+                    mbar_wait(barF + 8 * ((r + 1) % kRing), (uint32_t)((r + 1) / kRing) & 1u);
+                    issue_gemm1(r + 1);
                 }
             }
+            phC ^= 1u;
+            __syncwarp();
 
             if constexpr (ANYGRAD) {
                 mbar_wait(bar1, ph1);
@@ -622,7 +744,6 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                 // ---- epilogue: per-thread gradient sums over this thread's dimensions -------------------------------
                 uint32_t v[LW];
                 TmLd<LW>::go(trow + cV + hsel * DH, v);
-                const float *aH = sA + (size_t)b * (2 * ABYTES / 4), *aL = aH + ABYTES / 4;
 #pragma unroll
                 for (int i = 0; i < DH; ++i) {
                     const int d = hsel * DH + i;
@@ -631,9 +752,9 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
                     be[i] = fmaf(e, fmaf(e, gs, __uint_as_float(v[i])), be[i]);
                     ae[i] = fmaf(e, gd, ae[i]);
                 }
-                tc_fence_before();  // the next tile's MMAs overwrite V / X after the next barrier
             }
         }
+        r0 += ntile;
 
         // ---- segment record -----------------------------------------------------------------------------------
         // warp (quad, hsel) contributes: hacc (hsel = 0), A/Be of its dimensions, racc of its components
@@ -641,21 +762,19 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, int64_t half, i
         const double hs = warp_sum(hacc);
         if (lane == 0) myrec[0] = hs;
         if constexpr (ANYGRAD) {
+            {
+                float v[32];
 #pragma unroll
-            for (int i = 0; i < DH; ++i) {
-                const float a = warp_sum_f(ae[i]), bb = warp_sum_f(be[i]);
-                if (lane == 0) myrec[1 + hsel * DH + i] = (double)a, myrec[1 + DP + hsel * DH + i] = (double)bb;
+                for (int i = 0; i < 32; ++i) v[i] = i < DH ? ae[i < DH ? i : 0] : (i < 2 * DH ? be[i < 2 * DH ? i - DH : 0] : 0.f);
+                const float sres = warp_transpose_sum32(v, lane);
+                if (lane < DH) myrec[1 + hsel * DH + lane] = (double)sres;
+                else if (lane < 2 * DH) myrec[1 + DP + hsel * DH + lane - DH] = (double)sres;
             }
-#pragma unroll
-            for (int cc = 0; cc < kMaxChunks; ++cc) {
-                const int ci = c_begin + cc;
-                if (ci < c_end) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float r = warp_sum_f(racc[cc * 16 + i]);
-                        if (lane == 0 && 16 * ci + i < K) myrec[1 + 2 * DP + 16 * ci + i] = (double)r;
-                    }
-                }
+            static_assert(2 * (DP / 2) <= 32, "A/Be sums of one thread must fit one transposed warp reduction");
+            {
+                const float sres = warp_transpose_sum32(racc, lane);  // lane l: component 16 * (c_begin + l / 16) + l % 16
+                const int ci = c_begin + (lane >> 4), k = 16 * ci + (lane & 15);
+                if (ci < c_end && k < K) myrec[1 + 2 * DP + k] = (double)sres;
             }
         }
         __syncthreads();
@@ -701,30 +820,53 @@ uint32_t tc_tmem_cols(int DP, int K) {
     return c;
 }
 
-template <int DP, bool ANYGRAD, bool PHILOX>
-int tc_launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, const double *d_eps,
-                   double *d_part, const unsigned char *d_tab) {
-    auto kern = entmc_kernel_tc<DP, ANYGRAD, PHILOX>;
-    static size_t smem_set = 0;
-    if (plan.smem > smem_set) {
-        VBMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        smem_set = plan.smem;
-    }
-    kern<<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, plan.half, plan.pair0, plan.half_glob, plan.chunk,
-                                                     plan.maxseg, d_eps, d_part, entpart_stride(DP, lay.K), d_tab,
-                                                     tc_tmem_cols(DP, lay.K));
-    return VBMC_OK;
+TcWork tc_work(const EntmcPlan &plan, int K) {
+    TcWork w;
+    w.half = plan.half, w.pair0 = plan.pair0, w.half_glob = plan.half_glob, w.chunk = plan.chunk;
+    w.K = K;
+    w.tpc = (int)(plan.chunk / kTile) + plan.maxseg;  // sum_seg ceil(n_seg / 128) <= chunk / 128 + segments
+    return w;
 }
 
 template <int DP>
 int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
-                 const double *d_eps, double *d_part, const unsigned char *d_tab) {
-    if (anygrad) {
-        if (philox) return tc_launch_inst<DP, true, true>(c, d_params, lay, plan, d_eps, d_part, d_tab);
-        return tc_launch_inst<DP, true, false>(c, d_params, lay, plan, d_eps, d_part, d_tab);
+                 const double *d_eps, double *d_part) {
+    const int K = lay.K;
+    const TcTab T = tc_tab_layout(DP, K);
+    const TcWork wk = tc_work(plan, K);
+    const size_t TB = tc_tile_bytes(DP);
+    const size_t n_img = (size_t)plan.grid * wk.tpc;
+    VBMC_TRY(ensure(&c->d_tctab, &c->tctab_cap, ((size_t)K * T.total + 7) / 8));
+    VBMC_TRY(ensure(&c->d_tctiles, &c->tctiles_cap, (n_img * TB + 7) / 8));
+    unsigned char *d_tab = reinterpret_cast<unsigned char *>(c->d_tctab);
+    unsigned char *d_tiles = reinterpret_cast<unsigned char *>(c->d_tctiles);
+    // generator: tables (K CTAs) + noise tiles (one CTA each); its output stays in L2 for the main kernel
+    {
+        const int KP = tc_kp(K);
+        const size_t psm = (size_t)KP * DP * 4 + (size_t)KP * 16;
+        const unsigned grid = (unsigned)(K + n_img);
+        if (philox)
+            entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, d_tiles);
+        else
+            entmc_tc_gen_kernel<DP, false><<<grid, kThreads, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, d_tiles);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
     }
-    if (philox) return tc_launch_inst<DP, false, true>(c, d_params, lay, plan, d_eps, d_part, d_tab);
-    return tc_launch_inst<DP, false, false>(c, d_params, lay, plan, d_eps, d_part, d_tab);
+    static size_t smem_set[2] = {0, 0};
+    if (plan.smem > smem_set[anygrad ? 1 : 0]) {
+        if (anygrad)
+            VBMC_CUDA_CHECK(cudaFuncSetAttribute(entmc_kernel_tc<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        else
+            VBMC_CUDA_CHECK(cudaFuncSetAttribute(entmc_kernel_tc<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        smem_set[anygrad ? 1 : 0] = plan.smem;
+    }
+    const int ps = entpart_stride(DP, K);
+    const uint32_t cols = tc_tmem_cols(DP, K);
+    if (anygrad)
+        entmc_kernel_tc<DP, true><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
+    else
+        entmc_kernel_tc<DP, false><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
+    return VBMC_OK;
 }
 
 }  // namespace
@@ -739,6 +881,12 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
     const uint32_t cols = tc_tmem_cols(DP, K);
     int per_sm = (int)(512 / cols);  // tensor memory: 512 columns per SM
     if (per_sm > 2) per_sm = 2;      // __launch_bounds__(256, 2)
+    static int env_per_sm = -1;
+    if (env_per_sm < 0) {
+        const char *e = getenv("VBMC_TC_PER_SM");
+        env_per_sm = e ? atoi(e) : 0;
+    }
+    if (env_per_sm >= 1 && env_per_sm < per_sm) per_sm = env_per_sm;
     size_t smem = tc_smem_layout(DP, K, entpart_stride(DP, K)).total;
     VBMC_REQUIRE(smem <= 227 * 1024, VBMC_ERR_UNSUPPORTED, "entmc (tensor-core): tables do not fit in shared memory");
     // never let more CTAs become resident than tensor memory can serve (tcgen05.alloc would spin): pad the
@@ -766,21 +914,10 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
 
 int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
                     const double *d_eps, double *d_part) {
-    // per-component tables (one small launch; its result stays in L2 for the main kernel)
-    const TcTab T = tc_tab_layout(lay.DP, lay.K);
-    VBMC_TRY(ensure(&c->d_tctab, &c->tctab_cap, ((size_t)lay.K * T.total + 7) / 8));
-    unsigned char *d_tab = reinterpret_cast<unsigned char *>(c->d_tctab);
-    {
-        const int KP = tc_kp(lay.K);
-        const size_t psm = (size_t)KP * lay.DP * 4 + (size_t)KP * 16;
-        entmc_tc_prep_kernel<<<lay.K, 256, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab);
-        VBMC_CUDA_CHECK(cudaGetLastError());
-        c->launches++;
-    }
     switch (lay.DP) {
 #define VBMC_CASE(N) \
     case N:          \
-        return tc_launch_dp<N>(c, d_params, lay, plan, anygrad, philox, d_eps, d_part, d_tab)
+        return tc_launch_dp<N>(c, d_params, lay, plan, anygrad, philox, d_eps, d_part)
         VBMC_CASE(4);
         VBMC_CASE(8);
         VBMC_CASE(12);
