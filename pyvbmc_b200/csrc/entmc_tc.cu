@@ -23,7 +23,8 @@
 //                                                       (K-major, no swizzle), 3xTF32 (hi*hi + hi*lo + lo*hi)
 //     pass 1  tcgen05.ld X rows -> u(+-) (2 MUFU.EX2 per (pair, k)), q(+-), G(+-); u(+-) parked in TMEM
 //     pass 2  u(+-) -> racc_k (registers), c'_k = u+/q+ - u-/q- split hi/lo -> TMEM
-//     GEMM2   V[128 x N2]  = C'[128 x KP] (wis Delta)   A operand straight from TMEM, 3xTF32
+//     GEMM2   V[128 x N2]  = C'[128 x KP] (wis Delta)   A operand straight from TMEM, 3xTF32 (2xTF32 was tried: its
+//                                                       2^-12 per-term error breaks the 1e-4 gradient bound at tiny N_s)
 //     epilogue per-thread sums of e_d (v_d + e_d (G+/q+ + G-/q-)) and e_d (G+/q+ - G-/q-)
 //   X is double-buffered in TMEM; there is NO CTA-wide barrier in the tile loop: the two threads of a pair meet on
 //   a 64-thread named barrier, everything else is mbarriers (tile landed / X ready / V ready / warps done), so
@@ -53,6 +54,12 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// round-to-nearest tf32 (unbiased, unlike masking the low mantissa bits)
+__device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
+    uint32_t y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+    return y;
+}
 
 // ---- mbarrier ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -243,7 +250,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride)
     };
     s.Tab = take(tc_tab_layout(DP, K).smem_bytes);
     s.A = take(kRing * tc_tile_bytes(DP));
-    s.Q = take(2 * 4 * kTile * 4);  // [half][q+, q-, G+, G-][row]
+    s.Q = take(2 * 2 * 4 * kTile * 4);  // [tile parity][half][q+, q-, G+, G-][row]
     s.Bar = take(128);
     s.total = o;
     // the record scratch is only used between segments, when the ring is idle: it aliases the first slots
@@ -291,24 +298,37 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
     if ((int)blockIdx.x >= K) {
         // ---- (b) noise tile -------------------------------------------------------------------------------
         const int g = (int)blockIdx.x - K;
-        const int cta = g / wk.tpc, l = g - cta * wk.tpc;
-        const int64_t Tn = (int64_t)K * wk.half;
-        const int64_t g0 = (int64_t)cta * wk.chunk, g1 = min(g0 + wk.chunk, Tn);
-        if (g0 >= Tn) return;
-        int j = (int)(g0 / wk.half), cnt = 0, n = 0, t0 = 0;
-        int64_t p_lo = 0;
-        for (;; ++j) {
-            const int64_t lo = max(g0, (int64_t)j * wk.half), hi = min(g1, (int64_t)(j + 1) * wk.half);
-            if (j >= K || lo >= hi) return;  // image not used by this chunk
-            n = (int)(hi - lo);
-            const int ntile = (n + kTile - 1) / kTile;
-            if (l < cnt + ntile) {
-                t0 = (l - cnt) * kTile;
-                p_lo = lo - (int64_t)j * wk.half;
-                break;
+        __shared__ int s_info[4];  // j, n, t0, valid
+        __shared__ int64_t s_plo;
+        if (tid == 0) {  // which (component, pair range) is image g?  (64-bit divisions: once per CTA)
+            const int cta = g / wk.tpc, l = g - cta * wk.tpc;
+            const int64_t Tn = (int64_t)K * wk.half;
+            const int64_t g0 = (int64_t)cta * wk.chunk, g1 = min(g0 + wk.chunk, Tn);
+            int valid = 0, j = 0, n = 0, t0 = 0;
+            int64_t p_lo = 0;
+            if (g0 < Tn) {
+                int cnt = 0;
+                for (j = (int)(g0 / wk.half);; ++j) {
+                    const int64_t lo = max(g0, (int64_t)j * wk.half), hi = min(g1, (int64_t)(j + 1) * wk.half);
+                    if (j >= K || lo >= hi) break;  // image not used by this chunk
+                    n = (int)(hi - lo);
+                    const int ntile = (n + kTile - 1) / kTile;
+                    if (l < cnt + ntile) {
+                        t0 = (l - cnt) * kTile;
+                        p_lo = lo - (int64_t)j * wk.half;
+                        valid = 1;
+                        break;
+                    }
+                    cnt += ntile;
+                }
             }
-            cnt += ntile;
+            s_info[0] = j, s_info[1] = n, s_info[2] = t0, s_info[3] = valid;
+            s_plo = p_lo;
         }
+        __syncthreads();
+        if (!s_info[3]) return;
+        const int j = s_info[0], n = s_info[1], t0 = s_info[2];
+        const int64_t p_lo = s_plo;
         constexpr uint32_t ABYTES = (uint32_t)(D8 / 4) * kTile * 16, TB = 2 * ABYTES + 2 * kTile * 4;
         unsigned char *img = tiles + (size_t)g * TB;
         float *aH = reinterpret_cast<float *>(img), *aL = reinterpret_cast<float *>(img + ABYTES);
@@ -504,22 +524,23 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
     const uint32_t *sMask = reinterpret_cast<const uint32_t *>(sTab + T.Mask);
     const float *sScal = reinterpret_cast<const float *>(sTab + T.Scal);
     unsigned char *sA = smem + L.A;                     // ring of tile images [hi | lo | E]
-    float *sQ = reinterpret_cast<float *>(smem + L.Q);  // [half][4][128] partial q+, q-, G+, G-
+    float *sQ0 = reinterpret_cast<float *>(smem + L.Q);  // [tile parity][half][4][128] partial q+, q-, G+, G-
     double *sRec = reinterpret_cast<double *>(smem + L.Rec);
     double *sTot = reinterpret_cast<double *>(smem + L.Tot);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.Bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 8);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 8);  // (7 barriers above)
 
     const int64_t Tn = (int64_t)K * half;
     const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, Tn);
     if (g0 >= Tn) return;
 
     // ---- one-time set-up: barriers, tensor memory ---------------------------------------------------------------
-    // sBar: [0..2] tile landed (tx) | [3] X ready (GEMM1 commit) | [4] V ready (GEMM2 commit) | [5] warps done (8)
-    const uint32_t barF = smem_u32(sBar), bar0 = smem_u32(sBar + 3), bar1 = smem_u32(sBar + 4), barC = smem_u32(sBar + 5);
+    // sBar: [0..2] tile landed (tx) | [3] V ready (GEMM2 commit) | [4] warps done (8) | [5, 6] X0 / X1 ready (GEMM1 commit)
+    const uint32_t barF = smem_u32(sBar), bar1 = smem_u32(sBar + 3), barC = smem_u32(sBar + 4), barX = smem_u32(sBar + 5);
     if (tid == 0) {
         for (int i = 0; i < kRing; ++i) mbar_init(barF + 8 * i, 1);
-        mbar_init(bar0, 1);
+        mbar_init(barX, 1);
+        mbar_init(barX + 8, 1);
         mbar_init(bar1, 1);
         mbar_init(barC, kThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -538,7 +559,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
     // TMEM columns: X0 / X1 = GEMM1 output of even / odd tiles -> u+ -> c_hi (in place), U = u- -> c_lo, V = GEMM2 output
     const uint32_t cU = 2 * KP, cV = 3 * KP;
-    uint32_t ph0 = 0, ph1 = 0, phC = 0;
+    uint32_t ph1 = 0, phC = 0;
 
     const uint32_t idesc1 = umma_idesc_tf32(KP), idesc2 = umma_idesc_tf32(N2);
     // operand strides: rows 16 B apart, 8-row groups 128 B apart, K chunks one whole row-block apart
@@ -564,7 +585,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
             mma_ss(dcol, dAh, dBl, idesc1, 1u);
             mma_ss(dcol, dAl, dBh, idesc1, 1u);
         }
-        tc_commit(bar0);
+        tc_commit(barX + 8 * (uint32_t)(r & 1));
     };
 
     int r0 = 0;  // tiles of this CTA processed so far (ring slots and barrier parities run on across segments)
@@ -592,7 +613,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
         const float hj = sScal[1];
         const double is2j = *reinterpret_cast<const double *>(sScal + 2);
         const float *gDl = reinterpret_cast<const float *>(tab + (size_t)j * T.total + T.Dl);
-        if (tid == 0) {
+        if (tid == kTile) {
             mbar_wait(barF + 8 * (r0 % kRing), (uint32_t)(r0 / kRing) & 1u);
             tc_fence_after();
             issue_gemm1(r0);
@@ -607,7 +628,27 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
 #pragma unroll
             for (int i = 0; i < DH; ++i) ae[i] = be[i] = 0.f;
         }
+        float gs = 0.f, gd = 0.f;  // G+/q+ +- G-/q- of the tile whose epilogue is pending
 
+        // epilogue of tile r (its GEMM2 has completed): per-thread gradient sums over this thread's dimensions
+        auto epilogue = [&](int r) {
+            const unsigned char *img = sA + (size_t)(r % kRing) * TB;
+            const float *aH = reinterpret_cast<const float *>(img), *aL = reinterpret_cast<const float *>(img + ABYTES);
+            uint32_t v[LW];
+            TmLd<LW>::go(trow + cV + hsel * DH, v);
+#pragma unroll
+            for (int i = 0; i < DH; ++i) {
+                const int d = hsel * DH + i;
+                const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
+                const float e = aH[o] + aL[o];  // exact: hi + lo is the fp32 noise value
+                be[i] = fmaf(e, fmaf(e, gs, __uint_as_float(v[i])), be[i]);
+                ae[i] = fmaf(e, gd, ae[i]);
+            }
+        };
+
+        // Tile loop.  MMA latencies never sit on the compute warps' critical path: GEMM1(t + 1) is issued in the
+        // middle of tile t (its X buffer and noise tile are ready then), GEMM2(t) runs under the first half of pass 1
+        // of tile t + 1, and the epilogue of tile t is deferred into tile t + 1.
         for (int t = 0; t < ntile; ++t) {
             const int r = r0 + t;
             const bool live = t * kTile + row < n;
@@ -616,17 +657,18 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
             const float *aH = reinterpret_cast<const float *>(img), *aL = reinterpret_cast<const float *>(img + ABYTES);
             mbar_wait(barF + 8 * (r % kRing), (uint32_t)(r / kRing) & 1u);  // (long since complete: makes the image visible)
             const float E = reinterpret_cast<const float *>(img + 2 * ABYTES)[row] + reinterpret_cast<const float *>(img + 2 * ABYTES)[kTile + row];
-            mbar_wait(bar0, ph0);
-            ph0 ^= 1u;
+            mbar_wait(barX + 8 * (uint32_t)(r & 1), (uint32_t)(r >> 1) & 1u);  // X(t): issued one tile ago
             tc_fence_after();
 
             // ---- pass 1: density ratios u(+-) of this thread's components, partial mixture sums ----------------
             float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
+            uint32_t um_keep[2][16];
 #pragma unroll
             for (int cc = 0; cc < kMaxChunks; ++cc) {
                 const int ci = c_begin + cc;
+                uint32_t (&um)[16] = um_keep[cc & 1];
                 if (ci < c_end) {
-                    uint32_t x[16], um[16];
+                    uint32_t x[16];
                     tm_ld16(trow + cX + 16 * ci, x);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -665,13 +707,36 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
                             }
                         }
                     }
-                    if constexpr (ANYGRAD) {
-                        tm_st16(trow + cX + 16 * ci, x);
-                        tm_st16(trow + cU + 16 * ci, um);
+                    if constexpr (ANYGRAD) tm_st16(trow + cX + 16 * ci, x);
+                }
+                if constexpr (ANYGRAD) {
+                    if (cc == 0 && t > 0) {
+                        // U still feeds GEMM2 of the previous tile (c_lo): it ran under the arithmetic above
+                        mbar_wait(bar1, ph1);
+                        ph1 ^= 1u;
+                        tc_fence_after();
                     }
+                    if (ci < c_end) tm_st16(trow + cU + 16 * ci, um_keep[cc & 1]);
                 }
             }
+            if constexpr (ANYGRAD) {
+                if (t > 0) epilogue(r - 1);  // deferred epilogue of the previous tile (V complete: bar1 above)
+            }
+            if (tid == kTile && t + 1 < ntile) {
+                // second elected thread: GEMM1 of the NEXT tile.  Its X buffer was c' of tile t - 1 (GEMM2(t - 1) done:
+                // bar1 above; all warps past their pass 2 of t - 1: barC below, waited at the end of the previous
+                // iteration), its noise tile landed long ago
+                if (t > 0) {
+                    mbar_wait(barC, phC ^ 1u);
+                    tc_fence_after();
+                }
+                mbar_wait(barF + 8 * ((r + 1) % kRing), (uint32_t)((r + 1) / kRing) & 1u);
+                tc_fence_after();
+                issue_gemm1(r + 1);
+            }
+            __syncwarp();
             // exchange the partial sums of the two threads of a pair (they sit in the two warps of one quadrant)
+            float *sQ = sQ0 + (r & 1) * (8 * kTile);  // (by tile parity: a warp without components may run a tile ahead)
             sQ[(hsel * 4 + 0) * kTile + row] = qp, sQ[(hsel * 4 + 1) * kTile + row] = qm;
             if constexpr (ANYGRAD) sQ[(hsel * 4 + 2) * kTile + row] = Gp, sQ[(hsel * 4 + 3) * kTile + row] = Gm;
             pair_barrier(quad);
@@ -680,7 +745,6 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
             if (live && hsel == 0)
                 hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
 
-            float gs = 0.f, gd = 0.f;
             if constexpr (ANYGRAD) {
                 Gp = sQ[2 * kTile + row] + sQ[6 * kTile + row];
                 Gm = sQ[3 * kTile + row] + sQ[7 * kTile + row];
@@ -709,13 +773,13 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
                 }
                 tm_wait_st();
             }
-            // ---- this warp is done with X[r & 1] / U (and with the ring slot of tile r - 1) ------------------------
+            // ---- this warp is done with X[r & 1] / U / V (and with the ring slot of tile r - 1) --------------------
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(barC);
             if (tid == 0) {
-                // elected thread: once ALL warps are there, GEMM2 of this tile, the load of tile r + 2 (its ring slot
-                // was tile r - 1's, whose epilogue every warp finished before arriving) and GEMM1 of tile r + 1
+                // elected thread: once ALL warps are there, GEMM2 of this tile and the load of tile r + 2 (its ring
+                // slot was tile r - 1's, whose deferred epilogue every warp finished before arriving)
                 mbar_wait(barC, phC);
                 tc_fence_after();
                 if constexpr (ANYGRAD) {
@@ -729,35 +793,21 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
                     tc_commit(bar1);
                 }
                 if (t + 2 < ntile) issue_load(r + 2);
-                if (t + 1 < ntile) {
-                    mbar_wait(barF + 8 * ((r + 1) % kRing), (uint32_t)((r + 1) / kRing) & 1u);
-                    issue_gemm1(r + 1);
-                }
             }
             phC ^= 1u;
             __syncwarp();
-
-            if constexpr (ANYGRAD) {
-                mbar_wait(bar1, ph1);
-                ph1 ^= 1u;
-                tc_fence_after();
-                // ---- epilogue: per-thread gradient sums over this thread's dimensions -------------------------------
-                uint32_t v[LW];
-                TmLd<LW>::go(trow + cV + hsel * DH, v);
-#pragma unroll
-                for (int i = 0; i < DH; ++i) {
-                    const int d = hsel * DH + i;
-                    const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-                    const float e = aH[o] + aL[o];  // exact: hi + lo is the fp32 noise value
-                    be[i] = fmaf(e, fmaf(e, gs, __uint_as_float(v[i])), be[i]);
-                    ae[i] = fmaf(e, gd, ae[i]);
-                }
-            }
+        }
+        if constexpr (ANYGRAD) {  // drain: epilogue of the last tile
+            mbar_wait(bar1, ph1);
+            ph1 ^= 1u;
+            tc_fence_after();
+            epilogue(r0 + ntile - 1);
         }
         r0 += ntile;
 
         // ---- segment record -----------------------------------------------------------------------------------
         // warp (quad, hsel) contributes: hacc (hsel = 0), A/Be of its dimensions, racc of its components
+        __syncthreads();  // the record scratch aliases the tile ring: every warp must be past its last epilogue
         double *myrec = sRec + wid * part_stride;
         const double hs = warp_sum(hacc);
         if (lane == 0) myrec[0] = hs;
