@@ -1348,8 +1348,14 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     VBMC_REQUIRE(DP > 0, VBMC_ERR_UNSUPPORTED, "entmc: D > 32 is not supported");
     VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
     int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
-    if (variant < 0)  // auto: the warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
-        variant = (int64_t)K * half_local >= 65536 ? ENTMC_WARP : ENTMC_FAST;
+    if (variant < 0) {
+        // auto: the tensor-core kernel wins once every SM gets several 128-pair tiles and the component chunks are
+        // mostly real (measured on B200: C3 70 us vs 76 us; C2 / C4 are faster on the CUDA-core kernels); the
+        // warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
+        const int64_t T = (int64_t)K * half_local;
+        if (T >= 150000 && K >= 33 && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
+        else variant = T >= 65536 ? ENTMC_WARP : ENTMC_FAST;
+    }
     const size_t smem_cap = 227 * 1024;
     if (variant == ENTMC_TC) {
         if (entmc_tc_supported(DP, K)) return entmc_tc_plan(c, D, K, half_local, plan);

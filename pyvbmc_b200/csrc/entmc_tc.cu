@@ -263,8 +263,9 @@ __host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride)
 // Both kernels enumerate them with this walk; `tpc` images are reserved per CTA.
 struct TcWork {
     int64_t half, pair0, half_glob, chunk;
-    int K, tpc;
+    int K, tpc, n_img;
 };
+constexpr int kGenTiles = 4;  // noise-tile images per generator CTA
 
 // ------------------------------------------------------------------------------------------------------------
 // CTAs [0, K): tables of component j = blockIdx.x.  CTAs K + g: noise-tile image g.
@@ -297,10 +298,11 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
     extern __shared__ __align__(16) unsigned char psm[];
     if ((int)blockIdx.x >= K) {
         // ---- (b) noise tile -------------------------------------------------------------------------------
-        const int g = (int)blockIdx.x - K;
-        __shared__ int s_info[4];  // j, n, t0, valid
-        __shared__ int64_t s_plo;
-        if (tid == 0) {  // which (component, pair range) is image g?  (64-bit divisions: once per CTA)
+        __shared__ int s_info[kGenTiles][4];  // j, n, t0, valid
+        __shared__ int64_t s_plo[kGenTiles];
+        const int g_first = ((int)blockIdx.x - K) * kGenTiles;
+        if (tid < kGenTiles) {  // which (component, pair range) is image g?  (64-bit divisions: once per image)
+            const int g = g_first + tid;
             const int cta = g / wk.tpc, l = g - cta * wk.tpc;
             const int64_t Tn = (int64_t)K * wk.half;
             const int64_t g0 = (int64_t)cta * wk.chunk, g1 = min(g0 + wk.chunk, Tn);
@@ -322,13 +324,15 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
                     cnt += ntile;
                 }
             }
-            s_info[0] = j, s_info[1] = n, s_info[2] = t0, s_info[3] = valid;
-            s_plo = p_lo;
+            s_info[tid][0] = j, s_info[tid][1] = n, s_info[tid][2] = t0, s_info[tid][3] = valid && g < wk.n_img;
+            s_plo[tid] = p_lo;
         }
         __syncthreads();
-        if (!s_info[3]) return;
-        const int j = s_info[0], n = s_info[1], t0 = s_info[2];
-        const int64_t p_lo = s_plo;
+        for (int gi = 0; gi < kGenTiles; ++gi) {
+        if (!s_info[gi][3]) continue;
+        const int g = g_first + gi;
+        const int j = s_info[gi][0], n = s_info[gi][1], t0 = s_info[gi][2];
+        const int64_t p_lo = s_plo[gi];
         constexpr uint32_t ABYTES = (uint32_t)(D8 / 4) * kTile * 16, TB = 2 * ABYTES + 2 * kTile * 4;
         unsigned char *img = tiles + (size_t)g * TB;
         float *aH = reinterpret_cast<float *>(img), *aL = reinterpret_cast<float *>(img + ABYTES);
@@ -372,6 +376,7 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
                 }
             }
         }
+        }  // images of this CTA
         return;
     }
     // ---- (a) tables of component j ------------------------------------------------------------------------
@@ -875,6 +880,7 @@ TcWork tc_work(const EntmcPlan &plan, int K) {
     w.half = plan.half, w.pair0 = plan.pair0, w.half_glob = plan.half_glob, w.chunk = plan.chunk;
     w.K = K;
     w.tpc = (int)(plan.chunk / kTile) + plan.maxseg;  // sum_seg ceil(n_seg / 128) <= chunk / 128 + segments
+    w.n_img = plan.grid * w.tpc;
     return w;
 }
 
@@ -894,7 +900,7 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     {
         const int KP = tc_kp(K);
         const size_t psm = (size_t)KP * DP * 4 + (size_t)KP * 16;
-        const unsigned grid = (unsigned)(K + n_img);
+        const unsigned grid = (unsigned)(K + (n_img + kGenTiles - 1) / kGenTiles);
         if (philox)
             entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, d_tiles);
         else
