@@ -298,13 +298,24 @@ def run_b200(args):
         f_alg = flops_entmc(Ns_rank, K, D)
         k_s = k_ms * 1e-3
         achieved_gbs = b_alg / k_s / 1e9
+        variant = ctx.entmc_variant_used()
+        kname = {5: "entmc_tc_gen_kernel<20,PHILOX> + entmc_kernel_tc<20,ANYGRAD> (tcgen05/TMEM; timed together)",
+                 4: "entmc_kernel_w<20,WGRAD,ANYGRAD,PHILOX>", 0: "entmc_kernel_fast<20,...>"}.get(variant, f"entmc variant {variant}")
+        # DRAM bytes per launch of the same kernel(s) from the committed `ncu --set full` capture (cold L2 under ncu)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "entmc_traffic.json")))
+            traffic = tj.get(f"variant{variant}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-            "traffic": None, "kernel": "entmc_kernel_w<20,WGRAD,ANYGRAD,PHILOX>", "kernel_ms": k_ms,
+            "traffic": traffic, "kernel": kname, "entmc_variant": variant, "kernel_ms": k_ms,
             "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": b_alg, "peak_source": hbm_src,
-            "note": ("entmc is bound by the FP32 FMA pipe, not HBM (arithmetic intensity >> ridge; with device "
-                     "Philox draws its only HBM traffic is the parameter block and one record per CTA), so the "
-                     "mandated HBM fraction is tiny by construction; the binding roofline is `compute`."),
+            "note": ("entmc is bound by instruction issue (FP32 FMA / MUFU), not HBM: arithmetic intensity >> ridge; with "
+                     "device Philox draws its only ALGORITHMIC HBM traffic is the parameter block and one record per CTA, "
+                     "so the mandated HBM fraction is tiny by construction; the binding roofline is `compute`.  The "
+                     "tensor-core variant stages its noise tiles through L2 (`traffic`: DRAM bytes ncu sees with a cold L2)."),
             "compute": {
                 "bound": "fp32_fma", "achieved": f_alg / k_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": f_alg / k_s / 1e12 / fp32_peak if fp32_peak else None,

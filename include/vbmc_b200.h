@@ -190,6 +190,9 @@ int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst
  * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */
 int vbmc_set_kernel_timing(vbmc_ctx *ctx, int on);
 int vbmc_entmc_kernel_ms(vbmc_ctx *ctx, double *avg_ms, int64_t *launches);
+/* which fp32 entmc kernel the last staged evaluation used: 0 expanded ("fast"), 1 dimension-split, 2 packed,
+ * 3 scalar (also the all-fp64 kernel), 4 warp-autonomous, 5 tensor-core (tcgen05 / TMEM); -1 nothing planned yet */
+int vbmc_entmc_variant_used(vbmc_ctx *ctx);
 /* measurement only (VBMC_STAGE_TIMING=1 in the environment when the context is created): device time in
  * microseconds between the stage marks of the last synchronous evaluation --
  * us[0] H2D, [1] entmc (+ launch of gplj), [2] wait for the side stream, [3] reduce, [4] finalize,

@@ -164,6 +164,10 @@ class Context:
     def set_kernel_timing(self, on: bool):
         _capi.check(self._lib.vbmc_set_kernel_timing(self._h, int(bool(on))))
 
+    def entmc_variant_used(self):
+        """fp32 entmc kernel of the last staged evaluation (5 = tensor-core, 4 = warp-autonomous, 0 = expanded ...)."""
+        return int(self._lib.vbmc_entmc_variant_used(self._h))
+
     def entmc_kernel_ms(self):
         ms = C.c_double()
         n = C.c_int64()

@@ -805,6 +805,12 @@ int vbmc_entmc_kernel_ms(vbmc_ctx *p, double *avg_ms, int64_t *launches) {
     return VBMC_OK;
 }
 
+int vbmc_entmc_variant_used(vbmc_ctx *p) {
+    if (!p) return -1;
+    const Staged &st = ex(p)->st;
+    return st.plan.threads > 0 ? st.plan.variant : -1;
+}
+
 int vbmc_set_kernel_timing(vbmc_ctx *p, int on) {
     VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
     Ctx *c = &ex(p)->c;

@@ -479,3 +479,34 @@ def test_finite_difference_gradients(pv):
         assert np.abs(err).max() <= 8.0 / np.sqrt(Ns * K) * max(1.0, np.abs(dF).max()), err
     finally:
         pv.config.precision = "f32"
+
+
+# ---------------------------------------------------------------------------------------------------
+# every fp32 entmc kernel variant (the automatic choice only exercises one per problem size)
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
+@pytest.mark.parametrize("stem", ["c2", "c4", "c1", "c2_ill"])
+def test_entmc_every_variant_against_oracle_and_f64(pv, variant, stem, monkeypatch):
+    """Forced kernel variant (VBMC_ENTMC_VARIANT is read when a context is created): eps-input parity with
+    the reference's golden values, and Philox-mode agreement with the all-fp64 kernel on identical draws.
+    Variant 5 is the tcgen05 / TMEM kernel (it falls back to 4 for K > 64)."""
+    c = load_case(stem)
+    g = c.g
+    vp = case_vp(pv, c, "sa")
+    monkeypatch.setenv("VBMC_ENTMC_VARIANT", str(variant))
+    ctx = pv.Context(0)
+    try:
+        eps = eps_for(g["ent_seed"], c.K, c.Ns_K, c.D)
+        H, dH = ctx.entmc(vp, c.Ns_K, c.opt, True, eps=eps)
+        assert relerr(H, g["ent_H"]) < TOL_F32_VAL and relmax(dH, g["ent_dH"]) < TOL_F32_GRAD
+        assert ctx.entmc_variant_used() in ((variant, 4) if variant == 5 and c.K > 64 else (variant,))
+        # production RNG: same Philox key -> same draws in every kernel
+        for Ns in (2, 258, 4000):
+            Hd, dHd = ctx.entmc(vp, Ns, (True,) * 4, True, seed=11, offset=3, precision="f64")
+            Hs, dHs = ctx.entmc(vp, Ns, (True,) * 4, True, seed=11, offset=3)
+            assert abs(Hs - Hd) <= TOL_F32_VAL * max(abs(Hd), 1.0), (variant, stem, Ns)
+            assert relmax(dHs, dHd) < TOL_F32_GRAD, (variant, stem, Ns)
+            # value-only instantiation (no gradient groups)
+            H0, d0 = ctx.entmc(vp, Ns, (False,) * 4, True, seed=11, offset=3)
+            assert d0.shape == (0,) and abs(H0 - Hd) <= TOL_F32_VAL * max(abs(Hd), 1.0)
+    finally:
+        ctx.close()
