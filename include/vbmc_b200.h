@@ -179,6 +179,9 @@ int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const 
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
+/* world == 1: the raw phases are deferred and run fused with the following vbmc_negelcbo_finalize_async on the same
+ * raw_dev (one cluster kernel for the whole tail), i.e. raw_dev is complete only after that call is enqueued.
+ * world > 1: raw_dev holds this rank's partial raw vector when the call's work completes (all-reduce it, then finalize). */
 int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
 int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
 int vbmc_stream_synchronize(vbmc_ctx *ctx);

@@ -16,6 +16,8 @@ cat $O/${TAG}_variants.log
 timeout 200 python scripts/stage_times.py C3 > $O/${TAG}_stages.log 2>&1; cat $O/${TAG}_stages.log
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > $O/${TAG}_ncu_bench.log 2>&1
 VBMC_ENTMC_VARIANT=4 timeout 400 ncu --set full --clock-control none --import-source on -k regex:entmc -s 2 -c 1 -f -o $O/${TAG}_entmc_w python scripts/run_entmc.py C3 4 > $O/${TAG}_ncu_w.log 2>&1
-VBMC_ENTMC_VARIANT=5 timeout 400 ncu --set full --clock-control none --import-source on -k regex:entmc -s 2 -c 1 -f -o $O/${TAG}_entmc_tc python scripts/run_entmc.py C3 4 > $O/${TAG}_ncu_tc.log 2>&1
+VBMC_ENTMC_VARIANT=5 timeout 400 ncu --set full --clock-control none --import-source on -k regex:entmc -s 4 -c 2 -f -o $O/${TAG}_entmc_tc python scripts/run_entmc.py C3 4 > $O/${TAG}_ncu_tc.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:tail -s 2 -c 1 -f -o $O/${TAG}_tail python scripts/run_negelcbo.py C3 4 > $O/${TAG}_ncu_tail.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gplj -s 2 -c 1 -f -o $O/${TAG}_gplj python scripts/run_negelcbo.py C3 4 > $O/${TAG}_ncu_gplj.log 2>&1
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; cat $O/${TAG}_bench_ref.json
 ls -la $O
