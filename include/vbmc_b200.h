@@ -176,6 +176,19 @@ int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const 
  * -> [all-reduce SUM of raw_dev over ranks, e.g. NCCL] -> finalize (identical on every
  * rank).  raw_dev holds vbmc_raw_len(D, K) doubles.  Results stay on the device in
  * out_dev: [F, G, H, varF, varG_ss, 0, 0, 0, dF (P)...].  Nothing is synchronised.       */
+/* ---- batched sieve evaluation -------------------------------------------------------------
+ * Replaces the loop of variational_optimization.py:775-787 (`_sieve`): for b < B
+ *     F_b, _, G_b, H_b, _ = _neg_elcbo(theta_b, gp, vp_b, 0, Ns = 0, compute_grad = 0, compute_var = 0, theta_bnd)
+ * (deterministic entropy bound entlb_vbmc, expected log joint, soft bounds, weight penalty; values only) in ONE
+ * launch.  params: B parameter blocks of vbmc_param_len(D, K) doubles each, laid out
+ *     [mu (K*D, component-major = theta order) | sigma (K) | lambda (D) | w (K) | eta (K) |
+ *      ln sigma as in theta (K) | ln lambda as in theta (D) | eta as in theta (K)]      (the last three feed the bounds)
+ * after VariationalPosterior.set_parameters' normalisation; bounds as set by vbmc_set_bounds.
+ * out: [B][4] = F, G, H, L_bound + L_penalty.  Synchronous.                                                  */
+size_t vbmc_param_len(int D, int K);
+int vbmc_negelcbo_batch(vbmc_ctx *ctx, int B, int D, int K, const double *params, const int optimize[4],
+                        int use_bounds, double *out);
+
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);

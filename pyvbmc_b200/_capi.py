@@ -110,6 +110,8 @@ PROTOTYPES = {
     "vbmc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "vbmc_entmc_kernel_ms": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]),
     "vbmc_entmc_variant_used": (C.c_int, [C.c_void_p]),
+    "vbmc_param_len": (C.c_size_t, [C.c_int, C.c_int]),
+    "vbmc_negelcbo_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "vbmc_fma_peak": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vbmc_stage_times": (C.c_int, [C.c_void_p, c_double_p]),
 }

@@ -411,6 +411,21 @@ class Context:
         if rc:
             _capi.check(rc)
 
+    def param_len(self, D, K):
+        return int(self._lib.vbmc_param_len(int(D), int(K)))
+
+    def negelcbo_batch(self, D, K, params, optimize, use_bounds):
+        """``vbmc_negelcbo_batch``: ``params`` is ``(B, param_len)`` C-contiguous; returns ``(B, 4)`` = F, G, H, L."""
+        params = np.ascontiguousarray(params, dtype=_F64)
+        B = params.shape[0]
+        if params.shape[1] != self.param_len(D, K):
+            raise ValueError("negelcbo_batch: parameter blocks have the wrong length")
+        out = np.empty((B, 4), dtype=_F64)
+        og = (C.c_int * 4)(*[int(bool(o)) for o in optimize])
+        _capi.check(self._lib.vbmc_negelcbo_batch(self._h, B, int(D), int(K), params.ctypes.data, og, int(bool(use_bounds)),
+                                                  out.ctypes.data))
+        return out
+
     # split-phase API (multi-GPU / kernel-only timing); device pointers are plain ints
     def upload(self, vp, optimize, Ns, compute_grad=True, use_bounds=False, ln_sigma_b=None, ln_lambd_b=None,
                eta_b=None, eps=None, seed=0, offset=0, precision=None):

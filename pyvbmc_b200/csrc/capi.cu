@@ -391,7 +391,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     cudaStreamSynchronize(c->stream);
     drop_graph(x);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
-                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -732,6 +732,26 @@ int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const in
     }
     memcpy(out, o, sizeof(double) * (kOutHead + (compute_grad ? P : 0)));
     if (compute_grad && want_dH) memcpy(out + kOutHead + P, o + kOutHead + Pfull, sizeof(double) * P);
+    return VBMC_OK;
+}
+
+size_t vbmc_param_len(int D, int K) { return (size_t)ParamLayout{D, pad_dim(D), K}.total(); }
+
+int vbmc_negelcbo_batch(vbmc_ctx *p, int B, int D, int K, const double *params, const int optimize[4], int use_bounds,
+                        double *out) {
+    VBMC_REQUIRE(p && params && optimize && out, VBMC_ERR_ARG, "negelcbo_batch: null argument");
+    VBMC_REQUIRE(B >= 0 && D >= 1 && K >= 1, VBMC_ERR_ARG, "negelcbo_batch: bad sizes");
+    VBMC_REQUIRE(D <= kMaxD, VBMC_ERR_UNSUPPORTED, "D > 32 is not supported by the CUDA path");
+    if (B == 0) return VBMC_OK;
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    const size_t n_in = (size_t)B * vbmc_param_len(D, K), n_out = (size_t)B * 4;
+    VBMC_TRY(ensure(&c->d_bprm, &c->bprm_cap, n_in));
+    VBMC_TRY(ensure(&c->d_bout, &c->bout_cap, n_out));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_bprm, params, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VBMC_TRY(sieve_launch(c, B, D, K, optimize, use_bounds != 0, c->d_bprm, c->d_bout));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(out, c->d_bout, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return VBMC_OK;
 }
 

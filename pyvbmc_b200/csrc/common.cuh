@@ -164,6 +164,8 @@ struct Ctx {
     size_t var_cap = 0;
     double *d_outs = nullptr; // per-sample finalize outputs (avg_flag == 0)
     size_t outs_cap = 0;
+    double *d_bprm = nullptr, *d_bout = nullptr;  // batched sieve evaluation: parameter blocks in, [B][4] out
+    size_t bprm_cap = 0, bout_cap = 0;
 
     // state of the evaluation uploaded by vbmc_negelcbo_upload
     bool staged = false;
@@ -230,6 +232,9 @@ int gpvar_launch(Ctx *c, const double *d_params, int K, int avg);
 // entlb.cu
 int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4], double *d_raw_ent /*H at [0], block*/,
                  double *d_H);
+
+// sieve.cu: batched value-only negative ELCBO (entlb + log joint + bounds) of B candidates
+int sieve_launch(Ctx *c, int B, int D, int K, const int optimize[4], bool use_bounds, const double *d_prm, double *d_out);
 
 // finalize.cu
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,

@@ -122,6 +122,64 @@ def _vp_bound_loss(vp, theta, theta_bnd, tol_con=1e-3, compute_grad=True):
     return L, np.concatenate(parts)
 
 
+def _pack_params(prm, vp, theta, optimize, use_bounds):
+    """One parameter block of the C ABI (``ParamLayout`` in csrc/common.cuh) from a ``vp`` whose
+    ``set_parameters(theta)`` has just run: ``[mu | sigma | lambda | w | eta | bound inputs]``."""
+    D, K = vp.D, vp.K
+    DK = D * K
+    prm[:DK] = theta[:DK] if optimize[0] else np.ravel(vp.mu, order="F")
+    prm[DK : DK + K] = np.ravel(vp.sigma)
+    prm[DK + K : DK + K + D] = np.ravel(vp.lambd)
+    prm[DK + K + D : DK + 2 * K + D] = np.ravel(vp.w)
+    prm[DK + 2 * K + D : DK + 3 * K + D] = np.ravel(vp.eta)
+    if use_bounds:
+        ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
+        prm[DK + 3 * K + D : DK + 4 * K + D] = ln_sigma_b
+        prm[DK + 4 * K + D : DK + 4 * K + 2 * D] = ln_lambd_b
+        if eta_b is not None:
+            prm[DK + 4 * K + 2 * D :] = eta_b
+
+
+def neg_elcbo_batch(vp_vec, gp, theta_bnd=None, thetas=None):
+    """Value-only negative ELCBO of MANY candidate variational posteriors in one launch.
+
+    Replaces the loop of the reference's ``_sieve`` (variational_optimization.py:775-787)::
+
+        for i, vp0 in enumerate(vp0_vec):
+            theta = vp0.get_parameters()
+            nelbo_tmp, _, _, _, varF_tmp = _neg_elcbo(theta, gp, vp0, 0, ns_ent_K_fast, 0, compute_var, theta_bnd)
+
+    for the default ``ns_ent_K_fast == 0`` (deterministic entropy bound) and ``compute_var == 0``.
+    Every ``vp0`` is mutated exactly as that loop does (``get_parameters`` renormalises it in place,
+    ``_neg_elcbo`` calls ``set_parameters(theta)`` and shifts ``eta``, :1080-1085).  All candidates
+    must share ``D``, ``K`` and the ``optimize_*`` flags.  Returns ``(F, G, H)`` arrays of length B."""
+    vp_vec = list(vp_vec)
+    B = len(vp_vec)
+    if B == 0:
+        z = np.zeros(0)
+        return z, z.copy(), z.copy()
+    vp0 = vp_vec[0]
+    D, K = vp0.D, vp0.K
+    optimize = (bool(vp0.optimize_mu), bool(vp0.optimize_sigma), bool(vp0.optimize_lambd), bool(vp0.optimize_weights))
+    ctx = context_for_gp(gp, need_L=False)
+    use_bounds = ctx.set_bounds(theta_bnd)
+    n = ctx.param_len(D, K)
+    prm = np.zeros((B, n))
+    for b, vp in enumerate(vp_vec):
+        if (vp.D, vp.K) != (D, K) or (bool(vp.optimize_mu), bool(vp.optimize_sigma), bool(vp.optimize_lambd),
+                                      bool(vp.optimize_weights)) != optimize:
+            raise ValueError("neg_elcbo_batch: all candidates must share D, K and the optimize_* flags")
+        theta = np.asarray(vp.get_parameters() if thetas is None else thetas[b], dtype=float)
+        vp.set_parameters(theta)  # :1080
+        if vp.optimize_weights:
+            vp.eta = theta[-K:].copy()
+            vp.eta -= np.amax(vp.eta)
+            vp.eta = np.reshape(vp.eta, (1, -1))  # :1082-1085
+        _pack_params(prm[b], vp, theta, optimize, use_bounds)
+    out = ctx.negelcbo_batch(D, K, prm, optimize, use_bounds)
+    return out[:, 0].copy(), out[:, 1].copy(), out[:, 2].copy()
+
+
 def _neg_elcbo(
     theta,
     gp,
@@ -184,17 +242,7 @@ def _neg_elcbo(
         # hot path (minimize_adam / BFGS / sieve objective): one packed block in, one packed block out
         prm, out = ctx.flat_buffers(D, K)
         DK = D * K
-        prm[:DK] = theta[:DK] if optimize[0] else np.ravel(vp.mu, order="F")
-        prm[DK : DK + K] = np.ravel(vp.sigma)
-        prm[DK + K : DK + K + D] = np.ravel(vp.lambd)
-        prm[DK + K + D : DK + 2 * K + D] = np.ravel(vp.w)
-        prm[DK + 2 * K + D : DK + 3 * K + D] = np.ravel(vp.eta)
-        if use_bounds:
-            ln_sigma_b, ln_lambd_b, eta_b = _bound_inputs(vp, theta)
-            prm[DK + 3 * K + D : DK + 4 * K + D] = ln_sigma_b
-            prm[DK + 4 * K + D : DK + 4 * K + 2 * D] = ln_lambd_b
-            if eta_b is not None:
-                prm[DK + 4 * K + 2 * D :] = eta_b
+        _pack_params(prm, vp, theta, optimize, use_bounds)
         ctx.negelcbo_flat(D, K, prm, optimize, Ns_even, compute_grad, use_bounds, eps, seed or 0, None, False, out)
         F, G, H = float(out[0]), float(out[1]), float(out[2])
         dF = None

@@ -510,3 +510,51 @@ def test_entmc_every_variant_against_oracle_and_f64(pv, variant, stem, monkeypat
             assert d0.shape == (0,) and abs(H0 - Hd) <= TOL_F32_VAL * max(abs(Hd), 1.0)
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched sieve evaluation: one launch for all candidates of variational_optimization.py:775-787
+@pytest.mark.parametrize("shape", [(3, 2, 40, 2, "negquad"), (6, 30, 200, 6, "negquad"), (10, 20, 200, 4, "const"),
+                                   (4, 1, 60, 3, "zero"), (20, 50, 400, 8, "negquad")])
+def test_sieve_batch_matches_oracle_and_single_calls(pv, shape):
+    D, K, N, S, mean_kind = shape
+    rng = np.random.default_rng(D * 1000 + K)
+    gp, X = _random_problem(rng, D, K, N, S, mean_kind)[:2]
+    B = 7
+    cands, oracle_F = [], []
+    bnd = None
+    for b in range(B):
+        mu = X[rng.integers(0, N, size=K)].T + 0.3 * rng.normal(size=(D, K))
+        sigma = 0.3 * np.exp(0.5 * rng.normal(size=K))
+        lambd = np.exp(0.3 * rng.normal(size=D))
+        eta = 0.5 * rng.normal(size=K)
+        w = np.exp(eta - eta.max())
+        w /= w.sum()
+        vo = eo.OracleVP.create(D, K, mu, sigma, lambd, w, eta, (True,) * 4)
+        theta = eo.get_parameters(vo)
+        if bnd is None:
+            bnd = eo.get_bounds(vo, X, syn.OPTIONS, K)
+        if b % 2:  # push some candidates outside the soft bounds
+            theta = theta + 2.0 * rng.normal(size=theta.size)
+            eo.set_parameters(vo, theta)
+        Fo, _, Go, Ho, _ = eo.neg_elcbo(theta, gp, vo.copy(), 0.0, 0, False, False, bnd)
+        oracle_F.append((Fo, Go, Ho))
+        vp = make_vp(pv, D, K, vo.mu, vo.sigma, vo.lambd, vo.w, vo.eta)
+        cands.append((vp, theta))
+    F, G, H = pv.neg_elcbo_batch([c[0] for c in cands], gp, bnd, thetas=[c[1] for c in cands])
+    assert F.shape == (B,)
+    for b in range(B):
+        Fo, Go, Ho = oracle_F[b]
+        assert relerr(G[b], Go) < TOL_F64 and relerr(H[b], Ho) < TOL_F64, (shape, b)
+        assert abs(F[b] - Fo) <= TOL_F64 * max(abs(Fo), 1.0), (shape, b, F[b], Fo)
+        # ... and the one-at-a-time drop-in path (what the reference's loop would call)
+        vp1 = make_vp(pv, D, K, cands[b][0].mu, cands[b][0].sigma, cands[b][0].lambd, cands[b][0].w, cands[b][0].eta)
+        F1, dF1, G1, H1, _ = pv._neg_elcbo(cands[b][1], gp, vp1, 0.0, 0, False, False, bnd)
+        assert dF1 is None and abs(F[b] - F1) <= TOL_F64 * max(abs(F1), 1.0)
+    # empty batch, and candidates that disagree on K are rejected
+    F0, _, _ = pv.neg_elcbo_batch([], gp, bnd)
+    assert F0.shape == (0,)
+    if K > 1:
+        other = pv.VariationalPosterior(D, K - 1)
+        with pytest.raises(ValueError):
+            pv.neg_elcbo_batch([cands[0][0], other], gp, bnd)
