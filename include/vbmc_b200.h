@@ -189,6 +189,34 @@ size_t vbmc_param_len(int D, int K);
 int vbmc_negelcbo_batch(vbmc_ctx *ctx, int B, int D, int K, const double *params, const int optimize[4],
                         int use_bounds, double *out);
 
+/* ---- device-resident Adam -----------------------------------------------------------------
+ * minimize_adam(f, x0, lb, ub, tol_fun, max_iter, master_min, master_max, master_decay)
+ * (pyvbmc/vbmc/minimize_adam.py:61-145) with f = the closure of variational_optimization.py:238-249,
+ *     f(theta) = _neg_elcbo(theta, gp, vp, 0, Ns, compute_grad = True, compute_var = False, theta_bnd)[0:2].
+ * theta, the moment estimates and the iterate table stay on the device; one iteration (theta -> parameters,
+ * evaluation, Adam update, clamp) is a CUDA graph replayed without host synchronisation.  The early-stopping test
+ * (:106-138) stays with the caller: run batches of 20 steps and inspect y / x.
+ * Draws: VBMC_RNG_PHILOX keyed (seed, offset + iteration).  The fp32 -> fp64 overflow fallback of
+ * vbmc_negelcbo_flat does not exist here: a non-finite y must make the caller fall back to the host loop.      */
+typedef struct vbmc_adam_in {
+    int D, K;
+    const double *params;  /* parameter block (vbmc_param_len doubles, layout as vbmc_negelcbo_batch) of the CURRENT
+                              vp: supplies the groups theta does not carry (optimize[i] == 0)                  */
+    const double *theta0;  /* [P] start point, P = D*K, K, D, K summed over the optimised groups               */
+    int optimize[4];
+    int64_t Ns;            /* draws per component (> 0) */
+    int use_bounds;        /* soft bounds as set by vbmc_set_bounds */
+    uint64_t seed, offset;
+    const double *lb, *ub; /* [P] hard box of minimize_adam, or NULL */
+    int max_iter;
+    double master_min, master_max, master_decay;
+    int precision;
+} vbmc_adam_in;
+int vbmc_adam_init(vbmc_ctx *ctx, const vbmc_adam_in *in);
+/* run the next n iterations; y[n] = objective values f(x) seen by them, x[n][P] = iterates AFTER each update
+ * (row i = x_tab[:, i] of the reference).  Synchronous.                                                       */
+int vbmc_adam_steps(vbmc_ctx *ctx, int n, double *y, double *x);
+
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);

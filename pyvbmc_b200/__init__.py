@@ -16,6 +16,7 @@ from .context import Context, clear_caches, context_for_gp, entropy_context
 from .entropy import entlb_vbmc, entmc_vbmc
 from .install import install, uninstall
 from .variational_posterior import VariationalPosterior
+from .vbmc.minimize_adam import minimize_adam_elcbo
 from .vbmc.variational_optimization import _gp_log_joint, _neg_elcbo, _soft_bound_loss, _vp_bound_loss, neg_elcbo_batch
 
 __all__ = [
@@ -28,6 +29,7 @@ __all__ = [
     "entlb_vbmc",
     "_neg_elcbo",
     "neg_elcbo_batch",
+    "minimize_adam_elcbo",
     "_gp_log_joint",
     "_vp_bound_loss",
     "_soft_bound_loss",

@@ -53,6 +53,27 @@ class ElcboIn(C.Structure):
     ]
 
 
+class AdamIn(C.Structure):
+    _fields_ = [
+        ("D", C.c_int),
+        ("K", C.c_int),
+        ("params", C.c_void_p),
+        ("theta0", C.c_void_p),
+        ("optimize", C.c_int * 4),
+        ("Ns", C.c_int64),
+        ("use_bounds", C.c_int),
+        ("seed", C.c_uint64),
+        ("offset", C.c_uint64),
+        ("lb", C.c_void_p),
+        ("ub", C.c_void_p),
+        ("max_iter", C.c_int),
+        ("master_min", C.c_double),
+        ("master_max", C.c_double),
+        ("master_decay", C.c_double),
+        ("precision", C.c_int),
+    ]
+
+
 class ElcboOut(C.Structure):
     _fields_ = [
         ("F", C.c_double),
@@ -111,6 +132,8 @@ PROTOTYPES = {
     "vbmc_entmc_kernel_ms": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]),
     "vbmc_entmc_variant_used": (C.c_int, [C.c_void_p]),
     "vbmc_param_len": (C.c_size_t, [C.c_int, C.c_int]),
+    "vbmc_adam_init": (C.c_int, [C.c_void_p, C.POINTER(AdamIn)]),
+    "vbmc_adam_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vbmc_negelcbo_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "vbmc_fma_peak": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vbmc_stage_times": (C.c_int, [C.c_void_p, c_double_p]),

@@ -394,7 +394,7 @@ class Context:
         return buf
 
     def negelcbo_flat(self, D, K, params, optimize, Ns_even, compute_grad, use_bounds, eps, seed, precision, want_dH,
-                      out):
+                      out, offset=0):
         """``vbmc_negelcbo_flat``: one packed parameter block in, ``out`` filled in place."""
         og = self._opt_c.get(optimize)
         if og is None:
@@ -405,8 +405,8 @@ class Context:
             mode, eptr = _capi.RNG_PHILOX, None
         prec = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
         rc = self._lib.vbmc_negelcbo_flat(
-            self._h, D, K, params.ctypes.data, og, Ns_even, int(compute_grad), int(use_bounds), mode, eptr, seed, 0,
-            prec, int(want_dH), out.ctypes.data,
+            self._h, D, K, params.ctypes.data, og, Ns_even, int(compute_grad), int(use_bounds), mode, eptr, seed,
+            int(offset), prec, int(want_dH), out.ctypes.data,
         )
         if rc:
             _capi.check(rc)
@@ -425,6 +425,34 @@ class Context:
         _capi.check(self._lib.vbmc_negelcbo_batch(self._h, B, int(D), int(K), params.ctypes.data, og, int(bool(use_bounds)),
                                                   out.ctypes.data))
         return out
+
+    # ------------------------------------------------------------------ device-resident Adam
+    def adam_init(self, D, K, params, theta0, optimize, Ns_even, use_bounds, seed, offset, lb, ub, max_iter,
+                  master_min, master_max, master_decay, precision=None):
+        a = _capi.AdamIn()
+        keep = [np.ascontiguousarray(params, dtype=_F64), np.ascontiguousarray(theta0, dtype=_F64)]
+        a.D, a.K = int(D), int(K)
+        a.params, a.theta0 = keep[0].ctypes.data, keep[1].ctypes.data
+        for i in range(4):
+            a.optimize[i] = int(bool(optimize[i]))
+        a.Ns, a.use_bounds, a.seed, a.offset = int(Ns_even), int(bool(use_bounds)), int(seed), int(offset)
+        for name, arr in (("lb", lb), ("ub", ub)):
+            if arr is not None:
+                arr = np.ascontiguousarray(arr, dtype=_F64)
+                keep.append(arr)
+                setattr(a, name, arr.ctypes.data)
+        a.max_iter = int(max_iter)
+        a.master_min, a.master_max, a.master_decay = float(master_min), float(master_max), float(master_decay)
+        a.precision = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
+        _capi.check(self._lib.vbmc_adam_init(self._h, C.byref(a)))
+        self._adam_P = int(keep[1].size)
+
+    def adam_steps(self, n):
+        """Next ``n`` iterations: ``(y[n], x[n, P])`` (objective values seen, iterates after each update)."""
+        y = np.empty(n, dtype=_F64)
+        x = np.empty((n, self._adam_P), dtype=_F64)
+        _capi.check(self._lib.vbmc_adam_steps(self._h, int(n), y.ctypes.data, x.ctypes.data))
+        return y, x
 
     # split-phase API (multi-GPU / kernel-only timing); device pointers are plain ints
     def upload(self, vp, optimize, Ns, compute_grad=True, use_bounds=False, ln_sigma_b=None, ln_lambd_b=None,

@@ -1,0 +1,111 @@
+// adam.cu -- device-resident minimize_adam (pyvbmc/vbmc/minimize_adam.py:61-145) around the negative-ELCBO
+// evaluation: theta, the moment estimates, the iterate table and the iteration counter live in HBM, one iteration =
+//     adam_prepare_kernel   theta -> parameter block (VariationalPosterior.set_parameters, variational_posterior.py:
+//                           680-759 incl. the lambda normalisation, softmax weights; the eta shift :1082-1085; the
+//                           theta slices the bound loss reads :536-555; Philox offset = offset0 + iteration)
+//     gplj / entmc / tail   the evaluation itself, output (F, dF) left in device memory
+//     adam_update_kernel    moment update, bias correction, step-size schedule, clamp to [lb, ub], x_tab / y_tab
+// captured as ONE CUDA graph and replayed back to back: no H2D / D2H / host synchronisation per iteration.  The
+// early-stopping test (a linear fit every 20 iterations, :106-138) stays on the host and reads y_tab / x_tab in
+// batches.
+#include "common.cuh"
+
+namespace vbmc {
+namespace {
+
+__global__ void __launch_bounds__(256)
+adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
+    const ParamLayout lay = a.lay;
+    const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ double scratch[40];
+    const double *th = a.theta, *tm = a.tmpl;
+    const int pos_s = a.opt[0] ? D * K : 0, pos_l = pos_s + (a.opt[1] ? K : 0);
+    // mu (theta order is component-major already)
+    for (int e = tid; e < D * K; e += nt) prm[lay.mu() + e] = a.opt[0] ? th[e] : tm[lay.mu() + e];
+    // lambda: exp, then the unit-RMS normalisation shared with sigma (:749-756)
+    double l2 = 0.0;
+    for (int d = tid; d < D; d += nt) {
+        const double lm = a.opt[2] ? exp(th[pos_l + d]) : tm[lay.lambd() + d];
+        l2 += lm * lm;
+    }
+    l2 = block_sum(l2, scratch);
+    const double scale = sqrt(l2 / D);
+    for (int d = tid; d < D; d += nt) {
+        const double lm = (a.opt[2] ? exp(th[pos_l + d]) : tm[lay.lambd() + d]) / scale;
+        prm[lay.lambd() + d] = lm;
+        prm[lay.lnlam_b() + d] = a.opt[2] ? th[pos_l + d] : log(lm);  // (:536-555: theta's slice, else log of the field)
+    }
+    for (int k = tid; k < K; k += nt) {
+        const double sg = (a.opt[1] ? exp(th[pos_s + k]) : tm[lay.sigma() + k]) * scale;
+        prm[lay.sigma() + k] = sg;
+        prm[lay.lnsig_b() + k] = a.opt[1] ? th[pos_s + k] : log(sg);
+    }
+    // weights: softmax of eta with the max shift; eta itself is stored shifted (:1082-1085)
+    if (a.opt[3]) {
+        const double *eta = th + a.P - K;
+        double mx = -INFINITY;
+        for (int k = tid; k < K; k += nt) mx = fmax(mx, eta[k]);
+        mx = block_max(mx, scratch);
+        double se = 0.0;
+        for (int k = tid; k < K; k += nt) se += exp(eta[k] - mx);
+        se = block_sum(se, scratch);
+        for (int k = tid; k < K; k += nt) {
+            prm[lay.w() + k] = exp(eta[k] - mx) / se;
+            prm[lay.eta() + k] = eta[k] - mx;
+            prm[lay.eta_b() + k] = eta[k];
+        }
+    } else {
+        for (int k = tid; k < K; k += nt) {
+            prm[lay.w() + k] = tm[lay.w() + k];
+            prm[lay.eta() + k] = tm[lay.eta() + k];
+            prm[lay.eta_b() + k] = tm[lay.eta_b() + k];
+        }
+    }
+    if (tid == 0) {  // Philox key rides behind the parameter block
+        uint64_t *key = reinterpret_cast<uint64_t *>(prm + lay.total());
+        key[0] = a.seed;
+        key[1] = a.offset0 + (uint64_t)(*a.iter);
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+adam_update_kernel(AdamDev a, const double *__restrict__ out) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long long i = *a.iter;  // 0-based iteration
+    const double beta_1 = 0.9, beta_2 = 0.999, fudge = 1.4901161193847656e-08;  // sqrt(np.spacing(1))
+    const double c1 = 1.0 - pow(beta_1, (double)(i + 1)), c2 = 1.0 - pow(beta_2, (double)(i + 1));
+    const double step = a.master_min + (a.master_max - a.master_min) * exp(-(double)(i + 1) / a.master_decay);
+    double *xrow = a.xtab + (size_t)i * a.P;
+    for (int e = tid; e < a.P; e += nt) {
+        const double g = out[kOutHead + e];
+        const double m = beta_1 * a.m[e] + (1.0 - beta_1) * g;
+        const double v = beta_2 * a.v[e] + (1.0 - beta_2) * g * g;
+        a.m[e] = m, a.v[e] = v;
+        double x = a.theta[e] - step * (m / c1) / (sqrt(v / c2) + fudge);
+        if (a.lb) x = fmax(a.lb[e], x);
+        if (a.ub) x = fmin(a.ub[e], x);
+        a.theta[e] = x;
+        xrow[e] = x;
+    }
+    if (tid == 0) a.ytab[i] = out[0];
+    __syncthreads();
+    if (tid == 0) *a.iter = i + 1;
+}
+
+}  // namespace
+
+int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
+    adam_prepare_kernel<<<1, 256, 0, c->stream>>>(a, d_prm);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int adam_update_launch(Ctx *c, const AdamDev &a, const double *d_out) {
+    adam_update_kernel<<<1, 1024, 0, c->stream>>>(a, d_out);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+}  // namespace vbmc

@@ -113,6 +113,16 @@ struct CtxEx {
     cudaGraphExec_t gexec = nullptr;
     cudaGraph_t graph = nullptr;
     int64_t graph_launches = 0;
+    // device-resident Adam (vbmc_adam_init / vbmc_adam_steps)
+    bool adam_ready = false, adam_eager_done = false;
+    AdamDev adam{};
+    double *d_adam = nullptr;  // one allocation: theta, m, v, tmpl, lb, ub, ytab, xtab, iter
+    size_t adam_cap = 0;
+    int adam_max_iter = 0;
+    long long adam_done = 0;
+    cudaGraphExec_t adam_gexec = nullptr;
+    cudaGraph_t adam_graph = nullptr;
+    uint64_t adam_gen = 0;
 };
 
 CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
@@ -264,6 +274,22 @@ int run_single(CtxEx *x, const Spec &s, size_t n_out) {
     return VBMC_OK;
 }
 
+void drop_adam_graph(CtxEx *x) {
+    if (x->adam_gexec) cudaGraphExecDestroy(x->adam_gexec);
+    if (x->adam_graph) cudaGraphDestroy(x->adam_graph);
+    x->adam_gexec = nullptr, x->adam_graph = nullptr;
+}
+
+// one Adam iteration on the context stream: theta -> parameter block, evaluation, update (no host sync)
+int adam_iteration(CtxEx *x) {
+    Ctx *c = &x->c;
+    VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));
+    VBMC_TRY(partials(x, 0, 1, c->d_raw));
+    VBMC_TRY(finalize(x, c->d_raw, c->d_out));
+    VBMC_TRY(adam_update_launch(c, x->adam, c->d_out));
+    return VBMC_OK;
+}
+
 void drop_graph(CtxEx *x) {
     if (x->gexec) cudaGraphExecDestroy(x->gexec);
     if (x->graph) cudaGraphDestroy(x->graph);
@@ -390,6 +416,8 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     drop_graph(x);
+    drop_adam_graph(x);
+    if (x->d_adam) cudaFree(x->d_adam);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
                      c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var};
     for (double *d : dev)
@@ -732,6 +760,137 @@ int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const in
     }
     memcpy(out, o, sizeof(double) * (kOutHead + (compute_grad ? P : 0)));
     if (compute_grad && want_dH) memcpy(out + kOutHead + P, o + kOutHead + Pfull, sizeof(double) * P);
+    return VBMC_OK;
+}
+
+int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
+    VBMC_REQUIRE(p && in && in->params && in->theta0, VBMC_ERR_ARG, "adam_init: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    const int D = in->D, K = in->K;
+    VBMC_REQUIRE(in->max_iter >= 1, VBMC_ERR_ARG, "adam_init: max_iter must be >= 1");
+    VBMC_REQUIRE(in->Ns > 0, VBMC_ERR_ARG, "adam_init: the stochastic optimiser needs Ns > 0 (reference: :173-176)");
+    Spec s;
+    s.flat = in->params;
+    s.vp.D = D, s.vp.K = K;
+    s.vp.mu = s.vp.sigma = s.vp.lambd = s.vp.w = s.vp.eta = nullptr;
+    for (int i = 0; i < 4; ++i) s.optimize[i] = in->optimize[i] != 0, s.grad[i] = s.optimize[i];
+    s.jacobian = 1;
+    s.Ns = in->Ns;
+    s.use_bounds = in->use_bounds != 0;
+    s.rng_mode = VBMC_RNG_PHILOX, s.eps = nullptr, s.seed = in->seed, s.offset = in->offset, s.precision = in->precision;
+    s.parts = false;
+    const int P = packed_len(D, K, s.grad);
+    VBMC_REQUIRE(P > 0, VBMC_ERR_ARG, "adam_init: nothing to optimise");
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    VBMC_TRY(stage(x, s));  // flags, plan inputs, parameter block (the template) on the device
+    const ParamLayout lay{D, pad_dim(D), K};
+    const size_t T = (size_t)lay.total();
+    // theta, m, v, lb, ub (P each) | tmpl (T) | ytab (max_iter) | iter (1, as 8 bytes) | xtab (max_iter * P)
+    const size_t need = 5 * (size_t)P + T + (size_t)in->max_iter + 1 + (size_t)in->max_iter * P;
+    if (need > x->adam_cap) {
+        if (x->d_adam) cudaFree(x->d_adam);
+        x->d_adam = nullptr, x->adam_cap = 0;
+        VBMC_CUDA_CHECK(cudaMalloc((void **)&x->d_adam, need * sizeof(double)));
+        x->adam_cap = need;
+    }
+    drop_adam_graph(x);
+    AdamDev &a = x->adam;
+    a = AdamDev{};
+    a.lay = lay, a.P = P;
+    for (int i = 0; i < 4; ++i) a.opt[i] = s.optimize[i];
+    double *q = x->d_adam;
+    a.theta = q, q += P;
+    a.m = q, q += P;
+    a.v = q, q += P;
+    double *d_lb = q;
+    q += P;
+    double *d_ub = q;
+    q += P;
+    double *d_tmpl = q;
+    q += T;
+    a.ytab = q, q += in->max_iter;
+    a.iter = reinterpret_cast<long long *>(q), q += 1;
+    a.xtab = q;
+    VBMC_CUDA_CHECK(cudaMemsetAsync(a.m, 0, 2 * (size_t)P * sizeof(double), c->stream));  // m, v
+    VBMC_CUDA_CHECK(cudaMemsetAsync(a.iter, 0, sizeof(long long), c->stream));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(a.theta, in->theta0, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(d_tmpl, in->params, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    a.tmpl = d_tmpl;
+    a.lb = a.ub = nullptr;
+    if (in->lb) {
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(d_lb, in->lb, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        a.lb = d_lb;
+    }
+    if (in->ub) {
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(d_ub, in->ub, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        a.ub = d_ub;
+    }
+    a.seed = in->seed, a.offset0 = in->offset;
+    a.master_min = in->master_min, a.master_max = in->master_max, a.master_decay = in->master_decay;
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    x->adam_max_iter = in->max_iter;
+    x->adam_done = 0;
+    x->adam_ready = true, x->adam_eager_done = false;
+    return VBMC_OK;
+}
+
+int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
+    VBMC_REQUIRE(p && y && xs, VBMC_ERR_ARG, "adam_steps: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    VBMC_REQUIRE(x->adam_ready && c->staged, VBMC_ERR_STATE, "adam_steps: call vbmc_adam_init first");
+    VBMC_REQUIRE(n >= 0 && x->adam_done + n <= x->adam_max_iter, VBMC_ERR_ARG, "adam_steps: more steps than max_iter");
+    const long long i0 = x->adam_done;
+    for (int it = 0; it < n; ++it) {
+        if (g_realloc) {  // a buffer moved (another evaluation resized something): captured pointers are stale
+            x->gen++;
+            g_realloc = false;
+        }
+        if (x->adam_gexec && x->adam_gen == x->gen) {
+            VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
+            c->launches += x->st.launches_per_eval;
+            continue;
+        }
+        if (!x->adam_eager_done || !x->graphs_on) {  // first iteration: eager (sizes every buffer)
+            VBMC_TRY(adam_iteration(x));
+            x->adam_eager_done = true;
+            continue;
+        }
+        drop_adam_graph(x);
+        g_realloc = false;
+        const int64_t l0 = c->launches;
+        VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = adam_iteration(x);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+        if (rc != VBMC_OK || ce != cudaSuccess || g_realloc) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            x->gen++;
+            x->adam_eager_done = false;  // start over with an eager iteration
+            if (rc != VBMC_OK) return rc;
+            VBMC_TRY(adam_iteration(x));
+            x->adam_eager_done = true;
+            continue;
+        }
+        x->adam_graph = g;
+        x->st.launches_per_eval = (int)(c->launches - l0);
+        c->launches = l0;
+        VBMC_CUDA_CHECK(cudaGraphInstantiate(&x->adam_gexec, g, 0));
+        x->adam_gen = x->gen;
+        VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
+        c->launches += x->st.launches_per_eval;
+    }
+    x->adam_done += n;
+    const int P = x->adam.P;
+    if (n > 0) {
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(y, x->adam.ytab + i0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(xs, x->adam.xtab + (size_t)i0 * P, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return VBMC_OK;
 }
 

@@ -233,6 +233,21 @@ int gpvar_launch(Ctx *c, const double *d_params, int K, int avg);
 int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4], double *d_raw_ent /*H at [0], block*/,
                  double *d_H);
 
+// adam.cu: device-resident minimize_adam state (all pointers are device memory)
+struct AdamDev {
+    ParamLayout lay;
+    int P, opt[4];
+    double *theta, *m, *v;   // [P]
+    const double *tmpl;      // [lay.total()] parameter block supplying the groups theta does not carry
+    const double *lb, *ub;   // [P] or null
+    double *xtab, *ytab;     // [max_iter][P], [max_iter]
+    long long *iter;         // iterations done so far
+    uint64_t seed, offset0;
+    double master_min, master_max, master_decay;
+};
+int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm);
+int adam_update_launch(Ctx *c, const AdamDev &a, const double *d_out);
+
 // sieve.cu: batched value-only negative ELCBO (entlb + log joint + bounds) of B candidates
 int sieve_launch(Ctx *c, int B, int D, int K, const int optimize[4], bool use_bounds, const double *d_prm, double *d_out);
 

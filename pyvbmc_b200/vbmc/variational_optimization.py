@@ -194,6 +194,7 @@ def _neg_elcbo(
     *,
     eps=None,
     seed=None,
+    offset=0,
 ):
     """Negative evidence lower confidence bound and its gradient.
 
@@ -201,7 +202,7 @@ def _neg_elcbo(
     ``(F, dF, G, H, varF, dH, varG_ss, varG, varH, I_sk, J_sjk)`` with ``separate_K``.
     ``vp`` is mutated exactly like the reference does (``set_parameters(theta)`` and the
     shifted ``eta``, :1080-1085).  Keyword-only extensions: ``eps`` (explicit draws,
-    shape ``(K, Ns/2, D)``) and ``seed`` (explicit Philox seed)."""
+    shape ``(K, Ns/2, D)``), ``seed`` and ``offset`` (explicit Philox key)."""
     if not np.isfinite(beta):
         beta = 0
     if compute_var is None:
@@ -243,7 +244,8 @@ def _neg_elcbo(
         prm, out = ctx.flat_buffers(D, K)
         DK = D * K
         _pack_params(prm, vp, theta, optimize, use_bounds)
-        ctx.negelcbo_flat(D, K, prm, optimize, Ns_even, compute_grad, use_bounds, eps, seed or 0, None, False, out)
+        ctx.negelcbo_flat(D, K, prm, optimize, Ns_even, compute_grad, use_bounds, eps, seed or 0, None, False, out,
+                          offset=offset)
         F, G, H = float(out[0]), float(out[1]), float(out[2])
         dF = None
         if compute_grad:

@@ -558,3 +558,46 @@ def test_sieve_batch_matches_oracle_and_single_calls(pv, shape):
         other = pv.VariationalPosterior(D, K - 1)
         with pytest.raises(ValueError):
             pv.neg_elcbo_batch([cands[0][0], other], gp, bnd)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident Adam: minimize_adam.py:61-145 around the ELBO objective
+@pytest.mark.parametrize("case", ["c2_all", "c2_noweights", "c4_box"])
+def test_device_adam_matches_host_loop(pv, case):
+    """The CUDA-graph Adam loop against the oracle's restatement of the reference loop driving the
+    parity-pinned one-at-a-time evaluation with the same Philox key (seed, offset0 + iteration)."""
+    from oracle.minimize_adam_oracle import minimize_adam as adam_oracle
+
+    pr = syn.make_problem("C4" if case.startswith("c4") else "C2")
+    opt = (True, True, True, case != "c2_noweights")
+    Ns_K, seed, off0 = 200, 77, 5
+
+    def fresh_vp():
+        vp = make_vp(pv, pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta, opt)
+        return vp
+
+    vp_h = fresh_vp()
+    theta0 = np.asarray(vp_h.get_parameters(), dtype=float)
+    bnd = vp_h.get_bounds(pr.gp.X, syn.OPTIONS, pr.K)
+    kw = dict(tol_fun=1e-3, max_iter=90, master_min=0.001, master_max=0.05, master_decay=200)
+    if case == "c4_box":
+        kw.update(lb=theta0 - 0.02, ub=theta0 + 0.03, use_early_stopping=False, max_iter=45)
+    it = {"i": 0}
+
+    def f(theta):
+        F, dF, *_ = pv._neg_elcbo(theta, pr.gp, vp_h, 0.0, Ns_K, True, False, bnd, seed=seed, offset=off0 + it["i"])
+        it["i"] += 1
+        return F, dF
+
+    xo, yo, xto, yto, no = adam_oracle(f, theta0.copy(), **kw)
+    vp_d = fresh_vp()
+    x, y, x_tab, y_tab, n = pv.minimize_adam_elcbo(pr.gp, vp_d, theta0.copy(), Ns_K, bnd, seed=seed, offset=off0, **kw)
+    assert n == no and x_tab.shape == xto.shape and y_tab.shape == yto.shape
+    assert np.max(np.abs(y_tab - yto)) <= 1e-7 * max(1.0, np.max(np.abs(yto)))
+    assert np.max(np.abs(x_tab - xto)) <= 1e-7 * max(1.0, np.max(np.abs(xto)))
+    assert np.max(np.abs(x - xo)) <= 1e-7 * max(1.0, np.max(np.abs(xo))) and abs(y - yo) <= 1e-7 * max(1.0, abs(yo))
+    if case == "c4_box":
+        assert np.all(x_tab <= (theta0 + 0.03)[:, None] + 1e-15) and np.all(x_tab >= (theta0 - 0.02)[:, None] - 1e-15)
+    # vp is left at the last evaluated iterate, as after the reference loop
+    np.testing.assert_allclose(np.ravel(vp_d.sigma), np.ravel(vp_h.sigma), rtol=1e-6)
+    np.testing.assert_allclose(vp_d.mu, vp_h.mu, rtol=1e-6, atol=1e-9)

@@ -213,3 +213,22 @@ def test_errors():
         eo.neg_elcbo(c.g["theta2"], c.gp, c.vp(), 1.0, 0, True, None, None)
     with pytest.raises(NotImplementedError):
         eo.gp_log_joint(c.vp(), c.gp, True, True, True, True)
+
+
+def test_adam_oracle_matches_reference_minimize_adam():
+    """oracle/minimize_adam_oracle.py against the unmodified reference (pyvbmc/vbmc/minimize_adam.py) on the
+    seeded noisy quadratic of tests/golden/ref_adam.npz: default options, a hard box, no early stopping."""
+    import os
+
+    from oracle.minimize_adam_oracle import minimize_adam, noisy_quadratic
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_adam.npz"))
+    for name, kw in (("default", {}), ("box", {"lb": np.full(6, -0.5), "ub": np.full(6, 0.7), "max_iter": 130}),
+                     ("noearly", {"use_early_stopping": False, "max_iter": 75, "master_max": 0.05})):
+        f, x0 = noisy_quadratic()
+        x, y, x_tab, y_tab, n = minimize_adam(f, x0, **kw)
+        assert n == int(g[name + "_n"])
+        np.testing.assert_allclose(x_tab, g[name + "_xtab"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(y_tab, g[name + "_ytab"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(x, g[name + "_x"], rtol=0, atol=1e-13)
+        assert abs(y - float(g[name + "_y"])) < 1e-13
