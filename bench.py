@@ -282,6 +282,46 @@ def run_b200(args):
     k_ms, k_n = ctx.entmc_kernel_ms()
     ctx.set_kernel_timing(False)
 
+    # ---- informational extras (NOT part of value / e2e): the next rows of SURVEY 8(f), N = 1 only ----------------
+    extras = None
+    if world == 1:
+        try:
+            extras = {}
+            vpa = pv.VariationalPosterior(D, K)
+            vpa.mu, vpa.sigma, vpa.lambd, vpa.w, vpa.eta = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy(), pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
+            th0 = np.asarray(vpa.get_parameters(), dtype=float)
+            kw = dict(seed=1, max_iter=100, use_early_stopping=False, master_max=0.01)
+            pv.minimize_adam_elcbo(pr.gp, vpa, th0, pr.Ns_K, pr.theta_bnd, **dict(kw, max_iter=40))
+            t0 = time.perf_counter()
+            _, _, _, yt, n_it = pv.minimize_adam_elcbo(pr.gp, vpa, th0, pr.Ns_K, pr.theta_bnd, **kw)
+            dt = time.perf_counter() - t0
+            extras["device_adam"] = {
+                "iterations_per_s": n_it / dt, "us_per_iteration": 1e6 * dt / n_it, "iterations": int(n_it),
+                "what": ("pyvbmc_b200.minimize_adam_elcbo: minimize_adam.py:61-145 with theta, moments and iterates "
+                         "resident in HBM, one CUDA graph per iteration (evaluation + Adam update), host sync every 20 "
+                         "iterations; same workload as `value` (one negelcbo+grad evaluation per iteration)"),
+            }
+            Bs = 500
+            rng = np.random.default_rng(0)
+            cands = []
+            for _ in range(Bs):
+                v = pv.VariationalPosterior(D, K)
+                v.mu = pr.mu + 0.3 * rng.normal(size=pr.mu.shape)
+                v.sigma, v.lambd = pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy()
+                v.w, v.eta = pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
+                cands.append(v)
+            pv.neg_elcbo_batch(cands[:8], pr.gp, pr.theta_bnd)
+            t0 = time.perf_counter()
+            pv.neg_elcbo_batch(cands, pr.gp, pr.theta_bnd)
+            dt = time.perf_counter() - t0
+            extras["sieve_batch"] = {
+                "candidates_per_s": Bs / dt, "us_per_candidate": 1e6 * dt / Bs, "candidates": Bs,
+                "what": ("pyvbmc_b200.neg_elcbo_batch: the value-only candidate loop of variational_optimization.py:"
+                         "775-787 (entlb + log joint + bounds) as one launch, host packing included"),
+            }
+        except Exception as exc:  # extras must never take the headline down
+            extras = {"error": repr(exc)}
+
     line = None
     if rank == 0:
         peaks = {}
@@ -353,6 +393,8 @@ def run_b200(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if extras:
+            line["extras"] = extras
         print(json.dumps(line))
     torch.cuda.synchronize()
     ev.close()
