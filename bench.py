@@ -230,13 +230,19 @@ def run_b200(args):
     # The GPU sits in a low-power state after the imports and needs a while under load before its clocks settle
     # (measured: the same call takes 300 us for the first ~10^4 calls after start-up and 143 us afterwards).  Keep
     # warming up (untimed) until two consecutive 50-call blocks agree to 3 %, at most 3 s.
+    # (with N ranks every rank must run the SAME number of evaluations -- each holds an all-reduce -- so the
+    # data-dependent exit is replaced by a fixed count)
     spin_t0, prev = time.perf_counter(), None
-    while time.perf_counter() - spin_t0 < 3.0:
+    for blk_i in range(40):
         b0 = time.perf_counter()
         for _ in range(50):
             e2e_step()
         blk = time.perf_counter() - b0
-        if prev is not None and abs(blk - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5:
+        if world == 1:
+            if (prev is not None and abs(blk - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5) or \
+                    time.perf_counter() - spin_t0 > 3.0:
+                break
+        elif blk_i >= 9:
             break
         prev = blk
     barrier()
@@ -264,27 +270,32 @@ def run_b200(args):
     # same clock settling for the device-resident loop, with the flush / sync pattern of the timed region (untimed)
     spin_t0, prev = time.perf_counter(), None
     wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while time.perf_counter() - spin_t0 < 3.0:
+    for blk_i in range(100):
         acc = 0.0
         for i in range(20):
-            flush.fill_(float(i))
-            torch.cuda.synchronize()
+            with torch.cuda.stream(stream):
+                flush.fill_(float(i))
             wa.record(stream)
             ev.enqueue(D, K)
             wb.record(stream)
             wb.synchronize()
             acc += wa.elapsed_time(wb)
-        if prev is not None and abs(acc - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5:
+        if world == 1:
+            if (prev is not None and abs(acc - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5) or \
+                    time.perf_counter() - spin_t0 > 3.0:
+                break
+        elif blk_i >= 14:  # fixed count with N ranks (see above)
             break
         prev = acc
     barrier()
     launches1 = ctx.launch_count
     with ClockSampler(local) as clk:
         for i in range(args.steps):
-            flush.fill_(float(i))  # evict L2 (default stream) ...
-            torch.cuda.synchronize()  # ... and keep it out of the timed interval
-            if world > 1:
-                dist.barrier()
+            # evict L2 on the evaluation's own stream: stream order keeps the fill out of the [start, stop] interval
+            # without a host synchronisation per step (with N ranks a per-step host barrier only measures launch skew;
+            # the ranks stay in lock-step through the all-reduce of every step)
+            with torch.cuda.stream(stream):
+                flush.fill_(float(i))
             starts[i].record(stream)
             ev.enqueue(D, K)
             stops[i].record(stream)
@@ -407,7 +418,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (entropy kernel: fp32 compute, fp64 accumulation) + f64 (log-joint, finalize)",
             "data": "synthetic",
-            "config": {"workload": wname, "rng": "device Philox4x32-10 + Box-Muller", "l2": "flushed between steps (256 MiB fill)",
+            "config": {"workload": wname, "rng": "device Philox4x32-10 + Box-Muller", "l2": "flushed between steps (256 MiB fill on the same stream, outside the timed interval)",
                        "warmup_note": "W warm-up steps, then untimed spin-up until the step time is stable to 3 % (GPU clock settling, <= 3 s)",
                        "timing": "CUDA events per step on the launching stream, max over ranks",
                        "draws_per_component": pr.Ns_K, "S": pr.S, "parallelism": f"draws+hyper-samples sharded x{world}"},
