@@ -207,6 +207,7 @@ def run_b200(args):
     vp.mu, vp.sigma, vp.lambd, vp.w, vp.eta = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy(), pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
 
     ev = ShardedNegElcbo(pr.gp, device=local, seed=1234)
+    p2p = ev.enable_p2p(D, K) if world > 1 else False  # raw-vector all-reduce over NVLink peer memory (else NCCL)
     ctx = ev.ctx
     stream = ev.stream
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MiB > 126 MB L2
@@ -421,7 +422,9 @@ def run_b200(args):
             "config": {"workload": wname, "rng": "device Philox4x32-10 + Box-Muller", "l2": "flushed between steps (256 MiB fill on the same stream, outside the timed interval)",
                        "warmup_note": "W warm-up steps, then untimed spin-up until the step time is stable to 3 % (GPU clock settling, <= 3 s)",
                        "timing": "CUDA events per step on the launching stream, max over ranks",
-                       "draws_per_component": pr.Ns_K, "S": pr.S, "parallelism": f"draws+hyper-samples sharded x{world}"},
+                       "draws_per_component": pr.Ns_K, "S": pr.S, "parallelism": f"draws+hyper-samples sharded x{world}",
+                       "all_reduce": ("none" if world == 1 else ("peer memory (NVLink P2P stores + flags) inside the tail kernel"
+                                                                 if p2p else "NCCL"))},
             "evals_per_s_job": 1.0 / t_step,
             "e2e": {"value": world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e,

@@ -226,6 +226,23 @@ int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
 int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
 int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
 int vbmc_stream_synchronize(vbmc_ctx *ctx);
+
+/* ---- all-reduce of the raw vector over NVLink peer memory (optional; replaces the NCCL all-reduce between
+ * vbmc_negelcbo_partials_async and vbmc_negelcbo_finalize_async).  One process per GPU on ONE node:
+ *   1. every rank: vbmc_p2p_export(ctx, world, D, K, handle)  -- allocates this rank's exchange buffer (sized for
+ *      raw vectors up to vbmc_raw_len(D, K)) and returns its 64-byte CUDA IPC handle;
+ *   2. all-gather the handles by any host-side means (e.g. torch.distributed.all_gather_object);
+ *   3. every rank: vbmc_p2p_open(ctx, rank, world, handles[world][64]).
+ * From then on vbmc_negelcbo_partials_async(rank, world, raw) defers its reduce stage (as with world == 1) and
+ * vbmc_negelcbo_finalize_async runs raw phases -> peer stores + flags -> fixed-order sum -> final phase in ONE
+ * cluster kernel; raw holds the all-reduced vector afterwards.  Every rank must issue the same sequence of
+ * evaluations.  A peer that does not answer within ~2 s poisons the result (F = NaN, out[7] = 2) instead of
+ * hanging the GPU.  vbmc_p2p_close (or destroying the context) unmaps the peers.                              */
+#define VBMC_P2P_MAX_WORLD 8
+#define VBMC_P2P_HANDLE_BYTES 64
+int vbmc_p2p_export(vbmc_ctx *ctx, int world, int D, int K, unsigned char *handle);
+int vbmc_p2p_open(vbmc_ctx *ctx, int rank, int world, const unsigned char *handles);
+int vbmc_p2p_close(vbmc_ctx *ctx);
 /* copy n doubles from device memory to the host through the context's pinned staging buffer,
  * ordered after everything enqueued on the context stream (synchronises)                     */
 int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst_host);

@@ -127,6 +127,9 @@ PROTOTYPES = {
     "vbmc_negelcbo_partials_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_negelcbo_finalize_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbmc_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "vbmc_p2p_export": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vbmc_p2p_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vbmc_p2p_close": (C.c_int, [C.c_void_p]),
     "vbmc_read_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_double_p]),
     "vbmc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "vbmc_entmc_kernel_ms": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]),

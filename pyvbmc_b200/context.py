@@ -454,6 +454,22 @@ class Context:
         _capi.check(self._lib.vbmc_adam_steps(self._h, int(n), y.ctypes.data, x.ctypes.data))
         return y, x
 
+    # ------------------------------------------------------------------ peer-memory all-reduce (one node)
+    def p2p_export(self, world, D, K) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _capi.check(self._lib.vbmc_p2p_export(self._h, int(world), int(D), int(K), buf))
+        return bytes(buf)
+
+    def p2p_open(self, rank, world, handles):
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise ValueError("p2p_open: need one 64-byte handle per rank")
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _capi.check(self._lib.vbmc_p2p_open(self._h, int(rank), int(world), arr))
+
+    def p2p_close(self):
+        _capi.check(self._lib.vbmc_p2p_close(self._h))
+
     # split-phase API (multi-GPU / kernel-only timing); device pointers are plain ints
     def upload(self, vp, optimize, Ns, compute_grad=True, use_bounds=False, ln_sigma_b=None, ln_lambd_b=None,
                eta_b=None, eps=None, seed=0, offset=0, precision=None):

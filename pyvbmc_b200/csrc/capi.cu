@@ -239,8 +239,10 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     stage_mark(c, 3);
     st.f_partials = f;
-    // single GPU: the raw phases are fused into the finalize launch (one cluster kernel for the whole tail)
-    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, world == 1));
+    // single GPU: the raw phases are fused into the finalize launch (one cluster kernel for the whole tail); W ranks
+    // with mapped peer buffers: the same, with the all-reduce over peer memory between the phases
+    const bool p2p = world > 1 && c->p2p_world == world && c->p2p_rank == rank && rl.total() <= c->p2p_stride;
+    VBMC_TRY(reduce_launch(c, c->d_in, D, K, f, planp, Ns_glob, rank, world, c->S, raw_dev, world == 1 || p2p));
     return VBMC_OK;
 }
 
@@ -365,6 +367,14 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
 
 using namespace vbmc;
 
+static void p2p_unmap(Ctx *c) {
+    for (int q = 0; q < c->p2p_world; ++q)
+        if (c->p2p_peer[q] && q != c->p2p_rank) cudaIpcCloseMemHandle(c->p2p_peer[q]);
+    for (int q = 0; q < VBMC_P2P_MAX_WORLD; ++q) c->p2p_peer[q] = nullptr;
+    c->p2p_world = 0;
+}
+
+
 extern "C" {
 
 int vbmc_abi_version(void) { return VBMC_B200_ABI_VERSION; }
@@ -417,6 +427,8 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     cudaStreamSynchronize(c->stream);
     drop_graph(x);
     drop_adam_graph(x);
+    p2p_unmap(c);
+    if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
                      c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var};
@@ -939,6 +951,70 @@ int vbmc_negelcbo_finalize_async(vbmc_ctx *p, const double *raw_dev, double *out
     CtxEx *x = ex(p);
     Bind b(&x->c);
     return finalize(x, raw_dev, out_dev);
+}
+
+int vbmc_p2p_export(vbmc_ctx *p, int world, int D, int K, unsigned char *handle) {
+    VBMC_REQUIRE(p && handle, VBMC_ERR_ARG, "p2p_export: null argument");
+    VBMC_REQUIRE(world >= 2 && world <= VBMC_P2P_MAX_WORLD, VBMC_ERR_UNSUPPORTED, "p2p_export: world must be 2..8");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VBMC_P2P_HANDLE_BYTES, "CUDA IPC handle size");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    p2p_unmap(c);
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    c->p2p_local = nullptr;
+    const int stride = (int)((vbmc_raw_len(D, K) + 15) / 16 * 16);
+    const size_t bytes = ((size_t)2 * world * stride + (size_t)2 * world) * sizeof(double);
+    VBMC_CUDA_CHECK(cudaMalloc((void **)&c->p2p_local, bytes));
+    VBMC_CUDA_CHECK(cudaMemset(c->p2p_local, 0, bytes));  // flags = 0: no epoch published yet
+    VBMC_CUDA_CHECK(cudaDeviceSynchronize());
+    c->p2p_bytes = bytes, c->p2p_stride = stride, c->p2p_epoch = 0;
+    cudaIpcMemHandle_t h;
+    VBMC_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->p2p_local));
+    memcpy(handle, &h, sizeof(h));
+    return VBMC_OK;
+}
+
+int vbmc_p2p_open(vbmc_ctx *p, int rank, int world, const unsigned char *handles) {
+    VBMC_REQUIRE(p && handles, VBMC_ERR_ARG, "p2p_open: null argument");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_REQUIRE(c->p2p_local != nullptr, VBMC_ERR_STATE, "p2p_open: call vbmc_p2p_export first");
+    VBMC_REQUIRE(world >= 2 && world <= VBMC_P2P_MAX_WORLD && rank >= 0 && rank < world, VBMC_ERR_ARG, "p2p_open: bad rank/world");
+    p2p_unmap(c);
+    c->p2p_rank = rank;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) {
+            c->p2p_peer[q] = c->p2p_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)q * VBMC_P2P_HANDLE_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            c->p2p_world = q;  // unmap what was opened so far
+            p2p_unmap(c);
+            set_error(std::string("p2p_open: cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+            return VBMC_ERR_CUDA;
+        }
+        c->p2p_peer[q] = static_cast<double *>(ptr);
+    }
+    c->p2p_world = world;
+    c->p2p_epoch = 0;
+    return VBMC_OK;
+}
+
+int vbmc_p2p_close(vbmc_ctx *p) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    cudaStreamSynchronize(c->stream);
+    p2p_unmap(c);
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    c->p2p_local = nullptr;
+    return VBMC_OK;
 }
 
 int vbmc_read_device(vbmc_ctx *p, const double *src_dev, size_t n, double *dst_host) {

@@ -152,7 +152,14 @@ struct Ctx {
     size_t tctiles_cap = 0;
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
     size_t csum_cap = 0;
-    bool raw_pending = false;  // reduce stage deferred into the next finalize launch (single GPU)
+    // peer-memory all-reduce of the raw vector (vbmc_p2p_export / vbmc_p2p_open): exchange buffers of all ranks
+    int p2p_world = 0, p2p_rank = 0, p2p_stride = 0;
+    unsigned long long p2p_epoch = 0;
+    double *p2p_local = nullptr;  // owned (cudaMalloc, exported through CUDA IPC)
+    size_t p2p_bytes = 0;
+    double *p2p_peer[VBMC_P2P_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool raw_pending_p2p = false;
+    bool raw_pending = false;  // reduce stage deferred into the next finalize launch (single GPU, or W ranks with P2P)
     alignas(8) unsigned char raw_pending_blob[320];
     double *d_out = nullptr, *h_out = nullptr;
     size_t out_cap = 0;

@@ -424,16 +424,82 @@ __device__ __forceinline__ void final_phase(const double *__restrict__ prm, cons
 }
 
 constexpr int kTailThreads = 1024, kTailCluster = 8;
-enum { PH_RAW = 1, PH_FINAL = 2 };
+enum { PH_RAW = 1, PH_FINAL = 2, PH_XCHG = 4 };
+
+// All-reduce of the raw vector over NVLink peer memory, inside the tail kernel (no NCCL launch, no second tail
+// launch).  Every rank owns an exchange buffer (cudaMalloc + CUDA IPC, mapped by all peers):
+//     slot(par, src)  [2][W][stride] doubles : rank `src`'s raw vector of the step with parity `par`
+//     flag(par, src)  [2][W] uint64          : epoch of the step whose slot(par, src) is complete
+// Step `epoch`: a rank stores its raw vector into slot(epoch & 1, rank) of EVERY rank (its own included), fences at
+// system scope, publishes flag = epoch on every rank, waits until all W flags of its own buffer show `epoch`, and
+// sums the W slots in rank order -- the same data in the same order on every rank, so the results stay bitwise
+// replicated.  Two parities suffice: a rank can run at most one step ahead of the slowest one (it needs that
+// rank's flag to finish a step), and a slot is rewritten two steps later.
+struct XchgArgs {
+    int world, rank, n, stride;  // n = raw length, stride = slot pitch (doubles)
+    unsigned long long epoch;
+    double *peer[VBMC_P2P_MAX_WORLD];  // exchange buffers of all ranks (peer[rank] = the local one)
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// returns false (in every thread of the CTA that hosts a timed-out waiter ... the caller poisons the result) if a
+// peer's flag did not arrive within ~2 s
+template <class Cluster>
+__device__ __forceinline__ void raw_exchange(const XchgArgs &x, double *__restrict__ raw, int gtid, int GT, Cluster &cluster,
+                                             int *s_bad) {
+    const int W = x.world, par = (int)(x.epoch & 1ull);
+    const size_t flags_at = (size_t)2 * W * x.stride;
+    // 1. publish the local raw vector in every rank's slot(par, rank)
+    for (int q = 0; q < W; ++q) {
+        double *dst = x.peer[q] + ((size_t)par * W + x.rank) * x.stride;
+        for (int i = gtid; i < x.n; i += GT) dst[i] = raw[i];
+    }
+    __threadfence_system();
+    cluster.sync();
+    if (gtid < W) {
+        unsigned long long *f = reinterpret_cast<unsigned long long *>(x.peer[gtid] + flags_at) + (size_t)par * W + x.rank;
+        st_release_sys_u64(f, x.epoch);
+    }
+    // 2. wait for the W flags of the local buffer
+    if (gtid < W) {
+        const unsigned long long *f =
+            reinterpret_cast<const unsigned long long *>(x.peer[x.rank] + flags_at) + (size_t)par * W + gtid;
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(f) != x.epoch) {
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s: a lost peer must not hang the GPU
+                *s_bad = 1;
+                break;
+            }
+        }
+    }
+    cluster.sync();
+    // 3. fixed-order sum of the W slots -> raw (identical on every rank)
+    const double *mine = x.peer[x.rank] + (size_t)par * W * x.stride;
+    for (int i = gtid; i < x.n; i += GT) {
+        double v = 0.0;
+        for (int src = 0; src < W; ++src) v += mine[(size_t)src * x.stride + i];
+        raw[i] = v;
+    }
+}
 
 // One launch for everything behind the producers: a cluster of 8 CTAs; the phases are separated by cluster
 // barriers (release/acquire at cluster scope, so plain global stores of one phase are visible to the next).
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(const double *__restrict__ prm, RawArgs ra, FinalArgs fa,
-                                                           int phases) {
+                                                           int phases, XchgArgs xa) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double scratch[40];
     __shared__ double ssm[5];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
     extern __shared__ double tmp[];  // [K*D] bound-loss derivatives of the ln-scale entries | [K] exp(eta)
     const int nblk = (int)gridDim.x, gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x), GT = nblk * (int)blockDim.x;
     int nvb = 0;
@@ -461,6 +527,10 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const double *__rest
         cluster.sync();
         TS(3);
         raw_phase2(prm, ra, gtid, GT);
+        if (phases & PH_XCHG) {
+            cluster.sync();  // the local raw vector is complete
+            raw_exchange(xa, ra.raw, gtid, GT, cluster, &s_bad);
+        }
     }
     TS(4);
     if (phases & PH_FINAL) {
@@ -470,6 +540,11 @@ __global__ void __launch_bounds__(kTailThreads) tail_kernel(const double *__rest
             final_phase(prm, fa, vb, nblk, ssm, sek, tmp);
             __syncthreads();
         }
+    }
+    if ((phases & PH_XCHG) && (phases & PH_FINAL)) {
+        // a peer that never answered: make the failure visible instead of returning a partial sum
+        __syncthreads();
+        if (s_bad && threadIdx.x == 0) fa.out[0] = __longlong_as_double(0x7ff8000000000000LL), fa.out[7] = 2.0;
     }
     TS(6);
 #ifdef VBMC_TAIL_DEBUG
@@ -555,7 +630,8 @@ int fill_final_args(Ctx *c, int D, int K, const EvalFlags &f, const double *d_ra
 // raw phase deferred by reduce_launch(defer = true), consumed by the next finalize_launch of the same context
 static_assert(sizeof(RawArgs) <= sizeof(Ctx::raw_pending_blob), "Ctx::raw_pending_blob is too small");
 
-int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalArgs &fa, int phases, int D, int K) {
+int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalArgs &fa, int phases, int D, int K,
+                const XchgArgs &xa = XchgArgs{}) {
     const size_t smem = (phases & PH_FINAL) ? (size_t)(K * D + K) * sizeof(double) : 0;
     VBMC_REQUIRE(smem <= 200 * 1024, VBMC_ERR_UNSUPPORTED, "finalize: D*K too large");
     if (smem > c->finalize_smem_set && smem > 48 * 1024) {
@@ -570,7 +646,7 @@ int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalAr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kTailCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases));
+    VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases, xa));
     c->launches++;
     return VBMC_OK;
 }
@@ -586,6 +662,7 @@ int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags 
     if (defer) {
         memcpy(c->raw_pending_blob, &ra, sizeof(RawArgs));
         c->raw_pending = true;
+        c->raw_pending_p2p = s_step > 1;  // deferred with W > 1 ranks (s_step = W): the peer-memory all-reduce path
         return VBMC_OK;
     }
     c->raw_pending = false;
@@ -601,6 +678,14 @@ int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlag
         RawArgs ra;
         memcpy(&ra, c->raw_pending_blob, sizeof(RawArgs));
         VBMC_REQUIRE(ra.raw == d_raw, VBMC_ERR_STATE, "finalize: raw vector differs from the one given to partials");
+        if (c->raw_pending_p2p) {  // W ranks: raw phases -> peer-memory all-reduce -> final phase, ONE launch
+            c->raw_pending_p2p = false;
+            XchgArgs xa{};
+            xa.world = c->p2p_world, xa.rank = c->p2p_rank, xa.n = fa.rl.total(), xa.stride = c->p2p_stride;
+            xa.epoch = ++c->p2p_epoch;
+            for (int q = 0; q < c->p2p_world; ++q) xa.peer[q] = c->p2p_peer[q];
+            return tail_launch(c, d_params, ra, fa, PH_RAW | PH_XCHG | PH_FINAL, D, K, xa);
+        }
         return tail_launch(c, d_params, ra, fa, PH_RAW | PH_FINAL, D, K);
     }
     return tail_launch(c, d_params, RawArgs{}, fa, PH_FINAL, D, K);

@@ -58,6 +58,39 @@ class ShardedNegElcbo:
         self.seed = int(seed)
         self.step = 0
         self._raw = self._out = None
+        self.p2p = False  # all-reduce over NVLink peer memory inside the tail kernel (else: NCCL all-reduce)
+
+    def enable_p2p(self, D, K):
+        """Map every rank's exchange buffer (CUDA IPC, one node) so that the raw vector is all-reduced over peer
+        memory inside the tail kernel: one launch instead of raw kernel + NCCL all-reduce + final kernel.
+        Collective: every rank must call it.  Returns whether the fused path is active on ALL ranks."""
+        import os
+
+        if self.world < 2 or self.world > 8 or os.environ.get("VBMC_P2P", "1") == "0":
+            return False
+        ok = 1
+        try:
+            handle = self.ctx.p2p_export(self.world, D, K)
+        except Exception:
+            handle, ok = b"\0" * 64, 0
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, (ok, handle), group=self.group)
+        ok = int(all(h[0] for h in handles))
+        if ok:
+            try:
+                self.ctx.p2p_open(self.rank, self.world, [h[1] for h in handles])
+            except Exception:
+                ok = 0
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok, group=self.group)
+        self.p2p = bool(all(flags))
+        if not self.p2p:
+            try:
+                self.ctx.p2p_close()
+            except Exception:
+                pass
+        self.dist.barrier(group=self.group)  # nobody stores into a peer before every peer has zeroed its flags
+        return self.p2p
 
     def _buffers(self, D, K):
         torch = self.torch
@@ -72,10 +105,10 @@ class ShardedNegElcbo:
         """partials -> all-reduce -> finalize on the context stream (no host sync)."""
         raw, out = self._buffers(D, K)
         self.ctx.partials_async(self.rank, self.world, raw.data_ptr())
-        if self.world > 1:
+        if self.world > 1 and not self.p2p:
             with self.torch.cuda.stream(self.stream):
                 self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.ctx.finalize_async(raw.data_ptr(), out.data_ptr())
+        self.ctx.finalize_async(raw.data_ptr(), out.data_ptr())  # (with p2p: raw phases + peer all-reduce + final)
         return out
 
     def __call__(self, theta, vp, Ns, theta_bnd=None, eps=None):

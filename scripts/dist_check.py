@@ -27,10 +27,17 @@ for cfg, S in (("C2", 6), ("C3", 8)):
     vp.mu, vp.sigma, vp.lambd, vp.w, vp.eta = pr.mu, pr.sigma.reshape(1, -1), pr.lambd.reshape(-1, 1), pr.w.reshape(1, -1), pr.eta.reshape(1, -1)
     Ns_K = 2002  # not divisible by 2 * world: uneven shards
     sharded = ShardedNegElcbo(pr.gp, device=local, seed=99)
+    fused = ShardedNegElcbo(pr.gp, device=local, seed=99)
+    p2p = fused.enable_p2p(pr.D, pr.K)  # all-reduce over NVLink peer memory inside the tail kernel
+    if rank == 0:
+        print(f"{cfg}: peer-memory all-reduce {'active' if p2p else 'NOT available (NCCL path only)'}")
     single = ShardedNegElcbo(pr.gp, device=local, seed=99, single=True)
-    for it in range(2):
+    for it in range(6):
         theta = pr.theta + 0.01 * it
-        F, dF, G, H, _ = sharded(theta, vp, Ns_K, pr.theta_bnd)
+        ev_ = fused if (p2p and it >= 2) else sharded  # iterations 0-1: NCCL all-reduce, 2-5: peer-memory all-reduce
+        F, dF, G, H, _ = ev_(theta, vp, Ns_K, pr.theta_bnd)
+        ev_.step = it + 1  # (same Philox offset as `single`, whichever evaluator ran)
+        sharded.step = fused.step = it + 1
         F1, dF1, G1, H1, _ = single(theta, vp, Ns_K, pr.theta_bnd)
         eF, eG, eH = abs(F - F1) / abs(F1), abs(G - G1) / abs(G1), abs(H - H1) / abs(H1)
         eg = np.abs(dF - dF1).max() / np.abs(dF1).max()
@@ -46,6 +53,7 @@ for cfg, S in (("C2", 6), ("C3", 8)):
         # map depends on the shard size: gradients agree to ~1e-9 (bitwise in fp64 mode), values to ~1e-15
         ok = ok and eF < 1e-12 and eG < 1e-12 and eH < 1e-12 and eg < 1e-8 and same
     sharded.close()
+    fused.close()
     single.close()
 dist.barrier()
 if rank == 0:
