@@ -223,7 +223,9 @@ def run_b200(args):
             return pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd)
         return ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)
 
-    ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)  # stages theta / bounds on ev's context for the device-resident loop
+    F0 = ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)[0]  # stages theta / bounds on ev's context for the device-resident loop
+    if world > 1:
+        p2p = ev.p2p_self_check(F0)  # a timed-out peer exchange on any rank => NCCL all-reduce on all ranks
 
     for _ in range(max(args.warmup, 3)):
         F, dF, G, H, _ = e2e_step()

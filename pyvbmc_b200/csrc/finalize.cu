@@ -485,7 +485,7 @@ __device__ __forceinline__ void raw_exchange(const XchgArgs &x, double *__restri
     const double *mine = x.peer[x.rank] + (size_t)par * W * x.stride;
     for (int i = gtid; i < x.n; i += GT) {
         double v = 0.0;
-        for (int src = 0; src < W; ++src) v += mine[(size_t)src * x.stride + i];
+        for (int src = 0; src < W; ++src) v += __ldcg(mine + (size_t)src * x.stride + i);  // (L2: peers wrote it)
         raw[i] = v;
     }
 }

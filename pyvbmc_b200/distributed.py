@@ -101,6 +101,20 @@ class ShardedNegElcbo:
             self._out = torch.zeros(n_out, dtype=torch.float64, device=dev)
         return self._raw, self._out
 
+    def p2p_self_check(self, F):
+        """Collective: if ANY rank saw the peer exchange time out (poisoned result: F is NaN), every rank drops
+        back to the NCCL all-reduce.  Call it once after the first evaluation."""
+        if not self.p2p:
+            return True
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, bool(np.isfinite(F)), group=self.group)
+        if not all(flags):
+            self.p2p = False
+            self.ctx.synchronize()
+            self.ctx.p2p_close()
+        self.dist.barrier(group=self.group)
+        return self.p2p
+
     def enqueue(self, D, K):
         """partials -> all-reduce -> finalize on the context stream (no host sync)."""
         raw, out = self._buffers(D, K)
