@@ -34,6 +34,38 @@ def raw_layout(D: int, K: int):
     return {"H": 0, "G": 1, "ent": 4, "gp": 4 + block, "block": block, "total": 4 + 2 * block}
 
 
+def negotiate_p2p(dist, group, rank, world, export_fn, open_fn, close_fn):
+    """Collective set-up of the peer-memory exchange (host logic, backend-agnostic: also runs over gloo).
+
+    ``export_fn() -> bytes`` allocates the local exchange buffer and returns its IPC handle, ``open_fn(handles)``
+    maps all ranks' buffers, ``close_fn()`` releases everything.  Every rank executes the SAME sequence of
+    collectives whatever fails locally (two all-gathers and a barrier), and the path is only enabled if it works
+    on ALL ranks."""
+    ok = 1
+    try:
+        handle = export_fn()
+    except Exception:
+        handle, ok = b"\0" * 64, 0
+    handles = [None] * world
+    dist.all_gather_object(handles, (ok, handle), group=group)
+    ok = int(all(h[0] for h in handles))
+    if ok:
+        try:
+            open_fn([h[1] for h in handles])
+        except Exception:
+            ok = 0
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)
+    enabled = bool(all(flags))
+    if not enabled:
+        try:
+            close_fn()
+        except Exception:
+            pass
+    dist.barrier(group=group)  # nobody stores into a peer before every peer has zeroed its flags
+    return enabled
+
+
 class ShardedNegElcbo:
     """``_neg_elcbo(theta, gp, vp, 0, Ns, True, False, theta_bnd)`` evaluated by all ranks.
 
@@ -68,38 +100,13 @@ class ShardedNegElcbo:
 
         if self.world < 2 or self.world > 8 or os.environ.get("VBMC_P2P", "1") == "0":
             return False
-        ok = 1
-        try:
-            handle = self.ctx.p2p_export(self.world, D, K)
-        except Exception:
-            handle, ok = b"\0" * 64, 0
-        handles = [None] * self.world
-        self.dist.all_gather_object(handles, (ok, handle), group=self.group)
-        ok = int(all(h[0] for h in handles))
-        if ok:
-            try:
-                self.ctx.p2p_open(self.rank, self.world, [h[1] for h in handles])
-            except Exception:
-                ok = 0
-        flags = [None] * self.world
-        self.dist.all_gather_object(flags, ok, group=self.group)
-        self.p2p = bool(all(flags))
-        if not self.p2p:
-            try:
-                self.ctx.p2p_close()
-            except Exception:
-                pass
-        self.dist.barrier(group=self.group)  # nobody stores into a peer before every peer has zeroed its flags
+        self.p2p = negotiate_p2p(
+            self.dist, self.group, self.rank, self.world,
+            lambda: self.ctx.p2p_export(self.world, D, K),
+            lambda handles: self.ctx.p2p_open(self.rank, self.world, handles),
+            self.ctx.p2p_close,
+        )
         return self.p2p
-
-    def _buffers(self, D, K):
-        torch = self.torch
-        n_raw, n_out = self.ctx.raw_len(D, K), self.ctx.out_len(D, K)
-        if self._raw is None or self._raw.numel() != n_raw:
-            dev = torch.device("cuda", self.device)
-            self._raw = torch.zeros(n_raw, dtype=torch.float64, device=dev)
-            self._out = torch.zeros(n_out, dtype=torch.float64, device=dev)
-        return self._raw, self._out
 
     def p2p_self_check(self, F):
         """Collective: if ANY rank saw the peer exchange time out (poisoned result: F is NaN), every rank drops

@@ -91,6 +91,59 @@ def test_gloo_allreduce_of_shard_partials_equals_full():
     assert np.allclose(got, full, rtol=1e-12, atol=1e-13)
 
 
+def _p2p_worker(rank, world, port, q, scenario):
+    import torch.distributed as dist
+
+    from pyvbmc_b200.distributed import negotiate_p2p
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    log = []
+
+    def export_fn():
+        if scenario == "export_fails_on_1" and rank == 1:
+            raise RuntimeError("no IPC")
+        return bytes([rank]) * 64
+
+    def open_fn(handles):
+        log.append([h[0] for h in handles])
+        if scenario == "open_fails_on_0" and rank == 0:
+            raise RuntimeError("no peer access")
+
+    def close_fn():
+        log.append("closed")
+
+    enabled = negotiate_p2p(dist, None, rank, world, export_fn, open_fn, close_fn)
+    q.put((rank, enabled, log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario,port", [("ok", 29541), ("export_fails_on_1", 29542), ("open_fails_on_0", 29543)])
+def test_gloo_p2p_negotiation_is_collective(scenario, port):
+    """Host logic of ShardedNegElcbo.enable_p2p over a world_size-2 gloo group: the handles reach every rank in
+    rank order, and a failure on ANY rank disables the peer-memory path on ALL ranks without a deadlock (every rank
+    runs the same collectives)."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, world, port, q, scenario)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    enabled = [g[1] for g in got]
+    assert enabled == ([True, True] if scenario == "ok" else [False, False])
+    if scenario == "ok":
+        assert all(g[2] == [[0, 1]] for g in got)  # every rank opened the handles of ranks 0, 1 in order
+    else:
+        assert all("closed" in g[2] for g in got)
+
+
 @pytest.mark.gpu
 def test_two_gpu_sharded_equals_single():
     import torch
