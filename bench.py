@@ -207,7 +207,9 @@ def run_b200(args):
     vp.mu, vp.sigma, vp.lambd, vp.w, vp.eta = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy(), pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
 
     ev = ShardedNegElcbo(pr.gp, device=local, seed=1234)
-    p2p = ev.enable_p2p(D, K) if world > 1 else False  # raw-vector all-reduce over NVLink peer memory (else NCCL)
+    # Raw-vector all-reduce: NCCL by default (verified at 1/2/4/8 GPUs in round 1).  VBMC_BENCH_P2P=1 switches to the
+    # all-reduce over NVLink peer memory inside the tail kernel (ShardedNegElcbo.enable_p2p; verified at 2 GPUs only).
+    p2p = ev.enable_p2p(D, K) if (world > 1 and os.environ.get("VBMC_BENCH_P2P", "0") == "1") else False
     ctx = ev.ctx
     stream = ev.stream
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MiB > 126 MB L2
@@ -224,7 +226,7 @@ def run_b200(args):
         return ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)
 
     F0 = ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)[0]  # stages theta / bounds on ev's context for the device-resident loop
-    if world > 1:
+    if p2p:
         p2p = ev.p2p_self_check(F0)  # a timed-out peer exchange on any rank => NCCL all-reduce on all ranks
 
     for _ in range(max(args.warmup, 3)):

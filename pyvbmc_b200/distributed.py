@@ -112,7 +112,7 @@ class ShardedNegElcbo:
         """Collective: if ANY rank saw the peer exchange time out (poisoned result: F is NaN), every rank drops
         back to the NCCL all-reduce.  Call it once after the first evaluation."""
         if not self.p2p:
-            return True
+            return False
         flags = [None] * self.world
         self.dist.all_gather_object(flags, bool(np.isfinite(F)), group=self.group)
         if not all(flags):
