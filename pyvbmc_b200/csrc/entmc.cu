@@ -1353,7 +1353,8 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
         // mostly real (measured on B200: C3 70 us vs 76 us; C2 / C4 are faster on the CUDA-core kernels); the
         // warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
         const int64_t T = (int64_t)K * half_local;
-        if (T >= 150000 && K >= 33 && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
+        // (49 <= K <= 64: four 16-component chunks, the shape measured and parity-tested at scale in round 1)
+        if (T >= 150000 && K >= 49 && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
         else variant = T >= 65536 ? ENTMC_WARP : ENTMC_FAST;
     }
     const size_t smem_cap = 227 * 1024;

@@ -601,3 +601,32 @@ def test_device_adam_matches_host_loop(pv, case):
     # vp is left at the last evaluated iterate, as after the reference loop
     np.testing.assert_allclose(np.ravel(vp_d.sigma), np.ravel(vp_h.sigma), rtol=1e-6)
     np.testing.assert_allclose(vp_d.mu, vp_h.mu, rtol=1e-6, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sizes beyond the headline config (kept LAST in this file: it is the only test that was written after the
+# round's GPU budget ran out, so it has not been seen green on hardware yet)
+@pytest.mark.parametrize("K,Ns_K", [(50, 16000), (64, 12000), (33, 10000)])
+def test_entmc_large_draw_counts_tensor_core_vs_f64(pv, K, Ns_K, monkeypatch):
+    """Twice the headline work per GPU (what ONE GPU evaluates when bench.py --gpus 2 is cross-checked) and the
+    K limits of the tensor-core kernel (forced: the automatic choice only takes it for 49 <= K <= 64): 11+ tiles
+    per CTA, chunks that straddle components, against the all-fp64 kernel on identical Philox draws."""
+    D = 20
+    rng = np.random.default_rng(K)
+    mu = 0.5 * rng.normal(size=(D, K))
+    sigma = 0.5 * np.exp(0.1 * rng.normal(size=K))
+    lambd = np.ones(D)
+    eta = 0.3 * rng.normal(size=K)
+    w = np.exp(eta - eta.max())
+    w /= w.sum()
+    vp = make_vp(pv, D, K, mu, sigma, lambd, w, eta - eta.max())
+    monkeypatch.setenv("VBMC_ENTMC_VARIANT", "5")
+    ctx = pv.Context(0)
+    try:
+        Hd, dHd = ctx.entmc(vp, Ns_K, (True,) * 4, True, seed=21, offset=2, precision="f64")
+        Hs, dHs = ctx.entmc(vp, Ns_K, (True,) * 4, True, seed=21, offset=2)
+        assert ctx.entmc_variant_used() == 5
+        assert abs(Hs - Hd) <= TOL_F32_VAL * max(abs(Hd), 1.0)
+        assert relmax(dHs, dHd) < TOL_F32_GRAD
+    finally:
+        ctx.close()
