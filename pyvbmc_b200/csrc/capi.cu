@@ -118,7 +118,7 @@ struct CtxEx {
     AdamDev adam{};
     double *d_adam = nullptr;  // one allocation: theta, m, v, tmpl, lb, ub, ytab, xtab, iter
     size_t adam_cap = 0;
-    int adam_max_iter = 0;
+    int adam_max_iter = 0, adam_launches_per_iter = 0;
     long long adam_done = 0;
     cudaGraphExec_t adam_gexec = nullptr;
     cudaGraph_t adam_graph = nullptr;
@@ -863,7 +863,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         }
         if (x->adam_gexec && x->adam_gen == x->gen) {
             VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
-            c->launches += x->st.launches_per_eval;
+            c->launches += x->adam_launches_per_iter;
             continue;
         }
         if (!x->adam_eager_done || !x->graphs_on) {  // first iteration: eager (sizes every buffer)
@@ -889,12 +889,12 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
             continue;
         }
         x->adam_graph = g;
-        x->st.launches_per_eval = (int)(c->launches - l0);
+        x->adam_launches_per_iter = (int)(c->launches - l0);
         c->launches = l0;
         VBMC_CUDA_CHECK(cudaGraphInstantiate(&x->adam_gexec, g, 0));
         x->adam_gen = x->gen;
         VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
-        c->launches += x->st.launches_per_eval;
+        c->launches += x->adam_launches_per_iter;
     }
     x->adam_done += n;
     const int P = x->adam.P;
