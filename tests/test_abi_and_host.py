@@ -192,3 +192,80 @@ def test_neg_elcbo_argument_errors_without_gpu():
         pv._neg_elcbo(theta, None, vp, 0.0, 0, True, False, None, 0.0, True)
     with pytest.raises(NotImplementedError):
         pv._gp_log_joint(vp, None, True, True, True, True)
+
+
+def _make_closure(gp="GP", vp0="VP", elcbo_beta=0, ns_ent_K=100, compute_var=False, theta_bnd=None, call_name="_neg_elcbo"):
+    """A closure shaped like the reference's ``vb_train_mc_fun`` (variational_optimization.py:238-249)."""
+    ns = {}
+    src = (
+        "def outer(gp, vp0, elcbo_beta, ns_ent_K, compute_var, theta_bnd, %s):\n"
+        "    def vb_train_mc_fun(theta_):\n"
+        "        res = %s(theta_, gp, vp0, elcbo_beta, ns_ent_K, compute_grad=True, compute_var=compute_var, theta_bnd=theta_bnd)\n"
+        "        return res[0], res[1]\n"
+        "    return vb_train_mc_fun\n" % (call_name, call_name)
+    )
+    # `_neg_elcbo` must be a GLOBAL of the closure (as in the reference), not a free variable
+    src = src.replace(", %s):" % call_name, "):")
+    exec(src, ns)
+    ns[call_name] = lambda *a, **k: (1.5, np.zeros(3))
+    return ns["outer"](gp, vp0, elcbo_beta, ns_ent_K, compute_var, theta_bnd)
+
+
+def test_minimize_adam_wrapper_recognises_the_elcbo_closure_only():
+    from pyvbmc_b200.install import elcbo_closure_ingredients, make_minimize_adam
+
+    bnd = {"lb": 1}
+    assert elcbo_closure_ingredients(_make_closure(theta_bnd=bnd)) == ("GP", "VP", 100, bnd)
+    assert elcbo_closure_ingredients(_make_closure(elcbo_beta=0.5)) is None        # variance-weighted objective
+    assert elcbo_closure_ingredients(_make_closure(compute_var=True)) is None
+    assert elcbo_closure_ingredients(_make_closure(ns_ent_K=0)) is None            # deterministic entropy
+    assert elcbo_closure_ingredients(_make_closure(call_name="other_fun")) is None
+    assert elcbo_closure_ingredients(lambda x: (0.0, x)) is None                   # any other objective
+    assert elcbo_closure_ingredients(np.sin) is None
+
+    calls = []
+
+    def ref_adam(f, x0, *a):
+        calls.append(("ref", a))
+        return "ref-result"
+
+    def dev_loop(gp, vp0, x0, Ns, theta_bnd, *a):
+        calls.append(("dev", gp, vp0, Ns, theta_bnd, a))
+        if Ns == 7:
+            raise FloatingPointError
+        return "dev-result"
+
+    wrapped = make_minimize_adam(ref_adam, dev_loop)
+    x0 = np.zeros(3)
+    assert wrapped(_make_closure(theta_bnd=bnd), x0, None, None, 1e-3, 50, 0.001, 0.05, 200) == "dev-result"
+    assert calls[-1] == ("dev", "GP", "VP", 100, bnd, (None, None, 1e-3, 50, 0.001, 0.05, 200, True))
+    assert wrapped(lambda x: (0.0, x), x0, max_iter=5) == "ref-result" and calls[-1][0] == "ref"
+    assert calls[-1][1] == (None, None, 0.001, 5, 0.001, 0.1, 200, True)          # reference defaults forwarded
+    assert wrapped(_make_closure(ns_ent_K=7), x0) == "ref-result"                   # non-finite -> host loop
+    assert [c[0] for c in calls[-2:]] == ["dev", "ref"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+def test_minimize_adam_wrapper_matches_the_reference_closure_shape():
+    """The free variables and globals the wrapper keys on are those of the reference's own nested function."""
+    import types
+
+    from oracle import ref_loader
+    from pyvbmc_b200.install import _ELCBO_FREEVARS
+
+    ref_loader.load()
+    from pyvbmc.vbmc import variational_optimization as vo
+
+    def nested(code):
+        for c in code.co_consts:
+            if isinstance(c, types.CodeType):
+                yield c
+                yield from nested(c)
+
+    inner = [c for c in nested(vo.optimize_vp.__code__) if c.co_name == "vb_train_mc_fun"]
+    assert len(inner) == 1
+    assert set(_ELCBO_FREEVARS) <= set(inner[0].co_freevars) and "_neg_elcbo" in inner[0].co_names
+    import inspect
+
+    assert list(inspect.signature(vo.minimize_adam).parameters) == [
+        "f", "x0", "lb", "ub", "tol_fun", "max_iter", "master_min", "master_max", "master_decay", "use_early_stopping"]
