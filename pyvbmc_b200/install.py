@@ -19,7 +19,9 @@ that recognises the reference's ELBO closure (``vb_train_mc_fun``, variational_o
 variables ``gp, vp0, elcbo_beta, ns_ent_K, compute_var, theta_bnd`` around a call of ``_neg_elcbo``) and runs
 the device-resident loop ``minimize_adam_elcbo`` for it; any other objective, a non-default configuration
 (``elcbo_beta != 0``, ``compute_var``, deterministic entropy) or a non-finite objective goes to the
-reference's own ``minimize_adam``.
+reference's own ``minimize_adam``.  ``install(batched_sieve=True)`` rebinds ``variational_optimization._sieve``
+to a wrapper that lets the reference's ``_sieve`` do everything except its candidate loop (:775-787), which
+becomes one call of ``neg_elcbo_batch`` (see :func:`make_sieve`).
 """
 from __future__ import annotations
 
@@ -87,7 +89,55 @@ def make_minimize_adam(reference_minimize_adam, device_loop=None):
     return minimize_adam
 
 
-def install(device_adam=False):
+def make_sieve(reference_sieve, module, batch_fn=None):
+    """The rebound ``_sieve`` (variational_optimization.py:660-809): the reference's own function does everything
+    (options, soft bounds, candidate generation, return values); only its candidate loop (:775-787) is collapsed
+    into ONE batched launch.  While the reference function runs, the module's ``_neg_elcbo`` is a recorder that
+    notes ``(theta, vp0)`` and returns increasing placeholders, so the reference's ``argsort`` leaves the
+    candidates in creation order; the batched values are then computed and the same ``argsort`` applied here.
+    Any call that is not the default sieve evaluation (stochastic entropy, variance term, gradients) is passed
+    to the real ``_neg_elcbo`` and nothing is re-ordered."""
+    import numpy as np
+
+    def _sieve(*args, **kwargs):
+        real = module._neg_elcbo
+        rec, mode = [], {"batch": None}
+
+        def recorder(theta, gp, vp, beta=0.0, Ns=0, compute_grad=True, compute_var=None, theta_bnd=None, *a, **k):
+            plain = Ns == 0 and not compute_grad and not compute_var and beta == 0 and not a and not k
+            if mode["batch"] is None:
+                mode["batch"] = bool(plain)
+            if not (mode["batch"] and plain):
+                mode["batch"] = False
+                return real(theta, gp, vp, beta, Ns, compute_grad, compute_var, theta_bnd, *a, **k)
+            rec.append((np.array(theta, dtype=float, copy=True), gp, vp, theta_bnd))
+            return float(len(rec)), None, 0.0, 0.0, 0.0
+
+        module._neg_elcbo = recorder
+        try:
+            out = reference_sieve(*args, **kwargs)
+        finally:
+            module._neg_elcbo = real
+        if not rec:
+            return out
+        vp0_vec, vp0_type = out[0], out[1]
+        fn = batch_fn
+        if fn is None:
+            from .vbmc.variational_optimization import neg_elcbo_batch as fn
+        same = mode["batch"] and len(rec) == len(vp0_vec) and all(r[2] is v for r, v in zip(rec, vp0_vec))
+        if same:
+            F, _, _ = fn([r[2] for r in rec], rec[0][1], rec[0][3], thetas=[r[0] for r in rec])
+        else:  # (never seen: the loop changed shape) evaluate one at a time, in the order the reference returned
+            F = np.array([real(r[0], r[1], r[2], 0, 0, 0, False, r[3])[0] for r in rec])
+            vp0_vec = np.array([r[2] for r in rec], dtype=object)
+        order = np.argsort(np.asarray(F))  # :790
+        return (vp0_vec[order], np.asarray(vp0_type)[order]) + tuple(out[2:])
+
+    _sieve.__wrapped__ = reference_sieve
+    return _sieve
+
+
+def install(device_adam=False, batched_sieve=False):
     """Patch an importable ``pyvbmc``; returns the list of ``module.name`` sites rebound."""
     done = []
     for modname, names in _SITES.items():
@@ -104,6 +154,13 @@ def install(device_adam=False):
             _saved[(modname, "minimize_adam")] = mod.minimize_adam
             mod.minimize_adam = make_minimize_adam(mod.minimize_adam)
             done.append(f"{modname}.minimize_adam")
+    if batched_sieve:
+        modname = "pyvbmc.vbmc.variational_optimization"
+        mod = sys.modules.get(modname) or importlib.import_module(modname)
+        if hasattr(mod, "_sieve") and (modname, "_sieve") not in _saved:
+            _saved[(modname, "_sieve")] = mod._sieve
+            mod._sieve = make_sieve(mod._sieve, mod)
+            done.append(f"{modname}._sieve")
     return done
 
 

@@ -269,3 +269,75 @@ def test_minimize_adam_wrapper_matches_the_reference_closure_shape():
 
     assert list(inspect.signature(vo.minimize_adam).parameters) == [
         "f", "x0", "lb", "ub", "tol_fun", "max_iter", "master_min", "master_max", "master_decay", "use_early_stopping"]
+
+
+def test_sieve_wrapper_batches_the_candidate_loop_and_keeps_the_reference_order():
+    """make_sieve around a stand-in with the reference's loop shape (variational_optimization.py:775-800)."""
+    from pyvbmc_b200.install import make_sieve
+
+    mod = types.SimpleNamespace()
+    truth = {"a": 3.0, "b": -1.0, "c": 2.0, "d": 0.5}
+    real_calls = []
+
+    def real_neg_elcbo(theta, gp, vp, beta=0.0, Ns=0, compute_grad=True, compute_var=None, theta_bnd=None):
+        real_calls.append(vp)
+        return truth[vp] + (100.0 if Ns else 0.0), None, 0.0, 0.0, 0.0
+
+    mod._neg_elcbo = real_neg_elcbo
+
+    def ref_sieve(init_N, ns_fast=0):
+        # (shape of the reference: evaluate every candidate through the MODULE's _neg_elcbo, argsort, reorder)
+        vp0_vec = np.array(list("abcd")[:init_N], dtype=object)
+        vp0_type = np.arange(init_N) + 10
+        if init_N == 0:
+            return ("vp-copy", 1, 0, False, 7, ns_fast)
+        fill = np.zeros(init_N)
+        for i, vp0 in enumerate(vp0_vec):
+            fill[i] = mod._neg_elcbo(np.full(2, float(i)), "GP", vp0, 0, ns_fast, 0, False, {"lb": 0})[0]
+        order = np.argsort(fill)
+        return (vp0_vec[order], vp0_type[order], 0, False, 7, ns_fast)
+
+    batch_calls = []
+
+    def batch_fn(vps, gp, theta_bnd, thetas=None):
+        batch_calls.append((list(vps), gp, theta_bnd, [t.tolist() for t in thetas]))
+        F = np.array([truth[v] for v in vps])
+        return F, F, F
+
+    sieve = make_sieve(ref_sieve, mod, batch_fn)
+    out = sieve(4)
+    assert list(out[0]) == ["b", "d", "c", "a"] and list(out[1]) == [11, 13, 12, 10] and out[2:] == (0, False, 7, 0)
+    assert len(batch_calls) == 1 and real_calls == []                       # ONE batched call, no single calls
+    assert batch_calls[0][0] == list("abcd") and batch_calls[0][1] == "GP" and batch_calls[0][2] == {"lb": 0}
+    assert batch_calls[0][3] == [[0.0, 0.0], [1.0, 1.0], [2.0, 2.0], [3.0, 3.0]]
+    assert mod._neg_elcbo is real_neg_elcbo                                 # restored
+    # stochastic fast entropy (ns_ent_K_fast > 0): untouched reference flow through the real function
+    out = sieve(3, ns_fast=5)
+    assert list(out[0]) == ["b", "c", "a"] and len(batch_calls) == 1 and real_calls == list("abc")
+    # no candidates: the reference's early return passes through
+    assert sieve(0) == ("vp-copy", 1, 0, False, 7, 0)
+    # the module function is restored even if the reference raises
+    def boom(*a, **k):
+        raise RuntimeError("x")
+    with pytest.raises(RuntimeError):
+        make_sieve(boom, mod, batch_fn)()
+    assert mod._neg_elcbo is real_neg_elcbo
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+def test_sieve_wrapper_matches_the_reference_loop_shape():
+    """The reference's _sieve calls the module-level _neg_elcbo positionally as
+    (theta, gp, vp0, 0, ns_ent_K_fast, 0, compute_var, theta_bnd) and returns a 6-tuple led by (vp0_vec, vp0_type)."""
+    import inspect
+
+    from oracle import ref_loader
+
+    ref_loader.load()
+    from pyvbmc.vbmc import variational_optimization as vo
+
+    src = inspect.getsource(vo._sieve)
+    assert "_neg_elcbo(" in src and "ns_ent_K_fast" in src and "np.argsort(nelcbo_fill)" in src
+    assert "_neg_elcbo" in vo._sieve.__code__.co_names  # looked up in the module at call time => rebinding works
+    call = src[src.index("_neg_elcbo("):]
+    args = [a.strip() for a in call[call.index("(") + 1 : call.index(")")].split(",") if a.strip()]
+    assert args == ["theta", "gp", "vp0", "0", "ns_ent_K_fast", "0", "compute_var", "theta_bnd"]
