@@ -341,3 +341,65 @@ def test_sieve_wrapper_matches_the_reference_loop_shape():
     call = src[src.index("_neg_elcbo("):]
     args = [a.strip() for a in call[call.index("(") + 1 : call.index(")")].split(",") if a.strip()]
     assert args == ["theta", "gp", "vp0", "0", "ns_ent_K_fast", "0", "compute_var", "theta_bnd"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("best_N", [1, 5])
+def test_sieve_wrapper_end_to_end_on_the_unmodified_reference(best_N):
+    """make_sieve around the REAL pyvbmc _sieve (options, get_hpd, _vb_init, soft bounds all run as shipped), with
+    the reference's own _neg_elcbo as the stand-in for the batched kernel: same candidates, same order, same types
+    and same returned settings as the unwrapped reference with the same NumPy seed."""
+    from oracle import gp_posterior as gpp
+    from oracle import ref_loader
+    from pyvbmc_b200.install import make_sieve
+
+    ref_loader.load()
+    import pyvbmc.vbmc as vpk
+    from pyvbmc.vbmc import variational_optimization as vo
+    from pyvbmc.vbmc.options import Options
+
+    D, K, N, S = 3, 4, 60, 2
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(N, D))
+    y = -0.5 * np.sum(X**2, axis=1) + 0.1 * rng.normal(size=N)
+    lay = gpp.hyp_layout(D, 1, "negquad")
+    hyps = np.zeros((S, lay["H"]))
+    for s in range(S):
+        h = hyps[s]
+        h[:D] = rng.normal(0.0, 0.3, size=D)
+        h[D], h[D + 1] = rng.normal(0.5, 0.2), np.log(1e-2)
+        b = lay["mean_start"]
+        h[b] = y.max()
+        h[b + 1 : b + 1 + D] = 0.1 * rng.normal(size=D)
+        h[b + 1 + D : b + 1 + 2 * D] = np.log(2.0)
+    gp = ref_loader.make_ref_gp(X, y.reshape(-1, 1), gpp.posteriors(X, y, hyps))
+    base = os.path.join(os.path.dirname(vpk.__file__), "option_configs")
+    opts = Options(os.path.join(base, "basic_vbmc_options.ini"), evaluation_parameters={"D": D}, user_options=None)
+    opts.load_options_file(os.path.join(base, "advanced_vbmc_options.ini"), evaluation_parameters={"D": D})
+    optim_state = {"entropy_switch": False}
+
+    def fresh_vp():
+        eta = np.zeros(K)
+        return ref_loader.make_ref_vp(D, K, 0.3 * np.arange(D * K).reshape(D, K) / (D * K), 0.4 * np.ones(K), np.ones(D),
+                                      np.ones(K) / K, eta)
+
+    def describe(out):
+        vec, typ = out[0], out[1]
+        return [np.concatenate([v.get_parameters(), [t]]) for v, t in zip(vec, typ)], out[2:]
+
+    real_neg_elcbo = vo._neg_elcbo
+    batch_sizes = []
+
+    def batch_fn(vps, gp_, theta_bnd, thetas=None):  # CPU stand-in for neg_elcbo_batch: the reference, one at a time
+        batch_sizes.append(len(vps))
+        F = np.array([real_neg_elcbo(t, gp_, v, 0, 0, 0, False, theta_bnd)[0] for v, t in zip(vps, thetas)])
+        return F, F, F
+
+    np.random.seed(123)
+    want, want_rest = describe(vo._sieve(opts, optim_state, fresh_vp(), gp, init_N=12, best_N=best_N, K=K))
+    np.random.seed(123)
+    got, got_rest = describe(make_sieve(vo._sieve, vo, batch_fn)(opts, optim_state, fresh_vp(), gp, init_N=12, best_N=best_N, K=K))
+    assert batch_sizes == [12] and vo._neg_elcbo is real_neg_elcbo
+    assert got_rest == want_rest and len(got) == len(want) == 12
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
