@@ -403,3 +403,71 @@ def test_sieve_wrapper_end_to_end_on_the_unmodified_reference(best_N):
     assert got_rest == want_rest and len(got) == len(want) == 12
     for a, b in zip(got, want):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+def test_both_wrappers_inside_the_unmodified_optimize_vp():
+    """The real pyvbmc optimize_vp (sieve -> Adam on the best candidates -> full ELCBO -> pruning) with BOTH optional
+    wrappers installed and the reference's own functions as CPU stand-ins for the two device entry points: the
+    closure is recognised at the real call site, every argument is forwarded, and the result is bit-identical to the
+    unwrapped run with the same NumPy seed."""
+    from oracle import gp_posterior as gpp
+    from oracle import ref_loader
+    from pyvbmc_b200.install import make_minimize_adam, make_sieve
+
+    ref_loader.load()
+    import pyvbmc.vbmc as vpk
+    from pyvbmc.vbmc import variational_optimization as vo
+    from pyvbmc.vbmc.options import Options
+
+    D, K, N, S = 3, 3, 50, 2
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(N, D))
+    y = -0.5 * np.sum(X**2, axis=1) + 0.1 * rng.normal(size=N)
+    lay = gpp.hyp_layout(D, 1, "negquad")
+    hyps = np.zeros((S, lay["H"]))
+    for s in range(S):
+        h = hyps[s]
+        h[:D] = rng.normal(0.0, 0.3, size=D)
+        h[D], h[D + 1] = rng.normal(0.5, 0.2), np.log(1e-2)
+        b = lay["mean_start"]
+        h[b] = y.max()
+        h[b + 1 : b + 1 + D] = 0.1 * rng.normal(size=D)
+        h[b + 1 + D : b + 1 + 2 * D] = np.log(2.0)
+    gp = ref_loader.make_ref_gp(X, y.reshape(-1, 1), gpp.posteriors(X, y, hyps))
+    base = os.path.join(os.path.dirname(vpk.__file__), "option_configs")
+    opts = Options(os.path.join(base, "basic_vbmc_options.ini"), evaluation_parameters={"D": D},
+                   user_options={"max_iter_stochastic": 60})
+    opts.load_options_file(os.path.join(base, "advanced_vbmc_options.ini"), evaluation_parameters={"D": D})
+
+    def run():
+        vp = ref_loader.make_ref_vp(D, K, 0.3 * np.arange(D * K).reshape(D, K) / (D * K), 0.4 * np.ones(K), np.ones(D),
+                                    np.ones(K) / K, np.zeros(K))
+        np.random.seed(3)
+        vp2, var_ss, pruned = vo.optimize_vp(opts, {"entropy_switch": False, "warmup": False}, vp, gp, 4, 1, K)
+        return np.concatenate([vp2.get_parameters(), [vp2.stats["elbo"], vp2.stats["elbo_sd"], var_ss, pruned]])
+
+    want = run()
+    ref_adam, ref_sieve, real_neg_elcbo = vo.minimize_adam, vo._sieve, vo._neg_elcbo
+    seen = {"adam": [], "sieve": []}
+
+    def dev_loop(gp_, vp0, x0, Ns, theta_bnd, lb, ub, tol_fun, max_iter, master_min, master_max, master_decay, early):
+        seen["adam"].append((Ns, max_iter, master_min, master_max, master_decay, tol_fun, early))
+        f = lambda t: real_neg_elcbo(t, gp_, vp0, 0, Ns, compute_grad=True, compute_var=False, theta_bnd=theta_bnd)[:2]
+        return ref_adam(f, x0, lb, ub, tol_fun, max_iter, master_min, master_max, master_decay, early)
+
+    def batch_fn(vps, gp_, theta_bnd, thetas=None):
+        seen["sieve"].append(len(vps))
+        F = np.array([real_neg_elcbo(t, gp_, v, 0, 0, 0, False, theta_bnd)[0] for v, t in zip(vps, thetas)])
+        return F, F, F
+
+    vo.minimize_adam = make_minimize_adam(ref_adam, dev_loop)
+    vo._sieve = make_sieve(ref_sieve, vo, batch_fn)
+    try:
+        got = run()
+    finally:
+        vo.minimize_adam, vo._sieve = ref_adam, ref_sieve
+    assert vo._neg_elcbo is real_neg_elcbo
+    assert len(seen["sieve"]) == 1 and seen["sieve"][0] > 0      # the candidate loop became one batch
+    assert len(seen["adam"]) >= 1 and all(a[1] == 60 and a[0] > 0 for a in seen["adam"])  # every Adam run was routed
+    np.testing.assert_array_equal(got, want)
