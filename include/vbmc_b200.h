@@ -242,6 +242,9 @@ int vbmc_stream_synchronize(vbmc_ctx *ctx);
 #define VBMC_P2P_HANDLE_BYTES 64
 int vbmc_p2p_export(vbmc_ctx *ctx, int world, int D, int K, unsigned char *handle);
 int vbmc_p2p_open(vbmc_ctx *ctx, int rank, int world, const unsigned char *handles);
+/* vbmc_p2p_unmap only drops the mappings of the PEERS' buffers (the local buffer stays allocated): tear-down order
+ * is every rank unmaps -> host barrier -> every rank closes, so that no buffer is freed while a peer still maps it. */
+int vbmc_p2p_unmap(vbmc_ctx *ctx);
 int vbmc_p2p_close(vbmc_ctx *ctx);
 /* copy n doubles from device memory to the host through the context's pinned staging buffer,
  * ordered after everything enqueued on the context stream (synchronises)                     */

@@ -129,6 +129,7 @@ PROTOTYPES = {
     "vbmc_stream_synchronize": (C.c_int, [C.c_void_p]),
     "vbmc_p2p_export": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_p2p_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vbmc_p2p_unmap": (C.c_int, [C.c_void_p]),
     "vbmc_p2p_close": (C.c_int, [C.c_void_p]),
     "vbmc_read_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_double_p]),
     "vbmc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),

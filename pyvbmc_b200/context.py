@@ -467,6 +467,9 @@ class Context:
         arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         _capi.check(self._lib.vbmc_p2p_open(self._h, int(rank), int(world), arr))
 
+    def p2p_unmap(self):
+        _capi.check(self._lib.vbmc_p2p_unmap(self._h))
+
     def p2p_close(self):
         _capi.check(self._lib.vbmc_p2p_close(self._h))
 

@@ -1006,6 +1006,15 @@ int vbmc_p2p_open(vbmc_ctx *p, int rank, int world, const unsigned char *handles
     return VBMC_OK;
 }
 
+int vbmc_p2p_unmap(vbmc_ctx *p) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    cudaStreamSynchronize(c->stream);
+    p2p_unmap(c);
+    return VBMC_OK;
+}
+
 int vbmc_p2p_close(vbmc_ctx *p) {
     VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
     Ctx *c = &ex(p)->c;

@@ -34,7 +34,7 @@ def raw_layout(D: int, K: int):
     return {"H": 0, "G": 1, "ent": 4, "gp": 4 + block, "block": block, "total": 4 + 2 * block}
 
 
-def negotiate_p2p(dist, group, rank, world, export_fn, open_fn, close_fn):
+def negotiate_p2p(dist, group, rank, world, export_fn, open_fn, close_fn, unmap_fn=None):
     """Collective set-up of the peer-memory exchange (host logic, backend-agnostic: also runs over gloo).
 
     ``export_fn() -> bytes`` allocates the local exchange buffer and returns its IPC handle, ``open_fn(handles)``
@@ -57,12 +57,17 @@ def negotiate_p2p(dist, group, rank, world, export_fn, open_fn, close_fn):
     flags = [None] * world
     dist.all_gather_object(flags, ok, group=group)
     enabled = bool(all(flags))
-    if not enabled:
+    if not enabled and unmap_fn is not None:
         try:
-            close_fn()
+            unmap_fn()  # drop the peers' mappings first ...
         except Exception:
             pass
     dist.barrier(group=group)  # nobody stores into a peer before every peer has zeroed its flags
+    if not enabled:
+        try:
+            close_fn()  # ... and free the local buffer only when no peer can still map it
+        except Exception:
+            pass
     return enabled
 
 
@@ -105,6 +110,7 @@ class ShardedNegElcbo:
             lambda: self.ctx.p2p_export(self.world, D, K),
             lambda handles: self.ctx.p2p_open(self.rank, self.world, handles),
             self.ctx.p2p_close,
+            self.ctx.p2p_unmap,
         )
         return self.p2p
 
@@ -118,6 +124,8 @@ class ShardedNegElcbo:
         if not all(flags):
             self.p2p = False
             self.ctx.synchronize()
+            self.ctx.p2p_unmap()
+            self.dist.barrier(group=self.group)  # every rank has dropped its mappings of the peers' buffers
             self.ctx.p2p_close()
         self.dist.barrier(group=self.group)
         return self.p2p
@@ -152,4 +160,8 @@ class ShardedNegElcbo:
 
     def close(self):
         self.ctx.synchronize()
+        if self.p2p:  # collective tear-down: unmap everywhere, then free (no buffer is freed while a peer maps it)
+            self.p2p = False
+            self.ctx.p2p_unmap()
+            self.dist.barrier(group=self.group)
         self.ctx.close()

@@ -113,7 +113,10 @@ def _p2p_worker(rank, world, port, q, scenario):
     def close_fn():
         log.append("closed")
 
-    enabled = negotiate_p2p(dist, None, rank, world, export_fn, open_fn, close_fn)
+    def unmap_fn():
+        log.append("unmapped")
+
+    enabled = negotiate_p2p(dist, None, rank, world, export_fn, open_fn, close_fn, unmap_fn)
     q.put((rank, enabled, log))
     dist.barrier()
     dist.destroy_process_group()
@@ -140,8 +143,8 @@ def test_gloo_p2p_negotiation_is_collective(scenario, port):
     assert enabled == ([True, True] if scenario == "ok" else [False, False])
     if scenario == "ok":
         assert all(g[2] == [[0, 1]] for g in got)  # every rank opened the handles of ranks 0, 1 in order
-    else:
-        assert all("closed" in g[2] for g in got)
+    else:  # tear-down order on every rank: drop the peers' mappings, (barrier), then free the local buffer
+        assert all([x for x in g[2] if isinstance(x, str)] == ["unmapped", "closed"] for g in got)
 
 
 @pytest.mark.gpu
