@@ -78,20 +78,27 @@ class ShardedNegElcbo:
     ``(F, dF, G, H, varF)``.
     """
 
-    def __init__(self, gp, device=None, group=None, seed=0, single=False):
+    def __init__(self, gp, device=None, group=None, seed=0, single=False, ctx=None):
+        """``ctx``: an already built device context (tests inject a host stand-in with the same methods; the
+        raw / result vectors then live in host tensors and the collective runs over gloo)."""
         import torch
         import torch.distributed as dist
-
-        from .context import Context
 
         self.torch, self.dist, self.group = torch, dist, group
         use_dist = dist.is_initialized() and not single  # single=True: this rank evaluates everything itself
         self.rank = dist.get_rank(group) if use_dist else 0
         self.world = dist.get_world_size(group) if use_dist else 1
-        self.device = torch.cuda.current_device() if device is None else int(device)
-        self.ctx = Context(self.device)
-        self.ctx.pack_gp(gp)
-        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+        if ctx is None:
+            from .context import Context
+
+            self.device = torch.cuda.current_device() if device is None else int(device)
+            self.ctx = Context(self.device)
+            self.ctx.pack_gp(gp)
+            self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+            self._tensor_device = torch.device("cuda", self.device)
+        else:
+            self.device, self.ctx, self.stream = device, ctx, None
+            self._tensor_device = torch.device("cpu")
         self.seed = int(seed)
         self.step = 0
         self._raw = self._out = None
@@ -114,6 +121,16 @@ class ShardedNegElcbo:
         )
         return self.p2p
 
+    def _buffers(self, D, K):
+        """Device-resident raw (pre-Jacobian, all-reduced) and result vectors, allocated on first use and
+        re-allocated when the problem shape changes."""
+        torch = self.torch
+        n_raw, n_out = self.ctx.raw_len(D, K), self.ctx.out_len(D, K)
+        if self._raw is None or self._raw.numel() != n_raw or self._out.numel() != n_out:
+            self._raw = torch.zeros(n_raw, dtype=torch.float64, device=self._tensor_device)
+            self._out = torch.zeros(n_out, dtype=torch.float64, device=self._tensor_device)
+        return self._raw, self._out
+
     def p2p_self_check(self, F):
         """Collective: if ANY rank saw the peer exchange time out (poisoned result: F is NaN), every rank drops
         back to the NCCL all-reduce.  Call it once after the first evaluation."""
@@ -135,8 +152,11 @@ class ShardedNegElcbo:
         raw, out = self._buffers(D, K)
         self.ctx.partials_async(self.rank, self.world, raw.data_ptr())
         if self.world > 1 and not self.p2p:
-            with self.torch.cuda.stream(self.stream):
+            if self.stream is None:  # host stand-in context
                 self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM, group=self.group)
+            else:
+                with self.torch.cuda.stream(self.stream):
+                    self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM, group=self.group)
         self.ctx.finalize_async(raw.data_ptr(), out.data_ptr())  # (with p2p: raw phases + peer all-reduce + final)
         return out
 
