@@ -602,8 +602,12 @@ def neg_elcbo(
     theta = np.asarray(theta, dtype=float)
     set_parameters(vp, theta)  # :1080
     if vp.optimize_weights:
-        eta = theta[-K:].copy()
-        vp.eta = (eta - np.max(eta)).reshape(1, -1)  # :1082-1085
+        # :1082-1085 -- `vp.eta = theta[-K:]` is a VIEW of the caller's array and `vp.eta -= amax(vp.eta)` shifts it
+        # in place: the caller's theta leaves this function with max(eta) == 0 (minimize_adam's iterate is
+        # renormalised on every call) and the soft-bound loss below reads the SHIFTED eta.
+        eta = theta[-K:]
+        eta -= np.max(eta)
+        vp.eta = eta.reshape(1, -1)
     if compute_grad:
         grad_flags = (vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights)
     else:

@@ -163,21 +163,28 @@ def export_case(stem, cfg, kw, Ns_K, extras):
 
     # (1) the Adam objective: value + gradient, MC entropy, soft bounds  (:238-249)
     theta = _perturbed_theta(pr)
-    out["theta"] = theta
+    # a COPY: the reference shifts the eta block of its argument in place (:1082-1085), so the array handed in
+    # comes back with max(eta) == 0; `theta` is the input as the caller built it, `theta_after` what the caller holds
+    # afterwards
+    out["theta"] = theta.copy()
     np.random.seed(0)
     vp = fresh_vp()
     F, dF, G, H, varF = ref._neg_elcbo(theta, rgp, vp, 0.0, Ns_K, True, False, pr.theta_bnd)
+    out["theta_after"] = theta.copy()
     out.update(mc_F=F, mc_dF=dF, mc_G=G, mc_H=H, mc_varF=varF)
     out.update(post_mu=vp.mu, post_sigma=vp.sigma, post_lambd=vp.lambd, post_w=vp.w, post_eta=vp.eta)
 
     # (2) the BFGS / sieve objective: deterministic entropy, with and without gradient (:206-219, :777)
     theta2 = _perturbed_theta(pr, seed=6, violate=False)
-    out["theta2"] = theta2
+    if opt[3]:
+        theta2[-K:] += 5.5  # max(eta) far from 0: the bound loss must see the SHIFTED eta (:1082-1085, :1195-1209)
+    out["theta2"] = theta2.copy()
     vp = fresh_vp()
     F, dF, G, H, varF = ref._neg_elcbo(theta2, rgp, vp, 0.0, 0, True, False, pr.theta_bnd)
+    out["theta2_after"] = theta2.copy()
     out.update(lb_F=F, lb_dF=dF, lb_G=G, lb_H=H)
     vp = fresh_vp()
-    F, dF, G, H, varF = ref._neg_elcbo(theta2, rgp, vp, 0.0, 0, False, False, pr.theta_bnd)
+    F, dF, G, H, varF = ref._neg_elcbo(out["theta2"].copy(), rgp, vp, 0.0, 0, False, False, pr.theta_bnd)
     assert dF is None
     out.update(lbv_F=F)
 

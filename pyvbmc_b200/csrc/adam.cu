@@ -41,8 +41,12 @@ adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
         prm[lay.lnsig_b() + k] = a.opt[1] ? th[pos_s + k] : log(sg);
     }
     // weights: softmax of eta with the max shift; eta itself is stored shifted (:1082-1085)
+    // The reference shifts the eta block of the caller's theta IN PLACE (`vp.eta = theta[-K:]; vp.eta -= amax`,
+    // variational_optimization.py:1082-1085 -- the slice is a view): the soft-bound loss reads the shifted eta
+    // (:1195-1209) and minimize_adam's `x -= step` (minimize_adam.py:98) updates the renormalised iterate.  Same
+    // here: theta's eta block is rewritten with max == 0 before the evaluation and the update.
     if (a.opt[3]) {
-        const double *eta = th + a.P - K;
+        double *eta = a.theta + a.P - K;
         double mx = -INFINITY;
         for (int k = tid; k < K; k += nt) mx = fmax(mx, eta[k]);
         mx = block_max(mx, scratch);
@@ -50,9 +54,11 @@ adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
         for (int k = tid; k < K; k += nt) se += exp(eta[k] - mx);
         se = block_sum(se, scratch);
         for (int k = tid; k < K; k += nt) {
-            prm[lay.w() + k] = exp(eta[k] - mx) / se;
-            prm[lay.eta() + k] = eta[k] - mx;
-            prm[lay.eta_b() + k] = eta[k];
+            const double e = eta[k] - mx;
+            prm[lay.w() + k] = exp(e) / se;
+            prm[lay.eta() + k] = e;
+            prm[lay.eta_b() + k] = e;
+            eta[k] = e;
         }
     } else {
         for (int k = tid; k < K; k += nt) {

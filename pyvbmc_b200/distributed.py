@@ -161,13 +161,13 @@ class ShardedNegElcbo:
         return out
 
     def __call__(self, theta, vp, Ns, theta_bnd=None, eps=None):
-        from .vbmc.variational_optimization import _bound_inputs
+        from .vbmc.variational_optimization import _bound_inputs, _shift_eta
 
         theta = np.asarray(theta, dtype=float)
         K, D = vp.K, vp.D
         vp.set_parameters(theta)
         if vp.optimize_weights:
-            vp.eta = (theta[-K:] - np.amax(theta[-K:])).reshape(1, -1)
+            _shift_eta(vp, theta, K)  # in place on the caller's theta, like the reference (:1082-1085)
         optimize = (vp.optimize_mu, vp.optimize_sigma, vp.optimize_lambd, vp.optimize_weights)
         use_bounds = self.ctx.set_bounds(theta_bnd)
         b = _bound_inputs(vp, theta) if use_bounds else (None, None, None)

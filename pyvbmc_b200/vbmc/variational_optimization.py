@@ -71,6 +71,17 @@ def _soft_bound_loss(x, slb, sub, tol_con=1e-3, compute_grad=False):
     return y
 
 
+def _shift_eta(vp, theta, K):
+    """``vp.eta = theta[-K:]; vp.eta -= amax(vp.eta); vp.eta = reshape(vp.eta, (1, -1))`` (:1082-1085).
+
+    The slice is a view, so the subtraction lands in the caller's ``theta``: after ``_neg_elcbo`` returns, the
+    caller's array has ``max(eta) == 0`` (``minimize_adam`` keeps iterating on that renormalised array,
+    minimize_adam.py:87-98), ``vp.eta`` aliases it, and ``_vp_bound_loss`` (:1195-1209) reads the shifted eta."""
+    eta = theta[-K:]
+    eta -= np.amax(eta)
+    vp.eta = np.reshape(eta, (1, -1))
+
+
 def _bound_inputs(vp, theta):
     """The pieces of theta that ``_vp_bound_loss`` reads (:536-555)."""
     D, K = vp.D, vp.K
@@ -172,9 +183,7 @@ def neg_elcbo_batch(vp_vec, gp, theta_bnd=None, thetas=None):
         theta = np.asarray(vp.get_parameters() if thetas is None else thetas[b], dtype=float)
         vp.set_parameters(theta)  # :1080
         if vp.optimize_weights:
-            vp.eta = theta[-K:].copy()
-            vp.eta -= np.amax(vp.eta)
-            vp.eta = np.reshape(vp.eta, (1, -1))  # :1082-1085
+            _shift_eta(vp, theta, K)  # :1082-1085
         _pack_params(prm[b], vp, theta, optimize, use_bounds)
     out = ctx.negelcbo_batch(D, K, prm, optimize, use_bounds)
     return out[:, 0].copy(), out[:, 1].copy(), out[:, 2].copy()
@@ -220,9 +229,7 @@ def _neg_elcbo(
     K, D = vp.K, vp.D
     vp.set_parameters(theta)  # :1080
     if vp.optimize_weights:
-        vp.eta = theta[-K:].copy()
-        vp.eta -= np.amax(vp.eta)
-        vp.eta = np.reshape(vp.eta, (1, -1))  # :1082-1085
+        _shift_eta(vp, theta, K)  # :1082-1085 (in place on the CALLER's theta, like the reference)
 
     optimize = (bool(vp.optimize_mu), bool(vp.optimize_sigma), bool(vp.optimize_lambd), bool(vp.optimize_weights))
     ctx = context_for_gp(gp, need_L=bool(compute_var))

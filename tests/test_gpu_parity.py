@@ -215,6 +215,25 @@ def test_negelcbo_lb_golden(pv, stem):
     assert dF is None and relerr(F, g["lbv_F"]) < TOL_F64
 
 
+@pytest.mark.parametrize("stem", ["c2", "c3", "c4", "c2_noweights"])
+def test_negelcbo_shifts_eta_of_the_callers_theta_in_place(pv, stem):
+    """variational_optimization.py:1082-1085 mutates the CALLER's theta (eta block shifted to max == 0, vp.eta a
+    view of it) and the bound loss reads the shifted eta: theta2 carries max(eta) ~ 5.5, so an unshifted bound loss
+    would be off by orders of magnitude (lb_F is the unmodified reference's value)."""
+    c = load_case(stem)
+    g = c.g
+    theta = g["theta2"].copy()
+    vp = case_vp(pv, c)
+    F, dF, *_ = pv._neg_elcbo(theta, c.gp, vp, 0.0, 0, True, False, c.theta_bnd)
+    assert relerr(F, g["lb_F"]) < TOL_F64 and relmax(dF, g["lb_dF"]) < TOL_F64
+    assert np.array_equal(theta, g["theta2_after"])
+    if c.opt[3]:
+        assert theta[-c.K:].max() == 0.0 and np.shares_memory(vp.eta, theta)
+    theta = g["theta"].copy()
+    pv._neg_elcbo(theta, c.gp, case_vp(pv, c), 0.0, c.Ns_K, True, False, c.theta_bnd, eps=eps_for(0, c.K, c.Ns_K, c.D))
+    assert np.array_equal(theta, g["theta_after"])
+
+
 def test_negelcbo_errors(pv):
     c = load_case("c1")
     with pytest.raises(ValueError):
@@ -562,7 +581,7 @@ def test_sieve_batch_matches_oracle_and_single_calls(pv, shape):
 
 # ---------------------------------------------------------------------------------------------------
 # device-resident Adam: minimize_adam.py:61-145 around the ELBO objective
-@pytest.mark.parametrize("case", ["c2_all", "c2_noweights", "c4_box"])
+@pytest.mark.parametrize("case", ["c2_all", "c2_noweights", "c4_box", "c2_etashift"])
 def test_device_adam_matches_host_loop(pv, case):
     """The CUDA-graph Adam loop against the oracle's restatement of the reference loop driving the
     parity-pinned one-at-a-time evaluation with the same Philox key (seed, offset0 + iteration)."""
@@ -578,6 +597,10 @@ def test_device_adam_matches_host_loop(pv, case):
 
     vp_h = fresh_vp()
     theta0 = np.asarray(vp_h.get_parameters(), dtype=float)
+    if case == "c2_etashift":
+        # max(eta) far from 0: every objective call renormalises the iterate's eta block in place
+        # (variational_optimization.py:1082-1085) and the bound loss reads the shifted eta
+        theta0[-pr.K:] += 6.0
     bnd = vp_h.get_bounds(pr.gp.X, syn.OPTIONS, pr.K)
     kw = dict(tol_fun=1e-3, max_iter=90, master_min=0.001, master_max=0.05, master_decay=200)
     if case == "c4_box":
@@ -598,6 +621,8 @@ def test_device_adam_matches_host_loop(pv, case):
     assert np.max(np.abs(x - xo)) <= 1e-7 * max(1.0, np.max(np.abs(xo))) and abs(y - yo) <= 1e-7 * max(1.0, abs(yo))
     if case == "c4_box":
         assert np.all(x_tab <= (theta0 + 0.03)[:, None] + 1e-15) and np.all(x_tab >= (theta0 - 0.02)[:, None] - 1e-15)
+    if case == "c2_etashift":
+        assert np.all(np.abs(x_tab[-pr.K:, :].max(axis=0)) < 0.2)
     # vp is left at the last evaluated iterate, as after the reference loop
     np.testing.assert_allclose(np.ravel(vp_d.sigma), np.ravel(vp_h.sigma), rtol=1e-6)
     np.testing.assert_allclose(vp_d.mu, vp_h.mu, rtol=1e-6, atol=1e-9)

@@ -7,6 +7,7 @@ import pytest
 from golden_util import REF_CASES, VAR_CASES, eps_for, load_case, load_npz, relerr, relmax
 from oracle import elbo_oracle as eo
 from oracle import gp_posterior as gpp
+from oracle import synthetic as syn
 
 TOL = 1e-9  # oracle vs unmodified reference, fp64 both sides (direct vs log-sum-exp evaluation)
 
@@ -232,3 +233,51 @@ def test_adam_oracle_matches_reference_minimize_adam():
         np.testing.assert_allclose(y_tab, g[name + "_ytab"], rtol=0, atol=1e-13)
         np.testing.assert_allclose(x, g[name + "_x"], rtol=0, atol=1e-13)
         assert abs(y - float(g[name + "_y"])) < 1e-13
+
+
+@pytest.mark.parametrize("stem", ["c2", "c3", "c4", "c2_noweights"])
+def test_neg_elcbo_shifts_eta_of_the_callers_theta_in_place(stem):
+    """variational_optimization.py:1082-1085: ``vp.eta = theta[-K:]`` is a view and ``vp.eta -= amax`` lands in the
+    caller's array; the soft-bound loss then reads the SHIFTED eta.  The goldens hold theta as built (max(eta) != 0)
+    and the array the unmodified reference handed back."""
+    c = load_case(stem)
+    g = c.g
+    for name, Ns in (("theta", c.Ns_K), ("theta2", 0)):
+        theta = g[name].copy()
+        if c.opt[3]:
+            assert abs(theta[-c.K:].max()) > 1e-3  # the fixture really exercises the shift
+        eps = eps_for(0, c.K, c.Ns_K, c.D) if Ns else None
+        vp = c.vp()
+        eo.neg_elcbo(theta, c.gp, vp, 0.0, Ns, True, False, c.theta_bnd, eps_half=eps)
+        assert np.array_equal(theta, g[name + "_after"])
+        if c.opt[3]:
+            assert theta[-c.K:].max() == 0.0 and np.shares_memory(vp.eta, theta)
+        else:
+            assert np.array_equal(theta, g[name])
+
+
+def test_adam_oracle_on_the_real_elbo_closure_matches_reference():
+    """The oracle's Adam loop around the oracle's neg_elcbo against the unmodified minimize_adam around the unmodified
+    _neg_elcbo (tests/golden/ref_adam.npz `elbo_*`, theta0 with max(eta) ~ 3.3): the iterate's eta block is
+    renormalised in place by every objective call (variational_optimization.py:1082-1085), which shows in x_tab."""
+    import os
+
+    from oracle.minimize_adam_oracle import minimize_adam
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_adam.npz"))
+    pr = syn.make_problem("C2", N=int(g["elbo_N"]))
+    vp = pr.vp.copy()
+    Ns_K = int(g["elbo_Ns_K"])
+
+    def f(theta_):
+        r = eo.neg_elcbo(theta_, pr.gp, vp, 0.0, Ns_K, True, False, pr.theta_bnd)  # draws from np.random like the reference
+        return r[0], r[1]
+
+    np.random.seed(int(g["elbo_seed"]))
+    x, y, x_tab, y_tab, n = minimize_adam(f, g["elbo_theta0"].copy(), max_iter=60, master_max=0.05, use_early_stopping=True)
+    assert n == int(g["elbo_n"])
+    assert np.max(np.abs(y_tab - g["elbo_ytab"])) <= 1e-9 * np.max(np.abs(g["elbo_ytab"]))
+    assert np.max(np.abs(x_tab - g["elbo_xtab"])) <= 1e-9 * np.max(np.abs(g["elbo_xtab"]))
+    K = pr.K
+    # after the first update every iterate sits within one step of a max(eta) == 0 renormalisation
+    assert np.all(np.abs(x_tab[-K:, :].max(axis=0)) < 0.2) and g["elbo_theta0"][-K:].max() > 2.0
