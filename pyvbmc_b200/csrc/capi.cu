@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <vector>
@@ -15,11 +16,16 @@ namespace vbmc {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 
-static thread_local bool g_realloc = false;  // set whenever a device buffer moved: captured graphs are stale
+// Bumped whenever ANY context's device buffer moves (never reset).  Every context remembers the epoch it last looked
+// at (CtxEx::seen_epoch): a captured graph is only replayed if no buffer anywhere moved since it was captured.  The
+// counter is process-wide and monotonic on purpose -- a consumed-once flag shared by all contexts let context B (or
+// another thread) swallow the notification meant for context A, which then replayed freed pointers.  A reallocation
+// in one context costs the others one re-capture; it can never be missed.
+static std::atomic<uint64_t> g_realloc_epoch{1};
 
 int ensure(double **p, size_t *cap, size_t need) {
     if (need <= *cap && *p) return VBMC_OK;
-    g_realloc = true;
+    g_realloc_epoch.fetch_add(1, std::memory_order_relaxed);
     if (*p) VBMC_CUDA_CHECK(cudaFree(*p));
     *p = nullptr;
     size_t n = need + need / 4 + 64;
@@ -30,7 +36,7 @@ int ensure(double **p, size_t *cap, size_t need) {
 
 int ensure_pinned(double **d, double **h, size_t *cap, size_t need) {
     if (need <= *cap && *d && *h) return VBMC_OK;
-    g_realloc = true;
+    g_realloc_epoch.fetch_add(1, std::memory_order_relaxed);
     if (*d) VBMC_CUDA_CHECK(cudaFree(*d));
     if (*h) VBMC_CUDA_CHECK(cudaFreeHost(*h));
     *d = *h = nullptr;
@@ -109,6 +115,7 @@ struct CtxEx {
     // CUDA-graph replay of the flat evaluation
     bool graphs_on = true;
     uint64_t gen = 1;
+    uint64_t seen_epoch = 0;  // g_realloc_epoch when this context last looked (see there)
     GraphKey gkey, last_key;
     cudaGraphExec_t gexec = nullptr;
     cudaGraph_t graph = nullptr;
@@ -305,9 +312,9 @@ void drop_graph(CtxEx *x) {
 // one driver call instead of ~12, and no CPU-side gaps between the dependent kernels.
 int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     Ctx *c = &x->c;
-    if (g_realloc) {  // some buffer moved since the last look: every captured pointer is suspect
-        x->gen++;
-        g_realloc = false;
+    if (x->seen_epoch != g_realloc_epoch.load(std::memory_order_relaxed)) {  // some buffer moved since this context
+        x->gen++;                                                           // last looked: captured pointers are suspect
+        x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
     }
     const bool eligible = x->graphs_on && !c->stage_timing && !c->time_entmc && s.flat != nullptr &&
                           !(s.Ns > 0 && s.rng_mode == VBMC_RNG_EPS) && !s.compute_var;
@@ -334,7 +341,7 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     }
     // second call with the same signature: capture
     drop_graph(x);
-    g_realloc = false;
+    const uint64_t epoch0 = g_realloc_epoch.load(std::memory_order_relaxed);
     const int64_t l0 = c->launches;
     VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = stage(x, s);
@@ -342,10 +349,11 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     if (rc == VBMC_OK) rc = finalize(x, c->d_raw, c->h_out);
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
-    if (rc != VBMC_OK || ce != cudaSuccess || g_realloc) {
+    if (rc != VBMC_OK || ce != cudaSuccess || epoch0 != g_realloc_epoch.load(std::memory_order_relaxed)) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();
         x->gen++;  // whatever moved, start over with eager runs
+        x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
         x->last_key = GraphKey{};
         if (rc != VBMC_OK) return rc;
         return run_single(x, s, n_out);
@@ -857,9 +865,9 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
     VBMC_REQUIRE(n >= 0 && x->adam_done + n <= x->adam_max_iter, VBMC_ERR_ARG, "adam_steps: more steps than max_iter");
     const long long i0 = x->adam_done;
     for (int it = 0; it < n; ++it) {
-        if (g_realloc) {  // a buffer moved (another evaluation resized something): captured pointers are stale
+        if (x->seen_epoch != g_realloc_epoch.load(std::memory_order_relaxed)) {  // a buffer moved: captured pointers are stale
             x->gen++;
-            g_realloc = false;
+            x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
         }
         if (x->adam_gexec && x->adam_gen == x->gen) {
             VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
@@ -872,16 +880,17 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
             continue;
         }
         drop_adam_graph(x);
-        g_realloc = false;
+        const uint64_t epoch0 = g_realloc_epoch.load(std::memory_order_relaxed);
         const int64_t l0 = c->launches;
         VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int rc = adam_iteration(x);
         cudaGraph_t g = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
-        if (rc != VBMC_OK || ce != cudaSuccess || g_realloc) {
+        if (rc != VBMC_OK || ce != cudaSuccess || epoch0 != g_realloc_epoch.load(std::memory_order_relaxed)) {
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
             x->gen++;
+            x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
             x->adam_eager_done = false;  // start over with an eager iteration
             if (rc != VBMC_OK) return rc;
             VBMC_TRY(adam_iteration(x));

@@ -280,6 +280,32 @@ def test_graph_replay_is_transparent(pv):
     assert Fa != res[0][0]
 
 
+def test_graph_staleness_is_per_context(pv):
+    """Two GP contexts alive at once (the LRU holds 4): context A captures a graph, then A's buffers move (a much
+    larger draw count through the eager path), then context B runs first.  A's captured graph must NOT be replayed
+    with the freed pointers -- the reallocation notice cannot be swallowed by another context."""
+    ca, cb = load_case("c2"), load_case("c2_ill")
+    g = ca.g
+
+    def eval_a(Ns, seed=11):
+        return pv._neg_elcbo(g["theta"].copy(), ca.gp, case_vp(pv, ca), 0.0, Ns, True, False, ca.theta_bnd, seed=seed)
+
+    def eval_b():
+        return pv._neg_elcbo(g["theta"].copy(), cb.gp, case_vp(pv, cb), 0.0, 300, True, False, cb.theta_bnd, seed=11)
+
+    first = [eval_a(200) for _ in range(4)]  # eager, capture, replay, replay
+    eval_b(), eval_b(), eval_b()
+    eval_a(60000)  # A's per-CTA record / tile buffers grow: every pointer captured above is stale
+    Fb = eval_b()  # B looks at the reallocation notice first
+    again = eval_a(200)
+    assert again[0] == first[0][0] and np.array_equal(again[1], first[0][1])
+    for _ in range(3):
+        nxt = eval_a(200)
+        assert nxt[0] == first[0][0] and np.array_equal(nxt[1], first[0][1])
+    Fb2 = eval_b()
+    assert Fb2[0] == Fb[0] and np.array_equal(Fb2[1], Fb[1])
+
+
 # ------------------------------------------------------------------ variance path (full ELCBO evaluation)
 @pytest.mark.parametrize("stem", VAR_CASES)
 def test_variance_path_golden(pv, stem):
