@@ -2,7 +2,7 @@
 """Benchmark of the ELBO inner loop: negelcbo+grad evals/sec (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-  python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference CPU path (oracle port)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # the UNMODIFIED reference on the host CPU
 
 A "step" is ONE evaluation of ``_neg_elcbo(theta, gp, vp, 0, Ns_K, compute_grad=True,
 compute_var=False, theta_bnd)`` -- the ``minimize_adam`` objective
@@ -11,14 +11,22 @@ compute_var=False, theta_bnd)`` -- the ``minimize_adam`` objective
 N = 1 : config C3 of BASELINE.json (D=20, N=400, K=50, S=8, N_s=400k  =>  8000 draws/component).
 N > 1 : weak scaling, one C3 worth of entropy draws per GPU: N_s = 400k*N, S = max(8, 4*N)
         (N = 8 is exactly config C5: S=32, N_s=3.2M); draws and hyper-samples are sharded, one
-        NCCL all-reduce of the raw (pre-Jacobian) vector per step.  ``value`` counts
-        C3-equivalent evaluations (N per step) per second; ``evals_per_s_job`` is the plain
-        number of (N-times larger) evaluations per second.
+        all-reduce of the raw (pre-Jacobian) vector per step.  ``value`` counts C3-equivalent
+        evaluations (N per step) per second; ``evals_per_s_job`` is the plain number of
+        (N-times larger) evaluations per second.
 
 value : device-resident throughput (theta and GP already in HBM, CUDA events on the launching
-        stream, L2 flushed between steps, max over ranks).
+        stream, L2 flushed between steps, max over ranks).  N = 1: the library's own launch
+        sequence (``vbmc_negelcbo_enqueue``: the kernels the drop-in call runs, nothing else);
+        N > 1: ``ShardedNegElcbo.enqueue`` (partials -> all-reduce -> finalize).
 e2e   : the same evaluation through the reference-shaped public function with HOST NumPy
         buffers in and out (H2D of the parameters and D2H of (F, dF) inside the timed region).
+
+Reference arm (``--impl reference``): the unmodified ``pyvbmc`` ``_neg_elcbo`` (from /root/reference,
+or from the archive ``oracle/build_ref.py`` packs into the git-ignored ``oracle/_ref`` -- that is what
+exists on the GPU box), FULL evaluations, nothing extrapolated.  Every step is one C3 evaluation at any
+N (the host CPU does not grow with the GPU count; the reference's cost is linear in draws and
+hyper-samples, so its C3-equivalent evaluations per second are the same number at every N).
 """
 import argparse
 import json
@@ -36,6 +44,7 @@ if ROOT not in sys.path:
 
 METRIC = "negelcbo+grad evals/sec at D=20,N=400,K=50,S=8,N_s=400k"
 UNIT = "evals/s"
+QUICK = os.environ.get("VBMC_BENCH_QUICK", "0") == "1"  # tests: skip the long CPU legs and the extras
 
 
 def workload(n_gpus):
@@ -68,7 +77,7 @@ def bytes_entmc(Ns_total, K, D, eps_input):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled while the GPU is under the benchmark's load."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -88,7 +97,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -109,41 +118,12 @@ class ClockSampler:
             "sm_max_mhz": max(mx) if mx else None,
             "reasons": reasons,
             "samples": len(self.rows),
+            "window": ("the untimed device-resident spin-up (same launch / flush pattern, GPU under load) plus the timed "
+                       "region; the timed region alone lasts a few milliseconds, shorter than one nvidia-smi query"),
         }
 
 
 # ------------------------------------------------------------------------------- CPU arms
-def cpu_time_oracle(pr, frac, reps):
-    """Time the oracle port (fp64 NumPy restatement of the reference) on the host.
-
-    The log-joint term is timed in full; the Monte-Carlo entropy (linear in the number of
-    draws, 92 % of the reference's time) is timed on a ``frac`` sample of the draws of every
-    component and extrapolated linearly.  Returns seconds per full evaluation."""
-    from oracle import elbo_oracle as eo
-
-    K, D = pr.K, pr.D
-    vp = eo.OracleVP.create(D, K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta, pr.optimize)
-    Ns_s = max(2, 2 * int(np.ceil(pr.Ns_K * frac / 2)))
-    rs = np.random.RandomState(0)
-    ts = []
-    cpu0, wall0 = time.process_time(), time.perf_counter()
-    for _ in range(reps):
-        eps = np.stack([rs.randn(Ns_s // 2, D) for _ in range(K)], axis=0)  # the reference draws inside the call
-        t0 = time.perf_counter()
-        eo.set_parameters(vp, pr.theta)
-        G, dG, *_ = eo.gp_log_joint(vp, pr.gp, pr.optimize, True, True, False)
-        L, dL = eo.vp_bound_loss(vp, pr.theta, pr.theta_bnd, pr.theta_bnd["tol_con"])
-        t1 = time.perf_counter()
-        eps = np.stack([rs.randn(Ns_s // 2, D) for _ in range(K)], axis=0)
-        H, dH = eo.entmc(vp, eps, pr.optimize, True)
-        t2 = time.perf_counter()
-        ts.append((t1 - t0) + (t2 - t1) * (pr.Ns_K / Ns_s))
-    # host cores actually kept busy (process CPU time / wall time): NumPy's elementwise kernels are single-threaded,
-    # only the BLAS calls fan out
-    cpu_time_oracle.cores_used = max(1.0, round((time.process_time() - cpu0) / max(time.perf_counter() - wall0, 1e-9), 1))
-    return float(np.median(ts)), Ns_s
-
-
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -153,74 +133,225 @@ def blas_threads():
         return 1
 
 
-def _oracle_worker(job):
-    n_gpus, frac = job
-    pr, _ = workload(n_gpus)
-    t, _ = cpu_time_oracle(pr, frac, 1)
-    return t
+class CpuArm:
+    """FULL evaluations of the metric's call on the host CPU: the unmodified reference when it is available
+    (``kind == "reference"``), else the oracle's NumPy restatement (``kind == "port"``)."""
 
+    def __init__(self, pr, kind):
+        self.pr, self.kind = pr, kind
+        if kind == "reference":
+            from oracle import ref_loader
 
-def cpu_all_cores(n_gpus, frac):
-    """Throughput of the box's host cores on INDEPENDENT evaluations (one single-threaded oracle process per core):
-    the most the NumPy path can deliver when several chains / restarts run side by side.  One Adam chain is
-    sequential, so its evals/s is the single-process figure; this is the generous upper bound."""
-    import concurrent.futures as cf
-    import multiprocessing as mp
+            self.ref = ref_loader.load()
+            self.gp = ref_loader.make_ref_gp(pr.X, pr.y, pr.posts, pr.mean_kind)
+            self.vp = ref_loader.make_ref_vp(pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta, pr.optimize)
+            self.where = self.ref._neg_elcbo.__code__.co_filename
+        else:
+            from oracle import elbo_oracle as eo
 
-    procs = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    with cf.ProcessPoolExecutor(max_workers=procs, mp_context=mp.get_context("fork")) as ex:
-        ts = list(ex.map(_oracle_worker, [(n_gpus, frac)] * procs))
-    wall = time.perf_counter() - t0
-    # every process extrapolates its own full-evaluation time; they ran concurrently
-    return {"value": n_gpus * procs / float(np.max(ts)), "unit": UNIT, "processes": procs, "wall_s": wall,
-            "what": "independent evaluations, one oracle-port process per host core, concurrent; max over processes"}
+            self.eo = eo
+            self.gp = pr.gp
+            self.vp = eo.OracleVP.create(pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta, pr.optimize)
+            self.where = eo.__file__
+
+    @staticmethod
+    def best_kind():
+        if os.environ.get("VBMC_BENCH_CPU", "") == "port":
+            return "port"
+        try:
+            from oracle import ref_loader
+
+            return "reference" if ref_loader.available() else "port"
+        except Exception:
+            return "port"
+
+    def evaluate(self, Ns_K=None):
+        """One full ``_neg_elcbo(theta, gp, vp, 0, Ns_K, True, False, theta_bnd)``; the draws come from the global
+        NumPy stream inside the call, exactly as in the reference (entmc_vbmc.py:64-68)."""
+        pr = self.pr
+        Ns_K = pr.Ns_K if Ns_K is None else Ns_K
+        if self.kind == "reference":
+            return self.ref._neg_elcbo(pr.theta.copy(), self.gp, self.vp, 0.0, Ns_K, True, False, pr.theta_bnd)
+        return self.eo.neg_elcbo(pr.theta.copy(), self.gp, self.vp, 0.0, Ns_K, True, False, pr.theta_bnd)
+
+    def time(self, steps, warmup):
+        """-> (seconds per evaluation [mean of the timed steps], per-step list, cores kept busy, wall of timed part)."""
+        np.random.seed(0)
+        for _ in range(warmup):
+            self.evaluate()
+        ts = []
+        cpu0, wall0 = time.process_time(), time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            F, dF, *_ = self.evaluate()
+            ts.append(time.perf_counter() - t0)
+        wall = time.perf_counter() - wall0
+        cores = max(1.0, round((time.process_time() - cpu0) / max(wall, 1e-9), 1))
+        assert np.isfinite(F) and np.all(np.isfinite(dF))
+        return float(np.mean(ts)), ts, cores, wall
+
+    def describe(self, steps, warmup, wall):
+        what = ("UNMODIFIED reference pyvbmc._neg_elcbo (" + self.where + ")" if self.kind == "reference"
+                else "oracle port (fp64 NumPy restatement of the reference, oracle/elbo_oracle.py)")
+        pr = self.pr
+        return (f"{what}; {steps} FULL evaluations of C3 (all {pr.Ns_K} draws x {pr.K} components, all {pr.S} "
+                f"hyper-samples, gradient, soft bounds) after {warmup} full warm-up evaluation(s); nothing sampled or "
+                f"extrapolated; {wall:.1f} s wall")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    pr, wname = workload(args.gpus)
-    frac = 0.05
-    for _ in range(args.warmup):
-        cpu_time_oracle(pr, frac / 5, 1)
-    t_all = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        t, Ns_s = cpu_time_oracle(pr, frac, 1)
-        t_all.append(t)
-    wall = time.perf_counter() - t0
-    t_eval = float(np.median(t_all))
-    value = args.gpus / t_eval  # C3-equivalent evaluations per second (same unit as the CUDA arm)
-    sample = (f"oracle port (fp64 NumPy restatement of the reference); log-joint + bound loss timed in full, "
-              f"Monte-Carlo entropy timed on {Ns_s} of {pr.Ns_K} draws per component and scaled linearly; "
-              f"{args.steps} steps in {wall:.1f} s wall")
+    pr, _ = workload(1)  # one C3 evaluation per step at every N (see the module docstring)
+    kind = CpuArm.best_kind()
+    arm = CpuArm(pr, kind)
+    t_eval, ts, cores, wall = arm.time(args.steps, args.warmup)
+    value = 1.0 / t_eval  # C3 evaluations per second == C3-equivalent evaluations per second of the CUDA arm's unit
+    wname = "C3 (D=20,N=400,K=50,S=8,N_s=400k)"
+    if args.gpus > 1:
+        wname += (f"; the CUDA arm at {args.gpus} GPUs evaluates {args.gpus} C3-equivalents per step -- the host CPU does "
+                  "not grow with the GPU count and the reference's cost is linear in draws and hyper-samples, so one "
+                  "step here is one full C3 evaluation (1/N of the N-GPU step) and `value` is in the same unit")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_eval, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "timing": "host wall clock (time.perf_counter)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": getattr(cpu_time_oracle, "cores_used", 1.0), "kind": "port",
-                         "sample": sample, "host_cpus": os.cpu_count(), "blas_threads": blas_threads()},
+        "config": {"workload": wname, "timing": "host wall clock (time.perf_counter) around every evaluation",
+                   "ms_per_step_min": 1e3 * float(np.min(ts)), "ms_per_step_max": 1e3 * float(np.max(ts))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": arm.describe(args.steps, args.warmup, wall), "host_cpus": os.cpu_count(),
+                         "blas_threads": blas_threads(),
+                         "threads_note": ("NumPy's elementwise kernels (97 % of this path) are single-threaded; only the "
+                                          "np.dot / solve_triangular calls fan out over the BLAS threads; `cores` = process "
+                                          "CPU time / wall time")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    try:
-        line["cpu_all_cores"] = cpu_all_cores(args.gpus, frac)
-    except Exception as exc:  # informational only
-        line["cpu_all_cores"] = {"error": repr(exc)}
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------- CUDA arm
+def _make_vp(pv, pr):
+    vp = pv.VariationalPosterior(pr.D, pr.K)
+    vp.mu, vp.sigma, vp.lambd = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy()
+    vp.w, vp.eta = pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
+    return vp
+
+
+def _spin(step_fn, world, fixed_blocks, block, budget_s=3.0):
+    """Untimed spin-up: the GPU sits in a low-power state after the imports and needs a while under load before
+    its clocks settle.  One GPU: until two consecutive blocks agree to 3 % (at most ``budget_s``).  N ranks: every
+    rank must run the SAME number of evaluations (each holds an all-reduce), so a fixed count.  Returns the number of
+    untimed evaluations run."""
+    t0, prev, n = time.perf_counter(), None, 0
+    for blk_i in range(100):
+        b = step_fn(block)
+        n += block
+        if world == 1:
+            if (prev is not None and abs(b - prev) <= 0.03 * prev and time.perf_counter() - t0 > 0.5) or \
+                    time.perf_counter() - t0 > budget_s:
+                break
+        elif blk_i + 1 >= fixed_blocks:
+            break
+        prev = b
+    return n
+
+
+def _extras_n1(pv, pr, torch, flush):
+    """Informational lines for the next rows of SURVEY 8(f) and the smaller configs (NOT part of value / e2e)."""
+    from workloads import synthetic as syn
+
+    ex = {}
+
+    def small(name, prs, Ns_K, reps=200):
+        vp = _make_vp(pv, prs)
+        call = lambda: pv._neg_elcbo(prs.theta, prs.gp, vp, 0.0, Ns_K, True, False, prs.theta_bnd)  # noqa: E731
+        for _ in range(300):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        e2e_us = 1e6 * (time.perf_counter() - t0) / reps
+        ctx = pv.context_for_gp(prs.gp)
+        st = torch.cuda.ExternalStream(ctx.stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(20):
+            ctx.enqueue()
+        ctx.synchronize()
+        a.record(st)
+        for _ in range(reps):
+            ctx.enqueue()
+        b.record(st)
+        b.synchronize()
+        ex[name] = {"e2e_us_per_eval": e2e_us, "device_us_per_eval": 1e3 * a.elapsed_time(b) / reps,
+                    "draws_per_component": Ns_K, "D": prs.D, "K": prs.K, "N": prs.N, "S": prs.S,
+                    "what": "same call as the headline (value + gradient, soft bounds), warm L2, back to back"}
+
+    small("C2", syn.make_problem("C2"), syn.make_problem("C2").Ns_K)
+    small("C4", syn.make_problem("C4"), syn.make_problem("C4").Ns_K)
+    small("C3_at_28_draws_per_component", pr, 28)
+
+    # device-resident Adam (N2)
+    vpa = _make_vp(pv, pr)
+    th0 = np.asarray(vpa.get_parameters(), dtype=float)
+    kw = dict(seed=1, max_iter=200, use_early_stopping=False, master_max=0.01)
+    pv.minimize_adam_elcbo(pr.gp, vpa, th0.copy(), pr.Ns_K, pr.theta_bnd, **kw)  # warm-up (graph capture, clocks)
+    t0 = time.perf_counter()
+    _, _, _, yt, n_it = pv.minimize_adam_elcbo(pr.gp, vpa, th0.copy(), pr.Ns_K, pr.theta_bnd, **kw)
+    dt = time.perf_counter() - t0
+    ex["device_adam"] = {
+        "iterations_per_s": n_it / dt, "us_per_iteration": 1e6 * dt / n_it, "iterations": int(n_it),
+        "what": ("pyvbmc_b200.minimize_adam_elcbo: minimize_adam.py:61-145 with theta, moments and iterates resident in "
+                 "HBM, one CUDA graph per iteration (evaluation + Adam update), host sync every 20 iterations; same "
+                 "workload as `value` (one negelcbo+grad evaluation per iteration)"),
+    }
+    # batched sieve (N1)
+    Bs = 500
+    rng = np.random.default_rng(0)
+    cands = []
+    for _ in range(Bs):
+        v = _make_vp(pv, pr)
+        v.mu = pr.mu + 0.3 * rng.normal(size=pr.mu.shape)
+        cands.append(v)
+    pv.neg_elcbo_batch(cands, pr.gp, pr.theta_bnd)  # warm-up (clocks, kernel attributes)
+    t0 = time.perf_counter()
+    pv.neg_elcbo_batch(cands, pr.gp, pr.theta_bnd)
+    dt = time.perf_counter() - t0
+    ex["sieve_batch"] = {
+        "candidates_per_s": Bs / dt, "us_per_candidate": 1e6 * dt / Bs, "candidates": Bs,
+        "what": ("pyvbmc_b200.neg_elcbo_batch: the value-only candidate loop of variational_optimization.py:775-787 "
+                 "(entlb + log joint + bounds) as one launch, host packing included"),
+    }
+    # variance path (N3): _eval_full_elcbo's call, value + variance + per-component terms
+    try:
+        vpv = _make_vp(pv, pr)
+        callv = lambda: pv._neg_elcbo(pr.theta, pr.gp, vpv, 0.0, 0, False, True, None, 0.0, True)  # noqa: E731
+        for _ in range(3):
+            callv()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            callv()
+        us = 1e6 * (time.perf_counter() - t0) / 10
+        N, S, K = pr.N, pr.S, pr.K
+        b_alg, f_alg = S * N * N * 8.0, S * (2.0 * N * N * K + 2.0 * K * K * N)
+        ex["variance_path"] = {
+            "us_per_call": us, "algorithmic_bytes": b_alg, "algorithmic_flops": f_alg,
+            "hbm_GBps_achieved": b_alg / (us * 1e-6) / 1e9, "fp64_TFLOPs_achieved": f_alg / (us * 1e-6) / 1e12,
+            "what": ("_neg_elcbo(theta, gp, vp, 0, 0, False, True, None, 0, separate_K=True): _gp_log_joint variance path "
+                     "(variational_optimization.py:1472-1518) end to end through the drop-in call, deterministic entropy"),
+        }
+    except Exception as exc:
+        ex["variance_path"] = {"error": repr(exc)}
+    return ex
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     import pyvbmc_b200 as pv
-    from pyvbmc_b200.distributed import ShardedNegElcbo
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -235,15 +366,8 @@ def run_b200(args):
 
     pr, wname = workload(world)
     D, K = pr.D, pr.K
-    vp = pv.VariationalPosterior(D, K)
-    vp.mu, vp.sigma, vp.lambd, vp.w, vp.eta = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy(), pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
-
-    ev = ShardedNegElcbo(pr.gp, device=local, seed=1234)
-    # Raw-vector all-reduce: NCCL by default (verified at 1/2/4/8 GPUs in round 1).  VBMC_BENCH_P2P=1 switches to the
-    # all-reduce over NVLink peer memory inside the tail kernel (ShardedNegElcbo.enable_p2p; verified at 2 GPUs only).
-    p2p = ev.enable_p2p(D, K) if (world > 1 and os.environ.get("VBMC_BENCH_P2P", "0") == "1") else False
-    ctx = ev.ctx
-    stream = ev.stream
+    vp = _make_vp(pv, pr)
+    W = max(args.warmup, 3)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MiB > 126 MB L2
 
     def barrier():
@@ -251,37 +375,49 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- e2e: public function, host buffers (this also stages theta on the device) ---------------
-    def e2e_step():
-        if world == 1:  # the reference-shaped drop-in function itself
-            return pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd)
-        return ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)
+    ev = None
+    p2p = False
+    if world == 1:
+        # the drop-in function itself, and the library's own launch sequence for the device-resident steps
+        ctx = pv.context_for_gp(pr.gp)
 
-    F0 = ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)[0]  # stages theta / bounds on ev's context for the device-resident loop
+        def e2e_step():
+            return pv._neg_elcbo(pr.theta, pr.gp, vp, 0.0, pr.Ns_K, True, False, pr.theta_bnd)
+
+        enqueue = ctx.enqueue
+    else:
+        from pyvbmc_b200.distributed import ShardedNegElcbo
+
+        ev = ShardedNegElcbo(pr.gp, device=local, seed=1234)
+        # raw-vector all-reduce: over NVLink peer memory inside the tail kernel when every rank can map every peer
+        # (negotiated collectively, checked after the first evaluation), else NCCL.  VBMC_BENCH_P2P=0 forces NCCL.
+        if os.environ.get("VBMC_BENCH_P2P", "1") == "1":
+            p2p = ev.enable_p2p(D, K)
+        ctx = ev.ctx
+
+        def e2e_step():
+            return ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)
+
+        def enqueue():
+            ev.enqueue(D, K)
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    F0 = e2e_step()[0]  # stages theta / bounds for the device-resident loop as well
     if p2p:
         p2p = ev.p2p_self_check(F0)  # a timed-out peer exchange on any rank => NCCL all-reduce on all ranks
 
-    for _ in range(max(args.warmup, 3)):
+    # ---- e2e: public function, host buffers ----------------------------------------------------------------
+    for _ in range(W):
         F, dF, G, H, _ = e2e_step()
     assert np.isfinite(F) and np.all(np.isfinite(dF))
-    # The GPU sits in a low-power state after the imports and needs a while under load before its clocks settle
-    # (measured: the same call takes 300 us for the first ~10^4 calls after start-up and 143 us afterwards).  Keep
-    # warming up (untimed) until two consecutive 50-call blocks agree to 3 %, at most 3 s.
-    # (with N ranks every rank must run the SAME number of evaluations -- each holds an all-reduce -- so the
-    # data-dependent exit is replaced by a fixed count)
-    spin_t0, prev = time.perf_counter(), None
-    for blk_i in range(40):
+
+    def e2e_block(n):
         b0 = time.perf_counter()
-        for _ in range(50):
+        for _ in range(n):
             e2e_step()
-        blk = time.perf_counter() - b0
-        if world == 1:
-            if (prev is not None and abs(blk - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5) or \
-                    time.perf_counter() - spin_t0 > 3.0:
-                break
-        elif blk_i >= 9:
-            break
-        prev = blk
+        return time.perf_counter() - b0
+
+    spin_e2e = _spin(e2e_block, world, fixed_blocks=10, block=50)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -294,39 +430,33 @@ def run_b200(args):
         t_e2e = float(t.item())
     lay_total = K * D + 5 * K + 2 * D
     P = D * K + 2 * K + D
-    h2d = 8 * lay_total
+    h2d = 8 * (lay_total + 2)
     d2h = 8 * (8 + P)
 
-    # ---- device-resident steps: partials -> all-reduce -> finalize, CUDA events per step ----------
-    launches0 = ctx.launch_count
+    # ---- device-resident steps: CUDA events per step on the launching stream --------------------------------
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for _ in range(max(args.warmup, 3)):
-        ev.enqueue(D, K)
+    for _ in range(W):
+        enqueue()
     barrier()
-    # same clock settling for the device-resident loop, with the flush / sync pattern of the timed region (untimed)
-    spin_t0, prev = time.perf_counter(), None
     wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for blk_i in range(100):
+
+    def dev_block(n):
         acc = 0.0
-        for i in range(20):
+        for i in range(n):
             with torch.cuda.stream(stream):
                 flush.fill_(float(i))
             wa.record(stream)
-            ev.enqueue(D, K)
+            enqueue()
             wb.record(stream)
             wb.synchronize()
             acc += wa.elapsed_time(wb)
-        if world == 1:
-            if (prev is not None and abs(acc - prev) <= 0.03 * prev and time.perf_counter() - spin_t0 > 0.5) or \
-                    time.perf_counter() - spin_t0 > 3.0:
-                break
-        elif blk_i >= 14:  # fixed count with N ranks (see above)
-            break
-        prev = acc
-    barrier()
-    launches1 = ctx.launch_count
+        return acc
+
     with ClockSampler(local) as clk:
+        spin_dev = _spin(dev_block, world, fixed_blocks=15, block=20)
+        barrier()
+        launches1 = ctx.launch_count
         for i in range(args.steps):
             # evict L2 on the evaluation's own stream: stream order keeps the fill out of the [start, stop] interval
             # without a host synchronisation per step (with N ranks a per-step host barrier only measures launch skew;
@@ -334,7 +464,7 @@ def run_b200(args):
             with torch.cuda.stream(stream):
                 flush.fill_(float(i))
             starts[i].record(stream)
-            ev.enqueue(D, K)
+            enqueue()
             stops[i].record(stream)
         barrier()
     launches_timed = ctx.launch_count - launches1
@@ -345,61 +475,47 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step = float(t.item())
 
-    # ---- roofline of the dominant kernel (entmc), per-launch CUDA events on its stream ------------
+    # ---- roofline of the dominant kernel (entmc), per-launch CUDA events on its stream ----------------------
     ctx.set_kernel_timing(True)
     for _ in range(3):
-        ev.enqueue(D, K)
+        enqueue()
     ctx.synchronize()
     ctx.entmc_kernel_ms()
     for i in range(min(args.steps, 20)):
-        flush.fill_(float(i))
-        torch.cuda.synchronize()
-        ev.enqueue(D, K)
+        with torch.cuda.stream(stream):
+            flush.fill_(float(i))
+        enqueue()
     ctx.synchronize()
     k_ms, k_n = ctx.entmc_kernel_ms()
     ctx.set_kernel_timing(False)
+    barrier()
 
-    # ---- informational extras (NOT part of value / e2e): the next rows of SURVEY 8(f), N = 1 only ----------------
+    # ---- N > 1: the sharded result against ONE GPU evaluating the whole job on the same Philox key ----------
+    parity = None
+    if world > 1:
+        from pyvbmc_b200.distributed import ShardedNegElcbo
+
+        single = ShardedNegElcbo(pr.gp, device=local, seed=1234, single=True)
+        ev.step = single.step = 100
+        Fs, dFs, Gs, Hs, _ = ev(pr.theta, vp, pr.Ns_K, pr.theta_bnd)
+        F1, dF1, G1, H1, _ = single(pr.theta, _make_vp(pv, pr), pr.Ns_K, pr.theta_bnd)
+        single.close()
+        t = torch.tensor([Fs], dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        parity = {"rel_F": abs(Fs - F1) / abs(F1), "rel_G": abs(Gs - G1) / abs(G1), "rel_H": abs(Hs - H1) / abs(H1),
+                  "rel_dF": float(np.abs(dFs - dF1).max() / np.abs(dF1).max()),
+                  "replicated_bitwise": bool(float(lo) == float(hi)),
+                  "what": "sharded evaluation vs ONE GPU evaluating the whole N-GPU job, same Philox key"}
+
     extras = None
-    if world == 1:
+    if world == 1 and not QUICK:
         try:
-            extras = {}
-            vpa = pv.VariationalPosterior(D, K)
-            vpa.mu, vpa.sigma, vpa.lambd, vpa.w, vpa.eta = pr.mu.copy(), pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy(), pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
-            th0 = np.asarray(vpa.get_parameters(), dtype=float)
-            kw = dict(seed=1, max_iter=200, use_early_stopping=False, master_max=0.01)
-            pv.minimize_adam_elcbo(pr.gp, vpa, th0, pr.Ns_K, pr.theta_bnd, **kw)  # warm-up (graph capture, clocks)
-            t0 = time.perf_counter()
-            _, _, _, yt, n_it = pv.minimize_adam_elcbo(pr.gp, vpa, th0, pr.Ns_K, pr.theta_bnd, **kw)
-            dt = time.perf_counter() - t0
-            extras["device_adam"] = {
-                "iterations_per_s": n_it / dt, "us_per_iteration": 1e6 * dt / n_it, "iterations": int(n_it),
-                "what": ("pyvbmc_b200.minimize_adam_elcbo: minimize_adam.py:61-145 with theta, moments and iterates "
-                         "resident in HBM, one CUDA graph per iteration (evaluation + Adam update), host sync every 20 "
-                         "iterations; same workload as `value` (one negelcbo+grad evaluation per iteration)"),
-            }
-            Bs = 500
-            rng = np.random.default_rng(0)
-            cands = []
-            for _ in range(Bs):
-                v = pv.VariationalPosterior(D, K)
-                v.mu = pr.mu + 0.3 * rng.normal(size=pr.mu.shape)
-                v.sigma, v.lambd = pr.sigma.reshape(1, -1).copy(), pr.lambd.reshape(-1, 1).copy()
-                v.w, v.eta = pr.w.reshape(1, -1).copy(), pr.eta.reshape(1, -1).copy()
-                cands.append(v)
-            pv.neg_elcbo_batch(cands, pr.gp, pr.theta_bnd)  # warm-up (clocks, kernel attributes)
-            t0 = time.perf_counter()
-            pv.neg_elcbo_batch(cands, pr.gp, pr.theta_bnd)
-            dt = time.perf_counter() - t0
-            extras["sieve_batch"] = {
-                "candidates_per_s": Bs / dt, "us_per_candidate": 1e6 * dt / Bs, "candidates": Bs,
-                "what": ("pyvbmc_b200.neg_elcbo_batch: the value-only candidate loop of variational_optimization.py:"
-                         "775-787 (entlb + log joint + bounds) as one launch, host packing included"),
-            }
+            extras = _extras_n1(pv, pr, torch, flush)
         except Exception as exc:  # extras must never take the headline down
             extras = {"error": repr(exc)}
 
-    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -407,7 +523,7 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         fp32_peak = max(ctx.fma_peak(0), ctx.fma_peak(2))  # scalar FFMA vs packed FFMA2, whichever is higher
         fp64_peak = ctx.fma_peak(1)
         Ns_rank = pr.Ns_total / world
@@ -416,9 +532,8 @@ def run_b200(args):
         k_s = k_ms * 1e-3
         achieved_gbs = b_alg / k_s / 1e9
         variant = ctx.entmc_variant_used()
-        kname = {5: "entmc_tc_gen_kernel<20,PHILOX> + entmc_kernel_tc<20,ANYGRAD> (tcgen05/TMEM; timed together)",
+        kname = {5: "entmc_kernel_tc<20,...> (tcgen05/TMEM; with its generator kernel when one is launched: timed together)",
                  4: "entmc_kernel_w<20,WGRAD,ANYGRAD,PHILOX>", 0: "entmc_kernel_fast<20,...>"}.get(variant, f"entmc variant {variant}")
-        # DRAM bytes per launch of the same kernel(s) from the committed `ncu --set full` capture (cold L2 under ncu)
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "entmc_traffic.json")))
@@ -431,8 +546,7 @@ def run_b200(args):
             "kernel_launches_timed": k_n, "algorithmic_bytes_per_launch": b_alg, "peak_source": hbm_src,
             "note": ("entmc is bound by instruction issue (FP32 FMA / MUFU), not HBM: arithmetic intensity >> ridge; with "
                      "device Philox draws its only ALGORITHMIC HBM traffic is the parameter block and one record per CTA, "
-                     "so the mandated HBM fraction is tiny by construction; the binding roofline is `compute`.  The "
-                     "tensor-core variant stages its noise tiles through L2 (`traffic`: DRAM bytes ncu sees with a cold L2)."),
+                     "so the mandated HBM fraction is tiny by construction; the binding roofline is `compute`."),
             "compute": {
                 "bound": "fp32_fma", "achieved": f_alg / k_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": f_alg / k_s / 1e12 / fp32_peak if fp32_peak else None,
@@ -440,25 +554,31 @@ def run_b200(args):
                 "peak_source": "max(FFMA, FFMA2) issue peak measured by vbmc_fma_peak in this run", "fp64_fma_peak": fp64_peak,
             },
         }
-        # CPU baseline: oracle port on the host, bounded sample (about 10-30 s)
         cpu = None
         if world == 1:
-            t_cpu, Ns_s = cpu_time_oracle(pr, 0.1, 3)
-            cpu = {
-                "value": 1.0 / t_cpu, "unit": UNIT, "cores": getattr(cpu_time_oracle, "cores_used", 1.0), "kind": "port",
-                "blas_threads": blas_threads(),
-                "sample": (f"oracle port (fp64 NumPy restatement of the reference): log-joint + bound loss in full, "
-                           f"entropy on {Ns_s} of {pr.Ns_K} draws/component scaled linearly; median of 3"),
-                "host_cpus": os.cpu_count(),
-            }
+            kind = "port" if QUICK else CpuArm.best_kind()
+            arm = CpuArm(pr, kind)
+            n_cpu = 1 if QUICK else 3
+            t_cpu, ts_cpu, cores, wall = arm.time(n_cpu, 0 if QUICK else 1)
+            cpu = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": kind, "blas_threads": blas_threads(),
+                   "sample": arm.describe(n_cpu, 0 if QUICK else 1, wall), "host_cpus": os.cpu_count()}
+            if kind == "reference":  # the oracle port beside it (it is what the parity tests run on the box)
+                t_port, _, cores_p, wall_p = CpuArm(pr, "port").time(2, 1)
+                cpu["port_beside_it"] = {"value": 1.0 / t_port, "unit": UNIT, "cores": cores_p,
+                                         "sample": f"oracle port, 2 full C3 evaluations after 1 warm-up, {wall_p:.1f} s wall"}
         line = {
             "metric": METRIC, "value": world / t_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (entropy kernel: fp32 compute, fp64 accumulation) + f64 (log-joint, finalize)",
             "data": "synthetic",
-            "config": {"workload": wname, "rng": "device Philox4x32-10 + Box-Muller", "l2": "flushed between steps (256 MiB fill on the same stream, outside the timed interval)",
-                       "warmup_note": "W warm-up steps, then untimed spin-up until the step time is stable to 3 % (GPU clock settling, <= 3 s)",
+            "config": {"workload": wname, "rng": "device Philox4x32-10 + Box-Muller",
+                       "l2": "flushed between steps (256 MiB fill on the same stream, outside the timed interval)",
+                       "warmup_steps_run": W,
+                       "spinup_steps_untimed": {"e2e": spin_e2e, "device_resident": spin_dev,
+                                                "why": "GPU clock settling after start-up: blocks repeated until two agree to 3 % (<= 3 s); fixed count with N ranks"},
                        "timing": "CUDA events per step on the launching stream, max over ranks",
+                       "value_path": ("vbmc_negelcbo_enqueue (the library's own kernels of one drop-in call, parameters resident)"
+                                      if world == 1 else "ShardedNegElcbo.enqueue (partials -> all-reduce -> finalize)"),
                        "draws_per_component": pr.Ns_K, "S": pr.S, "parallelism": f"draws+hyper-samples sharded x{world}",
                        "all_reduce": ("none" if world == 1 else ("peer memory (NVLink P2P stores + flags) inside the tail kernel"
                                                                  if p2p else "NCCL"))},
@@ -474,11 +594,14 @@ def run_b200(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
         if extras:
             line["extras"] = extras
         print(json.dumps(line))
     torch.cuda.synchronize()
-    ev.close()
+    if ev is not None:
+        ev.close()
     pv.clear_caches()
     if world > 1:
         dist.barrier()
@@ -489,10 +612,15 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
+    # defaults that finish within minutes: a CUDA step lasts ~0.1 ms, a full reference evaluation several seconds
+    if args.steps is None:
+        args.steps = 50 if args.impl == "b200" else 10
+    if args.warmup is None:
+        args.warmup = 5 if args.impl == "b200" else 1
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -226,6 +226,11 @@ int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);
 int vbmc_negelcbo_partials_async(vbmc_ctx *ctx, int rank, int world, double *raw_dev);
 int vbmc_negelcbo_finalize_async(vbmc_ctx *ctx, const double *raw_dev, double *out_dev);
 int vbmc_stream_synchronize(vbmc_ctx *ctx);
+/* Re-enqueue the evaluation staged last (by vbmc_negelcbo_flat or vbmc_negelcbo_upload) on the context stream:
+ * the kernels of one evaluation with parameters and GP already resident in HBM, result left in the library's device
+ * out buffer, no host synchronisation.  This is the device-resident step bench.py times with CUDA events (`value`):
+ * what one `_neg_elcbo` call (variational_optimization.py:991-1235) costs the GPU, without the host round trip.   */
+int vbmc_negelcbo_enqueue(vbmc_ctx *ctx);
 
 /* ---- all-reduce of the raw vector over NVLink peer memory (optional; replaces the NCCL all-reduce between
  * vbmc_negelcbo_partials_async and vbmc_negelcbo_finalize_async).  One process per GPU on ONE node:

@@ -8,8 +8,10 @@ inner loop: ``_gp_log_joint`` consumes the GP as opaque arrays plus three
 We therefore pre-seed ``sys.modules`` with inert stubs, put the read-only
 reference tree on ``sys.path`` and import the reference functions verbatim.
 
-This only works where ``/root/reference`` exists (the build container).  The GPU
-box has no reference tree: nothing executed there may import this module.
+Where ``/root/reference`` does not exist (the GPU box) the same unmodified package is
+taken from ``oracle/_ref`` (installed there by ``oracle/build_ref.py`` during
+``__graft_entry__.build()``; git-ignored, shipped with the snapshot).  TEST / BENCH
+INFRASTRUCTURE ONLY: the product never imports this module.
 """
 from __future__ import annotations
 
@@ -21,7 +23,35 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PYVBMC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _is_ref(c):
+    return bool(c) and os.path.isfile(os.path.join(c, "pyvbmc", "vbmc", "variational_optimization.py"))
+
+
+def _find_root():
+    """The reference checkout where it exists (build container); else the archive that ``oracle/build_ref.py`` packed
+    into the git-ignored ``oracle/_ref`` (what travels to the GPU box), unpacked into a temporary directory."""
+    for c in (os.environ.get("PYVBMC_REFERENCE_ROOT"), "/root/reference"):
+        if _is_ref(c):
+            return c
+    archive = os.path.join(_HERE, "_ref", "pyvbmc_ref.zip")
+    if os.path.isfile(archive) and os.environ.get("PYVBMC_REFERENCE_ROOT") != "none":
+        import atexit
+        import shutil
+        import tempfile
+        import zipfile
+
+        tmp = tempfile.mkdtemp(prefix="pyvbmc_ref_")
+        atexit.register(shutil.rmtree, tmp, ignore_errors=True)
+        with zipfile.ZipFile(archive) as z:
+            z.extractall(tmp)
+        return tmp
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBBED = [
     "cma",
@@ -78,8 +108,8 @@ def load():
         return _CACHE
     if not available():
         raise RuntimeError(
-            f"reference tree not found at {REFERENCE_ROOT}; ref_loader only works "
-            "in the build container"
+            f"reference package not found at {REFERENCE_ROOT} nor under oracle/_ref "
+            "(run `python -m oracle.build_ref` in the build container)"
         )
     _install_stubs()
     if REFERENCE_ROOT not in sys.path:

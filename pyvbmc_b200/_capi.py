@@ -127,6 +127,7 @@ PROTOTYPES = {
     "vbmc_negelcbo_partials_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_negelcbo_finalize_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbmc_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "vbmc_negelcbo_enqueue": (C.c_int, [C.c_void_p]),
     "vbmc_p2p_export": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_p2p_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_p2p_unmap": (C.c_int, [C.c_void_p]),

@@ -490,6 +490,12 @@ class Context:
     def finalize_async(self, raw_dev_ptr, out_dev_ptr):
         _capi.check(self._lib.vbmc_negelcbo_finalize_async(self._h, C.c_void_p(raw_dev_ptr), C.c_void_p(out_dev_ptr)))
 
+    def enqueue(self):
+        """``vbmc_negelcbo_enqueue``: the evaluation staged last, again, on this context's stream; no host sync."""
+        rc = self._lib.vbmc_negelcbo_enqueue(self._h)
+        if rc:
+            _capi.check(rc)
+
     def raw_len(self, D, K):
         return int(self._lib.vbmc_raw_len(D, K))
 

@@ -962,6 +962,18 @@ int vbmc_negelcbo_finalize_async(vbmc_ctx *p, const double *raw_dev, double *out
     return finalize(x, raw_dev, out_dev);
 }
 
+int vbmc_negelcbo_enqueue(vbmc_ctx *p) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "enqueue: null ctx");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    VBMC_REQUIRE(c->staged && c->d_raw && c->d_out, VBMC_ERR_STATE,
+                 "enqueue: nothing staged (call vbmc_negelcbo_flat or vbmc_negelcbo_upload first)");
+    VBMC_REQUIRE(!x->st.s.compute_var, VBMC_ERR_UNSUPPORTED, "enqueue does not cover the variance path");
+    VBMC_TRY(partials(x, 0, 1, c->d_raw));
+    return finalize(x, c->d_raw, c->d_out);
+}
+
 int vbmc_p2p_export(vbmc_ctx *p, int world, int D, int K, unsigned char *handle) {
     VBMC_REQUIRE(p && handle, VBMC_ERR_ARG, "p2p_export: null argument");
     VBMC_REQUIRE(world >= 2 && world <= VBMC_P2P_MAX_WORLD, VBMC_ERR_UNSUPPORTED, "p2p_export: world must be 2..8");
