@@ -189,6 +189,23 @@ size_t vbmc_param_len(int D, int K);
 int vbmc_negelcbo_batch(vbmc_ctx *ctx, int B, int D, int K, const double *params, const int optimize[4],
                         int use_bounds, double *out);
 
+/* ---- acquisition-function ingredients ------------------------------------------------------
+ * Replaces, for the packed GP (vbmc_gp_pack WITH the factor L),
+ *     f_mu, f_s2 = gp.predict(x_star = Xs, separate_samples = True)
+ * (pyvbmc/acquisition_functions/abstract_acq_fcn.py:79; gpyreg's GP.predict: SE-ARD cross-covariance against the N
+ * training points, predictive mean m(x*) + k* . alpha and latent variance sf2 - |L^-T (sW k*)|^2 (Cholesky branch)
+ * or sf2 + k* . (L k*) (low-noise branch), clamped at 0, per hyper-sample).  Xs: [Nx][D] row-major host array;
+ * f_mu, f_s2: [Nx][S] row-major host arrays.  fp64; synchronous.                                               */
+int vbmc_gp_predict(vbmc_ctx *ctx, int Nx, const double *Xs, double *f_mu, double *f_s2);
+/* bench aid: average device time (ms) of the prediction kernel on the points uploaded by the last vbmc_gp_predict */
+int vbmc_gp_predict_device_ms(vbmc_ctx *ctx, int Nx, int reps, double *ms);
+/* Replaces VariationalPosterior.pdf(x, orig_flag = False, log_flag, grad_flag) for df = inf
+ * (pyvbmc/variational_posterior/variational_posterior.py:447-468,524-533; called by the acquisition functions,
+ * acq_fcn_log.py:38-47): y [Nx] = pdf or log pdf (-inf where the pdf underflows to 0), dy [Nx][D] = gradient of the
+ * pdf, or of the log pdf when log_flag (NULL unless grad_flag).  Transformed space; needs no packed GP.          */
+int vbmc_vp_pdf(vbmc_ctx *ctx, const vbmc_vp *vp, int Nx, const double *Xs, int log_flag, int grad_flag, double *y,
+                double *dy);
+
 /* ---- device-resident Adam -----------------------------------------------------------------
  * minimize_adam(f, x0, lb, ub, tol_fun, max_iter, master_min, master_max, master_decay)
  * (pyvbmc/vbmc/minimize_adam.py:61-145) with f = the closure of variational_optimization.py:238-249,

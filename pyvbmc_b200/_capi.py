@@ -128,6 +128,9 @@ PROTOTYPES = {
     "vbmc_negelcbo_finalize_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vbmc_stream_synchronize": (C.c_int, [C.c_void_p]),
     "vbmc_negelcbo_enqueue": (C.c_int, [C.c_void_p]),
+    "vbmc_gp_predict": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "vbmc_gp_predict_device_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "vbmc_vp_pdf": (C.c_int, [C.c_void_p, C.POINTER(VP), C.c_int, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     "vbmc_p2p_export": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_p2p_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vbmc_p2p_unmap": (C.c_int, [C.c_void_p]),

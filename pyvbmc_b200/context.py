@@ -490,6 +490,36 @@ class Context:
     def finalize_async(self, raw_dev_ptr, out_dev_ptr):
         _capi.check(self._lib.vbmc_negelcbo_finalize_async(self._h, C.c_void_p(raw_dev_ptr), C.c_void_p(out_dev_ptr)))
 
+    # ------------------------------------------------------------------ acquisition-function ingredients (N4)
+    def gp_predict(self, Xs):
+        """``vbmc_gp_predict``: ``(f_mu, f_s2)``, each ``(Nx, S)``, for the packed GP (needs the factor L)."""
+        Xs = _arr(Xs)
+        if Xs.ndim != 2 or Xs.shape[1] != self.D:
+            raise ValueError("gp_predict: x_star must have shape (Nx, D)")
+        Nx = Xs.shape[0]
+        f_mu = np.empty((Nx, self.S), dtype=_F64)
+        f_s2 = np.empty((Nx, self.S), dtype=_F64)
+        _capi.check(self._lib.vbmc_gp_predict(self._h, Nx, _ptr(Xs), _ptr(f_mu), _ptr(f_s2)))
+        return f_mu, f_s2
+
+    def gp_predict_device_ms(self, Nx, reps=10):
+        ms = C.c_double()
+        _capi.check(self._lib.vbmc_gp_predict_device_ms(self._h, int(Nx), int(reps), C.byref(ms)))
+        return float(ms.value)
+
+    def vp_pdf(self, vp, Xs, log_flag=False, grad_flag=False):
+        """``vbmc_vp_pdf``: density of the mixture at ``Xs`` (transformed space): ``(y (Nx,), dy (Nx, D) | None)``."""
+        v = _VPView(vp)
+        Xs = _arr(Xs)
+        if Xs.ndim != 2 or Xs.shape[1] != v.D:
+            raise ValueError("vp_pdf: x must have shape (Nx, D)")
+        Nx = Xs.shape[0]
+        y = np.empty(Nx, dtype=_F64)
+        dy = np.empty((Nx, v.D), dtype=_F64) if grad_flag else None
+        _capi.check(self._lib.vbmc_vp_pdf(self._h, C.byref(v.c), Nx, _ptr(Xs), int(bool(log_flag)), int(bool(grad_flag)),
+                                          _ptr(y), _ptr(dy)))
+        return y, dy
+
     def enqueue(self):
         """``vbmc_negelcbo_enqueue``: the evaluation staged last, again, on this context's stream; no host sync."""
         rc = self._lib.vbmc_negelcbo_enqueue(self._h)

@@ -439,7 +439,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
-                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var};
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var, c->d_xs, c->d_pred};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -960,6 +960,71 @@ int vbmc_negelcbo_finalize_async(vbmc_ctx *p, const double *raw_dev, double *out
     CtxEx *x = ex(p);
     Bind b(&x->c);
     return finalize(x, raw_dev, out_dev);
+}
+
+int vbmc_gp_predict(vbmc_ctx *p, int Nx, const double *Xs, double *f_mu, double *f_s2) {
+    VBMC_REQUIRE(p && Xs && f_mu && f_s2, VBMC_ERR_ARG, "gp_predict: null argument");
+    VBMC_REQUIRE(Nx >= 0, VBMC_ERR_ARG, "gp_predict: negative number of points");
+    if (Nx == 0) return VBMC_OK;
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "gp_predict: no GP packed");
+    const int D = c->gD, S = c->S;
+    VBMC_TRY(ensure(&c->d_xs, &c->xs_cap, (size_t)Nx * D));
+    VBMC_TRY(ensure(&c->d_pred, &c->pred_cap, (size_t)2 * Nx * S));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_xs, Xs, (size_t)Nx * D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VBMC_TRY(gppred_launch(c, c->d_xs, Nx, c->d_pred, c->d_pred + (size_t)Nx * S));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(f_mu, c->d_pred, (size_t)Nx * S * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(f_s2, c->d_pred + (size_t)Nx * S, (size_t)Nx * S * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return VBMC_OK;
+}
+
+int vbmc_gp_predict_device_ms(vbmc_ctx *p, int Nx, int reps, double *ms) {
+    // development / bench aid: average duration of the prediction kernel on the points uploaded last (no copies)
+    VBMC_REQUIRE(p && ms && reps >= 1, VBMC_ERR_ARG, "gp_predict_device_ms: bad argument");
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    VBMC_REQUIRE(c->d_xs && c->d_pred && (size_t)Nx * c->gD <= c->xs_cap, VBMC_ERR_STATE, "call vbmc_gp_predict first");
+    VBMC_TRY(gppred_launch(c, c->d_xs, Nx, c->d_pred, c->d_pred + (size_t)Nx * c->S));
+    VBMC_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) VBMC_TRY(gppred_launch(c, c->d_xs, Nx, c->d_pred, c->d_pred + (size_t)Nx * c->S));
+    VBMC_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+    VBMC_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+    float t = 0;
+    VBMC_CUDA_CHECK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    *ms = (double)t / reps;
+    return VBMC_OK;
+}
+
+int vbmc_vp_pdf(vbmc_ctx *p, const vbmc_vp *vp, int Nx, const double *Xs, int log_flag, int grad_flag, double *y,
+                double *dy) {
+    VBMC_REQUIRE(p && vp && Xs && y && (!grad_flag || dy), VBMC_ERR_ARG, "vp_pdf: null argument");
+    VBMC_REQUIRE(Nx >= 0, VBMC_ERR_ARG, "vp_pdf: negative number of points");
+    VBMC_TRY(check_vp(vp, false));
+    if (Nx == 0) return VBMC_OK;
+    Ctx *c = &ex(p)->c;
+    Bind b(c);
+    const int D = vp->D, K = vp->K;
+    const ParamLayout lay{D, pad_dim(D), K};
+    VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total() + 2));
+    double *h = c->h_in;
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the pinned block may still feed an earlier copy
+    memcpy(h + lay.mu(), vp->mu, sizeof(double) * K * D);
+    memcpy(h + lay.sigma(), vp->sigma, sizeof(double) * K);
+    memcpy(h + lay.lambd(), vp->lambd, sizeof(double) * D);
+    memcpy(h + lay.w(), vp->w, sizeof(double) * K);
+    c->staged = false;  // the parameter block no longer belongs to a staged evaluation
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * (K * D + 2 * K + D), cudaMemcpyHostToDevice, c->stream));
+    VBMC_TRY(ensure(&c->d_xs, &c->xs_cap, (size_t)Nx * D));
+    VBMC_TRY(ensure(&c->d_pred, &c->pred_cap, (size_t)Nx * (1 + D)));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_xs, Xs, (size_t)Nx * D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VBMC_TRY(vp_pdf_launch(c, c->d_in, D, K, c->d_xs, Nx, log_flag != 0, grad_flag != 0, c->d_pred, c->d_pred + Nx));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(y, c->d_pred, (size_t)Nx * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (grad_flag)
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(dy, c->d_pred + Nx, (size_t)Nx * D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return VBMC_OK;
 }
 
 int vbmc_negelcbo_enqueue(vbmc_ctx *p) {

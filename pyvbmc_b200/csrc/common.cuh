@@ -122,7 +122,9 @@ struct Ctx {
     double *d_alpha = nullptr; // [S][N]
     double *d_hyp = nullptr;   // [S][hyp_stride]
     double *d_L = nullptr;     // [S][N][N]
-    double *d_Linv = nullptr;  // lazily built for the variance path
+    double *d_Linv = nullptr;  // gppred.cu: [S][N][NP] L^-1 (or L) + [S][DP][N] scaled inputs, built on first use
+    double *d_xs = nullptr, *d_pred = nullptr;  // search points in, [f_mu | f_s2] or [y | dy] out
+    size_t xs_cap = 0, pred_cap = 0;
 
     // bounds
     int n_bnd = 0;
@@ -235,6 +237,11 @@ double *gpvar_Z(Ctx *c);
 double *gpvar_J(Ctx *c, int K);
 double *gpvar_out(Ctx *c, int K);  // [varG, var_ss, varG_s (S)]
 int gpvar_launch(Ctx *c, const double *d_params, int K, int avg);
+
+// gppred.cu: GP predictive mean / variance at search points, variational-posterior density
+int gppred_launch(Ctx *c, const double *d_Xs, int Nx, double *d_mu, double *d_s2);
+int vp_pdf_launch(Ctx *c, const double *d_params, int D, int K, const double *d_Xs, int Nx, int log_flag, int grad_flag,
+                  double *d_y, double *d_dy);
 
 // entlb.cu
 int entlb_launch(Ctx *c, const double *d_params, int D, int K, const int grad[4], double *d_raw_ent /*H at [0], block*/,

@@ -80,6 +80,15 @@ class VariationalPosterior:
         self._normalise()
         self._mode = None
 
+    def pdf(self, x, orig_flag=True, log_flag=False, grad_flag=False, df=np.inf):
+        """Density of the mixture (variational_posterior.py:241-552) on the device; this mirror carries no parameter
+        transformer, so only the transformed space (``orig_flag=False``) is available."""
+        from .acquisition_functions import vp_pdf
+
+        if orig_flag and getattr(self, "parameter_transformer", None) is None:
+            raise NotImplementedError("pyvbmc_b200.VariationalPosterior has no parameter transformer: use orig_flag=False")
+        return vp_pdf(self, x, orig_flag=orig_flag, log_flag=log_flag, grad_flag=grad_flag, df=df)
+
     def get_bounds(self, X, options, K=None):
         K = self.K if K is None else int(K)
         X = np.asarray(X, dtype=float)

@@ -281,3 +281,48 @@ def test_adam_oracle_on_the_real_elbo_closure_matches_reference():
     K = pr.K
     # after the first update every iterate sits within one step of a max(eta) == 0 renormalisation
     assert np.all(np.abs(x_tab[-K:, :].max(axis=0)) < 0.2) and g["elbo_theta0"][-K:].max() > 2.0
+
+
+# ------------------------------------------------------------------ acquisition-function ingredients
+@pytest.mark.parametrize("tag,cfg,kw", [("c2", "C2", dict(N=64)), ("c4", "C4", dict(N=60)), ("c1", "C1", {})])
+def test_acq_oracle_against_reference_goldens(tag, cfg, kw):
+    """oracle/acq_oracle.py: vp_pdf, total_variance and acq_log against the unmodified reference's
+    VariationalPosterior.pdf and AcqFcnLog.__call__ (tests/golden/ref_acq.npz), and gp_predict against an independent
+    dense solve with (K + diag(sn2))^-1 (gpyreg itself is absent: parity unpinned for that piece)."""
+    import sys
+
+    from oracle import acq_oracle as ao
+
+    g = load_npz("ref_acq")
+    pr = syn.make_problem(cfg, **kw)
+    Xs = g[f"{tag}_Xs"]
+    assert np.allclose(ao.vp_pdf(pr.vp, Xs), g[f"{tag}_pdf"], rtol=1e-13, atol=0)
+    with np.errstate(invalid="ignore"):
+        ly, dly = ao.vp_pdf(pr.vp, Xs, log_flag=True, grad_flag=True)
+    assert np.array_equal(ly, g[f"{tag}_logpdf"]) or np.allclose(ly, g[f"{tag}_logpdf"], rtol=1e-13, atol=0)
+    assert np.allclose(dly, g[f"{tag}_dlogpdf"], rtol=1e-12, atol=0, equal_nan=True)
+    _, dy = ao.vp_pdf(pr.vp, Xs, grad_flag=True)
+    assert np.allclose(dy, g[f"{tag}_dpdf"], rtol=1e-12, atol=0)
+
+    f_mu, f_s2 = ao.gp_predict(pr.X, pr.posts, Xs, pr.mean_kind, separate_samples=True)
+    assert np.array_equal(f_mu, g[f"{tag}_f_mu"]) and np.array_equal(f_s2, g[f"{tag}_f_s2"])
+    D, N = pr.D, pr.N
+    for s, p in enumerate(pr.posts):  # independent route: dense (K + diag(sn2))^-1, no factor
+        hyp = p["hyp"]
+        ell, sf2 = np.exp(hyp[:D]), np.exp(2 * hyp[D])
+        sn2 = np.full(N, np.exp(2 * hyp[D + 1])) + (0 if pr.s2 is None else np.ravel(pr.s2))
+        Kxx = gpp.se_ard(pr.X, pr.X, ell, sf2) + np.diag(sn2)
+        Ks = gpp.se_ard(Xs, pr.X, ell, sf2)
+        m = gpp.mean_fn(pr.X, hyp, D, 1, pr.mean_kind)
+        mu = gpp.mean_fn(Xs, hyp, D, 1, pr.mean_kind) + Ks @ np.linalg.solve(Kxx, pr.y - m)
+        s2 = np.maximum(sf2 - np.sum(Ks * np.linalg.solve(Kxx, Ks.T).T, axis=1), 0)
+        assert np.abs(mu - f_mu[:, s]).max() <= 1e-7 * np.abs(mu).max()
+        assert np.abs(s2 - f_s2[:, s]).max() <= 1e-7 * sf2
+
+    f_bar, var_tot = ao.total_variance(f_mu, f_s2)
+    acq = ao.acq_log(f_bar, var_tot, ly, float(g[f"{tag}_y_max"]))
+    low = var_tot < 1e-4
+    acq[low] += 1e-4 / var_tot[low] - 1  # abstract_acq_fcn.py:119-129 (log-valued acquisition)
+    acq = np.maximum(acq, -sys.float_info.max)
+    acq[np.any(np.abs(Xs) > 30.0, axis=1)] = np.inf  # hard bounds of the golden run (identity transform)
+    assert np.allclose(acq, g[f"{tag}_acq"], rtol=1e-12, atol=1e-12)
