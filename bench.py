@@ -344,6 +344,86 @@ def _extras_n1(pv, pr, torch, flush):
         }
     except Exception as exc:
         ex["variance_path"] = {"error": repr(exc)}
+    # acquisition-function ingredients (N4): GP prediction at the reference's search-cache size, mixture density
+    try:
+        rng = np.random.default_rng(0)
+        Nx = 8192
+        Xs = pr.X[rng.integers(0, pr.N, size=Nx)] + 0.5 * rng.normal(size=(Nx, pr.D))
+        pv.gp_predict(pr.gp, Xs, separate_samples=True)  # warm-up: packs L, builds the triangular inverses
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pv.gp_predict(pr.gp, Xs, separate_samples=True)
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / 5
+        ctxL = pv.context_for_gp(pr.gp, need_L=True)
+        dev_ms = ctxL.gp_predict_device_ms(Nx, 10)
+        N, S = pr.N, pr.S
+        f_alg = float(S) * Nx * (N * N + 2.0 * N)  # triangular product W = K* M (N^2 Nx flops) + the two dot products
+        vpp = _make_vp(pv, pr)
+        pv.vp_pdf(vpp, Xs, orig_flag=False, log_flag=True)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            pv.vp_pdf(vpp, Xs, orig_flag=False, log_flag=True)
+        pdf_ms = 1e3 * (time.perf_counter() - t0) / 5
+        from oracle import acq_oracle as ao
+
+        sub = 512
+        t0 = time.perf_counter()
+        ao.gp_predict(pr.X, pr.posts, Xs[:sub], pr.mean_kind, separate_samples=True)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        ex["gp_predict"] = {
+            "points": Nx, "e2e_ms": e2e_ms, "device_ms": dev_ms, "points_per_s_e2e": Nx / (e2e_ms * 1e-3),
+            "algorithmic_flops": f_alg, "fp64_TFLOPs_achieved": f_alg / (dev_ms * 1e-3) / 1e12,
+            "vp_pdf_e2e_ms": pdf_ms,
+            "cpu_oracle_ms_per_512_points": cpu_ms,
+            "what": ("pyvbmc_b200.gp_predict(gp, Xs, separate_samples=True) at the reference's search-cache size "
+                     "(abstract_acq_fcn.py:79); device_ms = gppred_kernel alone (DMMA fp64), e2e includes the H2D of Xs "
+                     "and the D2H of f_mu / f_s2; the CPU figure is the oracle's NumPy restatement of gpyreg's predict on "
+                     "512 of the points (its cost is linear in the number of points)"),
+        }
+    except Exception as exc:
+        ex["gp_predict"] = {"error": repr(exc)}
+    # the drop-in claim, timed: the UNMODIFIED reference optimize_vp (variational_optimization.py:90-391) on the C2 GP,
+    # unpatched (CPU) and on top of pyvbmc_b200.install(device_adam=True, batched_sieve=True)
+    try:
+        from oracle import ref_loader
+
+        if ref_loader.available():
+            ref = ref_loader.load()
+            import pyvbmc.vbmc as vpk
+            from pyvbmc.vbmc import variational_optimization as vo
+            from pyvbmc.vbmc.options import Options
+
+            p2 = syn.make_problem("C2")
+            base = os.path.join(os.path.dirname(vpk.__file__), "option_configs")
+            opts = Options(os.path.join(base, "basic_vbmc_options.ini"), evaluation_parameters={"D": p2.D},
+                           user_options={"max_iter_stochastic": 200})
+            opts.load_options_file(os.path.join(base, "advanced_vbmc_options.ini"), evaluation_parameters={"D": p2.D})
+            gp2 = ref_loader.make_ref_gp(p2.X, p2.y.reshape(-1, 1), p2.posts, p2.mean_kind)
+
+            def once():
+                np.random.seed(0)
+                v = ref_loader.make_ref_vp(p2.D, p2.K, p2.mu, p2.sigma, p2.lambd, p2.w, p2.eta)
+                t0 = time.perf_counter()
+                v2, _, _ = vo.optimize_vp(opts, {"warmup": False, "entropy_switch": False}, v, gp2, 100, 1, p2.K)
+                return time.perf_counter() - t0, float(v2.stats["elbo"])
+
+            t_ref, elbo_ref = once()
+            pv.install(device_adam=True, batched_sieve=True)
+            try:
+                once()  # warm-up (graph capture)
+                t_dev, elbo_dev = once()
+            finally:
+                pv.uninstall()
+            ex["dropin_optimize_vp"] = {
+                "unpatched_s": t_ref, "patched_s": t_dev, "speedup": t_ref / t_dev, "elbo_unpatched": elbo_ref,
+                "elbo_patched": elbo_dev,
+                "what": ("unmodified pyvbmc optimize_vp on the C2 GP (D=10, N=200, K=20, S=4; 100 sieve candidates, 1 slow "
+                         "start, <= 200 Adam iterations at the reference's default draw count, full-ELCBO evaluation, "
+                         "pruning trials): wall time on the reference's NumPy functions vs on pyvbmc_b200.install("
+                         "device_adam=True, batched_sieve=True)"),
+            }
+    except Exception as exc:
+        ex["dropin_optimize_vp"] = {"error": repr(exc)}
     return ex
 
 

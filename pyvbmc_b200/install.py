@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import importlib
 import sys
+import threading
 
 from .entropy import entlb_vbmc, entmc_vbmc
 from .vbmc.variational_optimization import _gp_log_joint, _neg_elcbo, _soft_bound_loss, _vp_bound_loss
@@ -44,6 +45,8 @@ _SITES = {
     "pyvbmc.vbmc.active_sample": {"_gp_log_joint": _gp_log_joint, "_neg_elcbo": _neg_elcbo},
 }
 _saved = {}
+# make_sieve swaps a module-level name while the reference's _sieve runs: one sieve at a time per process
+_sieve_lock = threading.RLock()
 
 _ELCBO_FREEVARS = ("gp", "vp0", "elcbo_beta", "ns_ent_K", "compute_var", "theta_bnd")
 
@@ -100,7 +103,7 @@ def make_sieve(reference_sieve, module, batch_fn=None):
     import numpy as np
 
     def _sieve(*args, **kwargs):
-        real = module._neg_elcbo
+        real = None
         rec, mode = [], {"batch": None}
 
         def recorder(theta, gp, vp, beta=0.0, Ns=0, compute_grad=True, compute_var=None, theta_bnd=None, *a, **k):
@@ -113,11 +116,13 @@ def make_sieve(reference_sieve, module, batch_fn=None):
             rec.append((np.array(theta, dtype=float, copy=True), gp, vp, theta_bnd))
             return float(len(rec)), None, 0.0, 0.0, 0.0
 
-        module._neg_elcbo = recorder
-        try:
-            out = reference_sieve(*args, **kwargs)
-        finally:
-            module._neg_elcbo = real
+        with _sieve_lock:  # (re-read under the lock: another thread's sieve may just have restored the name)
+            real = module._neg_elcbo
+            module._neg_elcbo = recorder
+            try:
+                out = reference_sieve(*args, **kwargs)
+            finally:
+                module._neg_elcbo = real
         if not rec:
             return out
         vp0_vec, vp0_type = out[0], out[1]
@@ -137,7 +142,23 @@ def make_sieve(reference_sieve, module, batch_fn=None):
     return _sieve
 
 
-def install(device_adam=False, batched_sieve=False):
+def make_pdf(reference_pdf):
+    """The rebound ``VariationalPosterior.pdf``: the Gaussian mixture (``df`` infinite or 0) is evaluated on the
+    device (``vbmc_vp_pdf``), the heavy-tailed variants go to the reference's own method."""
+    import numpy as np
+
+    def pdf(self, x, orig_flag=True, log_flag=False, grad_flag=False, df=np.inf):
+        if np.isfinite(df) and df != 0:
+            return reference_pdf(self, x, orig_flag=orig_flag, log_flag=log_flag, grad_flag=grad_flag, df=df)
+        from .acquisition_functions import vp_pdf
+
+        return vp_pdf(self, x, orig_flag=orig_flag, log_flag=log_flag, grad_flag=grad_flag, df=df)
+
+    pdf.__wrapped__ = reference_pdf
+    return pdf
+
+
+def install(device_adam=False, batched_sieve=False, device_pdf=False):
     """Patch an importable ``pyvbmc``; returns the list of ``module.name`` sites rebound."""
     done = []
     for modname, names in _SITES.items():
@@ -161,10 +182,24 @@ def install(device_adam=False, batched_sieve=False):
             _saved[(modname, "_sieve")] = mod._sieve
             mod._sieve = make_sieve(mod._sieve, mod)
             done.append(f"{modname}._sieve")
+    if device_pdf:  # acquisition functions call vp.pdf(Xs, orig_flag=False, log_flag=True) (acq_fcn_log.py:38-42)
+        modname = "pyvbmc.variational_posterior.variational_posterior"
+        mod = sys.modules.get(modname) or importlib.import_module(modname)
+        cls = mod.VariationalPosterior
+        if ("class:" + modname, "pdf") not in _saved_attrs:
+            _saved_attrs[("class:" + modname, "pdf")] = (cls, cls.pdf)
+            cls.pdf = make_pdf(cls.pdf)
+            done.append(f"{modname}.VariationalPosterior.pdf")
     return done
+
+
+_saved_attrs = {}
 
 
 def uninstall():
     for (modname, name), fn in list(_saved.items()):
         setattr(sys.modules[modname], name, fn)
         del _saved[(modname, name)]
+    for key, (owner, value) in list(_saved_attrs.items()):
+        setattr(owner, key[1], value)
+        del _saved_attrs[key]

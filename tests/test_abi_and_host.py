@@ -15,6 +15,12 @@ from oracle import elbo_oracle as eo
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _ref_available():
+    from oracle import ref_loader
+
+    return ref_loader.available()
+
+
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "vbmc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
@@ -245,7 +251,7 @@ def test_minimize_adam_wrapper_recognises_the_elcbo_closure_only():
     assert [c[0] for c in calls[-2:]] == ["dev", "ref"]
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+@pytest.mark.skipif(not _ref_available(), reason="needs the reference package (checkout or oracle/_ref archive)")
 def test_minimize_adam_wrapper_matches_the_reference_closure_shape():
     """The free variables and globals the wrapper keys on are those of the reference's own nested function."""
     import types
@@ -324,7 +330,7 @@ def test_sieve_wrapper_batches_the_candidate_loop_and_keeps_the_reference_order(
     assert mod._neg_elcbo is real_neg_elcbo
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+@pytest.mark.skipif(not _ref_available(), reason="needs the reference package (checkout or oracle/_ref archive)")
 def test_sieve_wrapper_matches_the_reference_loop_shape():
     """The reference's _sieve calls the module-level _neg_elcbo positionally as
     (theta, gp, vp0, 0, ns_ent_K_fast, 0, compute_var, theta_bnd) and returns a 6-tuple led by (vp0_vec, vp0_type)."""
@@ -343,7 +349,7 @@ def test_sieve_wrapper_matches_the_reference_loop_shape():
     assert args == ["theta", "gp", "vp0", "0", "ns_ent_K_fast", "0", "compute_var", "theta_bnd"]
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+@pytest.mark.skipif(not _ref_available(), reason="needs the reference package (checkout or oracle/_ref archive)")
 @pytest.mark.parametrize("best_N", [1, 5])
 def test_sieve_wrapper_end_to_end_on_the_unmodified_reference(best_N):
     """make_sieve around the REAL pyvbmc _sieve (options, get_hpd, _vb_init, soft bounds all run as shipped), with
@@ -405,7 +411,7 @@ def test_sieve_wrapper_end_to_end_on_the_unmodified_reference(best_N):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference/pyvbmc"), reason="needs the reference checkout (build container only)")
+@pytest.mark.skipif(not _ref_available(), reason="needs the reference package (checkout or oracle/_ref archive)")
 def test_both_wrappers_inside_the_unmodified_optimize_vp():
     """The real pyvbmc optimize_vp (sieve -> Adam on the best candidates -> full ELCBO -> pruning) with BOTH optional
     wrappers installed and the reference's own functions as CPU stand-ins for the two device entry points: the
