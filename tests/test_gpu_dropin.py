@@ -79,6 +79,7 @@ def _truth_moments(D, m):
 
 
 def _kl(mu1, S1, mu2, S2):
+    ref_loader.load()
     from pyvbmc.stats import kl_div_mvn
 
     return np.abs(kl_div_mvn(np.atleast_2d(mu1), np.atleast_2d(S1), np.atleast_2d(mu2), np.atleast_2d(S2)))
@@ -91,6 +92,8 @@ def _kl(mu1, S1, mu2, S2):
 ])
 def test_unmodified_optimize_vp_on_the_device(D, fast, slow, entropy_switch, elbo_tol, kl_tol):
     import pyvbmc_b200 as pv
+
+    ref_loader.load()  # puts the (stubbed) reference package on sys.path
     from pyvbmc.vbmc import variational_optimization as vo
 
     state = {"warmup": True, "entropy_switch": entropy_switch}
