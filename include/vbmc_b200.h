@@ -175,7 +175,10 @@ int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const 
  * BEFORE the sigma/lambda/softmax Jacobians, already scaled by the GLOBAL 1/Ns and 1/S)
  * -> [all-reduce SUM of raw_dev over ranks, e.g. NCCL] -> finalize (identical on every
  * rank).  raw_dev holds vbmc_raw_len(D, K) doubles.  Results stay on the device in
- * out_dev: [F, G, H, varF, varG_ss, 0, 0, 0, dF (P)...].  Nothing is synchronised.       */
+ * out_dev: [F, G, H, varF, varG_ss, 0, 0, 0, dF (P)...].  Nothing is synchronised.
+ * Philox mode: the first vbmc_negelcbo_partials_async after an upload evaluates the uploaded key (seed, offset);
+ * every further call WITHOUT a new upload is the next evaluation of a device-resident loop and uses
+ * (seed, offset + 1), (seed, offset + 2), ... -- its noise tiles are generated beside the previous call's tail.    */
 /* ---- batched sieve evaluation -------------------------------------------------------------
  * Replaces the loop of variational_optimization.py:775-787 (`_sieve`): for b < B
  *     F_b, _, G_b, H_b, _ = _neg_elcbo(theta_b, gp, vp_b, 0, Ns = 0, compute_grad = 0, compute_var = 0, theta_bnd)
@@ -246,7 +249,9 @@ int vbmc_stream_synchronize(vbmc_ctx *ctx);
 /* Re-enqueue the evaluation staged last (by vbmc_negelcbo_flat or vbmc_negelcbo_upload) on the context stream:
  * the kernels of one evaluation with parameters and GP already resident in HBM, result left in the library's device
  * out buffer, no host synchronisation.  This is the device-resident step bench.py times with CUDA events (`value`):
- * what one `_neg_elcbo` call (variational_optimization.py:991-1235) costs the GPU, without the host round trip.   */
+ * what one `_neg_elcbo` call (variational_optimization.py:991-1235) costs the GPU, without the host round trip.
+ * Every call is a NEW evaluation: Philox key (seed, offset + number of calls since staging), as in consecutive
+ * iterations of the Adam loop.                                                                                   */
 int vbmc_negelcbo_enqueue(vbmc_ctx *ctx);
 
 /* ---- all-reduce of the raw vector over NVLink peer memory (optional; replaces the NCCL all-reduce between

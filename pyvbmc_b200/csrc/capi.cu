@@ -130,6 +130,9 @@ struct CtxEx {
     cudaGraphExec_t adam_gexec = nullptr;
     cudaGraph_t adam_graph = nullptr;
     uint64_t adam_gen = 0;
+    int64_t partials_calls = 0;     // vbmc_negelcbo_partials_async calls since the last upload
+    int adam_graph_buf = 0;         // noise-tile buffer parity / look-ahead state the captured pair starts from
+    bool adam_graph_ready = false;
 };
 
 CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
@@ -160,7 +163,10 @@ int stage(CtxEx *x, const Spec &s) {
     }
     memcpy(h + lay.total(), &s.seed, sizeof(uint64_t));  // Philox key rides behind the parameter block
     memcpy(h + lay.total() + 1, &s.offset, sizeof(uint64_t));
-    VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * (lay.total() + 2), cudaMemcpyHostToDevice, c->stream));
+    // parameter block -> HBM.  A one-CTA kernel that reads the pinned block through its device alias (UVA) instead
+    // of a copy-engine memcpy: inside the captured graph a kernel node starts ~5 us sooner than a memcpy node, and
+    // this copy heads the critical path of every evaluation.
+    VBMC_TRY(stage_copy_launch(c, c->d_in, h, lay.total() + 2));
 
     if (s.use_bounds) {
         const int n_expect = (s.optimize[0] ? K * D : 0) + K * D + (s.optimize[3] ? K : 0);
@@ -191,6 +197,10 @@ int stage(CtxEx *x, const Spec &s) {
     f.parts = s.parts;
     st.planned = false;
     c->staged = true;
+    // a new Philox key sits behind the parameter block: nothing generated ahead can belong to it
+    c->key_serial += (uint64_t)1 << 32;
+    c->key_delta = 0;
+    c->lookahead = false;
     return VBMC_OK;
 }
 
@@ -258,6 +268,10 @@ int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
     Staged &st = x->st;
     VBMC_REQUIRE(c->staged, VBMC_ERR_STATE, "nothing staged");
     VBMC_TRY(finalize_launch(c, c->d_in, st.D, st.K, st.f, raw_dev, out_dev));
+    if (c->noise_pending_join) {  // side-stream generator of the next evaluation's draws (entmc_tc.cu): runs beside the tail
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
+        c->noise_pending_join = false;
+    }
     // the variance path needs the per-sample G_s completed by the assemble phase
     if (st.s.compute_var) VBMC_TRY(gpvar_launch(c, c->d_in, st.K, st.s.avg));
     return VBMC_OK;
@@ -292,7 +306,10 @@ void drop_adam_graph(CtxEx *x) {
 // one Adam iteration on the context stream: theta -> parameter block, evaluation, update (no host sync)
 int adam_iteration(CtxEx *x) {
     Ctx *c = &x->c;
-    VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));
+    VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));  // writes the key (seed, offset0 + iteration) behind the block
+    c->key_serial += 1;
+    c->key_delta = 0;
+    c->lookahead = true;  // the next iteration's draws are generated under this iteration's tail
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
     VBMC_TRY(finalize(x, c->d_raw, c->d_out));
     VBMC_TRY(adam_update_launch(c, x->adam, c->d_out));
@@ -329,6 +346,9 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
         memcpy(c->h_in, s.flat, sizeof(double) * lay.total());
         memcpy(c->h_in + lay.total(), &s.seed, sizeof(uint64_t));
         memcpy(c->h_in + lay.total() + 1, &s.offset, sizeof(uint64_t));
+        c->key_serial += (uint64_t)1 << 32;  // a new key behind the parameter block (see stage())
+        c->key_delta = 0;
+        c->lookahead = false;
         VBMC_CUDA_CHECK(cudaGraphLaunch(x->gexec, c->stream));
         VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         x->graph_launches++;
@@ -417,10 +437,17 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
         for (int i = 0; i < 8; ++i) VBMC_CUDA_CHECK(cudaEventCreate(&x->c.sev[i]));
     if (const char *v = getenv("VBMC_ENTMC_VARIANT")) x->c.entmc_variant = atoi(v);
     if (const char *g = getenv("VBMC_ENTMC_GUARD")) x->c.entmc_guard = (float)atof(g);
-    VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
-    VBMC_CUDA_CHECK(cudaStreamCreateWithFlags(&x->c.stream2, cudaStreamNonBlocking));
+    // the main stream outranks the side stream: when the tail (a cluster of 8 x 1024 threads) and the look-ahead noise
+    // generator (hundreds of CTAs) become runnable together behind the entropy kernel, the tail's cluster must get its
+    // 8 SMs first -- otherwise it waits for the generator to drain and nothing overlaps
+    int prio_least = 0, prio_greatest = 0;
+    VBMC_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    VBMC_CUDA_CHECK(cudaStreamCreateWithPriority(&x->c.stream, cudaStreamNonBlocking, prio_greatest));
+    VBMC_CUDA_CHECK(cudaStreamCreateWithPriority(&x->c.stream2, cudaStreamNonBlocking, prio_least));
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_fork, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_join, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_main, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_noise, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev0));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev1));
     *out = reinterpret_cast<vbmc_ctx *>(x);
@@ -439,7 +466,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
-                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles, c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var, c->d_xs, c->d_pred};
+                     c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles[0], c->d_tctiles[1], c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var, c->d_xs, c->d_pred};
     for (double *d : dev)
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
@@ -448,6 +475,8 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_noise) cudaEventDestroy(c->ev_noise);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete x;
@@ -864,26 +893,40 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
     VBMC_REQUIRE(x->adam_ready && c->staged, VBMC_ERR_STATE, "adam_steps: call vbmc_adam_init first");
     VBMC_REQUIRE(n >= 0 && x->adam_done + n <= x->adam_max_iter, VBMC_ERR_ARG, "adam_steps: more steps than max_iter");
     const long long i0 = x->adam_done;
-    for (int it = 0; it < n; ++it) {
+    // Iterations are captured and replayed in PAIRS: the tensor-core entropy kernel alternates between two noise-tile
+    // buffers (the draws of iteration i + 1 are generated under the tail of iteration i), so one captured pair leaves
+    // the buffers where it found them and can be replayed back to back.  Single iterations (the first one, which
+    // sizes every buffer; an odd remainder) run eagerly; an eager iteration also flips the buffer parity back when a
+    // remainder left it opposite to the one the pair was captured with.
+    for (int it = 0; it < n;) {
         if (x->seen_epoch != g_realloc_epoch.load(std::memory_order_relaxed)) {  // a buffer moved: captured pointers are stale
             x->gen++;
             x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
         }
-        if (x->adam_gexec && x->adam_gen == x->gen) {
+        const bool pair_ok = x->graphs_on && x->adam_eager_done && n - it >= 2;
+        const bool state_ok = c->noise_buf == x->adam_graph_buf && c->noise_ready == x->adam_graph_ready &&
+                              (!c->noise_ready || c->noise_tag == c->key_serial + 1);
+        if (pair_ok && x->adam_gexec && x->adam_gen == x->gen && state_ok) {
             VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
             c->launches += x->adam_launches_per_iter;
+            c->key_serial += 2;  // what the two captured iterations did to the host-side bookkeeping
+            if (c->noise_ready) c->noise_tag += 2;
+            it += 2;
             continue;
         }
-        if (!x->adam_eager_done || !x->graphs_on) {  // first iteration: eager (sizes every buffer)
+        if (!pair_ok || (x->adam_gexec && x->adam_gen == x->gen && !state_ok)) {
             VBMC_TRY(adam_iteration(x));
             x->adam_eager_done = true;
+            it += 1;
             continue;
         }
         drop_adam_graph(x);
         const uint64_t epoch0 = g_realloc_epoch.load(std::memory_order_relaxed);
         const int64_t l0 = c->launches;
+        x->adam_graph_buf = c->noise_buf, x->adam_graph_ready = c->noise_ready;
         VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = adam_iteration(x);
+        int rc = adam_iteration(x);
+        if (rc == VBMC_OK) rc = adam_iteration(x);
         cudaGraph_t g = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
         if (rc != VBMC_OK || ce != cudaSuccess || epoch0 != g_realloc_epoch.load(std::memory_order_relaxed)) {
@@ -891,10 +934,15 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
             cudaGetLastError();
             x->gen++;
             x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
-            x->adam_eager_done = false;  // start over with an eager iteration
+            x->adam_eager_done = false;  // start over with an eager iteration (nothing of the capture has run)
+            c->noise_ready = false;
+            c->noise_pending_join = false;
+            c->key_serial += (uint64_t)1 << 32;
             if (rc != VBMC_OK) return rc;
-            VBMC_TRY(adam_iteration(x));
-            x->adam_eager_done = true;
+            if (ce != cudaSuccess) {
+                set_error(std::string("adam_steps: stream capture failed: ") + cudaGetErrorString(ce));
+                return VBMC_ERR_CUDA;
+            }
             continue;
         }
         x->adam_graph = g;
@@ -904,6 +952,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         x->adam_gen = x->gen;
         VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
         c->launches += x->adam_launches_per_iter;
+        it += 2;
     }
     x->adam_done += n;
     const int P = x->adam.P;
@@ -945,6 +994,7 @@ int vbmc_negelcbo_upload(vbmc_ctx *p, const vbmc_elcbo_in *in) {
     Spec s;
     VBMC_TRY(spec_from_in(in, &s));
     VBMC_REQUIRE(!in->compute_var, VBMC_ERR_UNSUPPORTED, "split-phase evaluation does not cover the variance path");
+    x->partials_calls = 0;
     return stage(x, s);
 }
 
@@ -952,6 +1002,10 @@ int vbmc_negelcbo_partials_async(vbmc_ctx *p, int rank, int world, double *raw_d
     VBMC_REQUIRE(p && raw_dev, VBMC_ERR_ARG, "partials: null argument");
     CtxEx *x = ex(p);
     Bind b(&x->c);
+    // first call after vbmc_negelcbo_upload: the uploaded key; every further call: the next key (offset + 1, + 2, ...),
+    // like consecutive optimiser steps -- its draws are generated under the previous call's tail
+    x->c.key_delta = x->partials_calls++;
+    x->c.lookahead = true;
     return partials(x, rank, world, raw_dev);
 }
 
@@ -1035,6 +1089,10 @@ int vbmc_negelcbo_enqueue(vbmc_ctx *p) {
     VBMC_REQUIRE(c->staged && c->d_raw && c->d_out, VBMC_ERR_STATE,
                  "enqueue: nothing staged (call vbmc_negelcbo_flat or vbmc_negelcbo_upload first)");
     VBMC_REQUIRE(!x->st.s.compute_var, VBMC_ERR_UNSUPPORTED, "enqueue does not cover the variance path");
+    // every call is a NEW evaluation: Philox key (seed, offset + number of calls since staging), like consecutive
+    // iterations of the Adam loop; its draws were generated under the previous call's tail
+    c->key_delta += 1;
+    c->lookahead = true;
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
     return finalize(x, c->d_raw, c->d_out);
 }

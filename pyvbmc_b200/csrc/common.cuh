@@ -150,8 +150,21 @@ struct Ctx {
     size_t raw_cap = 0;
     double *d_tctab = nullptr;  // per-component table images of the tensor-core entmc kernel
     size_t tctab_cap = 0;
-    double *d_tctiles = nullptr;  // noise-tile images of the tensor-core entmc kernel
-    size_t tctiles_cap = 0;
+    // Noise-tile images of the tensor-core entmc kernel: two buffers.  The tiles are unscaled standard normals (a
+    // function of the Philox key only), so while the tail of evaluation n runs, a side-stream launch fills the OTHER
+    // buffer with the draws of evaluation n + 1 (key offset + 1): device-resident loops (vbmc_adam_steps,
+    // vbmc_negelcbo_enqueue, the split-phase multi-GPU step) never wait for the generator.
+    double *d_tctiles[2] = {nullptr, nullptr};
+    size_t tctiles_cap[2] = {0, 0};
+    int noise_buf = 0;             // buffer the next main kernel reads
+    bool noise_ready = false;      // ... already holds the draws tagged below (look-ahead launch of the previous evaluation)
+    uint64_t noise_tag = 0;        // key_serial + delta the ready buffer was generated for
+    uint64_t noise_sig[6] = {0, 0, 0, 0, 0, 0};  // shape / work split it was generated for
+    uint64_t key_serial = 0;       // identifies the Philox key currently behind the parameter block (see capi.cu)
+    int64_t key_delta = 0;         // evaluation = key + key_delta (vbmc_negelcbo_enqueue: one fresh key per call)
+    bool lookahead = false;        // the caller's next evaluation uses key + key_delta + 1
+    bool noise_pending_join = false;
+    cudaEvent_t ev_main = nullptr, ev_noise = nullptr;
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
     size_t csum_cap = 0;
     // peer-memory all-reduce of the raw vector (vbmc_p2p_export / vbmc_p2p_open): exchange buffers of all ranks
@@ -266,6 +279,7 @@ int adam_update_launch(Ctx *c, const AdamDev &a, const double *d_out);
 int sieve_launch(Ctx *c, int B, int D, int K, const int optimize[4], bool use_bounds, const double *d_prm, double *d_out);
 
 // finalize.cu
+int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n);
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
                   int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool defer);
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,

@@ -225,7 +225,7 @@ __host__ __device__ inline TcTab tc_tab_layout(int DP, int K) {
     s.Kc = take(KP * sizeof(KTc));
     s.Dir = take(KP * sizeof(KDir));
     s.Mask = take(16 * 4);
-    s.Scal = take(64);  // float sj, hj ; double is2j
+    s.Scal = take(64);  // float sj, hj * sj^2
     s.smem_bytes = o;
     s.Dl = take(KP * DP * 4);
     s.total = o;
@@ -292,15 +292,19 @@ __device__ __forceinline__ void store_half(const float (&eh)[DH], const float (&
 template <int DP, bool PHILOX>
 __global__ void __launch_bounds__(kThreads)
 entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard, unsigned char *__restrict__ tab,
-                    TcWork wk, const double *__restrict__ eps, unsigned char *__restrict__ tiles) {
+                    TcWork wk, const double *__restrict__ eps, unsigned char *__restrict__ tiles, int n_tab,
+                    int64_t key_delta) {
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     constexpr int DH = DP / 2, D8 = (DP + 7) / 8 * 8, N2 = D8 <= 16 ? 16 : 32;
     extern __shared__ __align__(16) unsigned char psm[];
-    if ((int)blockIdx.x >= K) {
+    // CTAs [0, n_tab): tables of component blockIdx.x (n_tab = K, or 0 when only noise is wanted: the look-ahead launch
+    // that fills the OTHER tile buffer for the next evaluation while this one's tail runs).  The noise tiles are
+    // UNSCALED standard normals: they depend on the Philox key only, never on theta.
+    if ((int)blockIdx.x >= n_tab) {
         // ---- (b) noise tile -------------------------------------------------------------------------------
         __shared__ int s_info[kGenTiles][4];  // j, n, t0, valid
         __shared__ int64_t s_plo[kGenTiles];
-        const int g_first = ((int)blockIdx.x - K) * kGenTiles;
+        const int g_first = ((int)blockIdx.x - n_tab) * kGenTiles;
         if (tid < kGenTiles) {  // which (component, pair range) is image g?  (64-bit divisions: once per image)
             const int g = g_first + tid;
             const int cta = g / wk.tpc, l = g - cta * wk.tpc;
@@ -338,14 +342,14 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         float *aH = reinterpret_cast<float *>(img), *aL = reinterpret_cast<float *>(img + ABYTES);
         float *gE = reinterpret_cast<float *>(img + 2 * ABYTES);
         const int row = tid & (kTile - 1), hsel = tid >> 7;
-        const float sj = (float)prm[lay.sigma() + j];
         const int off = t0 + row;
         const bool live = off < n;
         const int64_t gpair = wk.pair0 + p_lo + (live ? off : 0);
         float z[DH];
         if (PHILOX) {
             const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
-            philox_normals_half<DH>(rngp[0], rngp[1], (uint32_t)j, (uint64_t)gpair, hsel, D, z);
+            // key of THIS evaluation rides behind the parameter block; key_delta = 1: the next evaluation's draws
+            philox_normals_half<DH>(rngp[0], rngp[1] + (uint64_t)key_delta, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
         } else {
             const double *ep = eps + ((size_t)j * (size_t)wk.half_glob + (size_t)gpair) * (size_t)D;
 #pragma unroll
@@ -356,7 +360,7 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         float Eh = 0.f, eh[DH], el[DH];
 #pragma unroll
         for (int i = 0; i < DH; ++i) {
-            const float e = live ? sj * z[i] : 0.0f;
+            const float e = live ? z[i] : 0.0f;  // UNSCALED: sigma_j is folded into the tables, the tile depends on the key only
             Eh = fmaf(e, e, Eh);
             eh[i] = __uint_as_float(__float_as_uint(e) & 0xffffe000u);
             el[i] = e - eh[i];
@@ -399,60 +403,63 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
     const double sig_j = sigma[j];
     const double hjd = kHalfLog2e / (sig_j * sig_j);
     const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);
+    // (latency matters here: these K small CTAs sit in front of the main kernel.  One reciprocal per dimension instead
+    // of one per table entry, and the per-component constants -- two fp64 logarithms and three divisions each -- are
+    // computed by KP threads side by side instead of by lane 0 of eight warps, component after component.)
+    __shared__ double sInvL[kMaxD];
     if (tid < 16) sMask[tid] = 0u;
+    if (tid < DP) sInvL[tid] = tid < D ? 1.0 / lambd[tid] : 0.0;
+    __syncthreads();
     for (int i = tid; i < KP * DP; i += nt) {
         const int k = i / DP, d = i - k * DP;
-        const float v = (k < K && d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * (1.0 / lambd[d])) : 0.0f;
+        const float v = (k < K && d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * sInvL[d]) : 0.0f;
         sDl[i] = v;
         gDl[i] = v;
     }
     __syncthreads();
-    {
-        // one warp per component: lanes over the dimensions for |Delta_k|^2, lane 0 finishes the constants
-        const int lane = tid & 31, wid = tid >> 5;
-        for (int k = wid; k < KP; k += nt / 32) {
-            double A = 0.0;  // |Delta_k|^2 of the rounded table entries
-            if (k < K)
-                for (int d = lane; d < D; d += 32) A += (double)sDl[k * DP + d] * (double)sDl[k * DP + d];
-            A = warp_sum(A);
-            if (lane == 0) {
-                KTc c;
-                KDir dr;
-                c.ck2 = -200.0f, c.hd = 0.f, c.w = 0.f, c.wis = 0.f;  // padding / guarded: expanded-form u = 2^-200 = 0
-                dr.ck = -200.0f, dr.h = 0.f;
-                double h2 = 0.0, wis = 0.0;
-                if (k < K) {
-                    const double sk = sigma[k];
-                    const double hk = kHalfLog2e / (sk * sk);
-                    const double ck = D * (log2(sig_j) - log2(sk));
-                    c.w = (float)w[k];
-                    wis = w[k] / (sk * sk);
-                    c.wis = (float)wis;
-                    dr.ck = (float)ck;
-                    dr.h = (float)hk;
-                    // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
-                    if (k != j && hk * (A + Emax) > (double)guard) {
-                        atomicOr(&sMask[k >> 4], 1u << (k & 15));
-                    } else {
-                        c.ck2 = (float)(ck - hk * A);
-                        c.hd = (float)(hjd - hk);
-                        h2 = 2.0 * hk;
-                    }
-                }
-                gKc[k] = c;
-                gDir[k] = dr;
-                sH2[k] = h2;
-                sWis[k] = wis;
+    if (tid < KP) {
+        const int k = tid;
+        KTc c;
+        KDir dr;
+        c.ck2 = -200.0f, c.hd = 0.f, c.w = 0.f, c.wis = 0.f;  // padding / guarded: expanded-form u = 2^-200 = 0
+        dr.ck = -200.0f, dr.h = 0.f;
+        double h2 = 0.0, wis = 0.0;
+        if (k < K) {
+            double A0 = 0.0, A1 = 0.0;  // |Delta_k|^2 of the rounded table entries
+#pragma unroll
+            for (int d = 0; d < DP; d += 2) {
+                const double a = (double)sDl[k * DP + d], b2 = (double)sDl[k * DP + d + 1];
+                A0 = fma(a, a, A0), A1 = fma(b2, b2, A1);
+            }
+            const double A = A0 + A1;
+            const double sk = sigma[k];
+            const double hk = kHalfLog2e / (sk * sk);
+            const double ck = D * (log2(sig_j) - log2(sk));
+            c.w = (float)w[k];
+            wis = w[k] / (sk * sk);
+            c.wis = (float)wis;
+            dr.ck = (float)ck;
+            dr.h = (float)hk;
+            // conditioning of the expanded form (see entmc_kernel_fast): direct differences beyond the guard
+            if (k != j && hk * (A + Emax) > (double)guard) {
+                atomicOr(&sMask[k >> 4], 1u << (k & 15));
+            } else {
+                c.ck2 = (float)(ck - hk * A);
+                c.hd = (float)((hjd - hk) * sig_j * sig_j);  // multiplies |z|^2 = |e|^2 / sigma_j^2
+                h2 = 2.0 * hk;
             }
         }
+        gKc[k] = c;
+        gDir[k] = dr;
+        sH2[k] = h2;
+        sWis[k] = wis;
     }
     __syncthreads();
     if (tid < 16) gMask[tid] = sMask[tid];
     if (tid == 0) {
         float *sc = reinterpret_cast<float *>(base + L.Scal);
         sc[0] = (float)sig_j;
-        sc[1] = (float)hjd;
-        *reinterpret_cast<double *>(sc + 2) = 1.0 / (sig_j * sig_j);
+        sc[1] = (float)(hjd * sig_j * sig_j);  // direct path: log2 u = ck + (hj sigma_j^2) |z|^2 - h |t|^2
     }
     // operand tables of the two GEMMs (hi = upper 19 bits = exact tf32, lo = remainder); the per-component scales
     // are folded in: GEMM1 yields X_k = 2 h_k B_k directly, GEMM2 contracts (u+/q+ - u-/q-) with wis_k Delta_k
@@ -460,7 +467,7 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         const int k = i / D8, d = i - k * D8;
         const double dl = (k < K && d < DP) ? (double)sDl[k * DP + d] : 0.0;
         {
-            const float v = (float)(sH2[k] * dl);
+            const float v = (float)(sH2[k] * sig_j * dl);  // GEMM1 contracts the UNSCALED noise z: X_k = 2 h_k sigma_j Delta_k . z
             const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u), vl = v - vh;
             const int o1 = (d >> 2) * (KP * 4) + k * 4 + (d & 3);  // GEMM1 B operand: rows = components, K dim = d
             gB1h[o1] = vh, gB1l[o1] = vl;
@@ -615,8 +622,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
         }
         fence_async_smem();  // generic-proxy writes (tables) -> async proxy (MMA operand reads)
         __syncthreads();
-        const float hj = sScal[1];
-        const double is2j = *reinterpret_cast<const double *>(sScal + 2);
+        const float sj = sScal[0], hj = sScal[1];
         const float *gDl = reinterpret_cast<const float *>(tab + (size_t)j * T.total + T.Dl);
         if (tid == kTile) {
             mbar_wait(barF + 8 * (r0 % kRing), (uint32_t)(r0 / kRing) & 1u);
@@ -633,7 +639,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
 #pragma unroll
             for (int i = 0; i < DH; ++i) ae[i] = be[i] = 0.f;
         }
-        float gs = 0.f, gd = 0.f;  // G+/q+ +- G-/q- of the tile whose epilogue is pending
+        float gs = 0.f, gd = 0.f;  // sigma_j^2 (G+/q+ + G-/q-) and sigma_j (G+/q+ - G-/q-) of the tile whose epilogue is pending
 
         // epilogue of tile r (its GEMM2 has completed): per-thread gradient sums over this thread's dimensions
         auto epilogue = [&](int r) {
@@ -645,9 +651,9 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
             for (int i = 0; i < DH; ++i) {
                 const int d = hsel * DH + i;
                 const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-                const float e = aH[o] + aL[o];  // exact: hi + lo is the fp32 noise value
-                be[i] = fmaf(e, fmaf(e, gs, __uint_as_float(v[i])), be[i]);
-                ae[i] = fmaf(e, gd, ae[i]);
+                const float z = aH[o] + aL[o];  // exact: hi + lo is the fp32 noise value; e = sigma_j z
+                be[i] = fmaf(z, fmaf(z, gs, sj * __uint_as_float(v[i])), be[i]);
+                ae[i] = fmaf(z, gd, ae[i]);
             }
         };
 
@@ -698,7 +704,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
 #pragma unroll 1
                                 for (int d = 0; d < DP; ++d) {
                                     const int o = (d >> 2) * (kTile * 4) + row * 4 + (d & 3);
-                                    const float ed = aH[o] + aL[o], dd = __ldg(dl + d);
+                                    const float ed = sj * (aH[o] + aL[o]), dd = __ldg(dl + d);
                                     const float tp = dd + ed, tm = dd - ed;
                                     a0 = fmaf(tp, tp, a0), a1 = fmaf(tm, tm, a1);
                                 }
@@ -748,13 +754,13 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
             qp = sQ[0 * kTile + row] + sQ[4 * kTile + row];
             qm = sQ[1 * kTile + row] + sQ[5 * kTile + row];
             if (live && hsel == 0)
-                hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
+                hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E;  // E = |z|^2 = |e|^2 / sigma_j^2
 
             if constexpr (ANYGRAD) {
                 Gp = sQ[2 * kTile + row] + sQ[6 * kTile + row];
                 Gm = sQ[3 * kTile + row] + sQ[7 * kTile + row];
                 const float iqp = live ? __frcp_rn(qp) : 0.f, iqm = live ? __frcp_rn(qm) : 0.f;
-                gs = fmaf(Gp, iqp, Gm * iqm), gd = fmaf(Gp, iqp, -(Gm * iqm));
+                gs = sj * sj * fmaf(Gp, iqp, Gm * iqm), gd = sj * fmaf(Gp, iqp, -(Gm * iqm));
                 tm_wait_st();  // own u(+-) stores of pass 1
                 // ---- pass 2: racc_k += u+/q+ + u-/q- ;  c'_k = u+/q+ - u-/q- split hi/lo -------------------------
 #pragma unroll
@@ -893,21 +899,37 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     const size_t TB = tc_tile_bytes(DP);
     const size_t n_img = (size_t)plan.grid * wk.tpc;
     VBMC_TRY(ensure(&c->d_tctab, &c->tctab_cap, ((size_t)K * T.total + 7) / 8));
-    VBMC_TRY(ensure(&c->d_tctiles, &c->tctiles_cap, (n_img * TB + 7) / 8));
     unsigned char *d_tab = reinterpret_cast<unsigned char *>(c->d_tctab);
-    unsigned char *d_tiles = reinterpret_cast<unsigned char *>(c->d_tctiles);
-    // generator: tables (K CTAs) + noise tiles (one CTA each); its output stays in L2 for the main kernel
-    {
-        const int KP = tc_kp(K);
-        const size_t psm = (size_t)KP * DP * 4 + (size_t)KP * 16;
-        const unsigned grid = (unsigned)(K + (n_img + kGenTiles - 1) / kGenTiles);
+    const int KP = tc_kp(K);
+    const size_t psm = (size_t)KP * DP * 4 + (size_t)KP * 16;
+    const unsigned tile_ctas = (unsigned)((n_img + kGenTiles - 1) / kGenTiles);
+    auto gen = [&](cudaStream_t st, unsigned char *tiles, int n_tab, bool with_tiles, int64_t delta) -> int {
+        const unsigned grid = (unsigned)n_tab + (with_tiles ? tile_ctas : 0u);
         if (philox)
-            entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, d_tiles);
+            entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta);
         else
-            entmc_tc_gen_kernel<DP, false><<<grid, kThreads, psm, c->stream>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, d_tiles);
+            entmc_tc_gen_kernel<DP, false><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta);
         VBMC_CUDA_CHECK(cudaGetLastError());
         c->launches++;
+        return VBMC_OK;
+    };
+    // shape / work split the tile images depend on (besides the Philox key)
+    const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
+                             (uint64_t)plan.chunk, (uint64_t)plan.half, (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
+    const uint64_t want = c->key_serial + (uint64_t)c->key_delta;
+    bool have = philox && c->noise_ready && c->noise_tag == want;
+    for (int i = 0; i < 6 && have; ++i) have = c->noise_sig[i] == sig[i];
+    const int b = c->noise_buf;
+    VBMC_TRY(ensure(&c->d_tctiles[b], &c->tctiles_cap[b], (n_img * TB + 7) / 8));
+    unsigned char *d_tiles = reinterpret_cast<unsigned char *>(c->d_tctiles[b]);
+    if (have) {
+        // the draws of this evaluation were generated under the previous evaluation's tail: tables only
+        // (finalize() of that evaluation re-joined the side stream, so the tiles are complete in stream order)
+        VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
+    } else {
+        VBMC_TRY(gen(c->stream, d_tiles, K, true, c->key_delta));
     }
+    c->noise_ready = false;
     static size_t smem_set[2] = {0, 0};
     if (plan.smem > smem_set[anygrad ? 1 : 0]) {
         if (anygrad)
@@ -922,6 +944,22 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         entmc_kernel_tc<DP, true><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
     else
         entmc_kernel_tc<DP, false><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    if (philox && c->lookahead) {
+        // draws of the NEXT evaluation (key offset + 1) into the other buffer, on the side stream, behind this main
+        // kernel: it runs while the tail (8 CTAs) leaves the machine idle.  finalize() re-joins the side stream.
+        const int nb = 1 - b;
+        VBMC_TRY(ensure(&c->d_tctiles[nb], &c->tctiles_cap[nb], (n_img * TB + 7) / 8));
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_main, 0));
+        VBMC_TRY(gen(c->stream2, reinterpret_cast<unsigned char *>(c->d_tctiles[nb]), 0, true, c->key_delta + 1));
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
+        c->noise_pending_join = true;
+        c->noise_ready = true;
+        c->noise_tag = want + 1;
+        for (int i = 0; i < 6; ++i) c->noise_sig[i] = sig[i];
+        c->noise_buf = nb;
+    }
     return VBMC_OK;
 }
 

@@ -653,6 +653,20 @@ int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalAr
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(1024) stage_copy_kernel(double *__restrict__ dst, const double *__restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+// pinned host block (device-addressable under the same pointer) -> device buffer, as a kernel on the context stream
+int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n) {
+    stage_copy_kernel<<<1, 1024, 0, c->stream>>>(d_dst, h_pinned_src, n);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
 // records / per-sample terms -> raw vector (device pointer d_raw).  defer = true (single GPU): nothing is
 // launched; the raw phases run fused with the next finalize_launch on the same raw vector (one launch).
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
