@@ -170,6 +170,25 @@ int vbmc_negelcbo_flat(vbmc_ctx *ctx, int D, int K, const double *params, const 
                        int compute_grad, int use_bounds, int rng_mode, const double *eps, uint64_t seed,
                        uint64_t offset, int precision, int want_dH, double *out);
 
+/* Same evaluation with the RAW optimiser vector in: VariationalPosterior.set_parameters(theta) (variational_posterior.py:
+ * 680-759: exp, lambda normalisation, softmax weights), the eta shift (variational_optimization.py:1082-1085) and the
+ * bound-loss inputs (:536-555) run on the device, so the host does no O(P) arithmetic per call.
+ *   theta  [P]  in/out: P = D*K, K, D, K summed over the optimised groups; on return its eta block is shifted so that
+ *               max(eta) == 0 -- the reference's own in-place side effect on the caller's array
+ *   tmpl        parameter block (vbmc_param_len doubles, layout as vbmc_negelcbo_flat) supplying the groups theta does
+ *               not carry; may be NULL when all four groups are optimised
+ *   out         [F, G, H, 0, 0, L_bound, L_penalty, nonfinite | dF (P)]
+ *   vp_out      [sigma (K) | lambda (D) | w (K)] after normalisation: what set_parameters leaves in the posterior
+ * Draws: VBMC_RNG_PHILOX keyed (seed, offset).                                                                    */
+int vbmc_negelcbo_theta(vbmc_ctx *ctx, int D, int K, double *theta, const double *tmpl, const int optimize[4],
+                        int64_t Ns, int compute_grad, int use_bounds, uint64_t seed, uint64_t offset, int precision,
+                        double *out, double *vp_out);
+/* Start generating the Monte-Carlo noise of the evaluation with Philox key (seed, offset) NOW, on a side stream: the
+ * noise does not depend on theta, so the generator runs while the host is still preparing the call.  A following
+ * vbmc_negelcbo_theta / vbmc_negelcbo_flat with the same (D, K, Ns, seed, offset) uses it; anything else ignores it.
+ * A no-op for problem sizes that do not take the tensor-core entropy kernel.                                      */
+int vbmc_noise_prefetch(vbmc_ctx *ctx, int D, int K, int64_t Ns, uint64_t seed, uint64_t offset);
+
 /* ---- split-phase, device-resident variants ----------------------------------------
  * One evaluation = partials (this rank's shard of draws and hyper-samples, raw sums
  * BEFORE the sigma/lambda/softmax Jacobians, already scaled by the GLOBAL 1/Ns and 1/S)

@@ -121,6 +121,12 @@ PROTOTYPES = {
         [C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_int_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
          C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p],
     ),
+    "vbmc_negelcbo_theta": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_int_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
+         C.c_uint64, C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "vbmc_noise_prefetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint64]),
     "vbmc_raw_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_out_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_negelcbo_upload": (C.c_int, [C.c_void_p, C.POINTER(ElcboIn)]),

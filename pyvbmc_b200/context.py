@@ -411,6 +411,38 @@ class Context:
         if rc:
             _capi.check(rc)
 
+    # ------------------------------------------------------------------ theta-in fast path
+    def theta_buffers(self, D, K):
+        """Preallocated host arrays of ``vbmc_negelcbo_theta``: (out, vp_out, tmpl)."""
+        key = ("theta", D, K)
+        buf = self._flat.get(key)
+        if buf is None:
+            P = D * K + 2 * K + D
+            buf = (np.zeros(8 + P, dtype=_F64), np.zeros(2 * K + D, dtype=_F64), np.zeros(self.param_len(D, K), dtype=_F64))
+            self._flat[key] = buf
+        return buf
+
+    def noise_prefetch(self, D, K, Ns_even, seed, offset=0):
+        """``vbmc_noise_prefetch``: start the generator of this evaluation's draws on the side stream."""
+        rc = self._lib.vbmc_noise_prefetch(self._h, D, K, Ns_even, seed, int(offset))
+        if rc:
+            _capi.check(rc)
+
+    def negelcbo_theta(self, D, K, theta, tmpl, optimize, Ns_even, compute_grad, use_bounds, seed, offset, precision, out,
+                       vp_out):
+        """``vbmc_negelcbo_theta``: raw optimiser vector in (its eta block is shifted in place), ``out`` / ``vp_out``
+        filled in place."""
+        og = self._opt_c.get(optimize)
+        if og is None:
+            og = self._opt_c[optimize] = (C.c_int * 4)(*[int(bool(o)) for o in optimize])
+        prec = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
+        rc = self._lib.vbmc_negelcbo_theta(
+            self._h, D, K, theta.ctypes.data, tmpl.ctypes.data if tmpl is not None else None, og, Ns_even,
+            int(compute_grad), int(use_bounds), seed, int(offset), prec, out.ctypes.data, vp_out.ctypes.data,
+        )
+        if rc:
+            _capi.check(rc)
+
     def param_len(self, D, K):
         return int(self._lib.vbmc_param_len(int(D), int(K)))
 

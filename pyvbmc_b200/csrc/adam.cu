@@ -13,8 +13,11 @@
 namespace vbmc {
 namespace {
 
-__global__ void __launch_bounds__(256)
-adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
+// theta -> parameter block: shared by the Adam loop (theta in HBM) and by vbmc_negelcbo_theta (theta, the template of
+// the groups theta does not carry, and the Philox key in PINNED HOST memory, read through their device aliases; the
+// normalised sigma / lambda / w go back to the host the same way in `vp_out` = [sigma (K) | lambda (D) | w (K)]).
+__device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__restrict__ prm, double *__restrict__ vp_out,
+                                                const uint64_t *__restrict__ key_src) {
     const ParamLayout lay = a.lay;
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[40];
@@ -33,11 +36,13 @@ adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
     for (int d = tid; d < D; d += nt) {
         const double lm = (a.opt[2] ? exp(th[pos_l + d]) : tm[lay.lambd() + d]) / scale;
         prm[lay.lambd() + d] = lm;
+        if (vp_out) vp_out[K + d] = lm;
         prm[lay.lnlam_b() + d] = a.opt[2] ? th[pos_l + d] : log(lm);  // (:536-555: theta's slice, else log of the field)
     }
     for (int k = tid; k < K; k += nt) {
         const double sg = (a.opt[1] ? exp(th[pos_s + k]) : tm[lay.sigma() + k]) * scale;
         prm[lay.sigma() + k] = sg;
+        if (vp_out) vp_out[k] = sg;
         prm[lay.lnsig_b() + k] = a.opt[1] ? th[pos_s + k] : log(sg);
     }
     // weights: softmax of eta with the max shift; eta itself is stored shifted (:1082-1085)
@@ -55,7 +60,9 @@ adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
         se = block_sum(se, scratch);
         for (int k = tid; k < K; k += nt) {
             const double e = eta[k] - mx;
-            prm[lay.w() + k] = exp(e) / se;
+            const double wk = exp(e) / se;
+            prm[lay.w() + k] = wk;
+            if (vp_out) vp_out[K + D + k] = wk;
             prm[lay.eta() + k] = e;
             prm[lay.eta_b() + k] = e;
             eta[k] = e;
@@ -63,15 +70,29 @@ adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
     } else {
         for (int k = tid; k < K; k += nt) {
             prm[lay.w() + k] = tm[lay.w() + k];
+            if (vp_out) vp_out[K + D + k] = tm[lay.w() + k];
             prm[lay.eta() + k] = tm[lay.eta() + k];
             prm[lay.eta_b() + k] = tm[lay.eta_b() + k];
         }
     }
     if (tid == 0) {  // Philox key rides behind the parameter block
         uint64_t *key = reinterpret_cast<uint64_t *>(prm + lay.total());
-        key[0] = a.seed;
-        key[1] = a.offset0 + (uint64_t)(*a.iter);
+        if (key_src) {
+            key[0] = key_src[0], key[1] = key_src[1];
+        } else {
+            key[0] = a.seed;
+            key[1] = a.offset0 + (uint64_t)(*a.iter);
+        }
     }
+}
+
+__global__ void __launch_bounds__(256) adam_prepare_kernel(AdamDev a, double *__restrict__ prm) {
+    theta_to_params(a, prm, nullptr, nullptr);
+}
+
+__global__ void __launch_bounds__(256)
+theta_prepare_kernel(AdamDev a, double *__restrict__ prm, double *__restrict__ vp_out, const uint64_t *__restrict__ key_src) {
+    theta_to_params(a, prm, vp_out, key_src);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -102,6 +123,13 @@ adam_update_kernel(AdamDev a, const double *__restrict__ out) {
 
 int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
     adam_prepare_kernel<<<1, 256, 0, c->stream>>>(a, d_prm);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src) {
+    theta_prepare_kernel<<<1, 256, 0, c->stream>>>(a, d_prm, vp_out, key_src);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

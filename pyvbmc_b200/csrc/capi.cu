@@ -47,6 +47,17 @@ int ensure_pinned(double **d, double **h, size_t *cap, size_t need) {
     return VBMC_OK;
 }
 
+int ensure_host_pinned(double **h, size_t *cap, size_t need) {
+    if (need <= *cap && *h) return VBMC_OK;
+    g_realloc_epoch.fetch_add(1, std::memory_order_relaxed);
+    if (*h) VBMC_CUDA_CHECK(cudaFreeHost(*h));
+    *h = nullptr;
+    size_t n = need + need / 4 + 64;
+    VBMC_CUDA_CHECK(cudaMallocHost((void **)h, n * sizeof(double)));
+    *cap = n;
+    return VBMC_OK;
+}
+
 namespace {
 
 struct Bind {
@@ -68,6 +79,10 @@ int packed_len(int D, int K, const int g[4]) {
 
 // internal description of one evaluation
 struct Spec {
+    // theta-in fast path (vbmc_negelcbo_theta): the raw optimiser vector; VariationalPosterior.set_parameters runs on
+    // the device.  tmpl = parameter block supplying the groups theta does not carry (may be null when all are optimised)
+    const double *theta = nullptr, *tmpl = nullptr;
+    int P = 0;
     const double *flat = nullptr;  // whole parameter block in ParamLayout order (fast path), else vp + *_b
     vbmc_vp vp;
     int grad[4];
@@ -131,6 +146,7 @@ struct CtxEx {
     cudaGraph_t adam_graph = nullptr;
     uint64_t adam_gen = 0;
     int64_t partials_calls = 0;     // vbmc_negelcbo_partials_async calls since the last upload
+    long long adam_issued = 0;      // Adam iterations issued (eager + captured) since vbmc_adam_init
     int adam_graph_buf = 0;         // noise-tile buffer parity / look-ahead state the captured pair starts from
     bool adam_graph_ready = false;
 };
@@ -139,7 +155,7 @@ CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
 
 int stage(CtxEx *x, const Spec &s) {
     Ctx *c = &x->c;
-    VBMC_TRY(check_vp(&s.vp, s.flat != nullptr));
+    VBMC_TRY(check_vp(&s.vp, s.flat != nullptr || s.theta != nullptr));
     const int D = s.vp.D, K = s.vp.K, DP = pad_dim(D);
     if (s.have_gp) {
         VBMC_REQUIRE(c->has_gp, VBMC_ERR_STATE, "no GP packed (call vbmc_gp_pack first)");
@@ -149,6 +165,22 @@ int stage(CtxEx *x, const Spec &s) {
     RawLayout rl{D, K};
     VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total() + 2));
     double *h = c->h_in;
+    if (s.theta) {
+        // theta, template and key go to PINNED host memory; one small kernel reads them through their device aliases
+        // and writes the parameter block (set_parameters + eta shift + bound inputs on the device)
+        const size_t T = (size_t)lay.total();
+        VBMC_TRY(ensure_host_pinned(&c->h_theta, &c->theta_cap, (size_t)s.P + T + 2 + (size_t)(2 * K + D)));
+        double *th = c->h_theta, *tm = th + s.P, *key = tm + T, *vpo = key + 2;
+        memcpy(th, s.theta, sizeof(double) * s.P);
+        if (s.tmpl) memcpy(tm, s.tmpl, sizeof(double) * T);
+        memcpy(key, &s.seed, sizeof(uint64_t));
+        memcpy(key + 1, &s.offset, sizeof(uint64_t));
+        AdamDev a{};
+        a.lay = lay, a.P = s.P;
+        for (int i = 0; i < 4; ++i) a.opt[i] = s.optimize[i];
+        a.theta = th, a.tmpl = tm;
+        VBMC_TRY(theta_prepare_launch(c, a, c->d_in, vpo, reinterpret_cast<const uint64_t *>(key)));
+    } else {
     if (s.flat) {
         memcpy(h, s.flat, sizeof(double) * lay.total());
     } else {
@@ -167,6 +199,7 @@ int stage(CtxEx *x, const Spec &s) {
     // of a copy-engine memcpy: inside the captured graph a kernel node starts ~5 us sooner than a memcpy node, and
     // this copy heads the critical path of every evaluation.
     VBMC_TRY(stage_copy_launch(c, c->d_in, h, lay.total() + 2));
+    }
 
     if (s.use_bounds) {
         const int n_expect = (s.optimize[0] ? K * D : 0) + K * D + (s.optimize[3] ? K : 0);
@@ -197,8 +230,8 @@ int stage(CtxEx *x, const Spec &s) {
     f.parts = s.parts;
     st.planned = false;
     c->staged = true;
-    // a new Philox key sits behind the parameter block: nothing generated ahead can belong to it
-    c->key_serial += (uint64_t)1 << 32;
+    // host mirror of the Philox key behind the parameter block (noise tiles generated ahead are matched against it)
+    c->cur_seed = s.seed, c->cur_offset = s.offset;
     c->key_delta = 0;
     c->lookahead = false;
     return VBMC_OK;
@@ -307,7 +340,8 @@ void drop_adam_graph(CtxEx *x) {
 int adam_iteration(CtxEx *x) {
     Ctx *c = &x->c;
     VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));  // writes the key (seed, offset0 + iteration) behind the block
-    c->key_serial += 1;
+    c->cur_seed = x->adam.seed, c->cur_offset = x->adam.offset0 + (uint64_t)x->adam_issued;
+    x->adam_issued++;
     c->key_delta = 0;
     c->lookahead = true;  // the next iteration's draws are generated under this iteration's tail
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
@@ -333,7 +367,7 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
         x->gen++;                                                           // last looked: captured pointers are suspect
         x->seen_epoch = g_realloc_epoch.load(std::memory_order_relaxed);
     }
-    const bool eligible = x->graphs_on && !c->stage_timing && !c->time_entmc && s.flat != nullptr &&
+    const bool eligible = x->graphs_on && !c->stage_timing && !c->time_entmc && (s.flat != nullptr || s.theta != nullptr) &&
                           !(s.Ns > 0 && s.rng_mode == VBMC_RNG_EPS) && !s.compute_var;
     if (!eligible) return run_single(x, s, n_out);
     GraphKey k;
@@ -341,18 +375,37 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     k.variant = c->entmc_variant, k.S = c->S, k.N = c->N, k.gen = x->gen;
     for (int i = 0; i < 4; ++i) k.flags |= (s.grad[i] ? 1 : 0) << i | (s.optimize[i] ? 1 : 0) << (4 + i);
     k.flags |= (s.use_bounds ? 1 : 0) << 8 | (s.have_gp ? 1 : 0) << 9 | (s.have_ent ? 1 : 0) << 10 | (s.parts ? 1 : 0) << 11;
+    // noise tiles generated ahead by vbmc_noise_prefetch for exactly this key: the graph then holds no generator
+    const bool pre = s.Ns > 0 && s.rng_mode == VBMC_RNG_PHILOX && c->noise_ready && c->noise_seed == s.seed &&
+                     c->noise_offset == s.offset && c->noise_sig[0] == ((uint64_t)k.D << 32 | (uint64_t)k.K) &&
+                     c->noise_sig[3] == (uint64_t)(even_ns(s.Ns) / 2);
+    if (!pre) c->noise_ready = false;
+    k.flags |= (s.theta ? 1 : 0) << 12 | (pre ? 1 : 0) << 13 | (c->noise_buf & 1) << 14 | (s.tmpl ? 1 : 0) << 15;
+    if (pre && c->noise_needs_wait) {  // order the side-stream generator before everything this call enqueues
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
+        c->noise_needs_wait = false;
+    }
     if (x->gexec && k == x->gkey) {
         const ParamLayout lay{k.D, pad_dim(k.D), k.K};
-        memcpy(c->h_in, s.flat, sizeof(double) * lay.total());
-        memcpy(c->h_in + lay.total(), &s.seed, sizeof(uint64_t));
-        memcpy(c->h_in + lay.total() + 1, &s.offset, sizeof(uint64_t));
-        c->key_serial += (uint64_t)1 << 32;  // a new key behind the parameter block (see stage())
+        if (s.theta) {
+            double *th = c->h_theta, *tm = th + s.P, *key = tm + lay.total();
+            memcpy(th, s.theta, sizeof(double) * s.P);
+            if (s.tmpl) memcpy(tm, s.tmpl, sizeof(double) * lay.total());
+            memcpy(key, &s.seed, sizeof(uint64_t));
+            memcpy(key + 1, &s.offset, sizeof(uint64_t));
+        } else {
+            memcpy(c->h_in, s.flat, sizeof(double) * lay.total());
+            memcpy(c->h_in + lay.total(), &s.seed, sizeof(uint64_t));
+            memcpy(c->h_in + lay.total() + 1, &s.offset, sizeof(uint64_t));
+        }
+        c->cur_seed = s.seed, c->cur_offset = s.offset;  // a new key behind the parameter block (see stage())
         c->key_delta = 0;
         c->lookahead = false;
         VBMC_CUDA_CHECK(cudaGraphLaunch(x->gexec, c->stream));
         VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         x->graph_launches++;
         c->launches += x->st.launches_per_eval;
+        c->noise_ready = false;  // (a prefetched buffer is consumed by the replay)
         return VBMC_OK;
     }
     if (!(k == x->last_key)) {  // first sighting: eager run (allocations happen here)
@@ -471,6 +524,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
         if (d) cudaFree(d);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -812,6 +866,61 @@ int vbmc_negelcbo_flat(vbmc_ctx *p, int D, int K, const double *params, const in
     return VBMC_OK;
 }
 
+int vbmc_noise_prefetch(vbmc_ctx *p, int D, int K, int64_t Ns, uint64_t seed, uint64_t offset) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "noise_prefetch: null ctx");
+    if (Ns <= 0 || D < 1 || K < 1 || D > kMaxD) return VBMC_OK;
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    const int64_t half = even_ns(Ns) / 2;
+    EntmcPlan plan{};
+    if (entmc_plan(c, D, K, half, true, VBMC_PREC_F32, &plan) != VBMC_OK || plan.variant != ENTMC_TC) return VBMC_OK;
+    plan.pair0 = 0, plan.half_glob = half;
+    return entmc_tc_prefetch(c, ParamLayout{D, pad_dim(D), K}, plan, seed, offset);
+}
+
+int vbmc_negelcbo_theta(vbmc_ctx *p, int D, int K, double *theta, const double *tmpl, const int optimize[4], int64_t Ns,
+                        int compute_grad, int use_bounds, uint64_t seed, uint64_t offset, int precision, double *out,
+                        double *vp_out) {
+    VBMC_REQUIRE(p && theta && optimize && out && vp_out, VBMC_ERR_ARG, "negelcbo_theta: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    Spec s;
+    s.theta = theta, s.tmpl = tmpl;
+    s.vp.D = D, s.vp.K = K;
+    s.vp.mu = s.vp.sigma = s.vp.lambd = s.vp.w = s.vp.eta = nullptr;
+    for (int i = 0; i < 4; ++i) {
+        s.optimize[i] = optimize[i] != 0;
+        s.grad[i] = compute_grad ? s.optimize[i] : 0;
+    }
+    s.P = packed_len(D, K, s.optimize);
+    VBMC_REQUIRE(s.P > 0, VBMC_ERR_ARG, "negelcbo_theta: no parameter group is optimised (theta is empty)");
+    VBMC_REQUIRE(tmpl || (s.optimize[0] && s.optimize[1] && s.optimize[2] && s.optimize[3]), VBMC_ERR_ARG,
+                 "negelcbo_theta: a template block is required for the groups theta does not carry");
+    s.jacobian = 1;
+    s.Ns = Ns;
+    s.use_bounds = use_bounds != 0;
+    s.rng_mode = VBMC_RNG_PHILOX, s.eps = nullptr, s.seed = seed, s.offset = offset, s.precision = precision;
+    s.parts = false;
+    const int Pg = packed_len(D, K, s.grad);
+    const size_t n_dev = kOutHead + (size_t)Pg;
+    VBMC_TRY(run_flat(x, s, n_dev));
+    const double *o = c->h_out;
+    if (o[7] != 0.0 && s.precision == VBMC_PREC_F32 && s.Ns > 0) {
+        s.precision = VBMC_PREC_F64;  // fp32 density ratios overflowed: redo the entropy in fp64 on the GPU
+        VBMC_TRY(run_single(x, s, n_dev));
+        o = c->h_out;
+    }
+    memcpy(out, o, sizeof(double) * (kOutHead + Pg));
+    const double *vpo = c->h_theta + s.P + ParamLayout{D, pad_dim(D), K}.total() + 2;
+    memcpy(vp_out, vpo, sizeof(double) * (2 * K + D));
+    // the reference shifts the eta block of the caller's theta in place (variational_optimization.py:1082-1085);
+    // the prepare kernel did it on the pinned copy
+    if (s.optimize[3]) memcpy(theta + s.P - K, c->h_theta + s.P - K, sizeof(double) * K);
+    return VBMC_OK;
+}
+
 int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     VBMC_REQUIRE(p && in && in->params && in->theta0, VBMC_ERR_ARG, "adam_init: null argument");
     CtxEx *x = ex(p);
@@ -881,6 +990,7 @@ int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     x->adam_max_iter = in->max_iter;
     x->adam_done = 0;
+    x->adam_issued = 0;
     x->adam_ready = true, x->adam_eager_done = false;
     return VBMC_OK;
 }
@@ -905,12 +1015,13 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         }
         const bool pair_ok = x->graphs_on && x->adam_eager_done && n - it >= 2;
         const bool state_ok = c->noise_buf == x->adam_graph_buf && c->noise_ready == x->adam_graph_ready &&
-                              (!c->noise_ready || c->noise_tag == c->key_serial + 1);
+                              (!c->noise_ready || (c->noise_seed == x->adam.seed &&
+                                                   c->noise_offset == x->adam.offset0 + (uint64_t)x->adam_issued));
         if (pair_ok && x->adam_gexec && x->adam_gen == x->gen && state_ok) {
             VBMC_CUDA_CHECK(cudaGraphLaunch(x->adam_gexec, c->stream));
             c->launches += x->adam_launches_per_iter;
-            c->key_serial += 2;  // what the two captured iterations did to the host-side bookkeeping
-            if (c->noise_ready) c->noise_tag += 2;
+            x->adam_issued += 2;  // what the two captured iterations did to the host-side bookkeeping
+            if (c->noise_ready) c->noise_offset += 2;
             it += 2;
             continue;
         }
@@ -937,7 +1048,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
             x->adam_eager_done = false;  // start over with an eager iteration (nothing of the capture has run)
             c->noise_ready = false;
             c->noise_pending_join = false;
-            c->key_serial += (uint64_t)1 << 32;
+            x->adam_issued = x->adam_done + it;  // nothing of the capture has run
             if (rc != VBMC_OK) return rc;
             if (ce != cudaSuccess) {
                 set_error(std::string("adam_steps: stream capture failed: ") + cudaGetErrorString(ce));

@@ -135,6 +135,8 @@ struct Ctx {
     // per-evaluation buffers (grown on demand)
     double *d_in = nullptr, *h_in = nullptr;
     size_t in_cap = 0;
+    double *h_theta = nullptr;  // pinned: [theta (P) | template block (param_len) | key (2) | vp_out (2K + D)] (vbmc_negelcbo_theta)
+    size_t theta_cap = 0;
     double *d_entpart = nullptr;
     size_t entpart_cap = 0;
     double *d_lamc = nullptr; // [S][K][D] lambda-gradient contributions of the log joint
@@ -158,9 +160,10 @@ struct Ctx {
     size_t tctiles_cap[2] = {0, 0};
     int noise_buf = 0;             // buffer the next main kernel reads
     bool noise_ready = false;      // ... already holds the draws tagged below (look-ahead launch of the previous evaluation)
-    uint64_t noise_tag = 0;        // key_serial + delta the ready buffer was generated for
+    uint64_t noise_seed = 0, noise_offset = 0;   // Philox key the ready buffer was generated for
     uint64_t noise_sig[6] = {0, 0, 0, 0, 0, 0};  // shape / work split it was generated for
-    uint64_t key_serial = 0;       // identifies the Philox key currently behind the parameter block (see capi.cu)
+    bool noise_needs_wait = false; // generated by vbmc_noise_prefetch on the side stream: not yet ordered before the main stream
+    uint64_t cur_seed = 0, cur_offset = 0;       // host mirror of the key currently behind the parameter block
     int64_t key_delta = 0;         // evaluation = key + key_delta (vbmc_negelcbo_enqueue: one fresh key per call)
     bool lookahead = false;        // the caller's next evaluation uses key + key_delta + 1
     bool noise_pending_join = false;
@@ -236,6 +239,7 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
                  uint64_t offset, double *d_part);
 int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
 // entmc_tc.cu (tcgen05 / TMEM kernel)
+int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset);
 bool entmc_tc_supported(int DP, int K);
 int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *plan);
 int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,
@@ -274,6 +278,8 @@ struct AdamDev {
 };
 int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm);
 int adam_update_launch(Ctx *c, const AdamDev &a, const double *d_out);
+// theta (+ template + key, all in pinned host memory) -> parameter block; vp_out = [sigma | lambda | w] (pinned host)
+int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src);
 
 // sieve.cu: batched value-only negative ELCBO (entlb + log joint + bounds) of B candidates
 int sieve_launch(Ctx *c, int B, int D, int K, const int optimize[4], bool use_bounds, const double *d_prm, double *d_out);

@@ -293,7 +293,7 @@ template <int DP, bool PHILOX>
 __global__ void __launch_bounds__(kThreads)
 entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard, unsigned char *__restrict__ tab,
                     TcWork wk, const double *__restrict__ eps, unsigned char *__restrict__ tiles, int n_tab,
-                    int64_t key_delta) {
+                    int64_t key_delta, int key_by_value, uint64_t seed_v, uint64_t offset_v) {
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     constexpr int DH = DP / 2, D8 = (DP + 7) / 8 * 8, N2 = D8 <= 16 ? 16 : 32;
     extern __shared__ __align__(16) unsigned char psm[];
@@ -347,9 +347,14 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         const int64_t gpair = wk.pair0 + p_lo + (live ? off : 0);
         float z[DH];
         if (PHILOX) {
-            const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
-            // key of THIS evaluation rides behind the parameter block; key_delta = 1: the next evaluation's draws
-            philox_normals_half<DH>(rngp[0], rngp[1] + (uint64_t)key_delta, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
+            // the key of THIS evaluation rides behind the parameter block (key_delta = 1: the next evaluation's draws);
+            // a prefetch launched before the parameters exist on the device passes the key by value
+            uint64_t ks = seed_v, ko = offset_v;
+            if (!key_by_value) {
+                const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+                ks = rngp[0], ko = rngp[1] + (uint64_t)key_delta;
+            }
+            philox_normals_half<DH>(ks, ko, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
         } else {
             const double *ep = eps + ((size_t)j * (size_t)wk.half_glob + (size_t)gpair) * (size_t)D;
 #pragma unroll
@@ -906,9 +911,9 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     auto gen = [&](cudaStream_t st, unsigned char *tiles, int n_tab, bool with_tiles, int64_t delta) -> int {
         const unsigned grid = (unsigned)n_tab + (with_tiles ? tile_ctas : 0u);
         if (philox)
-            entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta);
+            entmc_tc_gen_kernel<DP, true><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta, 0, 0, 0);
         else
-            entmc_tc_gen_kernel<DP, false><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta);
+            entmc_tc_gen_kernel<DP, false><<<grid, kThreads, psm, st>>>(d_params, lay, c->entmc_guard, d_tab, wk, d_eps, tiles, n_tab, delta, 0, 0, 0);
         VBMC_CUDA_CHECK(cudaGetLastError());
         c->launches++;
         return VBMC_OK;
@@ -916,15 +921,20 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     // shape / work split the tile images depend on (besides the Philox key)
     const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
                              (uint64_t)plan.chunk, (uint64_t)plan.half, (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
-    const uint64_t want = c->key_serial + (uint64_t)c->key_delta;
-    bool have = philox && c->noise_ready && c->noise_tag == want;
+    const uint64_t want_seed = c->cur_seed, want_offset = c->cur_offset + (uint64_t)c->key_delta;
+    bool have = philox && c->noise_ready && c->noise_seed == want_seed && c->noise_offset == want_offset;
     for (int i = 0; i < 6 && have; ++i) have = c->noise_sig[i] == sig[i];
     const int b = c->noise_buf;
     VBMC_TRY(ensure(&c->d_tctiles[b], &c->tctiles_cap[b], (n_img * TB + 7) / 8));
     unsigned char *d_tiles = reinterpret_cast<unsigned char *>(c->d_tctiles[b]);
     if (have) {
-        // the draws of this evaluation were generated under the previous evaluation's tail: tables only
-        // (finalize() of that evaluation re-joined the side stream, so the tiles are complete in stream order)
+        // the draws of this evaluation were generated under the previous evaluation's tail (finalize() of that
+        // evaluation re-joined the side stream, so the tiles are complete in stream order), or by vbmc_noise_prefetch
+        // while the host was still packing the parameters: tables only
+        if (c->noise_needs_wait) {
+            VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
+            c->noise_needs_wait = false;
+        }
         VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
     } else {
         VBMC_TRY(gen(c->stream, d_tiles, K, true, c->key_delta));
@@ -956,10 +966,35 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
         c->noise_pending_join = true;
         c->noise_ready = true;
-        c->noise_tag = want + 1;
+        c->noise_seed = want_seed, c->noise_offset = want_offset + 1;
         for (int i = 0; i < 6; ++i) c->noise_sig[i] = sig[i];
         c->noise_buf = nb;
     }
+    return VBMC_OK;
+}
+
+// vbmc_noise_prefetch: the noise tiles of the evaluation with Philox key (seed, offset), on the side stream, before
+// its parameters have reached the device (the tiles do not depend on them)
+template <int DP>
+int tc_prefetch_dp(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset) {
+    const int K = lay.K;
+    const TcWork wk = tc_work(plan, K);
+    const size_t TB = tc_tile_bytes(DP);
+    const size_t n_img = (size_t)plan.grid * wk.tpc;
+    const int b = c->noise_buf;
+    VBMC_TRY(ensure(&c->d_tctiles[b], &c->tctiles_cap[b], (n_img * TB + 7) / 8));
+    const unsigned tile_ctas = (unsigned)((n_img + kGenTiles - 1) / kGenTiles);
+    entmc_tc_gen_kernel<DP, true><<<tile_ctas, kThreads, 0, c->stream2>>>(nullptr, lay, 0.f, nullptr, wk, nullptr,
+                                                                         reinterpret_cast<unsigned char *>(c->d_tctiles[b]), 0,
+                                                                         0, 1, seed, offset);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
+    c->launches++;
+    const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
+                             (uint64_t)plan.chunk, (uint64_t)plan.half, (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
+    for (int i = 0; i < 6; ++i) c->noise_sig[i] = sig[i];
+    c->noise_ready = true, c->noise_needs_wait = true;
+    c->noise_seed = seed, c->noise_offset = offset;
     return VBMC_OK;
 }
 
@@ -1004,6 +1039,25 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
     plan->half_glob = half_local;
     plan->smem = smem;
     return VBMC_OK;
+}
+
+int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset) {
+    switch (lay.DP) {
+#define VBMC_CASE(N) \
+    case N:          \
+        return tc_prefetch_dp<N>(c, lay, plan, seed, offset)
+        VBMC_CASE(4);
+        VBMC_CASE(8);
+        VBMC_CASE(12);
+        VBMC_CASE(16);
+        VBMC_CASE(20);
+        VBMC_CASE(24);
+        VBMC_CASE(28);
+        VBMC_CASE(32);
+#undef VBMC_CASE
+    }
+    set_error("entmc: unsupported padded dimension");
+    return VBMC_ERR_UNSUPPORTED;
 }
 
 int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,

@@ -227,15 +227,57 @@ def _neg_elcbo(
 
     theta = np.asarray(theta, dtype=float)
     K, D = vp.K, vp.D
+    optimize = (bool(vp.optimize_mu), bool(vp.optimize_sigma), bool(vp.optimize_lambd), bool(vp.optimize_weights))
+    Ns_even = int(np.ceil(Ns / 2)) * 2 if Ns > 0 else 0
+
+    if (not compute_var and not separate_K and eps is None and any(optimize) and theta.ndim == 1
+            and (Ns_even == 0 or config.rng_mode != "numpy")):
+        # Hot path (minimize_adam / BFGS / sieve objective): the raw theta goes to the device, where set_parameters
+        # (:1080), the eta shift (:1082-1085) and the bound-loss inputs are evaluated; the host only moves O(P) bytes.
+        ctx = context_for_gp(gp, need_L=False)
+        if Ns_even > 0:
+            if seed is None:
+                seed = draw_seed()
+            ctx.noise_prefetch(D, K, Ns_even, seed, offset)  # theta-independent: overlaps the rest of this call's host work
+        use_bounds = ctx.set_bounds(theta_bnd)
+        out, vpo, tmpl = ctx.theta_buffers(D, K)
+        th = theta if theta.flags.c_contiguous and theta.flags.writeable else np.array(theta, dtype=float)
+        DK = D * K
+        if optimize == (True, True, True, True):
+            tm = None
+        else:  # the groups theta does not carry come from the posterior as it stands (variational_posterior.py:680-759)
+            tm = tmpl
+            if not optimize[0]:
+                tm[:DK] = np.ravel(vp.mu, order="F")
+            tm[DK : DK + K] = np.ravel(vp.sigma)
+            tm[DK + K : DK + K + D] = np.ravel(vp.lambd)
+            tm[DK + K + D : DK + 2 * K + D] = np.ravel(vp.w)
+            tm[DK + 2 * K + D : DK + 3 * K + D] = np.ravel(vp.eta)
+        ctx.negelcbo_theta(D, K, th, tm, optimize, Ns_even, compute_grad, use_bounds, seed or 0, offset, None, out, vpo)
+        # side effects on vp and on the caller's theta, as the reference leaves them
+        if optimize[0]:
+            vp.mu = np.array(th[:DK]).reshape((D, K), order="F")
+        vp.sigma = vpo[:K].reshape(1, K).copy()
+        vp.lambd = vpo[K : K + D].reshape(D, 1).copy()
+        if optimize[3]:
+            vp.w = vpo[K + D :].reshape(1, K).copy()
+            if th is not theta:
+                theta[-K:] = th[-K:]
+            vp.eta = theta[-K:].reshape(1, -1)  # a view of the caller's array (:1082-1085)
+        vp._mode = None
+        dF = None
+        if compute_grad:
+            P = (DK if optimize[0] else 0) + (K if optimize[1] else 0) + (D if optimize[2] else 0) + (K if optimize[3] else 0)
+            dF = out[8 : 8 + P].copy()
+        return float(out[0]), dF, float(out[1]), float(out[2]), 0  # (beta != 0 implies compute_var: never here)
+
     vp.set_parameters(theta)  # :1080
     if vp.optimize_weights:
         _shift_eta(vp, theta, K)  # :1082-1085 (in place on the CALLER's theta, like the reference)
 
-    optimize = (bool(vp.optimize_mu), bool(vp.optimize_sigma), bool(vp.optimize_lambd), bool(vp.optimize_weights))
     ctx = context_for_gp(gp, need_L=bool(compute_var))
     use_bounds = ctx.set_bounds(theta_bnd)
 
-    Ns_even = int(np.ceil(Ns / 2)) * 2 if Ns > 0 else 0
     if Ns_even > 0 and eps is None and seed is None:
         if config.rng_mode == "numpy":
             eps = draw_eps_numpy(K, Ns_even, D)
