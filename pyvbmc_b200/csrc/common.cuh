@@ -257,6 +257,8 @@ int gpvar_launch(Ctx *c, const double *d_params, int K, int avg);
 
 // gppred.cu: GP predictive mean / variance at search points, variational-posterior density
 int gppred_launch(Ctx *c, const double *d_Xs, int Nx, double *d_mu, double *d_s2);
+int gppred_prepare(Ctx *c);  // builds d_Linv = [S][N][NP] L^-1 (Cholesky samples) or L (low-noise samples) once per GP
+int gppred_np(int N);
 int vp_pdf_launch(Ctx *c, const double *d_params, int D, int K, const double *d_Xs, int Nx, int log_flag, int grad_flag,
                   double *d_y, double *d_dy);
 

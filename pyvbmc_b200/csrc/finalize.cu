@@ -14,6 +14,7 @@
 // lanes stride over the summed index, butterfly tree => fixed summation order, bitwise reproducible).
 // Small global scalars (softmax sums, penalty) are recomputed by every CTA instead of being exchanged.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -638,13 +639,19 @@ int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalAr
         VBMC_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->finalize_smem_set = smem;
     }
+    static int tail_cluster = 0, tail_threads = 0;
+    if (tail_cluster == 0) {
+        const char *e1 = getenv("VBMC_TAIL_CLUSTER"), *e2 = getenv("VBMC_TAIL_THREADS");
+        tail_cluster = e1 ? atoi(e1) : kTailCluster;
+        tail_threads = e2 ? atoi(e2) : kTailThreads;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(kTailCluster), cfg.blockDim = dim3(kTailThreads);
+    cfg.gridDim = dim3(tail_cluster), cfg.blockDim = dim3(tail_threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kTailCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = tail_cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases, xa));
     c->launches++;
