@@ -21,29 +21,42 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
     const ParamLayout lay = a.lay;
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[40];
+    __shared__ uint64_t skey[2];
+    extern __shared__ double stg[];  // theta behind the means [<= 2K + D] | template sigma, lambda, w, eta [3K + D]
+    double *sth = stg, *stm = stg + 2 * K + D;
     const double *th = a.theta, *tm = a.tmpl;
-    const int pos_s = a.opt[0] ? D * K : 0, pos_l = pos_s + (a.opt[1] ? K : 0);
+    const int n_mu = a.opt[0] ? D * K : 0, n_tail = a.P - n_mu;
+    const int pos_s = 0, pos_l = a.opt[1] ? K : 0;  // offsets inside sth
+    const bool need_tm = !(a.opt[0] && a.opt[1] && a.opt[2] && a.opt[3]);
+    // ONE pass over the inputs, every load independent: on the drop-in path theta, the template and the key live in
+    // pinned HOST memory, and each dependent round of reads would cost a PCIe round trip (the first version read theta
+    // phase by phase: 16 us for this 1-CTA kernel)
+    for (int e = tid; e < n_tail; e += nt) sth[e] = th[n_mu + e];
+    if (need_tm)
+        for (int e = tid; e < 3 * K + D; e += nt) stm[e] = tm[lay.sigma() + e];  // sigma | lambda | w | eta are contiguous
+    if (tid == 0 && key_src) skey[0] = key_src[0], skey[1] = key_src[1];
     // mu (theta order is component-major already)
     for (int e = tid; e < D * K; e += nt) prm[lay.mu() + e] = a.opt[0] ? th[e] : tm[lay.mu() + e];
+    __syncthreads();
     // lambda: exp, then the unit-RMS normalisation shared with sigma (:749-756)
     double l2 = 0.0;
     for (int d = tid; d < D; d += nt) {
-        const double lm = a.opt[2] ? exp(th[pos_l + d]) : tm[lay.lambd() + d];
+        const double lm = a.opt[2] ? exp(sth[pos_l + d]) : stm[K + d];
         l2 += lm * lm;
     }
     l2 = block_sum(l2, scratch);
     const double scale = sqrt(l2 / D);
     for (int d = tid; d < D; d += nt) {
-        const double lm = (a.opt[2] ? exp(th[pos_l + d]) : tm[lay.lambd() + d]) / scale;
+        const double lm = (a.opt[2] ? exp(sth[pos_l + d]) : stm[K + d]) / scale;
         prm[lay.lambd() + d] = lm;
         if (vp_out) vp_out[K + d] = lm;
-        prm[lay.lnlam_b() + d] = a.opt[2] ? th[pos_l + d] : log(lm);  // (:536-555: theta's slice, else log of the field)
+        prm[lay.lnlam_b() + d] = a.opt[2] ? sth[pos_l + d] : log(lm);  // (:536-555: theta's slice, else log of the field)
     }
     for (int k = tid; k < K; k += nt) {
-        const double sg = (a.opt[1] ? exp(th[pos_s + k]) : tm[lay.sigma() + k]) * scale;
+        const double sg = (a.opt[1] ? exp(sth[pos_s + k]) : stm[k]) * scale;
         prm[lay.sigma() + k] = sg;
         if (vp_out) vp_out[k] = sg;
-        prm[lay.lnsig_b() + k] = a.opt[1] ? th[pos_s + k] : log(sg);
+        prm[lay.lnsig_b() + k] = a.opt[1] ? sth[pos_s + k] : log(sg);
     }
     // weights: softmax of eta with the max shift; eta itself is stored shifted (:1082-1085)
     // The reference shifts the eta block of the caller's theta IN PLACE (`vp.eta = theta[-K:]; vp.eta -= amax`,
@@ -51,7 +64,7 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
     // (:1195-1209) and minimize_adam's `x -= step` (minimize_adam.py:98) updates the renormalised iterate.  Same
     // here: theta's eta block is rewritten with max == 0 before the evaluation and the update.
     if (a.opt[3]) {
-        double *eta = a.theta + a.P - K;
+        const double *eta = sth + n_tail - K;
         double mx = -INFINITY;
         for (int k = tid; k < K; k += nt) mx = fmax(mx, eta[k]);
         mx = block_max(mx, scratch);
@@ -65,20 +78,20 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
             if (vp_out) vp_out[K + D + k] = wk;
             prm[lay.eta() + k] = e;
             prm[lay.eta_b() + k] = e;
-            eta[k] = e;
+            a.theta[a.P - K + k] = e;
         }
     } else {
         for (int k = tid; k < K; k += nt) {
-            prm[lay.w() + k] = tm[lay.w() + k];
-            if (vp_out) vp_out[K + D + k] = tm[lay.w() + k];
-            prm[lay.eta() + k] = tm[lay.eta() + k];
-            prm[lay.eta_b() + k] = tm[lay.eta_b() + k];
+            prm[lay.w() + k] = stm[K + D + k];
+            if (vp_out) vp_out[K + D + k] = stm[K + D + k];
+            prm[lay.eta() + k] = stm[2 * K + D + k];
+            prm[lay.eta_b() + k] = stm[2 * K + D + k];
         }
     }
     if (tid == 0) {  // Philox key rides behind the parameter block
         uint64_t *key = reinterpret_cast<uint64_t *>(prm + lay.total());
         if (key_src) {
-            key[0] = key_src[0], key[1] = key_src[1];
+            key[0] = skey[0], key[1] = skey[1];
         } else {
             key[0] = a.seed;
             key[1] = a.offset0 + (uint64_t)(*a.iter);
@@ -122,14 +135,14 @@ adam_update_kernel(AdamDev a, const double *__restrict__ out) {
 }  // namespace
 
 int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
-    adam_prepare_kernel<<<1, 256, 0, c->stream>>>(a, d_prm);
+    adam_prepare_kernel<<<1, 256, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_prm);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;
 }
 
 int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src) {
-    theta_prepare_kernel<<<1, 256, 0, c->stream>>>(a, d_prm, vp_out, key_src);
+    theta_prepare_kernel<<<1, 256, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_prm, vp_out, key_src);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;
