@@ -300,6 +300,9 @@ int vbmc_read_device(vbmc_ctx *ctx, const double *src_dev, size_t n, double *dst
  * vbmc_entmc_kernel_ms returns the average device time (ms) since the last call.        */
 int vbmc_set_kernel_timing(vbmc_ctx *ctx, int on);
 int vbmc_entmc_kernel_ms(vbmc_ctx *ctx, double *avg_ms, int64_t *launches);
+/* ... and of the dominant kernel alone (entmc_kernel_tc, without the table kernel launched in front of it); call it
+ * BEFORE vbmc_entmc_kernel_ms, which resets the counters.  0 when another kernel variant ran.                     */
+int vbmc_entmc_main_kernel_ms(vbmc_ctx *ctx, double *avg_ms);
 /* which fp32 entmc kernel the last staged evaluation used: 0 expanded ("fast"), 1 dimension-split, 2 packed,
  * 3 scalar (also the all-fp64 kernel), 4 warp-autonomous, 5 tensor-core (tcgen05 / TMEM); -1 nothing planned yet */
 int vbmc_entmc_variant_used(vbmc_ctx *ctx);

@@ -144,6 +144,7 @@ PROTOTYPES = {
     "vbmc_read_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_double_p]),
     "vbmc_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "vbmc_entmc_kernel_ms": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64)]),
+    "vbmc_entmc_main_kernel_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "vbmc_entmc_variant_used": (C.c_int, [C.c_void_p]),
     "vbmc_param_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_adam_init": (C.c_int, [C.c_void_p, C.POINTER(AdamIn)]),

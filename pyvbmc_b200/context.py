@@ -168,6 +168,12 @@ class Context:
         """fp32 entmc kernel of the last staged evaluation (5 = tensor-core, 4 = warp-autonomous, 0 = expanded ...)."""
         return int(self._lib.vbmc_entmc_variant_used(self._h))
 
+    def entmc_main_kernel_ms(self):
+        """Average duration of the dominant entropy kernel alone (call before ``entmc_kernel_ms``, which resets)."""
+        ms = C.c_double()
+        _capi.check(self._lib.vbmc_entmc_main_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def entmc_kernel_ms(self):
         ms = C.c_double()
         n = C.c_int64()

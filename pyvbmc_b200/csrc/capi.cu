@@ -503,6 +503,7 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_noise, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev0));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev1));
+    VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev2));
     *out = reinterpret_cast<vbmc_ctx *>(x);
     return VBMC_OK;
 }
@@ -527,6 +528,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -1320,7 +1322,14 @@ int vbmc_entmc_kernel_ms(vbmc_ctx *p, double *avg_ms, int64_t *launches) {
     Ctx *c = &ex(p)->c;
     *launches = c->entmc_ms_n;
     *avg_ms = c->entmc_ms_n ? c->entmc_ms_sum / (double)c->entmc_ms_n : 0.0;
-    c->entmc_ms_sum = 0, c->entmc_ms_n = 0;
+    c->entmc_ms_sum = 0, c->entmc_ms_n = 0, c->entmc_main_ms_sum = 0;
+    return VBMC_OK;
+}
+
+int vbmc_entmc_main_kernel_ms(vbmc_ctx *p, double *avg_ms) {
+    VBMC_REQUIRE(p && avg_ms, VBMC_ERR_ARG, "null argument");
+    Ctx *c = &ex(p)->c;
+    *avg_ms = c->entmc_ms_n ? c->entmc_main_ms_sum / (double)c->entmc_ms_n : 0.0;
     return VBMC_OK;
 }
 
@@ -1334,7 +1343,7 @@ int vbmc_set_kernel_timing(vbmc_ctx *p, int on) {
     VBMC_REQUIRE(p, VBMC_ERR_ARG, "null ctx");
     Ctx *c = &ex(p)->c;
     c->time_entmc = on != 0;
-    c->entmc_ms_sum = 0, c->entmc_ms_n = 0;
+    c->entmc_ms_sum = 0, c->entmc_ms_n = 0, c->entmc_main_ms_sum = 0;
     return VBMC_OK;
 }
 

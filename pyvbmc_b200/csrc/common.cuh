@@ -212,11 +212,26 @@ struct Ctx {
     bool time_entmc = false;
     double entmc_ms_sum = 0;
     int64_t entmc_ms_n = 0;
+    cudaEvent_t ev2 = nullptr;      // recorded right before the dominant kernel (entmc_kernel_tc) when timing is on
+    bool ev2_recorded = false;
+    double entmc_main_ms_sum = 0;   // ... that kernel alone (without the table / generator launch in front of it)
 };
 
 static inline void stage_mark(Ctx *c, int i) {
     if (c->stage_timing) cudaEventRecord(c->sev[i], c->stream);
 }
+// piecewise-uniform split of the flattened (component, pair) space over CTAs (see EntmcPlan::n_big)
+struct ChunkMap {
+    long long big, small;
+    int n_big;
+    __host__ __device__ long long start(int c) const {
+        return c < n_big ? (long long)c * big : (long long)n_big * big + (long long)(c - n_big) * small;
+    }
+    __host__ __device__ int cta_of(long long p) const {
+        const long long B = (long long)n_big * big;
+        return p < B ? (int)(p / big) : n_big + (int)((p - B) / small);
+    }
+};
 int ensure(double **p, size_t *cap, size_t need);
 int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
@@ -226,6 +241,10 @@ enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENT
 struct EntmcPlan {
     int variant;
     int64_t chunk;    // ENTMC_WARP / ENTMC_TC: pairs of the flattened (component, pair) space per CTA
+    // ENTMC_TC: the first n_big CTAs take `chunk` pairs, the others `chunk_small` (one tile less): with 10.56 tiles per
+    // SM at C3, two resident CTAs of 6 + 5 tiles finish sooner than 6 + 6 next to SMs holding a single CTA
+    int64_t chunk_small;
+    int n_big;
     int grid, maxseg; // ENTMC_WARP: CTAs, records reserved per CTA
     int threads, slabs, pairs_per_thread;
     int64_t half;      // pairs per component handled by THIS rank

@@ -1457,6 +1457,11 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
             VBMC_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
             c->entmc_ms_sum += ms;
             c->entmc_ms_n++;
+            if (c->ev2_recorded) {
+                VBMC_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev2, c->ev1));
+                c->entmc_main_ms_sum += ms;
+                c->ev2_recorded = false;
+            }
         }
         return VBMC_OK;
     }

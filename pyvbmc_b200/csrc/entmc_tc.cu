@@ -264,6 +264,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int DP, int K, int part_stride)
 struct TcWork {
     int64_t half, pair0, half_glob, chunk;
     int K, tpc, n_img;
+    ChunkMap cm;
 };
 constexpr int kGenTiles = 4;  // noise-tile images per generator CTA
 
@@ -309,7 +310,7 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
             const int g = g_first + tid;
             const int cta = g / wk.tpc, l = g - cta * wk.tpc;
             const int64_t Tn = (int64_t)K * wk.half;
-            const int64_t g0 = (int64_t)cta * wk.chunk, g1 = min(g0 + wk.chunk, Tn);
+            const int64_t g0 = wk.cm.start(cta), g1 = min((int64_t)wk.cm.start(cta + 1), Tn);
             int valid = 0, j = 0, n = 0, t0 = 0;
             int64_t p_lo = 0;
             if (g0 < Tn) {
@@ -524,7 +525,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
     constexpr int LW = DH <= 8 ? 8 : 16;    // columns of V loaded per thread in the epilogue (DH + LW <= N2)
     constexpr uint32_t ABYTES = (uint32_t)NC1 * kTile * 16, TB = 2 * ABYTES + 2 * kTile * 4;
     const int D = lay.D, K = lay.K;
-    const int64_t half = wk.half, chunk = wk.chunk;
+    const int64_t half = wk.half;
     const int nch = (K + 15) >> 4, KP = nch * 16;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int row = tid & (kTile - 1), hsel = tid >> 7, quad = wid & 3;
@@ -548,7 +549,7 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
     uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 8);  // (7 barriers above)
 
     const int64_t Tn = (int64_t)K * half;
-    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(g0 + chunk, Tn);
+    const int64_t g0 = wk.cm.start((int)blockIdx.x), g1 = min((int64_t)wk.cm.start((int)blockIdx.x + 1), Tn);
     if (g0 >= Tn) return;
 
     // ---- one-time set-up: barriers, tensor memory ---------------------------------------------------------------
@@ -889,6 +890,7 @@ uint32_t tc_tmem_cols(int DP, int K) {
 TcWork tc_work(const EntmcPlan &plan, int K) {
     TcWork w;
     w.half = plan.half, w.pair0 = plan.pair0, w.half_glob = plan.half_glob, w.chunk = plan.chunk;
+    w.cm = ChunkMap{(long long)plan.chunk, (long long)plan.chunk_small, plan.n_big};
     w.K = K;
     w.tpc = (int)(plan.chunk / kTile) + plan.maxseg;  // sum_seg ceil(n_seg / 128) <= chunk / 128 + segments
     w.n_img = plan.grid * w.tpc;
@@ -920,7 +922,8 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     };
     // shape / work split the tile images depend on (besides the Philox key)
     const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
-                             (uint64_t)plan.chunk, (uint64_t)plan.half, (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
+                             (uint64_t)plan.chunk << 20 ^ (uint64_t)plan.chunk_small << 8 ^ (uint64_t)plan.n_big, (uint64_t)plan.half,
+                             (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
     const uint64_t want_seed = c->cur_seed, want_offset = c->cur_offset + (uint64_t)c->key_delta;
     bool have = philox && c->noise_ready && c->noise_seed == want_seed && c->noise_offset == want_offset;
     for (int i = 0; i < 6 && have; ++i) have = c->noise_sig[i] == sig[i];
@@ -950,6 +953,10 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     }
     const int ps = entpart_stride(DP, K);
     const uint32_t cols = tc_tmem_cols(DP, K);
+    if (c->time_entmc && c->ev2) {
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev2, c->stream));
+        c->ev2_recorded = true;
+    }
     if (anygrad)
         entmc_kernel_tc<DP, true><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
     else
@@ -991,7 +998,8 @@ int tc_prefetch_dp(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed
     VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
     c->launches++;
     const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
-                             (uint64_t)plan.chunk, (uint64_t)plan.half, (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
+                             (uint64_t)plan.chunk << 20 ^ (uint64_t)plan.chunk_small << 8 ^ (uint64_t)plan.n_big, (uint64_t)plan.half,
+                             (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
     for (int i = 0; i < 6; ++i) c->noise_sig[i] = sig[i];
     c->noise_ready = true, c->noise_needs_wait = true;
     c->noise_seed = seed, c->noise_offset = offset;
@@ -1024,14 +1032,34 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
     if (smem < floor_smem) smem = floor_smem;
     const int64_t T = (int64_t)K * half_local;
     const int64_t slots = (int64_t)c->sm_count * per_sm;
-    int64_t chunk = (T + slots - 1) / slots;
-    chunk = ((chunk + kTile - 1) / kTile) * kTile;
-    if (chunk < kTile) chunk = kTile;
+    // tiles of 128 pairs over `slots` resident CTAs: the first n_big CTAs take one tile more than the others.  (A
+    // uniform chunk of ceil(tiles / slots) tiles left SMs with 12 tiles next to SMs with 6 at C3: 0.88 waves.)
+    const int64_t n_tiles = (T + kTile - 1) / kTile;
+    int64_t base = n_tiles / slots, rem = n_tiles - base * slots;
+    static int env_even = -1;
+    if (env_even < 0) {
+        const char *e = getenv("VBMC_TC_EVEN_CHUNKS");
+        env_even = e ? atoi(e) : 0;
+    }
+    int64_t chunk, chunk_small;
+    int grid, n_big;
+    if (base == 0) {  // fewer tiles than CTA slots: one tile per CTA
+        chunk = chunk_small = kTile;
+        grid = (int)std::max<int64_t>(1, n_tiles), n_big = grid;
+    } else if (rem == 0 || env_even) {
+        chunk = chunk_small = (base + (rem ? 1 : 0)) * kTile;
+        grid = (int)((T + chunk - 1) / chunk), n_big = grid;
+    } else {
+        chunk = (base + 1) * kTile, chunk_small = base * kTile;
+        grid = (int)slots, n_big = (int)rem;
+    }
     plan->variant = ENTMC_TC;
     plan->threads = kThreads;
     plan->pairs_per_thread = (int)(chunk / kTile);
     plan->chunk = chunk;
-    plan->grid = (int)std::max<int64_t>(1, (T + chunk - 1) / chunk);
+    plan->chunk_small = chunk_small;
+    plan->n_big = n_big;
+    plan->grid = grid;
     plan->maxseg = half_local > 0 ? (int)((chunk - 1) / half_local) + 2 : 1;
     plan->slabs = plan->grid * plan->maxseg;
     plan->half = half_local;

@@ -34,6 +34,7 @@ struct RawArgs {
     const double *entpart;
     int slabs, ent_stride, maxseg;
     long long chunk, half;
+    ChunkMap cm;  // CTA c covers pairs [cm.start(c), cm.start(c + 1)) of the flattened (component, pair) space
     double Ns_glob;      // draws per component over all ranks
     double draws_local;  // draws per component on this rank
     // log joint: gps[s] = [G_s | mu | sigma | lambda | w] per-sample raw block, lamc[s][k][d]
@@ -48,18 +49,11 @@ struct RawArgs {
 __device__ __forceinline__ double slab_sum(const RawArgs &a, int j, int f) {
     double v = 0.0;
     if (a.chunk > 0) {
-        // CTA c covers pairs [c*chunk, (c+1)*chunk) of the flattened space; component j spans CTAs c0..c1.  Every
-        // CTA after c0 STARTS inside component j (c*chunk > j*half), so j is its segment 0; only c0 needs a division.
+        // component j spans CTAs c0..c1 of the flattened space.  Every CTA after c0 STARTS inside component j, so j is
+        // its segment 0; only c0 needs the segment index.
         const long long lo = (long long)j * a.half, hi = lo + a.half - 1;
-        int c0, c1, seg0;
-        if (hi < 0x7fffffffLL && a.chunk < 0x7fffffffLL) {
-            const unsigned ch = (unsigned)a.chunk;
-            c0 = (int)((unsigned)lo / ch), c1 = (int)((unsigned)hi / ch);
-            seg0 = j - (int)(((unsigned)c0 * ch) / (unsigned)a.half);
-        } else {
-            c0 = (int)(lo / a.chunk), c1 = (int)(hi / a.chunk);
-            seg0 = j - (int)(((long long)c0 * a.chunk) / a.half);
-        }
+        const int c0 = a.cm.cta_of(lo), c1 = a.cm.cta_of(hi);
+        const int seg0 = j - (int)(a.cm.start(c0) / a.half);
         const double *rec = a.entpart + f;
         v = rec[((size_t)c0 * a.maxseg + seg0) * a.ent_stride];
         const size_t step = (size_t)a.maxseg * a.ent_stride;
@@ -590,6 +584,8 @@ int fill_raw_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *pla
     if (plan) {
         a.slabs = plan->slabs;
         a.chunk = (plan->variant == ENTMC_WARP || plan->variant == ENTMC_TC) ? plan->chunk : 0;
+        a.cm = plan->variant == ENTMC_TC ? ChunkMap{(long long)plan->chunk, (long long)plan->chunk_small, plan->n_big}
+                                         : ChunkMap{(long long)plan->chunk, (long long)plan->chunk, plan->grid};
         a.maxseg = plan->maxseg;
         a.half = plan->half;
         a.Ns_glob = (double)Ns_glob;
