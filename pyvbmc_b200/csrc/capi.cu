@@ -519,6 +519,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     p2p_unmap(c);
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
+    if (c->d_tailsync) cudaFree(c->d_tailsync);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
                      c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles[0], c->d_tctiles[1], c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var, c->d_xs, c->d_pred};
     for (double *d : dev)
@@ -951,6 +952,7 @@ int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     const size_t need = 5 * (size_t)P + T + (size_t)in->max_iter + 1 + (size_t)in->max_iter * P;
     if (need > x->adam_cap) {
         if (x->d_adam) cudaFree(x->d_adam);
+    if (c->d_tailsync) cudaFree(c->d_tailsync);
         x->d_adam = nullptr, x->adam_cap = 0;
         VBMC_CUDA_CHECK(cudaMalloc((void **)&x->d_adam, need * sizeof(double)));
         x->adam_cap = need;

@@ -169,6 +169,7 @@ struct Ctx {
     bool noise_pending_join = false;
     cudaEvent_t ev_main = nullptr, ev_noise = nullptr;
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
+    unsigned *d_tailsync = nullptr;  // barrier words of the tail kernel (grid mode)
     size_t csum_cap = 0;
     // peer-memory all-reduce of the raw vector (vbmc_p2p_export / vbmc_p2p_open): exchange buffers of all ranks
     int p2p_world = 0, p2p_rank = 0, p2p_stride = 0;

@@ -418,7 +418,7 @@ __device__ __forceinline__ void final_phase(const double *__restrict__ prm, cons
     }
 }
 
-constexpr int kTailThreads = 1024, kTailCluster = 8;
+constexpr int kTailThreads = 1024, kTailCluster = 8, kTailGridCtas = 8;
 enum { PH_RAW = 1, PH_FINAL = 2, PH_XCHG = 4 };
 
 // All-reduce of the raw vector over NVLink peer memory, inside the tail kernel (no NCCL launch, no second tail
@@ -447,6 +447,38 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 
 // returns false (in every thread of the CTA that hosts a timed-out waiter ... the caller poisons the result) if a
 // peer's flag did not arrive within ~2 s
+// Barrier over all CTAs of the tail kernel.  cluster mode: hardware cluster barrier (the kernel is launched as ONE
+// thread-block cluster).  grid mode: sense-reversing counter in global memory (the <= 32 CTAs are always co-resident:
+// one per SM on an otherwise idle machine); the counter returns to zero and the sense flips on every use, so the two
+// words survive from launch to launch and CUDA-graph replays need no reset.
+struct TailBarrier {
+    unsigned *count;
+    volatile unsigned *sense;
+    unsigned nblk;
+    int use_cluster;
+    __device__ __forceinline__ void sync() const {
+        if (use_cluster) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            return;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned s = *sense;
+            __threadfence();
+            if (atomicAdd(count, 1u) == nblk - 1u) {
+                *count = 0u;
+                __threadfence();
+                *sense = s ^ 1u;
+            } else {
+                while (*sense == s) {
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
 template <class Cluster>
 __device__ __forceinline__ void raw_exchange(const XchgArgs &x, double *__restrict__ raw, int gtid, int GT, Cluster &cluster,
                                              int *s_bad) {
@@ -488,9 +520,7 @@ __device__ __forceinline__ void raw_exchange(const XchgArgs &x, double *__restri
 // One launch for everything behind the producers: a cluster of 8 CTAs; the phases are separated by cluster
 // barriers (release/acquire at cluster scope, so plain global stores of one phase are visible to the next).
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(const double *__restrict__ prm, RawArgs ra, FinalArgs fa,
-                                                           int phases, XchgArgs xa) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+                                                           int phases, XchgArgs xa, TailBarrier cluster) {
     __shared__ double scratch[40];
     __shared__ double ssm[5];
     __shared__ int s_bad;
@@ -598,15 +628,15 @@ int fill_raw_args(Ctx *c, int D, int K, const EvalFlags &f, const EntmcPlan *pla
     a.S_local = f.have_gp ? (c->S - s_begin + s_step - 1) / s_step : 0;
     if (a.S_local < 0) a.S_local = 0;
     a.raw = d_raw;
-    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * a.ent_stride + 16));
-    a.csum = c->d_csum + 16;
+    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * a.ent_stride + 64));
+    a.csum = c->d_csum + 64;
     *out = a;
     return VBMC_OK;
 }
 
 int fill_final_args(Ctx *c, int D, int K, const EvalFlags &f, const double *d_raw, double *d_out, FinalArgs *out) {
     FinalArgs a{};
-    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * entpart_stride(pad_dim(D), K) + 16));
+    VBMC_TRY(ensure(&c->d_csum, &c->csum_cap, (size_t)K * entpart_stride(pad_dim(D), K) + 64));
     a.lpart = c->d_csum;
     a.lay = ParamLayout{D, pad_dim(D), K};
     a.rl = RawLayout{D, K};
@@ -635,21 +665,30 @@ int tail_launch(Ctx *c, const double *d_params, const RawArgs &ra, const FinalAr
         VBMC_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->finalize_smem_set = smem;
     }
-    static int tail_cluster = 0, tail_threads = 0;
-    if (tail_cluster == 0) {
-        const char *e1 = getenv("VBMC_TAIL_CLUSTER"), *e2 = getenv("VBMC_TAIL_THREADS");
-        tail_cluster = e1 ? atoi(e1) : kTailCluster;
+    static int tail_ctas = 0, tail_threads = 0, tail_grid_mode = -1;
+    if (tail_ctas == 0) {
+        const char *e1 = getenv("VBMC_TAIL_CLUSTER"), *e2 = getenv("VBMC_TAIL_THREADS"), *e3 = getenv("VBMC_TAIL_MODE");
+        // measured (C3, 1 GPU): hardware cluster barrier 75.4 us per step, global-memory barrier 78.2-78.7 us (8-32 CTAs)
+        tail_grid_mode = (e3 && !strcmp(e3, "grid")) ? 1 : 0;
+        tail_ctas = e1 ? atoi(e1) : (tail_grid_mode ? kTailGridCtas : kTailCluster);
         tail_threads = e2 ? atoi(e2) : kTailThreads;
+        if (tail_ctas > 32) tail_ctas = 32;
+        if (!tail_grid_mode && tail_ctas > 8) tail_ctas = 8;
     }
+    if (!c->d_tailsync) {  // barrier words of the grid mode: zero once, self-resetting afterwards
+        VBMC_CUDA_CHECK(cudaMalloc((void **)&c->d_tailsync, 64));
+        VBMC_CUDA_CHECK(cudaMemsetAsync(c->d_tailsync, 0, 64, c->stream));
+    }
+    TailBarrier tb{c->d_tailsync, c->d_tailsync + 8, (unsigned)tail_ctas, tail_grid_mode ? 0 : 1};
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tail_cluster), cfg.blockDim = dim3(tail_threads);
+    cfg.gridDim = dim3(tail_ctas), cfg.blockDim = dim3(tail_threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = tail_cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases, xa));
+    attr[0].val.clusterDim.x = tail_ctas, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = tail_grid_mode ? 0 : 1;
+    VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tail_kernel, d_params, ra, fa, phases, xa, tb));
     c->launches++;
     return VBMC_OK;
 }
