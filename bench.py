@@ -289,6 +289,7 @@ def _extras_n1(pv, pr, torch, flush):
                     "draws_per_component": Ns_K, "D": prs.D, "K": prs.K, "N": prs.N, "S": prs.S,
                     "what": "same call as the headline (value + gradient, soft bounds), warm L2, back to back"}
 
+    small("C3_back_to_back", pr, pr.Ns_K)  # the headline workload without the L2 flush between steps
     small("C2", syn.make_problem("C2"), syn.make_problem("C2").Ns_K)
     small("C4", syn.make_problem("C4"), syn.make_problem("C4").Ns_K)
     small("C3_at_28_draws_per_component", pr, 28)
