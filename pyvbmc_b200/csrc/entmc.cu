@@ -1349,12 +1349,16 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     VBMC_REQUIRE(half_local >= 0, VBMC_ERR_ARG, "entmc: negative draw count");
     int variant = precision == VBMC_PREC_F64 ? ENTMC_SCALAR : c->entmc_variant;
     if (variant < 0) {
-        // auto: the tensor-core kernel wins once every SM gets several 128-pair tiles and the component chunks are
-        // mostly real (measured on B200: C3 70 us vs 76 us; C2 / C4 are faster on the CUDA-core kernels); the
-        // warp-autonomous kernel pays off once there is a wave of >= 4-batch CTAs
+        // auto: the tensor-core kernel wins once every SM gets several 128-pair tiles; the warp-autonomous kernel pays
+        // off once there is a wave of >= 4-batch CTAs
         const int64_t T = (int64_t)K * half_local;
-        // (49 <= K <= 64: four 16-component chunks, the shape measured and parity-tested at scale in round 1)
-        if (T >= 150000 && K >= 49 && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
+        // Measured in round 2 (scripts/variant_sweep.py, profiles/r3d_variant_sweep.txt; ~400k draws): the tensor-core
+        // MAIN kernel beats both CUDA-core kernels at every (D, K) tried; what it adds is the table kernel (~7 us) in
+        // front of it -- its noise generator runs beside the previous tail (device-resident loops) or beside the host's
+        // preparation of the call (vbmc_noise_prefetch).  Table + main wins from K >= 32 (D = 6, 10, 20, 32) and from
+        // K >= 24 at D >= 16; below that the warp-autonomous / expanded kernels stay ahead (C2: D=10, K=20; C4: D=6, K=30).
+        const bool tc_shape = K >= 32 || (D >= 16 && K >= 24);
+        if (T >= 150000 && tc_shape && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
         else variant = T >= 65536 ? ENTMC_WARP : ENTMC_FAST;
     }
     const size_t smem_cap = 227 * 1024;

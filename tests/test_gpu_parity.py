@@ -681,3 +681,28 @@ def test_entmc_large_draw_counts_tensor_core_vs_f64(pv, K, Ns_K, monkeypatch):
         assert relmax(dHs, dHd) < TOL_F32_GRAD
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("D,K,Ns_K,want", [(20, 32, 12500, 5), (20, 24, 16668, 5), (10, 32, 12500, 5), (6, 48, 8334, 5),
+                                           (10, 20, 20000, 4), (6, 30, 13334, 4), (20, 16, 25000, 4)])
+def test_entmc_auto_selection_matches_the_measured_crossover(pv, D, K, Ns_K, want, monkeypatch):
+    """Automatic choice of the fp32 entropy kernel at ~400k draws (scripts/variant_sweep.py): the tensor-core kernel from
+    K >= 32, and from K >= 24 at D >= 16; the CUDA-core kernels below -- each against the all-fp64 kernel on identical
+    Philox draws."""
+    monkeypatch.delenv("VBMC_ENTMC_VARIANT", raising=False)
+    rng = np.random.default_rng(K * 100 + D)
+    mu = 0.5 * rng.normal(size=(D, K))
+    sigma = 0.5 * np.exp(0.1 * rng.normal(size=K))
+    eta = 0.3 * rng.normal(size=K)
+    w = np.exp(eta - eta.max())
+    w /= w.sum()
+    vp = make_vp(pv, D, K, mu, sigma, np.ones(D), w, eta - eta.max())
+    ctx = pv.Context(0)
+    try:
+        Hd, dHd = ctx.entmc(vp, Ns_K, (True,) * 4, True, seed=9, offset=1, precision="f64")
+        Hs, dHs = ctx.entmc(vp, Ns_K, (True,) * 4, True, seed=9, offset=1)
+        assert ctx.entmc_variant_used() == want
+        assert abs(Hs - Hd) <= TOL_F32_VAL * max(abs(Hd), 1.0)
+        assert relmax(dHs, dHd) < TOL_F32_GRAD
+    finally:
+        ctx.close()
