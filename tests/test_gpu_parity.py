@@ -151,6 +151,24 @@ def test_philox_mode_matches_oracle_on_dumped_draws(pv):
     assert abs(np.mean(big**4) - 3.0) < 0.05
 
 
+def test_philox_full_size_dump_and_replay_c3(pv):
+    """The headline workload in production mode, end to end against the oracle: the device's Philox draws for C3
+    (8000 per component, 50 components, D = 20) are dumped and replayed through the NumPy restatement of entmc_vbmc;
+    the tensor-core kernel (automatic choice at this size) must reproduce H and dH on exactly those draws."""
+    pr = syn.make_problem("C3")
+    vp = make_vp(pv, pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta)
+    ctx = pv.Context(0)
+    try:
+        eps = ctx.philox_normals(pr.D, pr.K, pr.Ns_K, seed=4321, offset=3)
+        assert eps.shape == (pr.K, pr.Ns_K // 2, pr.D)
+        H, dH = ctx.entmc(vp, pr.Ns_K, (True,) * 4, True, seed=4321, offset=3)
+        assert ctx.entmc_variant_used() == 5
+    finally:
+        ctx.close()
+    Ho, dHo = eo.entmc(pr.vp.copy(), eps, (True,) * 4, True)
+    assert relerr(H, Ho) < TOL_F32_VAL and relmax(dH, dHo) < TOL_F32_GRAD
+
+
 # ------------------------------------------------------------------ GP log joint
 @pytest.mark.parametrize("stem", REF_CASES)
 def test_gplogjoint_golden(pv, stem):
