@@ -237,6 +237,17 @@ int stage(CtxEx *x, const Spec &s) {
     return VBMC_OK;
 }
 
+// A vbmc_noise_prefetch launch runs on the side stream and is not yet ordered before the main stream.  Every entry
+// point joins it HERE, outside any stream capture (a wait on an event recorded outside a capture cannot be captured),
+// whether or not the prefetched tiles end up being used.
+int settle_prefetch(Ctx *c) {
+    if (c->noise_needs_wait) {
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
+        c->noise_needs_wait = false;
+    }
+    return VBMC_OK;
+}
+
 int partials(CtxEx *x, int rank, int world, double *raw_dev) {
     Ctx *c = &x->c;
     Staged &st = x->st;
@@ -313,6 +324,7 @@ int finalize(CtxEx *x, const double *raw_dev, double *out_dev) {
 // run everything on one GPU and bring `n` leading doubles of out back to the host
 int run_single(CtxEx *x, const Spec &s, size_t n_out) {
     Ctx *c = &x->c;
+    VBMC_TRY(settle_prefetch(c));
     const auto t0 = std::chrono::steady_clock::now();
     stage_mark(c, 0);
     VBMC_TRY(stage(x, s));
@@ -381,10 +393,7 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
                      c->noise_sig[3] == (uint64_t)(even_ns(s.Ns) / 2);
     if (!pre) c->noise_ready = false;
     k.flags |= (s.theta ? 1 : 0) << 12 | (pre ? 1 : 0) << 13 | (c->noise_buf & 1) << 14 | (s.tmpl ? 1 : 0) << 15;
-    if (pre && c->noise_needs_wait) {  // order the side-stream generator before everything this call enqueues
-        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
-        c->noise_needs_wait = false;
-    }
+    VBMC_TRY(settle_prefetch(c));  // order the side-stream generator before everything this call enqueues
     if (x->gexec && k == x->gkey) {
         const ParamLayout lay{k.D, pad_dim(k.D), k.K};
         if (s.theta) {
@@ -1006,6 +1015,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
     Bind b(c);
     VBMC_REQUIRE(x->adam_ready && c->staged, VBMC_ERR_STATE, "adam_steps: call vbmc_adam_init first");
     VBMC_REQUIRE(n >= 0 && x->adam_done + n <= x->adam_max_iter, VBMC_ERR_ARG, "adam_steps: more steps than max_iter");
+    VBMC_TRY(settle_prefetch(c));
     const long long i0 = x->adam_done;
     // Iterations are captured and replayed in PAIRS: the tensor-core entropy kernel alternates between two noise-tile
     // buffers (the draws of iteration i + 1 are generated under the tail of iteration i), so one captured pair leaves
@@ -1119,6 +1129,7 @@ int vbmc_negelcbo_partials_async(vbmc_ctx *p, int rank, int world, double *raw_d
     Bind b(&x->c);
     // first call after vbmc_negelcbo_upload: the uploaded key; every further call: the next key (offset + 1, + 2, ...),
     // like consecutive optimiser steps -- its draws are generated under the previous call's tail
+    VBMC_TRY(settle_prefetch(&x->c));
     x->c.key_delta = x->partials_calls++;
     x->c.lookahead = true;
     return partials(x, rank, world, raw_dev);
@@ -1206,6 +1217,7 @@ int vbmc_negelcbo_enqueue(vbmc_ctx *p) {
     VBMC_REQUIRE(!x->st.s.compute_var, VBMC_ERR_UNSUPPORTED, "enqueue does not cover the variance path");
     // every call is a NEW evaluation: Philox key (seed, offset + number of calls since staging), like consecutive
     // iterations of the Adam loop; its draws were generated under the previous call's tail
+    VBMC_TRY(settle_prefetch(c));
     c->key_delta += 1;
     c->lookahead = true;
     VBMC_TRY(partials(x, 0, 1, c->d_raw));

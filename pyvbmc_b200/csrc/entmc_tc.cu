@@ -934,10 +934,7 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         // the draws of this evaluation were generated under the previous evaluation's tail (finalize() of that
         // evaluation re-joined the side stream, so the tiles are complete in stream order), or by vbmc_noise_prefetch
         // while the host was still packing the parameters: tables only
-        if (c->noise_needs_wait) {
-            VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
-            c->noise_needs_wait = false;
-        }
+        // (a prefetch launch was joined into the main stream by the entry point: capi.cu settle_prefetch)
         VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
     } else {
         VBMC_TRY(gen(c->stream, d_tiles, K, true, c->key_delta));

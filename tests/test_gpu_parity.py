@@ -724,3 +724,39 @@ def test_entmc_auto_selection_matches_the_measured_crossover(pv, D, K, Ns_K, wan
         assert relmax(dHs, dHd) < TOL_F32_GRAD
     finally:
         ctx.close()
+
+
+def test_noise_prefetch_is_only_used_for_its_own_key(pv):
+    """vbmc_noise_prefetch generates the draws of ONE key ahead of the call.  A call with another key (or another draw
+    count) must ignore them and give exactly what it gives without any prefetch; the stale side-stream work must not leak
+    into a later graph capture (drop-in call, device Adam)."""
+    pr = syn.make_problem("C3")
+    Ns_K = 6000  # smallest draw count that takes the tensor-core kernel (the only one with separate noise tiles)
+
+    def fresh_vp():
+        return make_vp(pv, pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta)
+
+    def call(seed, Ns=Ns_K):
+        return pv._neg_elcbo(pr.theta.copy(), pr.gp, fresh_vp(), 0.0, Ns, True, False, pr.theta_bnd, seed=seed)
+
+    base = [call(5) for _ in range(3)]  # eager, capture, replay: each prefetches its own key
+    ctx = pv.context_for_gp(pr.gp)
+    assert ctx.entmc_variant_used() == 5
+    for F, dF, *_ in base[1:]:
+        assert F == base[0][0] and np.array_equal(dF, base[0][1])
+    ctx.noise_prefetch(pr.D, pr.K, Ns_K, 777, 0)       # wrong key
+    again = call(5)
+    assert again[0] == base[0][0] and np.array_equal(again[1], base[0][1])
+    ctx.noise_prefetch(pr.D, pr.K, Ns_K // 2, 5, 0)    # right key, wrong draw count
+    again = call(5)
+    assert again[0] == base[0][0] and np.array_equal(again[1], base[0][1])
+    other = call(6)
+    assert other[0] != base[0][0]
+    # a stale prefetch in front of the device Adam loop (captures a graph of iteration pairs)
+    ctx.noise_prefetch(pr.D, pr.K, Ns_K, 999, 0)
+    vp_a = fresh_vp()
+    th0 = np.asarray(vp_a.get_parameters(), dtype=float)
+    kw = dict(seed=3, max_iter=8, use_early_stopping=False, master_max=0.01)
+    x1, y1, xt1, yt1, n1 = pv.minimize_adam_elcbo(pr.gp, vp_a, th0.copy(), Ns_K, pr.theta_bnd, **kw)
+    x2, y2, xt2, yt2, n2 = pv.minimize_adam_elcbo(pr.gp, fresh_vp(), th0.copy(), Ns_K, pr.theta_bnd, **kw)
+    assert n1 == n2 == 8 and np.array_equal(yt1, yt2) and np.array_equal(xt1, xt2)
