@@ -234,6 +234,9 @@ def _neg_elcbo(
             and (Ns_even == 0 or config.rng_mode != "numpy")):
         # Hot path (minimize_adam / BFGS / sieve objective): the raw theta goes to the device, where set_parameters
         # (:1080), the eta shift (:1082-1085) and the bound-loss inputs are evaluated; the host only moves O(P) bytes.
+        P_in = (D * K if optimize[0] else 0) + (K if optimize[1] else 0) + (D if optimize[2] else 0) + (K if optimize[3] else 0)
+        if theta.size != P_in:
+            raise ValueError(f"theta has {theta.size} entries, the optimised groups of this posterior need {P_in}")
         ctx = context_for_gp(gp, need_L=False)
         if Ns_even > 0:
             if seed is None:

@@ -198,6 +198,12 @@ def test_neg_elcbo_argument_errors_without_gpu():
         pv._neg_elcbo(theta, None, vp, 0.0, 0, True, False, None, 0.0, True)
     with pytest.raises(NotImplementedError):
         pv._gp_log_joint(vp, None, True, True, True, True)
+    # a theta that does not match the optimised groups never reaches the device (the C entry point trusts its length)
+    with pytest.raises(ValueError):
+        pv._neg_elcbo(theta[:-1], None, vp, 0.0, 10, True, False, None)
+    vp.optimize_weights = False
+    with pytest.raises(ValueError):
+        pv._neg_elcbo(theta, None, vp, 0.0, 0, True, False, None)
 
 
 def _make_closure(gp="GP", vp0="VP", elcbo_beta=0, ns_ent_K=100, compute_var=False, theta_bnd=None, call_name="_neg_elcbo"):
