@@ -298,6 +298,9 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     constexpr int DH = DP / 2, D8 = (DP + 7) / 8 * 8, N2 = D8 <= 16 ? 16 : 32;
     extern __shared__ __align__(16) unsigned char psm[];
+    // programmatic dependent launch: the main kernel may become resident (barrier init, TMEM allocation) while this
+    // grid is still running; it reads nothing this grid writes before its own griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;");
     // CTAs [0, n_tab): tables of component blockIdx.x (n_tab = K, or 0 when only noise is wanted: the look-ahead launch
     // that fills the OTHER tile buffer for the next evaluation while this one's tail runs).  The noise tiles are
     // UNSCALED standard normals: they depend on the Philox key only, never on theta.
@@ -575,6 +578,8 @@ entmc_kernel_tc(const double *__restrict__ prm, ParamLayout lay, TcWork wk, int 
     tc_fence_after();
     const uint32_t tmem = *sTmem;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's lane quadrant
+    // everything above overlapped the table (+ inline noise) kernel in front of this one; its outputs are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // TMEM columns: X0 / X1 = GEMM1 output of even / odd tiles -> u+ -> c_hi (in place), U = u- -> c_lo, V = GEMM2 output
     const uint32_t cU = 2 * KP, cV = 3 * KP;
     uint32_t ph1 = 0, phC = 0;
@@ -954,10 +959,26 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         VBMC_CUDA_CHECK(cudaEventRecord(c->ev2, c->stream));
         c->ev2_recorded = true;
     }
-    if (anygrad)
-        entmc_kernel_tc<DP, true><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
-    else
-        entmc_kernel_tc<DP, false><<<plan.grid, kThreads, plan.smem, c->stream>>>(d_params, lay, wk, plan.maxseg, d_part, ps, d_tab, d_tiles, cols);
+    {
+        static int pdl = -1;
+        if (pdl < 0) {
+            const char *e = getenv("VBMC_PDL");
+            pdl = e ? atoi(e) : 1;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(plan.grid), cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+        const unsigned char *tab_c = d_tab, *tiles_c = d_tiles;
+        if (anygrad)
+            VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, entmc_kernel_tc<DP, true>, d_params, lay, wk, plan.maxseg, d_part, ps, tab_c, tiles_c, cols));
+        else
+            VBMC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, entmc_kernel_tc<DP, false>, d_params, lay, wk, plan.maxseg, d_part, ps, tab_c, tiles_c, cols));
+    }
     VBMC_CUDA_CHECK(cudaGetLastError());
     if (philox && c->lookahead) {
         // draws of the NEXT evaluation (key offset + 1) into the other buffer, on the side stream, behind this main
