@@ -108,8 +108,7 @@ theta_prepare_kernel(AdamDev a, double *__restrict__ prm, double *__restrict__ v
     theta_to_params(a, prm, vp_out, key_src);
 }
 
-__global__ void __launch_bounds__(1024)
-adam_update_kernel(AdamDev a, const double *__restrict__ out) {
+__device__ __forceinline__ void adam_update(const AdamDev &a, const double *__restrict__ out) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const long long i = *a.iter;  // 0-based iteration
     const double beta_1 = 0.9, beta_2 = 0.999, fudge = 1.4901161193847656e-08;  // sqrt(np.spacing(1))
@@ -132,6 +131,18 @@ adam_update_kernel(AdamDev a, const double *__restrict__ out) {
     if (tid == 0) *a.iter = i + 1;
 }
 
+__global__ void __launch_bounds__(1024) adam_update_kernel(AdamDev a, const double *__restrict__ out) { adam_update(a, out); }
+
+// update of iteration i FUSED with the parameter block of iteration i + 1 (one launch less on the critical path of every
+// iteration; the block prepared after the last iteration is simply never used)
+__global__ void __launch_bounds__(1024)
+adam_update_prepare_kernel(AdamDev a, const double *__restrict__ out, double *__restrict__ prm) {
+    adam_update(a, out);
+    __threadfence_block();
+    __syncthreads();  // the new theta and the incremented iteration counter are visible to the whole CTA
+    theta_to_params(a, prm, nullptr, nullptr);
+}
+
 }  // namespace
 
 int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
@@ -143,6 +154,13 @@ int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
 
 int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src) {
     theta_prepare_kernel<<<1, 256, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_prm, vp_out, key_src);
+    VBMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    return VBMC_OK;
+}
+
+int adam_update_prepare_launch(Ctx *c, const AdamDev &a, const double *d_out, double *d_prm) {
+    adam_update_prepare_kernel<<<1, 1024, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_out, d_prm);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

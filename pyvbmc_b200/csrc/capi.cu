@@ -147,6 +147,8 @@ struct CtxEx {
     uint64_t adam_gen = 0;
     int64_t partials_calls = 0;     // vbmc_negelcbo_partials_async calls since the last upload
     long long adam_issued = 0;      // Adam iterations issued (eager + captured) since vbmc_adam_init
+    bool adam_params_ready = false; // d_in holds the parameter block of the NEXT Adam iteration (fused update kernel)
+    bool adam_graph_params_ready = false;
     int adam_graph_buf = 0;         // noise-tile buffer parity / look-ahead state the captured pair starts from
     bool adam_graph_ready = false;
 };
@@ -230,6 +232,7 @@ int stage(CtxEx *x, const Spec &s) {
     f.parts = s.parts;
     st.planned = false;
     c->staged = true;
+    x->adam_params_ready = false;  // d_in no longer holds the block the Adam loop left for its next iteration
     // host mirror of the Philox key behind the parameter block (noise tiles generated ahead are matched against it)
     c->cur_seed = s.seed, c->cur_offset = s.offset;
     c->key_delta = 0;
@@ -351,14 +354,17 @@ void drop_adam_graph(CtxEx *x) {
 // one Adam iteration on the context stream: theta -> parameter block, evaluation, update (no host sync)
 int adam_iteration(CtxEx *x) {
     Ctx *c = &x->c;
-    VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));  // writes the key (seed, offset0 + iteration) behind the block
+    // the parameter block (and the key (seed, offset0 + iteration) behind it) of this iteration: left by the previous
+    // iteration's fused update kernel, unless this is the first iteration or something else used the context in between
+    if (!x->adam_params_ready) VBMC_TRY(adam_prepare_launch(c, x->adam, c->d_in));
     c->cur_seed = x->adam.seed, c->cur_offset = x->adam.offset0 + (uint64_t)x->adam_issued;
     x->adam_issued++;
     c->key_delta = 0;
     c->lookahead = true;  // the next iteration's draws are generated under this iteration's tail
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
     VBMC_TRY(finalize(x, c->d_raw, c->d_out));
-    VBMC_TRY(adam_update_launch(c, x->adam, c->d_out));
+    VBMC_TRY(adam_update_prepare_launch(c, x->adam, c->d_out, c->d_in));
+    x->adam_params_ready = true;
     return VBMC_OK;
 }
 
@@ -1004,6 +1010,7 @@ int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     x->adam_max_iter = in->max_iter;
     x->adam_done = 0;
     x->adam_issued = 0;
+    x->adam_params_ready = false;
     x->adam_ready = true, x->adam_eager_done = false;
     return VBMC_OK;
 }
@@ -1029,6 +1036,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         }
         const bool pair_ok = x->graphs_on && x->adam_eager_done && n - it >= 2;
         const bool state_ok = c->noise_buf == x->adam_graph_buf && c->noise_ready == x->adam_graph_ready &&
+                              x->adam_params_ready == x->adam_graph_params_ready &&
                               (!c->noise_ready || (c->noise_seed == x->adam.seed &&
                                                    c->noise_offset == x->adam.offset0 + (uint64_t)x->adam_issued));
         if (pair_ok && x->adam_gexec && x->adam_gen == x->gen && state_ok) {
@@ -1049,6 +1057,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         const uint64_t epoch0 = g_realloc_epoch.load(std::memory_order_relaxed);
         const int64_t l0 = c->launches;
         x->adam_graph_buf = c->noise_buf, x->adam_graph_ready = c->noise_ready;
+        x->adam_graph_params_ready = x->adam_params_ready;
         VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = adam_iteration(x);
         if (rc == VBMC_OK) rc = adam_iteration(x);
@@ -1063,6 +1072,7 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
             c->noise_ready = false;
             c->noise_pending_join = false;
             x->adam_issued = x->adam_done + it;  // nothing of the capture has run
+            x->adam_params_ready = x->adam_graph_params_ready;
             if (rc != VBMC_OK) return rc;
             if (ce != cudaSuccess) {
                 set_error(std::string("adam_steps: stream capture failed: ") + cudaGetErrorString(ce));
@@ -1195,6 +1205,7 @@ int vbmc_vp_pdf(vbmc_ctx *p, const vbmc_vp *vp, int Nx, const double *Xs, int lo
     memcpy(h + lay.lambd(), vp->lambd, sizeof(double) * D);
     memcpy(h + lay.w(), vp->w, sizeof(double) * K);
     c->staged = false;  // the parameter block no longer belongs to a staged evaluation
+    ex(p)->adam_params_ready = false;
     VBMC_CUDA_CHECK(cudaMemcpyAsync(c->d_in, h, sizeof(double) * (K * D + 2 * K + D), cudaMemcpyHostToDevice, c->stream));
     VBMC_TRY(ensure(&c->d_xs, &c->xs_cap, (size_t)Nx * D));
     VBMC_TRY(ensure(&c->d_pred, &c->pred_cap, (size_t)Nx * (1 + D)));

@@ -300,6 +300,7 @@ struct AdamDev {
 };
 int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm);
 int adam_update_launch(Ctx *c, const AdamDev &a, const double *d_out);
+int adam_update_prepare_launch(Ctx *c, const AdamDev &a, const double *d_out, double *d_prm);  // + next iteration's block
 // theta (+ template + key, all in pinned host memory) -> parameter block; vp_out = [sigma | lambda | w] (pinned host)
 int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src);
 
