@@ -38,14 +38,30 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
     // mu (theta order is component-major already)
     for (int e = tid; e < D * K; e += nt) prm[lay.mu() + e] = a.opt[0] ? th[e] : tm[lay.mu() + e];
     __syncthreads();
-    // lambda: exp, then the unit-RMS normalisation shared with sigma (:749-756)
-    double l2 = 0.0;
-    for (int d = tid; d < D; d += nt) {
-        const double lm = a.opt[2] ? exp(sth[pos_l + d]) : stm[K + d];
-        l2 += lm * lm;
+    // The three reductions (sum of lambda^2; max and sum of exp of eta) run in TWO WARPS side by side with shuffles only,
+    // then one barrier publishes them: this 1-CTA kernel heads the critical path of every evaluation, and each
+    // block-wide reduction of the first version cost two more barriers (13 us for the fused Adam kernel under ncu).
+    const int lane = tid & 31, wid = tid >> 5;
+    if (wid == 0) {  // lambda: exp, then the unit-RMS normalisation shared with sigma (:749-756)
+        double l2 = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            const double lm = a.opt[2] ? exp(sth[pos_l + d]) : stm[K + d];
+            l2 += lm * lm;
+        }
+        l2 = warp_sum(l2);
+        if (lane == 0) scratch[0] = sqrt(l2 / D);
+    } else if (wid == 1 && a.opt[3]) {  // weights: softmax of eta with the max shift (:735-741)
+        const double *eta = sth + n_tail - K;
+        double mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmax(mx, eta[k]);
+        mx = warp_max(mx);
+        double se = 0.0;
+        for (int k = lane; k < K; k += 32) se += exp(eta[k] - mx);
+        se = warp_sum(se);
+        if (lane == 0) scratch[1] = mx, scratch[2] = se;
     }
-    l2 = block_sum(l2, scratch);
-    const double scale = sqrt(l2 / D);
+    __syncthreads();
+    const double scale = scratch[0];
     for (int d = tid; d < D; d += nt) {
         const double lm = (a.opt[2] ? exp(sth[pos_l + d]) : stm[K + d]) / scale;
         prm[lay.lambd() + d] = lm;
@@ -58,19 +74,13 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
         if (vp_out) vp_out[k] = sg;
         prm[lay.lnsig_b() + k] = a.opt[1] ? sth[pos_s + k] : log(sg);
     }
-    // weights: softmax of eta with the max shift; eta itself is stored shifted (:1082-1085)
-    // The reference shifts the eta block of the caller's theta IN PLACE (`vp.eta = theta[-K:]; vp.eta -= amax`,
-    // variational_optimization.py:1082-1085 -- the slice is a view): the soft-bound loss reads the shifted eta
-    // (:1195-1209) and minimize_adam's `x -= step` (minimize_adam.py:98) updates the renormalised iterate.  Same
-    // here: theta's eta block is rewritten with max == 0 before the evaluation and the update.
+    // eta itself is stored shifted (:1082-1085).  The reference shifts the eta block of the caller's theta IN PLACE
+    // (`vp.eta = theta[-K:]; vp.eta -= amax`: the slice is a view): the soft-bound loss reads the shifted eta
+    // (:1195-1209) and minimize_adam's `x -= step` (minimize_adam.py:98) updates the renormalised iterate.  Same here:
+    // theta's eta block is rewritten with max == 0 before the evaluation and the update.
     if (a.opt[3]) {
         const double *eta = sth + n_tail - K;
-        double mx = -INFINITY;
-        for (int k = tid; k < K; k += nt) mx = fmax(mx, eta[k]);
-        mx = block_max(mx, scratch);
-        double se = 0.0;
-        for (int k = tid; k < K; k += nt) se += exp(eta[k] - mx);
-        se = block_sum(se, scratch);
+        const double mx = scratch[1], se = scratch[2];
         for (int k = tid; k < K; k += nt) {
             const double e = eta[k] - mx;
             const double wk = exp(e) / se;
@@ -112,8 +122,14 @@ __device__ __forceinline__ void adam_update(const AdamDev &a, const double *__re
     const int tid = threadIdx.x, nt = blockDim.x;
     const long long i = *a.iter;  // 0-based iteration
     const double beta_1 = 0.9, beta_2 = 0.999, fudge = 1.4901161193847656e-08;  // sqrt(np.spacing(1))
-    const double c1 = 1.0 - pow(beta_1, (double)(i + 1)), c2 = 1.0 - pow(beta_2, (double)(i + 1));
-    const double step = a.master_min + (a.master_max - a.master_min) * exp(-(double)(i + 1) / a.master_decay);
+    __shared__ double s_sc[3];
+    if (tid < 3) {  // three lanes, one transcendental each (instead of two pow() and an exp() in every thread)
+        s_sc[tid] = tid == 0 ? 1.0 - pow(beta_1, (double)(i + 1))
+                             : (tid == 1 ? 1.0 - pow(beta_2, (double)(i + 1))
+                                         : a.master_min + (a.master_max - a.master_min) * exp(-(double)(i + 1) / a.master_decay));
+    }
+    __syncthreads();
+    const double c1 = s_sc[0], c2 = s_sc[1], step = s_sc[2];
     double *xrow = a.xtab + (size_t)i * a.P;
     for (int e = tid; e < a.P; e += nt) {
         const double g = out[kOutHead + e];
