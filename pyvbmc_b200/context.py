@@ -419,12 +419,13 @@ class Context:
 
     # ------------------------------------------------------------------ theta-in fast path
     def theta_buffers(self, D, K):
-        """Preallocated host arrays of ``vbmc_negelcbo_theta``: (out, vp_out, tmpl)."""
+        """Preallocated host arrays of ``vbmc_negelcbo_theta``: (out, vp_out, tmpl, their addresses)."""
         key = ("theta", D, K)
         buf = self._flat.get(key)
         if buf is None:
             P = D * K + 2 * K + D
-            buf = (np.zeros(8 + P, dtype=_F64), np.zeros(2 * K + D, dtype=_F64), np.zeros(self.param_len(D, K), dtype=_F64))
+            out, vpo, tmpl = np.zeros(8 + P, dtype=_F64), np.zeros(2 * K + D, dtype=_F64), np.zeros(self.param_len(D, K), dtype=_F64)
+            buf = (out, vpo, tmpl, (out.ctypes.data, vpo.ctypes.data, tmpl.ctypes.data))
             self._flat[key] = buf
         return buf
 
@@ -434,17 +435,16 @@ class Context:
         if rc:
             _capi.check(rc)
 
-    def negelcbo_theta(self, D, K, theta, tmpl, optimize, Ns_even, compute_grad, use_bounds, seed, offset, precision, out,
-                       vp_out):
-        """``vbmc_negelcbo_theta``: raw optimiser vector in (its eta block is shifted in place), ``out`` / ``vp_out``
-        filled in place."""
+    def negelcbo_theta(self, D, K, theta, use_tmpl, optimize, Ns_even, compute_grad, use_bounds, seed, offset, precision, ptrs):
+        """``vbmc_negelcbo_theta``: raw optimiser vector in (its eta block is shifted in place); ``ptrs`` = addresses of
+        the ``(out, vp_out, tmpl)`` arrays of :meth:`theta_buffers`, filled in place."""
         og = self._opt_c.get(optimize)
         if og is None:
             og = self._opt_c[optimize] = (C.c_int * 4)(*[int(bool(o)) for o in optimize])
         prec = _capi.PREC_F64 if (precision or config.precision) == "f64" else _capi.PREC_F32
         rc = self._lib.vbmc_negelcbo_theta(
-            self._h, D, K, theta.ctypes.data, tmpl.ctypes.data if tmpl is not None else None, og, Ns_even,
-            int(compute_grad), int(use_bounds), seed, int(offset), prec, out.ctypes.data, vp_out.ctypes.data,
+            self._h, D, K, theta.ctypes.data, ptrs[2] if use_tmpl else None, og, Ns_even,
+            int(compute_grad), int(use_bounds), seed, int(offset), prec, ptrs[0], ptrs[1],
         )
         if rc:
             _capi.check(rc)

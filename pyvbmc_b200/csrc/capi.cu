@@ -167,6 +167,17 @@ int stage(CtxEx *x, const Spec &s) {
     RawLayout rl{D, K};
     VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total() + 2));
     double *h = c->h_in;
+    // Monte-Carlo draws not generated ahead for this key: fork the generator's stream HERE, before the parameter
+    // kernel (the tiles depend on the key only; entmc_tc.cu launches the generator on it and joins it in front of
+    // the main kernel, partials() joins it in any case)
+    c->root_forked = false;
+    static const bool root_fork_on = getenv("VBMC_ROOT_FORK") ? atoi(getenv("VBMC_ROOT_FORK")) != 0 : true;
+    if (root_fork_on && s.have_ent && s.Ns > 0 && s.rng_mode == VBMC_RNG_PHILOX &&
+        !(c->noise_ready && c->noise_seed == s.seed && c->noise_offset == s.offset)) {
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root, c->stream));
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream3, c->ev_root, 0));
+        c->root_forked = true;
+    }
     if (s.theta) {
         // theta, template and key go to PINNED host memory; one small kernel reads them through their device aliases
         // and writes the parameter block (set_parameters + eta shift + bound inputs on the device)
@@ -177,6 +188,7 @@ int stage(CtxEx *x, const Spec &s) {
         if (s.tmpl) memcpy(tm, s.tmpl, sizeof(double) * T);
         memcpy(key, &s.seed, sizeof(uint64_t));
         memcpy(key + 1, &s.offset, sizeof(uint64_t));
+        c->key_host = key;
         AdamDev a{};
         a.lay = lay, a.P = s.P;
         for (int i = 0; i < 4; ++i) a.opt[i] = s.optimize[i];
@@ -197,10 +209,11 @@ int stage(CtxEx *x, const Spec &s) {
     }
     memcpy(h + lay.total(), &s.seed, sizeof(uint64_t));  // Philox key rides behind the parameter block
     memcpy(h + lay.total() + 1, &s.offset, sizeof(uint64_t));
+    c->key_host = h + lay.total();
     // parameter block -> HBM.  A one-CTA kernel that reads the pinned block through its device alias (UVA) instead
     // of a copy-engine memcpy: inside the captured graph a kernel node starts ~5 us sooner than a memcpy node, and
     // this copy heads the critical path of every evaluation.
-    VBMC_TRY(stage_copy_launch(c, c->d_in, h, lay.total() + 2));
+    VBMC_TRY(stage_copy_launch(c, c->d_in, h, lay.total() + 2, c->stream));
     }
 
     if (s.use_bounds) {
@@ -298,6 +311,11 @@ int partials(CtxEx *x, int rank, int world, double *raw_dev) {
         } else {
             f.have_ent = 0;
         }
+    }
+    if (c->root_forked) {  // forked in stage() and not used by the entropy kernel that ran: close the fork
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root_join, c->stream3));
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_root_join, 0));
+        c->root_forked = false;
     }
     stage_mark(c, 2);
     if (fork) VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -516,6 +534,10 @@ int vbmc_ctx_create(int device, vbmc_ctx **out) {
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_join, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_main, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_noise, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaStreamCreateWithPriority(&x->c.stream3, cudaStreamNonBlocking, prio_least));
+    VBMC_CUDA_CHECK(cudaMalloc((void **)&x->c.d_key, 2 * sizeof(double)));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_root, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&x->c.ev_root_join, cudaEventDisableTiming));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev0));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev1));
     VBMC_CUDA_CHECK(cudaEventCreate(&x->c.ev2));
@@ -535,6 +557,7 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
     if (c->d_tailsync) cudaFree(c->d_tailsync);
+    if (c->d_key) cudaFree(c->d_key);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
                      c->d_entpart, c->d_gps, c->d_raw, c->d_csum, c->d_tctab, c->d_tctiles[0], c->d_tctiles[1], c->d_bprm, c->d_bout, c->d_out, c->d_eps, c->d_lbws, c->d_var, c->d_xs, c->d_pred};
     for (double *d : dev)
@@ -549,6 +572,9 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_noise) cudaEventDestroy(c->ev_noise);
+    if (c->ev_root) cudaEventDestroy(c->ev_root);
+    if (c->ev_root_join) cudaEventDestroy(c->ev_root_join);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete x;
@@ -967,7 +993,6 @@ int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     const size_t need = 5 * (size_t)P + T + (size_t)in->max_iter + 1 + (size_t)in->max_iter * P;
     if (need > x->adam_cap) {
         if (x->d_adam) cudaFree(x->d_adam);
-    if (c->d_tailsync) cudaFree(c->d_tailsync);
         x->d_adam = nullptr, x->adam_cap = 0;
         VBMC_CUDA_CHECK(cudaMalloc((void **)&x->d_adam, need * sizeof(double)));
         x->adam_cap = need;

@@ -168,6 +168,14 @@ struct Ctx {
     bool lookahead = false;        // the caller's next evaluation uses key + key_delta + 1
     bool noise_pending_join = false;
     cudaEvent_t ev_main = nullptr, ev_noise = nullptr;
+    // root fork: an evaluation whose draws were NOT generated ahead runs its (theta-independent) tile generator on a
+    // third stream forked BEFORE the parameter kernel, beside parameter block + tables; it reads the Philox key from
+    // the pinned host block through its device alias (`key_host`), so it does not depend on the parameter kernel
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_root = nullptr, ev_root_join = nullptr;
+    bool root_forked = false;
+    const double *key_host = nullptr;
+    double *d_key = nullptr;  // device copy of the key for the root-forked generator (one PCIe read per evaluation, not one per CTA)
     double *d_csum = nullptr;  // [K][entpart_stride] per-component record sums (tail kernel scratch)
     unsigned *d_tailsync = nullptr;  // barrier words of the tail kernel (grid mode)
     size_t csum_cap = 0;
@@ -308,7 +316,7 @@ int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out
 int sieve_launch(Ctx *c, int B, int D, int K, const int optimize[4], bool use_bounds, const double *d_prm, double *d_out);
 
 // finalize.cu
-int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n);
+int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n, cudaStream_t st);
 int reduce_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const EntmcPlan *plan,
                   int64_t Ns_glob, int s_begin, int s_step, int S_glob, double *d_raw, bool defer);
 int finalize_launch(Ctx *c, const double *d_params, int D, int K, const EvalFlags &f, const double *d_raw,

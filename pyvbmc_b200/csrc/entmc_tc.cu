@@ -308,7 +308,18 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         // ---- (b) noise tile -------------------------------------------------------------------------------
         __shared__ int s_info[kGenTiles][4];  // j, n, t0, valid
         __shared__ int64_t s_plo[kGenTiles];
+        __shared__ uint64_t s_key[2];
         const int g_first = ((int)blockIdx.x - n_tab) * kGenTiles;
+        if (PHILOX && tid == kGenTiles) {
+            // the key of THIS evaluation rides behind the parameter block (key_delta = 1: the next evaluation's draws); a
+            // prefetch launched before the parameters exist on the device passes the key by value.  One load per CTA.
+            uint64_t ks = seed_v, ko = offset_v;
+            if (!key_by_value) {
+                const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+                ks = rngp[0], ko = rngp[1] + (uint64_t)key_delta;
+            }
+            s_key[0] = ks, s_key[1] = ko;
+        }
         if (tid < kGenTiles) {  // which (component, pair range) is image g?  (64-bit divisions: once per image)
             const int g = g_first + tid;
             const int cta = g / wk.tpc, l = g - cta * wk.tpc;
@@ -351,14 +362,7 @@ entmc_tc_gen_kernel(const double *__restrict__ prm, ParamLayout lay, float guard
         const int64_t gpair = wk.pair0 + p_lo + (live ? off : 0);
         float z[DH];
         if (PHILOX) {
-            // the key of THIS evaluation rides behind the parameter block (key_delta = 1: the next evaluation's draws);
-            // a prefetch launched before the parameters exist on the device passes the key by value
-            uint64_t ks = seed_v, ko = offset_v;
-            if (!key_by_value) {
-                const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
-                ks = rngp[0], ko = rngp[1] + (uint64_t)key_delta;
-            }
-            philox_normals_half<DH>(ks, ko, (uint32_t)j, (uint64_t)gpair, hsel, D, z);
+            philox_normals_half<DH>(s_key[0], s_key[1], (uint32_t)j, (uint64_t)gpair, hsel, D, z);
         } else {
             const double *ep = eps + ((size_t)j * (size_t)wk.half_glob + (size_t)gpair) * (size_t)D;
 #pragma unroll
@@ -941,6 +945,22 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         // while the host was still packing the parameters: tables only
         // (a prefetch launch was joined into the main stream by the entry point: capi.cu settle_prefetch)
         VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
+    } else if (philox && c->root_forked && c->key_delta == 0 && c->key_host) {
+        // tiles on the stream forked before the parameter kernel (capi.cu stage()); the key comes from the pinned host
+        // block (not from the parameter block the main stream is still building): `prm + lay.total()` of the generator
+        // lands on its device copy.  Tables on the main stream, join in front of the main kernel.
+        // (every generator CTA reading the host copy itself serialises ~1 us PCIe reads of one line: 1.1 ms measured;
+        // a one-warp kernel brings the 16 bytes over once)
+        VBMC_TRY(stage_copy_launch(c, c->d_key, c->key_host, 2, c->stream3));
+        const unsigned grid = tile_ctas;
+        entmc_tc_gen_kernel<DP, true><<<grid, kThreads, 0, c->stream3>>>(c->d_key - lay.total(), lay, 0.f, nullptr, wk, nullptr,
+                                                                       d_tiles, 0, 0, 0, 0, 0);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        c->launches++;
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root_join, c->stream3));
+        VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_root_join, 0));
+        c->root_forked = false;
     } else {
         VBMC_TRY(gen(c->stream, d_tiles, K, true, c->key_delta));
     }

@@ -701,9 +701,9 @@ __global__ void __launch_bounds__(1024) stage_copy_kernel(double *__restrict__ d
 }
 }  // namespace
 
-// pinned host block (device-addressable under the same pointer) -> device buffer, as a kernel on the context stream
-int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n) {
-    stage_copy_kernel<<<1, 1024, 0, c->stream>>>(d_dst, h_pinned_src, n);
+// pinned host block (device-addressable under the same pointer) -> device buffer, as a kernel on stream `st`
+int stage_copy_launch(Ctx *c, double *d_dst, const double *h_pinned_src, int n, cudaStream_t st) {
+    stage_copy_kernel<<<1, n >= 1024 ? 1024 : 32, 0, st>>>(d_dst, h_pinned_src, n);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

@@ -241,9 +241,10 @@ def _neg_elcbo(
         if Ns_even > 0:
             if seed is None:
                 seed = draw_seed()
-            ctx.noise_prefetch(D, K, Ns_even, seed, offset)  # theta-independent: overlaps the rest of this call's host work
+            if config.host_noise_prefetch:  # theta-independent: overlaps the rest of this call's host work
+                ctx.noise_prefetch(D, K, Ns_even, seed, offset)
         use_bounds = ctx.set_bounds(theta_bnd)
-        out, vpo, tmpl = ctx.theta_buffers(D, K)
+        out, vpo, tmpl, ptrs = ctx.theta_buffers(D, K)
         th = theta if theta.flags.c_contiguous and theta.flags.writeable else np.array(theta, dtype=float)
         DK = D * K
         if optimize == (True, True, True, True):
@@ -256,7 +257,7 @@ def _neg_elcbo(
             tm[DK + K : DK + K + D] = np.ravel(vp.lambd)
             tm[DK + K + D : DK + 2 * K + D] = np.ravel(vp.w)
             tm[DK + 2 * K + D : DK + 3 * K + D] = np.ravel(vp.eta)
-        ctx.negelcbo_theta(D, K, th, tm, optimize, Ns_even, compute_grad, use_bounds, seed or 0, offset, None, out, vpo)
+        ctx.negelcbo_theta(D, K, th, tm is not None, optimize, Ns_even, compute_grad, use_bounds, seed or 0, offset, None, ptrs)
         # side effects on vp and on the caller's theta, as the reference leaves them
         if optimize[0]:
             vp.mu = np.array(th[:DK]).reshape((D, K), order="F")
