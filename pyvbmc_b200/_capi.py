@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvbmc_b200.so")
+LIB_PATH = os.environ.get("VBMC_LIB") or os.path.join(_HERE, "csrc", "libvbmc_b200.so")  # (VBMC_LIB: development builds)
 
 OK, ERR_CUDA, ERR_ARG, ERR_UNSUPPORTED, ERR_STATE = 0, 1, 2, 3, 4
 MEAN_ZERO, MEAN_CONST, MEAN_NEGQUAD = 0, 1, 2
