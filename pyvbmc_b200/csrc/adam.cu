@@ -17,7 +17,7 @@ namespace {
 // the groups theta does not carry, and the Philox key in PINNED HOST memory, read through their device aliases; the
 // normalised sigma / lambda / w go back to the host the same way in `vp_out` = [sigma (K) | lambda (D) | w (K)]).
 __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__restrict__ prm, double *__restrict__ vp_out,
-                                                const uint64_t *__restrict__ key_src) {
+                                                const uint64_t *__restrict__ key_src, bool skip_mu = false) {
     const ParamLayout lay = a.lay;
     const int D = lay.D, K = lay.K, tid = threadIdx.x, nt = blockDim.x;
     __shared__ double scratch[40];
@@ -36,7 +36,8 @@ __device__ __forceinline__ void theta_to_params(const AdamDev &a, double *__rest
         for (int e = tid; e < 3 * K + D; e += nt) stm[e] = tm[lay.sigma() + e];  // sigma | lambda | w | eta are contiguous
     if (tid == 0 && key_src) skey[0] = key_src[0], skey[1] = key_src[1];
     // mu (theta order is component-major already)
-    for (int e = tid; e < D * K; e += nt) prm[lay.mu() + e] = a.opt[0] ? th[e] : tm[lay.mu() + e];
+    if (!skip_mu)
+        for (int e = tid; e < D * K; e += nt) prm[lay.mu() + e] = a.opt[0] ? th[e] : tm[lay.mu() + e];
     __syncthreads();
     // The three reductions (sum of lambda^2; max and sum of exp of eta) run in TWO WARPS side by side with shuffles only,
     // then one barrier publishes them: this 1-CTA kernel heads the critical path of every evaluation, and each
@@ -115,7 +116,15 @@ __global__ void __launch_bounds__(256) adam_prepare_kernel(AdamDev a, double *__
 
 __global__ void __launch_bounds__(256)
 theta_prepare_kernel(AdamDev a, double *__restrict__ prm, double *__restrict__ vp_out, const uint64_t *__restrict__ key_src) {
-    theta_to_params(a, prm, vp_out, key_src);
+    // theta lives in pinned HOST memory here, and reads over PCIe are limited by the requests in flight, not by their
+    // size: the D*K means (9 of the 10 KB) are copied by CTAs 1.. while CTA 0 works on the 2K + D entries behind them
+    if (blockIdx.x > 0) {
+        const int n = a.lay.D * a.lay.K, stride = ((int)gridDim.x - 1) * (int)blockDim.x;
+        const double *src = a.opt[0] ? a.theta : a.tmpl + a.lay.mu();
+        for (int e = ((int)blockIdx.x - 1) * (int)blockDim.x + (int)threadIdx.x; e < n; e += stride) prm[a.lay.mu() + e] = src[e];
+        return;
+    }
+    theta_to_params(a, prm, vp_out, key_src, gridDim.x > 1);
 }
 
 __device__ __forceinline__ void adam_update(const AdamDev &a, const double *__restrict__ out) {
@@ -169,7 +178,8 @@ int adam_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm) {
 }
 
 int theta_prepare_launch(Ctx *c, const AdamDev &a, double *d_prm, double *vp_out, const uint64_t *key_src) {
-    theta_prepare_kernel<<<1, 256, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_prm, vp_out, key_src);
+    static const int mu_ctas = getenv("VBMC_PREP_MU_CTAS") ? atoi(getenv("VBMC_PREP_MU_CTAS")) : 4;
+    theta_prepare_kernel<<<1 + mu_ctas, 256, (size_t)(5 * a.lay.K + 2 * a.lay.D) * sizeof(double), c->stream>>>(a, d_prm, vp_out, key_src);
     VBMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     return VBMC_OK;

@@ -155,7 +155,7 @@ struct CtxEx {
 
 CtxEx *ex(vbmc_ctx *p) { return reinterpret_cast<CtxEx *>(p); }
 
-int stage(CtxEx *x, const Spec &s) {
+int stage(CtxEx *x, const Spec &s, bool single_gpu = false) {
     Ctx *c = &x->c;
     VBMC_TRY(check_vp(&s.vp, s.flat != nullptr || s.theta != nullptr));
     const int D = s.vp.D, K = s.vp.K, DP = pad_dim(D);
@@ -167,17 +167,34 @@ int stage(CtxEx *x, const Spec &s) {
     RawLayout rl{D, K};
     VBMC_TRY(ensure_pinned(&c->d_in, &c->h_in, &c->in_cap, (size_t)lay.total() + 2));
     double *h = c->h_in;
-    // Monte-Carlo draws not generated ahead for this key: fork the generator's stream HERE, before the parameter
-    // kernel (the tiles depend on the key only; entmc_tc.cu launches the generator on it and joins it in front of
-    // the main kernel, partials() joins it in any case)
+    // Monte-Carlo draws not generated ahead for this key (single-GPU evaluation through run_flat / run_single): the tile
+    // generator depends on the key only, so it is forked off HERE, in front of the parameter kernel, on a third stream
+    // (launched below, once the key sits in the pinned block); entmc_tc.cu joins it in front of the main kernel and
+    // partials() in any case.  It must be enqueued BEFORE the kernels that wait for the parameter kernel: a captured
+    // graph submits its kernels in creation order, and a launch behind such a wait does not start before it either.
     c->root_forked = false;
     static const bool root_fork_on = getenv("VBMC_ROOT_FORK") ? atoi(getenv("VBMC_ROOT_FORK")) != 0 : true;
-    if (root_fork_on && s.have_ent && s.Ns > 0 && s.rng_mode == VBMC_RNG_PHILOX &&
+    EntmcPlan root_plan{};
+    bool root_gen = false;
+    if (root_fork_on && single_gpu && s.have_ent && s.Ns > 0 && s.rng_mode == VBMC_RNG_PHILOX && s.precision != VBMC_PREC_F64 &&
         !(c->noise_ready && c->noise_seed == s.seed && c->noise_offset == s.offset)) {
+        const int64_t half = even_ns(s.Ns) / 2;
+        if (entmc_plan(c, D, K, half, s.grad[3] != 0, s.precision, &root_plan) == VBMC_OK && root_plan.variant == ENTMC_TC) {
+            root_plan.pair0 = 0, root_plan.half_glob = half;
+            root_gen = true;
+        }
+    }
+    if (root_gen) {
         VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root, c->stream));
         VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream3, c->ev_root, 0));
         c->root_forked = true;
     }
+    // (enqueued in FRONT of the parameter kernel.  Measured alternatives, profiles/r4_e2e_timeline.md: behind it, the
+    // generator's branch starts ~4 us late and its single wave then keeps the table kernel waiting for SM resources;
+    // whichever of the two root branches of the captured graph is created second starts 4-8 us after the first.)
+    auto launch_root_gen = [&]() -> int {
+        return root_gen ? entmc_tc_prefetch(c, lay, root_plan, s.seed, s.offset, true) : VBMC_OK;
+    };
     if (s.theta) {
         // theta, template and key go to PINNED host memory; one small kernel reads them through their device aliases
         // and writes the parameter block (set_parameters + eta shift + bound inputs on the device)
@@ -189,6 +206,7 @@ int stage(CtxEx *x, const Spec &s) {
         memcpy(key, &s.seed, sizeof(uint64_t));
         memcpy(key + 1, &s.offset, sizeof(uint64_t));
         c->key_host = key;
+        VBMC_TRY(launch_root_gen());
         AdamDev a{};
         a.lay = lay, a.P = s.P;
         for (int i = 0; i < 4; ++i) a.opt[i] = s.optimize[i];
@@ -210,6 +228,7 @@ int stage(CtxEx *x, const Spec &s) {
     memcpy(h + lay.total(), &s.seed, sizeof(uint64_t));  // Philox key rides behind the parameter block
     memcpy(h + lay.total() + 1, &s.offset, sizeof(uint64_t));
     c->key_host = h + lay.total();
+    VBMC_TRY(launch_root_gen());
     // parameter block -> HBM.  A one-CTA kernel that reads the pinned block through its device alias (UVA) instead
     // of a copy-engine memcpy: inside the captured graph a kernel node starts ~5 us sooner than a memcpy node, and
     // this copy heads the critical path of every evaluation.
@@ -348,7 +367,7 @@ int run_single(CtxEx *x, const Spec &s, size_t n_out) {
     VBMC_TRY(settle_prefetch(c));
     const auto t0 = std::chrono::steady_clock::now();
     stage_mark(c, 0);
-    VBMC_TRY(stage(x, s));
+    VBMC_TRY(stage(x, s, true));
     stage_mark(c, 1);  // after the H2D copies
     VBMC_TRY(partials(x, 0, 1, c->d_raw));
     stage_mark(c, 4);  // after the reduce stage (2 = entmc done, 3 = side stream joined)
@@ -450,7 +469,7 @@ int run_flat(CtxEx *x, const Spec &s, size_t n_out) {
     const uint64_t epoch0 = g_realloc_epoch.load(std::memory_order_relaxed);
     const int64_t l0 = c->launches;
     VBMC_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = stage(x, s);
+    int rc = stage(x, s, true);
     if (rc == VBMC_OK) rc = partials(x, 0, 1, c->d_raw);
     if (rc == VBMC_OK) rc = finalize(x, c->d_raw, c->h_out);
     cudaGraph_t g = nullptr;

@@ -267,7 +267,7 @@ int entmc_launch(Ctx *c, const double *d_params, int D, int K, const EntmcPlan &
                  uint64_t offset, double *d_part);
 int philox_normals_launch(Ctx *c, int D, int K, int64_t half, uint64_t seed, uint64_t offset, double *d_eps);
 // entmc_tc.cu (tcgen05 / TMEM kernel)
-int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset);
+int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset, bool root = false);
 bool entmc_tc_supported(int DP, int K);
 int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *plan);
 int entmc_tc_launch(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan &plan, bool anygrad, bool philox,

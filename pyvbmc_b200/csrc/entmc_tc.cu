@@ -953,26 +953,14 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
         // while the host was still packing the parameters: tables only
         // (a prefetch launch was joined into the main stream by the entry point: capi.cu settle_prefetch)
         VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
-    } else if (philox && c->root_forked && c->key_delta == 0 && c->key_host) {
-        // tiles on the stream forked before the parameter kernel (capi.cu stage()); the key comes from the pinned host
-        // block (not from the parameter block the main stream is still building): `prm + lay.total()` of the generator
-        // lands on its device copy.  Tables on the main stream, join in front of the main kernel.
-        // (every generator CTA reading the host copy itself serialises ~1 us PCIe reads of one line: 1.1 ms measured;
-        // a one-warp kernel brings the 16 bytes over once)
-        VBMC_TRY(stage_copy_launch(c, c->d_key, c->key_host, 2, c->stream3));
-        const unsigned grid = tile_ctas;
-        entmc_tc_gen_kernel<DP, true><<<grid, kThreads, 0, c->stream3>>>(c->d_key - lay.total(), lay, 0.f, nullptr, wk, nullptr,
-                                                                       d_tiles, 0, 0, 0, 0, 0);
-        VBMC_CUDA_CHECK(cudaGetLastError());
-        c->launches++;
-        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root_join, c->stream3));
-        VBMC_TRY(gen(c->stream, d_tiles, K, false, 0));
-        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_root_join, 0));
-        c->root_forked = false;
     } else {
         VBMC_TRY(gen(c->stream, d_tiles, K, true, c->key_delta));
     }
     c->noise_ready = false;
+    if (c->root_forked) {  // tiles generated on the stream forked in front of the parameter kernel (capi.cu stage()): join
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_root_join, 0));
+        c->root_forked = false;
+    }
     static size_t smem_set[2] = {0, 0};
     if (plan.smem > smem_set[anygrad ? 1 : 0]) {
         if (anygrad)
@@ -1011,6 +999,8 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
     if (philox && c->lookahead) {
         // draws of the NEXT evaluation (key offset + 1) into the other buffer, on the side stream, behind this main
         // kernel: it runs while the tail (8 CTAs) leaves the machine idle.  finalize() re-joins the side stream.
+        // (Measured alternatives, profiles/r4_e2e_timeline.md: released by the tail's launch-completion event, enqueued
+        // behind the tail, or as the tail's programmatic dependent on the main stream -- none faster, the last one slower.)
         const int nb = 1 - b;
         VBMC_TRY(ensure(&c->d_tctiles[nb], &c->tctiles_cap[nb], (n_img * TB + 7) / 8));
         VBMC_CUDA_CHECK(cudaEventRecord(c->ev_main, c->stream));
@@ -1028,8 +1018,11 @@ int tc_launch_dp(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPla
 
 // vbmc_noise_prefetch: the noise tiles of the evaluation with Philox key (seed, offset), on the side stream, before
 // its parameters have reached the device (the tiles do not depend on them)
+// root = true: launched by stage() of an evaluation on the stream forked in front of its parameter kernel; the key is
+// read from the device copy `d_key` of the pinned host key (a one-warp copy kernel in front of the generator), so that a
+// captured graph picks up the key of every replay
 template <int DP>
-int tc_prefetch_dp(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset) {
+int tc_prefetch_dp(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset, bool root) {
     const int K = lay.K;
     const TcWork wk = tc_work(plan, K);
     const size_t TB = tc_tile_bytes(DP);
@@ -1037,17 +1030,36 @@ int tc_prefetch_dp(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed
     const int b = c->noise_buf;
     VBMC_TRY(ensure(&c->d_tctiles[b], &c->tctiles_cap[b], (n_img * TB + 7) / 8));
     const unsigned tile_ctas = (unsigned)((n_img + kGenTiles - 1) / kGenTiles);
-    entmc_tc_gen_kernel<DP, true><<<tile_ctas, kThreads, 0, c->stream2>>>(nullptr, lay, 0.f, nullptr, wk, nullptr,
-                                                                         reinterpret_cast<unsigned char *>(c->d_tctiles[b]), 0,
-                                                                         0, 1, seed, offset);
-    VBMC_CUDA_CHECK(cudaGetLastError());
-    VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
+    if (root) {
+        // (every generator CTA reading the host copy itself serialises ~1 us PCIe reads of one line: 1.1 ms measured)
+        VBMC_TRY(stage_copy_launch(c, c->d_key, c->key_host, 2, c->stream3));
+        // padded shared-memory request: 3 generator CTAs per SM instead of 4, so that the parameter kernel and the table
+        // kernel (main stream) find room beside this grid instead of waiting for its single wave to drain
+        static const size_t pad = (size_t)(getenv("VBMC_ROOT_SMEM") ? atoi(getenv("VBMC_ROOT_SMEM")) : 57) * 1024;
+        static bool pad_set = false;
+        if (!pad_set && pad > 48 * 1024) {
+            VBMC_CUDA_CHECK(cudaFuncSetAttribute(entmc_tc_gen_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+            pad_set = true;
+        }
+        entmc_tc_gen_kernel<DP, true><<<tile_ctas, kThreads, pad, c->stream3>>>(c->d_key - lay.total(), lay, 0.f, nullptr, wk, nullptr,
+                                                                             reinterpret_cast<unsigned char *>(c->d_tctiles[b]), 0,
+                                                                             0, 0, 0, 0);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_root_join, c->stream3));
+    } else {
+        entmc_tc_gen_kernel<DP, true><<<tile_ctas, kThreads, 0, c->stream2>>>(nullptr, lay, 0.f, nullptr, wk, nullptr,
+                                                                             reinterpret_cast<unsigned char *>(c->d_tctiles[b]), 0,
+                                                                             0, 1, seed, offset);
+        VBMC_CUDA_CHECK(cudaGetLastError());
+        VBMC_CUDA_CHECK(cudaEventRecord(c->ev_noise, c->stream2));
+    }
     c->launches++;
     const uint64_t sig[6] = {(uint64_t)lay.D << 32 | (uint64_t)K, (uint64_t)plan.grid << 32 | (uint64_t)plan.maxseg,
                              (uint64_t)plan.chunk << 20 ^ (uint64_t)plan.chunk_small << 8 ^ (uint64_t)plan.n_big, (uint64_t)plan.half,
                              (uint64_t)plan.pair0, (uint64_t)plan.half_glob};
     for (int i = 0; i < 6; ++i) c->noise_sig[i] = sig[i];
-    c->noise_ready = true, c->noise_needs_wait = true;
+    c->noise_ready = true;
+    if (!root) c->noise_needs_wait = true;
     c->noise_seed = seed, c->noise_offset = offset;
     return VBMC_OK;
 }
@@ -1115,11 +1127,11 @@ int entmc_tc_plan(const Ctx *c, int D, int K, int64_t half_local, EntmcPlan *pla
     return VBMC_OK;
 }
 
-int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset) {
+int entmc_tc_prefetch(Ctx *c, ParamLayout lay, const EntmcPlan &plan, uint64_t seed, uint64_t offset, bool root) {
     switch (lay.DP) {
 #define VBMC_CASE(N) \
     case N:          \
-        return tc_prefetch_dp<N>(c, lay, plan, seed, offset)
+        return tc_prefetch_dp<N>(c, lay, plan, seed, offset, root)
         VBMC_CASE(4);
         VBMC_CASE(8);
         VBMC_CASE(12);
