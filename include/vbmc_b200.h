@@ -256,6 +256,13 @@ int vbmc_adam_init(vbmc_ctx *ctx, const vbmc_adam_in *in);
  * (row i = x_tab[:, i] of the reference).  Synchronous.                                                       */
 int vbmc_adam_steps(vbmc_ctx *ctx, int n, double *y, double *x);
 
+/* Split-phase form of vbmc_adam_steps, for a host loop that keeps one batch in flight while it evaluates the
+ * early-stopping rule (minimize_adam.py:106-138) on the previous one: vbmc_adam_enqueue issues n iterations and returns
+ * without synchronising; vbmc_adam_fetch waits for iterations [i0, i0 + n) ONLY (not for what was issued behind them)
+ * and copies their objective values y[n] and iterates x[n][P] to the host. */
+int vbmc_adam_enqueue(vbmc_ctx *ctx, int n);
+int vbmc_adam_fetch(vbmc_ctx *ctx, int64_t i0, int n, double *y, double *x);
+
 size_t vbmc_raw_len(int D, int K);
 size_t vbmc_out_len(int D, int K);
 int vbmc_negelcbo_upload(vbmc_ctx *ctx, const vbmc_elcbo_in *in);

@@ -149,6 +149,8 @@ PROTOTYPES = {
     "vbmc_param_len": (C.c_size_t, [C.c_int, C.c_int]),
     "vbmc_adam_init": (C.c_int, [C.c_void_p, C.POINTER(AdamIn)]),
     "vbmc_adam_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vbmc_adam_enqueue": (C.c_int, [C.c_void_p, C.c_int]),
+    "vbmc_adam_fetch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "vbmc_negelcbo_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "vbmc_fma_peak": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vbmc_stage_times": (C.c_int, [C.c_void_p, c_double_p]),

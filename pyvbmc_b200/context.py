@@ -492,6 +492,17 @@ class Context:
         _capi.check(self._lib.vbmc_adam_steps(self._h, int(n), y.ctypes.data, x.ctypes.data))
         return y, x
 
+    def adam_enqueue(self, n):
+        """``vbmc_adam_enqueue``: issue the next ``n`` iterations, no synchronisation."""
+        _capi.check(self._lib.vbmc_adam_enqueue(self._h, int(n)))
+
+    def adam_fetch(self, i0, n):
+        """``vbmc_adam_fetch``: wait for iterations ``[i0, i0 + n)`` only and return ``(y[n], x[n, P])``."""
+        y = np.empty(n, dtype=_F64)
+        x = np.empty((n, self._adam_P), dtype=_F64)
+        _capi.check(self._lib.vbmc_adam_fetch(self._h, int(i0), int(n), y.ctypes.data, x.ctypes.data))
+        return y, x
+
     # ------------------------------------------------------------------ peer-memory all-reduce (one node)
     def p2p_export(self, world, D, K) -> bytes:
         buf = (C.c_ubyte * 64)()

@@ -148,6 +148,12 @@ struct CtxEx {
     int64_t partials_calls = 0;     // vbmc_negelcbo_partials_async calls since the last upload
     long long adam_issued = 0;      // Adam iterations issued (eager + captured) since vbmc_adam_init
     bool adam_params_ready = false; // d_in holds the parameter block of the NEXT Adam iteration (fused update kernel)
+    static constexpr int kAdamTickets = 8;
+    struct AdamTicket {
+        cudaEvent_t ev = nullptr;
+        long long i_end = 0;  // iterations [.., i_end) are complete once `ev` has fired
+    } adam_tickets[kAdamTickets];
+    int adam_ticket_next = 0;
     bool adam_graph_params_ready = false;
     int adam_graph_buf = 0;         // noise-tile buffer parity / look-ahead state the captured pair starts from
     bool adam_graph_ready = false;
@@ -575,6 +581,8 @@ void vbmc_ctx_destroy(vbmc_ctx *p) {
     p2p_unmap(c);
     if (c->p2p_local) cudaFree(c->p2p_local);
     if (x->d_adam) cudaFree(x->d_adam);
+    for (auto &t : x->adam_tickets)
+        if (t.ev) cudaEventDestroy(t.ev);
     if (c->d_tailsync) cudaFree(c->d_tailsync);
     if (c->d_key) cudaFree(c->d_key);
     double *dev[] = {c->d_Xt, c->d_alpha, c->d_hyp, c->d_L,  c->d_Linv, c->d_lb,   c->d_ub, c->d_in, c->d_lamc, c->d_outs,
@@ -1054,16 +1062,16 @@ int vbmc_adam_init(vbmc_ctx *p, const vbmc_adam_in *in) {
     x->adam_max_iter = in->max_iter;
     x->adam_done = 0;
     x->adam_issued = 0;
+    x->adam_ticket_next = 0;
+    for (auto &t : x->adam_tickets) t.i_end = 0;
     x->adam_params_ready = false;
     x->adam_ready = true, x->adam_eager_done = false;
     return VBMC_OK;
 }
 
-int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
-    VBMC_REQUIRE(p && y && xs, VBMC_ERR_ARG, "adam_steps: null argument");
-    CtxEx *x = ex(p);
+// enqueue n iterations on the context stream (no synchronisation)
+static int adam_enqueue(CtxEx *x, int n) {
     Ctx *c = &x->c;
-    Bind b(c);
     VBMC_REQUIRE(x->adam_ready && c->staged, VBMC_ERR_STATE, "adam_steps: call vbmc_adam_init first");
     VBMC_REQUIRE(n >= 0 && x->adam_done + n <= x->adam_max_iter, VBMC_ERR_ARG, "adam_steps: more steps than max_iter");
     VBMC_TRY(settle_prefetch(c));
@@ -1134,12 +1142,69 @@ int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
         it += 2;
     }
     x->adam_done += n;
+    (void)i0;
+    return VBMC_OK;
+}
+
+int vbmc_adam_steps(vbmc_ctx *p, int n, double *y, double *xs) {
+    VBMC_REQUIRE(p && y && xs, VBMC_ERR_ARG, "adam_steps: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    const long long i0 = x->adam_done;
+    VBMC_TRY(adam_enqueue(x, n));
     const int P = x->adam.P;
     if (n > 0) {
         VBMC_CUDA_CHECK(cudaMemcpyAsync(y, x->adam.ytab + i0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         VBMC_CUDA_CHECK(cudaMemcpyAsync(xs, x->adam.xtab + (size_t)i0 * P, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return VBMC_OK;
+}
+
+// Split-phase form: vbmc_adam_enqueue(n) returns as soon as the n iterations are in the stream; vbmc_adam_fetch(i0, n)
+// waits for iterations [i0, i0 + n) only (an event recorded behind the enqueue call that issued them) and copies their
+// objective values and iterates on a second stream.  The host loop keeps ONE batch in flight while it digests the
+// previous one (early-stopping fit, minimize_adam.py:106-138), so the device never waits for the host.
+int vbmc_adam_enqueue(vbmc_ctx *p, int n) {
+    VBMC_REQUIRE(p, VBMC_ERR_ARG, "adam_enqueue: null ctx");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    VBMC_TRY(adam_enqueue(x, n));
+    auto &t = x->adam_tickets[x->adam_ticket_next % CtxEx::kAdamTickets];
+    if (!t.ev) VBMC_CUDA_CHECK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+    VBMC_CUDA_CHECK(cudaEventRecord(t.ev, c->stream));
+    t.i_end = x->adam_done;
+    x->adam_ticket_next++;
+    return VBMC_OK;
+}
+
+int vbmc_adam_fetch(vbmc_ctx *p, int64_t i0, int n, double *y, double *xs) {
+    VBMC_REQUIRE(p && y && xs, VBMC_ERR_ARG, "adam_fetch: null argument");
+    CtxEx *x = ex(p);
+    Ctx *c = &x->c;
+    Bind b(c);
+    VBMC_REQUIRE(x->adam_ready, VBMC_ERR_STATE, "adam_fetch: call vbmc_adam_init first");
+    VBMC_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= x->adam_done, VBMC_ERR_ARG, "adam_fetch: iterations not issued yet");
+    if (n == 0) return VBMC_OK;
+    // the oldest live ticket that covers the range
+    cudaEvent_t ev = nullptr;
+    const int first = x->adam_ticket_next > CtxEx::kAdamTickets ? x->adam_ticket_next - CtxEx::kAdamTickets : 0;
+    for (int k = first; k < x->adam_ticket_next && !ev; ++k) {
+        auto &t = x->adam_tickets[k % CtxEx::kAdamTickets];
+        if (t.ev && t.i_end >= i0 + n) ev = t.ev;
+    }
+    const int P = x->adam.P;
+    if (!ev) {  // issued through vbmc_adam_steps, or the ticket ring wrapped: everything in the stream
+        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+        VBMC_CUDA_CHECK(cudaStreamWaitEvent(c->stream3, ev, 0));
+    }
+    cudaStream_t cs = ev ? c->stream3 : c->stream;
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(y, x->adam.ytab + i0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    VBMC_CUDA_CHECK(cudaMemcpyAsync(xs, x->adam.xtab + (size_t)i0 * P, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    VBMC_CUDA_CHECK(cudaStreamSynchronize(cs));
     return VBMC_OK;
 }
 

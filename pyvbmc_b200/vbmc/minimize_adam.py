@@ -11,7 +11,8 @@ and pays a host round trip (pack theta, H2D, launch, D2H, NumPy update) per iter
 objective is named by its ingredients, theta / the moment estimates / the iterate table stay in HBM,
 and one iteration (theta -> parameters, evaluation, Adam update, clamp; minimize_adam.py:87-104) is a
 CUDA graph replayed back to back (captured in iteration pairs: the entropy kernel alternates between two noise
-buffers).  The control flow around it -- batches of 20 iterations, the linear-fit early-stopping test, the returned
+buffers); batches of 20 iterations are issued one ahead of the host, which reads a batch back while the next one
+runs.  The control flow around it -- batches of 20 iterations, the linear-fit early-stopping test, the returned
 averages (:106-145) -- follows the reference's semantics; the fit is evaluated in closed form.
 """
 from __future__ import annotations
@@ -75,9 +76,22 @@ def minimize_adam_elcbo(
     x_tab = np.zeros((n_vars, max_iter))
     y_tab = np.full((max_iter,), np.nan)
     i = -1
-    while i + 1 < max_iter:
-        n = min(batch_size, max_iter - (i + 1))
-        y, xs = ctx.adam_steps(n)
+    issued = 0
+
+    def issue():
+        nonlocal issued
+        n_ = min(batch_size, max_iter - issued)
+        if n_ > 0:
+            ctx.adam_enqueue(n_)
+            issued += n_
+        return n_
+
+    # One batch is always in flight while the host digests the previous one (D2H of its values, the stopping rule):
+    # the device never idles at a batch boundary.  If the rule fires, the speculative batch is simply not read.
+    n = issue()
+    while n > 0:
+        n_next = issue()
+        y, xs = ctx.adam_fetch(i + 1, n)
         y_tab[i + 1 : i + 1 + n] = y
         x_tab[:, i + 1 : i + 1 + n] = xs.T
         i += n
@@ -101,6 +115,7 @@ def minimize_adam_elcbo(
             flat_loose = abs(slope) < np.sqrt(slope_var + tol_fun_max**2)
             if (dx < tol_x and flat_loose) or (flat_strict and dx < tol_x_max):
                 break
+        n = n_next
 
     x = np.mean(x_tab[:, i - batch_size + 1 : i + 1], axis=1)
     y = np.mean(y_tab[i - batch_size + 1 : i + 1])

@@ -760,3 +760,47 @@ def test_noise_prefetch_is_only_used_for_its_own_key(pv):
     x1, y1, xt1, yt1, n1 = pv.minimize_adam_elcbo(pr.gp, vp_a, th0.copy(), Ns_K, pr.theta_bnd, **kw)
     x2, y2, xt2, yt2, n2 = pv.minimize_adam_elcbo(pr.gp, fresh_vp(), th0.copy(), Ns_K, pr.theta_bnd, **kw)
     assert n1 == n2 == 8 and np.array_equal(yt1, yt2) and np.array_equal(xt1, xt2)
+
+
+@pytest.mark.gpu
+def test_device_adam_split_phase_equals_one_shot():
+    """vbmc_adam_enqueue / vbmc_adam_fetch (one batch in flight ahead of the host) return bit for bit what
+    vbmc_adam_steps returns; a speculative batch issued past the stopping point changes nothing that is read; the root-forked
+    generator of a host-buffer call in between does not disturb the loop's look-ahead bookkeeping."""
+    pr = syn.make_problem("C2")
+    Ns_K = 400
+
+    def fresh_vp():
+        return make_vp(pv, pr.D, pr.K, pr.mu, pr.sigma, pr.lambd, pr.w, pr.eta)
+
+    from pyvbmc_b200.vbmc.variational_optimization import _pack_params
+
+    def init(ctx, max_iter):
+        vp = fresh_vp()
+        th0 = np.asarray(vp.get_parameters(), dtype=float)
+        vp.set_parameters(th0)
+        optimize = (True, True, True, True)
+        ub = ctx.set_bounds(pr.theta_bnd)
+        prm = np.zeros(ctx.param_len(pr.D, pr.K))
+        _pack_params(prm, vp, th0, optimize, ub)
+        ctx.adam_init(pr.D, pr.K, prm, th0, optimize, Ns_K, ub, 11, 0, None, None, max_iter, 0.001, 0.02, 200)
+
+    ctx = pv.context_for_gp(pr.gp, need_L=False)
+    init(ctx, 64)
+    y_ref, x_ref = ctx.adam_steps(47)
+    init(ctx, 64)
+    ctx.adam_enqueue(20)
+    ctx.adam_enqueue(20)                       # second batch in flight before the first one is read
+    y0, x0 = ctx.adam_fetch(0, 20)
+    ctx.adam_enqueue(7)
+    y1, x1 = ctx.adam_fetch(20, 20)
+    ctx.adam_enqueue(10)                       # speculative: never read
+    y2, x2 = ctx.adam_fetch(40, 7)
+    assert np.array_equal(np.concatenate([y0, y1, y2]), y_ref)
+    assert np.array_equal(np.concatenate([x0, x1, x2]), x_ref)
+    with pytest.raises(Exception):
+        ctx.adam_fetch(50, 20)                 # not issued yet
+    # a host-buffer evaluation behind the speculative batch is ordered after it and unaffected by it
+    a = pv._neg_elcbo(pr.theta.copy(), pr.gp, fresh_vp(), 0.0, Ns_K, True, False, pr.theta_bnd, seed=5)
+    b = pv._neg_elcbo(pr.theta.copy(), pr.gp, fresh_vp(), 0.0, Ns_K, True, False, pr.theta_bnd, seed=5)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
