@@ -762,8 +762,7 @@ def test_noise_prefetch_is_only_used_for_its_own_key(pv):
     assert n1 == n2 == 8 and np.array_equal(yt1, yt2) and np.array_equal(xt1, xt2)
 
 
-@pytest.mark.gpu
-def test_device_adam_split_phase_equals_one_shot():
+def test_device_adam_split_phase_equals_one_shot(pv):
     """vbmc_adam_enqueue / vbmc_adam_fetch (one batch in flight ahead of the host) return bit for bit what
     vbmc_adam_steps returns; a speculative batch issued past the stopping point changes nothing that is read; the root-forked
     generator of a host-buffer call in between does not disturb the loop's look-ahead bookkeeping."""
