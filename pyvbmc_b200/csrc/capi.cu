@@ -875,13 +875,22 @@ int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
         o = c->h_out;
     }
     out->F = o[0], out->G = o[1], out->H = o[2], out->varF = 0.0, out->varG_ss = 0.0;
+    // every device-to-host copy of the extra outputs is enqueued first, ONE synchronisation for all of them
+    const bool want_I = in->separate_K && out->I_sk;
+    std::vector<double> ov, gps;
     if (s.compute_var) {
-        std::vector<double> ov(2 + c->S);
+        ov.resize(2 + c->S);
         VBMC_CUDA_CHECK(cudaMemcpyAsync(ov.data(), gpvar_out(c, K), ov.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (in->separate_K && out->J_sjk)
             VBMC_CUDA_CHECK(cudaMemcpyAsync(out->J_sjk, gpvar_J(c, K), (size_t)c->S * K * K * sizeof(double),
                                             cudaMemcpyDeviceToHost, c->stream));
-        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    if (want_I) {
+        gps.resize((size_t)c->S * (1 + Pfull));
+        VBMC_CUDA_CHECK(cudaMemcpyAsync(gps.data(), c->d_gps, gps.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (s.compute_var || want_I) VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (s.compute_var) {
         out->varF = ov[0];     // varG (+ varH == 0, :1179-1181)
         out->varG_ss = ov[1];  // the 5th output of _gp_log_joint, i.e. var_ss (:1121,1586)
     }
@@ -891,11 +900,8 @@ int vbmc_negelcbo(vbmc_ctx *p, const vbmc_elcbo_in *in, vbmc_elcbo_out *out) {
         if (out->dH)
             for (int i = 0; i < P; ++i) out->dH[i] = o[kOutHead + Pfull + i];
     }
-    if (in->separate_K && out->I_sk) {
+    if (want_I) {
         RawLayout rl{D, K};
-        std::vector<double> gps((size_t)c->S * (1 + Pfull));
-        VBMC_CUDA_CHECK(cudaMemcpyAsync(gps.data(), c->d_gps, gps.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        VBMC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         for (int si = 0; si < c->S; ++si)
             for (int k = 0; k < K; ++k) out->I_sk[(size_t)si * K + k] = gps[(size_t)si * (1 + Pfull) + 1 + rl.o_w() + k];
     }
