@@ -246,7 +246,7 @@ int ensure_pinned(double **d, double **h, size_t *cap, size_t need);
 
 // ----------------------------------------------------------------------------- launchers
 // entmc.cu
-enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENTMC_WARP = 4, ENTMC_TC = 5 };
+enum { ENTMC_FAST = 0, ENTMC_DSPLIT = 1, ENTMC_PACKED = 2, ENTMC_SCALAR = 3, ENTMC_WARP = 4, ENTMC_TC = 5, ENTMC_SMALL = 6 };
 struct EntmcPlan {
     int variant;
     int64_t chunk;    // ENTMC_WARP / ENTMC_TC: pairs of the flattened (component, pair) space per CTA

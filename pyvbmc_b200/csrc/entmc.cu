@@ -848,6 +848,272 @@ entmc_kernel_fast(const double *__restrict__ prm, ParamLayout lay, int64_t half,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 kernel for SMALL draw counts (the reference's defaults: ~28 draws per component).  Same arithmetic,
+// tables, guard and record layout as entmc_kernel_fast; what changes is the mapping.  With 14 antithetic pairs per
+// component, one thread per pair leaves 14 lanes of one warp walking serially over all K components (22.6 us at C3,
+// 9.6 % issue-active, every other warp parked at the final reduction: profiles/r4d).  Here EIGHT lanes share a pair and
+// split the components (k = lane, lane + 8, ...): the component loop is 8x shorter and every warp of the CTA works.
+// Only q+ and q- (the mixture densities) are needed in full by every lane -- three butterfly shuffles each; everything
+// else a pair contributes (the l+- / G+- partial sums) enters the results LINEARLY once 1/q+- is known, so each lane
+// folds its own partial sums into its private accumulators and the CTA-wide column reduction at the end adds them up.
+template <int DP, bool WGRAD, bool ANYGRAD, bool PHILOX>
+__global__ void __launch_bounds__(128, 2)
+entmc_kernel_small(const double *__restrict__ prm, ParamLayout lay, int64_t half, int64_t pair0, int64_t half_glob,
+                   int R, const double *__restrict__ eps, uint64_t seed, uint64_t offset, double *__restrict__ part,
+                   int part_stride, float guard) {
+    constexpr int H = DP / 2;  // packed pairs of dimensions
+    constexpr int KL = 8;      // lanes per antithetic pair
+    const int D = lay.D, K = lay.K;
+    {  // the Philox key lives behind the parameter block so that a captured CUDA graph stays valid
+        const uint64_t *rngp = reinterpret_cast<const uint64_t *>(prm + lay.total());
+        seed = rngp[0], offset = rngp[1];
+    }
+    const int j = blockIdx.y, slab = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int G = nt / KL, g = tid / KL, l = tid % KL;  // pair slots per sweep; this thread's slot and component lane
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sDl = reinterpret_cast<float *>(smem_raw);      // [K][DP]
+    KFast *sKc = reinterpret_cast<KFast *>(sDl + K * DP);  // [K]
+    float *sU = reinterpret_cast<float *>(sKc + K);        // Up [K][G], Um [K][G], racc [K][G] (WGRAD); spill [2 DP][nt]
+    const int u_floats = WGRAD ? max(3 * K * G, 2 * DP * nt) : (ANYGRAD ? 2 * DP * nt : 0);
+    double *scratch = reinterpret_cast<double *>(sU + ((u_floats + 3) & ~3));
+
+    const double *mu = prm + lay.mu();
+    const double *sigma = prm + lay.sigma();
+    const double *lambd = prm + lay.lambd();
+    const double *w = prm + lay.w();
+    const double sig_j = sigma[j];
+    const double kHalfLog2e = 0.72134752044448170368;  // log2(e) / 2
+
+    // The set-up is a large share of this kernel (one wave of K CTAs, a few microseconds in all): one reciprocal per
+    // dimension instead of a division per table entry, the loads of four entries in flight at a time, one logarithm per
+    // component (of the ratio), four partial sums for |Delta_k|^2.
+    double *sInvL = scratch + 40;  // [DP] 1 / lambda_d, then mu_j / lambda_d
+    if (tid < DP) sInvL[tid] = tid < D ? 1.0 / lambd[tid] : 0.0;
+    __syncthreads();
+#pragma unroll 4
+    for (int i = tid; i < K * DP; i += nt) {
+        const int k = i / DP, d = i - k * DP;
+        sDl[i] = (d < D) ? (float)((mu[j * D + d] - mu[k * D + d]) * sInvL[d]) : 0.0f;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+        const double sk = sigma[k];
+        const double hk = kHalfLog2e / (sk * sk), hjd = kHalfLog2e / (sig_j * sig_j);
+        const double ck = D * log2(sig_j / sk);
+        double A0 = 0.0, A1 = 0.0, A2 = 0.0, A3 = 0.0;  // |Delta_k|^2 of the ROUNDED table entries (what the FFMA2s will see)
+        const float4 *row = reinterpret_cast<const float4 *>(sDl + k * DP);  // (DP % 4 == 0, padded entries are zero)
+#pragma unroll
+        for (int q = 0; q < DP / 4; ++q) {
+            const float4 v = row[q];
+            A0 += (double)v.x * (double)v.x, A1 += (double)v.y * (double)v.y;
+            A2 += (double)v.z * (double)v.z, A3 += (double)v.w * (double)v.w;
+        }
+        const double A = (A0 + A1) + (A2 + A3);
+        const double Emax = sig_j * sig_j * (D + 8.0 * sqrt(2.0 * D) + 32.0);  // (see entmc_kernel_fast)
+        KFast c;
+        c.ck2 = (float)(ck - hk * A);
+        c.h2 = (float)(2.0 * hk);
+        c.hd = (float)(hjd - hk);
+        c.w = (float)w[k];
+        c.wis2 = (float)(w[k] / (sk * sk));
+        c.flag = (hk * (A + Emax) > (double)guard && k != j) ? 1.0f : 0.0f;
+        c.ck = (float)ck;
+        c.h = (float)hk;
+        sKc[k] = c;
+    }
+    if (WGRAD)
+        for (int i = tid; i < K * G; i += nt) sU[2 * K * G + i] = 0.0f;
+    __syncthreads();
+
+    float *Up = sU + g, *Um = sU + K * G + g, *racc = sU + 2 * K * G + g;  // element k at [k * G]
+    const float hj = (float)(kHalfLog2e / (sig_j * sig_j));
+    const double is2j = 1.0 / (sig_j * sig_j);
+    const float sj = (float)sig_j;
+    double hacc = 0.0;
+    float2 accA[ANYGRAD ? H : 1], accB[ANYGRAD ? H : 1];
+    if constexpr (ANYGRAD) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) accA[i] = accB[i] = make_float2(0.f, 0.f);
+    }
+
+    const int64_t slab_base = (int64_t)slab * G * R;
+    for (int r = 0; r < R; ++r) {  // (uniform trip count: the shuffles below need every lane of the warp)
+        const int64_t p = slab_base + (int64_t)r * G + g;  // local pair index of this thread's slot
+        const bool live = p < half;
+        const int64_t gpair = pair0 + (live ? p : 0);
+
+        float2 e2[H];
+        {
+            float z[DP];
+            if (PHILOX) {
+                philox_normals<DP>(seed, offset, (uint32_t)j, (uint64_t)gpair, D, z);  // (the 8 lanes of a slot draw the same numbers)
+            } else {
+                const double *ep = eps + ((size_t)j * (size_t)half_glob + (size_t)gpair) * (size_t)D;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = (d < D) ? (float)__ldg(ep + d) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) e2[i] = make_float2(sj * z[2 * i], sj * z[2 * i + 1]);
+        }
+        float2 ee = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < H; ++i) ee = __ffma2_rn(e2[i], e2[i], ee);
+        const float E = ee.x + ee.y;
+        const float base = hj * E;
+
+        // partial sums over this lane's components
+        float2 lp[ANYGRAD ? H : 1], lm[ANYGRAD ? H : 1];
+        if constexpr (ANYGRAD) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) lp[i] = lm[i] = make_float2(0.f, 0.f);
+        }
+        float qp = 0.f, qm = 0.f, Gp = 0.f, Gm = 0.f;
+
+        if (live) {
+            for (int k = l; k < K; k += KL) {
+                const KFast c = sKc[k];
+                const float2 *dl2 = reinterpret_cast<const float2 *>(sDl + k * DP);
+                float2 dl[H];
+#pragma unroll
+                for (int i = 0; i < H; ++i) dl[i] = dl2[i];
+                float up, um;
+                if (c.flag == 0.0f) {
+                    float2 b0 = make_float2(0.f, 0.f), b1 = b0;
+#pragma unroll
+                    for (int i = 0; i + 1 < H; i += 2) {
+                        b0 = __ffma2_rn(dl[i], e2[i], b0);
+                        b1 = __ffma2_rn(dl[i + 1], e2[i + 1], b1);
+                    }
+                    if (H & 1) b0 = __ffma2_rn(dl[H - 1], e2[H - 1], b0);
+                    const float2 bb = __fadd2_rn(b0, b1);
+                    const float B = bb.x + bb.y;
+                    const float s0 = fmaf(c.hd, E, c.ck2);
+                    up = M<float>::ex2(fmaf(-c.h2, B, s0));
+                    um = M<float>::ex2(fmaf(c.h2, B, s0));
+                    qp = fmaf(c.w, up, qp);
+                    qm = fmaf(c.w, um, qm);
+                    if constexpr (ANYGRAD) {
+                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                        Gp += gpv;
+                        Gm += gmv;
+                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                        for (int i = 0; i < H; ++i) {
+                            lp[i] = __ffma2_rn(gp2, dl[i], lp[i]);
+                            lm[i] = __ffma2_rn(gm2, dl[i], lm[i]);
+                        }
+                    }
+                } else {
+                    // direct path: differences first, squared term by term (no cancellation)
+                    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+                    float2 tp[H], tm[H];
+#pragma unroll
+                    for (int i = 0; i < H; ++i) {
+                        tp[i] = __fadd2_rn(dl[i], e2[i]);
+                        tm[i] = __fadd2_rn(dl[i], make_float2(-e2[i].x, -e2[i].y));
+                        a0 = __ffma2_rn(tp[i], tp[i], a0);
+                        a1 = __ffma2_rn(tm[i], tm[i], a1);
+                    }
+                    const float cb = c.ck + base;
+                    up = M<float>::ex2(fmaf(-c.h, a0.x + a0.y, cb));
+                    um = M<float>::ex2(fmaf(-c.h, a1.x + a1.y, cb));
+                    qp = fmaf(c.w, up, qp);
+                    qm = fmaf(c.w, um, qm);
+                    if constexpr (ANYGRAD) {
+                        const float gpv = c.wis2 * up, gmv = c.wis2 * um;
+                        const float2 gp2 = make_float2(gpv, gpv), gm2 = make_float2(gmv, gmv);
+#pragma unroll
+                        for (int i = 0; i < H; ++i) {
+                            lp[i] = __ffma2_rn(gp2, tp[i], lp[i]);
+                            lm[i] = __ffma2_rn(gm2, tm[i], lm[i]);
+                        }
+                    }
+                }
+                if (WGRAD) {
+                    Up[k * G] = up;
+                    Um[k * G] = um;
+                }
+            }
+        }
+        // the mixture densities of the pair: butterfly over the 8 lanes of the slot (fixed order => reproducible)
+#pragma unroll
+        for (int o = 1; o < KL; o <<= 1) {
+            qp += __shfl_xor_sync(0xffffffffu, qp, o);
+            qm += __shfl_xor_sync(0xffffffffu, qm, o);
+        }
+        if (live) {
+            if (l == 0) hacc += 0.69314718055994530942 * ((double)log2f(qp) + (double)log2f(qm)) - (double)E * is2j;
+            if constexpr (ANYGRAD) {
+                const float iqp = __frcp_rn(qp), iqm = __frcp_rn(qm);
+                const float2 ip2 = make_float2(iqp, iqp), im2 = make_float2(iqm, iqm);
+                const float2 Gp2 = make_float2(Gp, Gp), nGm2 = make_float2(-Gm, -Gm);
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float2 a = __fmul2_rn(__ffma2_rn(e2[i], Gp2, lp[i]), ip2);   // this lane's share of l+ / q+
+                    const float2 b = __fmul2_rn(__ffma2_rn(e2[i], nGm2, lm[i]), im2);  // ... of l- / q-
+                    accA[i] = __fadd2_rn(accA[i], __fadd2_rn(a, b));
+                    accB[i] = __ffma2_rn(e2[i], __fadd2_rn(a, make_float2(-b.x, -b.y)), accB[i]);
+                }
+                if (WGRAD) {
+                    for (int k = l; k < K; k += KL) racc[k * G] += fmaf(Up[k * G], iqp, Um[k * G] * iqm);
+                }
+            }
+        }
+    }
+
+    // ---- CTA record: fixed-order fp64 reduction over the thread columns ------------------
+    double *rec = part + ((size_t)j * gridDim.x + slab) * (size_t)part_stride;
+    const double hs = block_sum(hacc, scratch);
+    if (tid == 0) rec[0] = hs;
+    if constexpr (ANYGRAD) {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        __syncthreads();
+        if (WGRAD) {
+            // G (= 16) columns per row: two rows per warp pass, one per half-warp
+            const int hw = lane >> 4, hl = lane & 15;
+            for (int r0 = 2 * wid; r0 < K; r0 += 2 * nw) {
+                const int row = r0 + hw;
+                double v = 0.0;
+                if (row < K) {
+                    const float *src = sU + 2 * K * G + row * G;
+                    for (int c = hl; c < G; c += 16) v += (double)src[c];
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (row < K && hl == 0) rec[1 + 2 * DP + row] = v;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            sU[(2 * i) * nt + tid] = accA[i].x;
+            sU[(2 * i + 1) * nt + tid] = accA[i].y;
+            sU[(DP + 2 * i) * nt + tid] = accB[i].x;
+            sU[(DP + 2 * i + 1) * nt + tid] = accB[i].y;
+        }
+        __syncthreads();
+        for (int row = wid; row < 2 * DP; row += nw) {
+            const float *src = sU + row * nt;
+            double v = 0.0;
+            for (int c = lane; c < nt; c += 32) v += (double)src[c];
+            v = warp_sum(v);
+            if (lane == 0) rec[1 + row] = v;
+        }
+    }
+}
+
+static size_t entmc_smem_small(int DP, int K, int nt, bool wgrad, bool anygrad) {
+    size_t b = (size_t)K * DP * sizeof(float) + (size_t)K * sizeof(KFast);
+    size_t u = wgrad ? (size_t)3 * K * (nt / 8) : 0;
+    if (anygrad && u < (size_t)2 * DP * nt) u = (size_t)2 * DP * nt;
+    u = (u + 3) & ~(size_t)3;
+    b += u * sizeof(float);
+    b = (b + 15) & ~(size_t)15;
+    return b + (40 + DP) * sizeof(double);
+}
+
 static size_t entmc_smem_fast(int DP, int K, int nt, bool wgrad, bool anygrad) {
     size_t b = (size_t)K * DP * sizeof(float) + (size_t)K * sizeof(KFast);
     size_t u = wgrad ? (size_t)3 * K * nt : 0;
@@ -1246,6 +1512,9 @@ int launch_inst(Ctx *c, const double *d_params, ParamLayout lay, const EntmcPlan
             case ENTMC_FAST:
                 VBMC_LAUNCH((entmc_kernel_fast<DP, WGRAD, ANYGRAD, PHILOX>), , c->entmc_guard);
                 break;
+            case ENTMC_SMALL:
+                VBMC_LAUNCH((entmc_kernel_small<DP, WGRAD, ANYGRAD, PHILOX>), , c->entmc_guard);
+                break;
             case ENTMC_DSPLIT:
                 VBMC_LAUNCH((entmc_kernel_f32x2_ds<DP, WGRAD, ANYGRAD, PHILOX>));
                 break;
@@ -1334,6 +1603,8 @@ static size_t entmc_smem_variant(int variant, int precision, int DP, int K, int 
             return entmc_smem_w(DP, K, nt, wgrad, anygrad);
         case ENTMC_FAST:
             return entmc_smem_fast(DP, K, nt, wgrad, anygrad);
+        case ENTMC_SMALL:
+            return entmc_smem_small(DP, K, nt, wgrad, anygrad);
         case ENTMC_DSPLIT:
             return entmc_smem_ds(DP, K, nt, wgrad, anygrad);
         case ENTMC_PACKED:
@@ -1360,6 +1631,9 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
         const bool tc_shape = K >= 32 || (D >= 16 && K >= 24);
         if (T >= 150000 && tc_shape && entmc_tc_supported(DP, K)) variant = ENTMC_TC;
         else variant = T >= 65536 ? ENTMC_WARP : ENTMC_FAST;
+        // the reference's default draw counts (tens of draws per component): eight lanes per pair instead of one thread
+        static const int64_t small_half = getenv("VBMC_SMALL_HALF") ? atoll(getenv("VBMC_SMALL_HALF")) : 64;
+        if (variant == ENTMC_FAST && half_local <= small_half) variant = ENTMC_SMALL;
     }
     const size_t smem_cap = 227 * 1024;
     if (variant == ENTMC_TC) {
@@ -1411,7 +1685,7 @@ int entmc_plan(const Ctx *c, int D, int K, int64_t half_local, bool wgrad, int p
     if (per_sm < 1) per_sm = 1;
     const int64_t slots = (int64_t)c->sm_count * per_sm;
     // pairs evaluated per CTA sweep: one per thread, or one per two lanes (dimension-split kernel)
-    const int ppi = (precision != VBMC_PREC_F64 && variant == ENTMC_DSPLIT) ? nt / 2 : nt;
+    const int ppi = precision == VBMC_PREC_F64 ? nt : (variant == ENTMC_DSPLIT ? nt / 2 : (variant == ENTMC_SMALL ? nt / 8 : nt));
 
     // candidate R: cost ~ waves * (R + overhead); overhead ~ table set-up + record reduction
     int bestR = 1;

@@ -546,12 +546,13 @@ def test_finite_difference_gradients(pv):
 
 # ---------------------------------------------------------------------------------------------------
 # every fp32 entmc kernel variant (the automatic choice only exercises one per problem size)
-@pytest.mark.parametrize("variant", [0, 2, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5, 6])
 @pytest.mark.parametrize("stem", ["c2", "c4", "c1", "c2_ill"])
 def test_entmc_every_variant_against_oracle_and_f64(pv, variant, stem, monkeypatch):
     """Forced kernel variant (VBMC_ENTMC_VARIANT is read when a context is created): eps-input parity with
     the reference's golden values, and Philox-mode agreement with the all-fp64 kernel on identical draws.
-    Variant 5 is the tcgen05 / TMEM kernel (it falls back to 4 for K > 64)."""
+    Variant 5 is the tcgen05 / TMEM kernel (it falls back to 4 for K > 64), variant 6 the eight-lanes-per-pair kernel the
+    automatic choice takes at the reference's default draw counts."""
     c = load_case(stem)
     g = c.g
     vp = case_vp(pv, c, "sa")
@@ -702,11 +703,14 @@ def test_entmc_large_draw_counts_tensor_core_vs_f64(pv, K, Ns_K, monkeypatch):
 
 
 @pytest.mark.parametrize("D,K,Ns_K,want", [(20, 32, 12500, 5), (20, 24, 16668, 5), (10, 32, 12500, 5), (6, 48, 8334, 5),
-                                           (10, 20, 20000, 4), (6, 30, 13334, 4), (20, 16, 25000, 4)])
+                                           (10, 20, 20000, 4), (6, 30, 13334, 4), (20, 16, 25000, 4),
+                                           (20, 50, 28, 6), (20, 50, 128, 6), (20, 50, 130, 0), (10, 20, 22, 6), (2, 3, 2, 6),
+                                           (32, 64, 100, 6)])
 def test_entmc_auto_selection_matches_the_measured_crossover(pv, D, K, Ns_K, want, monkeypatch):
     """Automatic choice of the fp32 entropy kernel at ~400k draws (scripts/variant_sweep.py): the tensor-core kernel from
-    K >= 32, and from K >= 24 at D >= 16; the CUDA-core kernels below -- each against the all-fp64 kernel on identical
-    Philox draws."""
+    K >= 32, and from K >= 24 at D >= 16; the CUDA-core kernels below; and at the reference's default draw counts (up to 128
+    draws per component, scripts/small_sweep.py) the eight-lanes-per-pair kernel -- each against the all-fp64 kernel on
+    identical Philox draws."""
     monkeypatch.delenv("VBMC_ENTMC_VARIANT", raising=False)
     rng = np.random.default_rng(K * 100 + D)
     mu = 0.5 * rng.normal(size=(D, K))
