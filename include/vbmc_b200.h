@@ -186,7 +186,8 @@ int vbmc_negelcbo_theta(vbmc_ctx *ctx, int D, int K, double *theta, const double
 /* Start generating the Monte-Carlo noise of the evaluation with Philox key (seed, offset) NOW, on a side stream: the
  * noise does not depend on theta, so the generator runs while the host is still preparing the call.  A following
  * vbmc_negelcbo_theta / vbmc_negelcbo_flat with the same (D, K, Ns, seed, offset) uses it; anything else ignores it.
- * A no-op for problem sizes that do not take the tensor-core entropy kernel.                                      */
+ * A no-op for problem sizes that do not take the tensor-core entropy kernel.  OPTIONAL: without it the evaluation forks
+ * the generator at the root of its own CUDA graph, beside the parameter kernel (the default of the Python shim).    */
 int vbmc_noise_prefetch(vbmc_ctx *ctx, int D, int K, int64_t Ns, uint64_t seed, uint64_t offset);
 
 /* ---- split-phase, device-resident variants ----------------------------------------
