@@ -483,3 +483,78 @@ def test_both_wrappers_inside_the_unmodified_optimize_vp():
     assert len(seen["sieve"]) == 1 and seen["sieve"][0] > 0      # the candidate loop became one batch
     assert len(seen["adam"]) >= 1 and all(a[1] == 60 and a[0] > 0 for a in seen["adam"])  # every Adam run was routed
     np.testing.assert_array_equal(got, want)
+
+
+class _AdamStandIn:
+    """Host stand-in for the device side of minimize_adam_elcbo: the same enqueue / fetch protocol, the Adam update of
+    the reference (minimize_adam.py:87-99) on a seeded noisy quadratic.  Issues are recorded to check the pipelining."""
+
+    def __init__(self, f):
+        self.f = f
+        self.log = []
+
+    def set_bounds(self, theta_bnd):
+        return False
+
+    def param_len(self, D, K):
+        return D * K + 5 * K + 2 * D
+
+    def adam_init(self, D, K, prm, x0, optimize, Ns, use_bounds, seed, offset, lb, ub, max_iter, mmin, mmax, mdecay):
+        self.x = np.array(x0, dtype=float)
+        self.m = self.v = 0.0
+        self.i = 0
+        self.cfg = (mmin, mmax, mdecay)
+        self.y_tab, self.x_tab = [], []
+
+    def adam_enqueue(self, n):
+        self.log.append(("enqueue", self.i, n))
+        mmin, mmax, mdecay = self.cfg
+        for _ in range(n):
+            y, g = self.f(self.x)
+            self.m = 0.9 * self.m + 0.1 * g
+            self.v = 0.999 * self.v + 0.001 * g**2
+            i = self.i
+            step = mmin + (mmax - mmin) * np.exp(-(i + 1) / mdecay)
+            self.x = self.x - step * (self.m / (1 - 0.9 ** (i + 1))) / (np.sqrt(self.v / (1 - 0.999 ** (i + 1))) + np.sqrt(np.spacing(1)))
+            self.y_tab.append(y)
+            self.x_tab.append(self.x.copy())
+            self.i += 1
+
+    def adam_fetch(self, i0, n):
+        self.log.append(("fetch", i0, n))
+        assert i0 + n <= self.i
+        return np.array(self.y_tab[i0 : i0 + n]), np.array(self.x_tab[i0 : i0 + n])
+
+
+@pytest.mark.parametrize("early,max_iter", [(True, 400), (False, 70), (True, 30)])
+def test_minimize_adam_elcbo_host_loop_matches_the_reference_loop(monkeypatch, early, max_iter):
+    """Control flow of pyvbmc_b200.minimize_adam_elcbo (batches issued one ahead of the host, closed-form stopping rule,
+    returned averages) against the oracle's restatement of minimize_adam.py:61-145 (itself pinned to the unmodified
+    reference): same iterates, same stopping iteration."""
+    import pyvbmc_b200 as pv
+    from oracle.minimize_adam_oracle import minimize_adam, noisy_quadratic
+    from pyvbmc_b200.vbmc import minimize_adam as mod
+
+    D, K = 1, 2  # theta = [mu (2) | ln sigma (2) | ln lambda (1) | eta (2)]: 7 entries; a 7-variable quadratic
+    f1, _ = noisy_quadratic(n=7, seed=3)
+    f2, _ = noisy_quadratic(n=7, seed=3)
+    x0 = np.full(7, 2.0)
+    x0[-2:] = [-0.5, 0.0]  # max(eta) == 0 already: the in-place shift of the real objective is a no-op here
+    kw = dict(max_iter=max_iter, master_max=0.05, use_early_stopping=early)
+    ref = minimize_adam(f1, x0.copy(), **kw)
+    fake = _AdamStandIn(f2)
+    monkeypatch.setattr(mod, "context_for_gp", lambda gp, need_L=False: fake)
+    vp = pv.VariationalPosterior(D, K)
+    got = pv.minimize_adam_elcbo(object(), vp, x0.copy(), 10, None, seed=1, **kw)
+    assert got[4] == ref[4]
+    assert np.allclose(got[0], ref[0], rtol=0, atol=1e-12) and abs(got[1] - ref[1]) < 1e-12
+    assert np.allclose(got[2], ref[2], rtol=0, atol=1e-12) and np.allclose(got[3], ref[3], rtol=0, atol=1e-12)
+    # pipelining: every fetch of a batch is preceded by the enqueue of the NEXT one (while iterations remain)
+    enq = [e for e in fake.log if e[0] == "enqueue"]
+    for idx, e in enumerate(fake.log):
+        if e[0] == "fetch":
+            issued_before = sum(n for k, _, n in fake.log[:idx] if k == "enqueue")
+            assert issued_before >= min(e[1] + e[2] + 20, max_iter) or issued_before == max_iter
+    assert sum(n for _, _, n in enq) <= max_iter
+    if early and max_iter == 400:
+        assert ref[4] < max_iter  # the rule fired (otherwise this case tests nothing)
