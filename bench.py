@@ -27,6 +27,9 @@ or from the archive ``oracle/build_ref.py`` packs into the git-ignored ``oracle/
 exists on the GPU box), FULL evaluations, nothing extrapolated.  Every step is one C3 evaluation at any
 N (the host CPU does not grow with the GPU count; the reference's cost is linear in draws and
 hyper-samples, so its C3-equivalent evaluations per second are the same number at every N).
+``value`` is the faithful figure: one evaluation at a time, as the reference's optimiser calls it (NumPy's
+BLAS threads where the path has any BLAS).  ``cpu_all_cores`` beside it: one single-threaded process per host
+core, each running one full evaluation, started together -- what the host delivers on independent evaluations.
 """
 import argparse
 import json
@@ -199,14 +202,59 @@ class CpuArm:
                 f"extrapolated; {wall:.1f} s wall")
 
 
+def _cpu_worker(start_at):
+    """One process of the all-cores figure: set up, warm up on a small draw count, wait for the common start time, run ONE
+    full evaluation, print its duration."""
+    pr, _ = workload(1)
+    arm = CpuArm(pr, CpuArm.best_kind())
+    np.random.seed(os.getpid() % 65536)
+    arm.evaluate(Ns_K=40)
+    late = time.time() - start_at
+    if late < 0:
+        time.sleep(-late)
+    t0 = time.perf_counter()
+    F, dF, *_ = arm.evaluate()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"worker_s": dt, "late_s": max(late, 0.0), "ok": bool(np.isfinite(F))}))
+    return 0
+
+
+def cpu_all_cores(n_proc, setup_s=30.0):
+    """The same evaluation on every host core at once: `n_proc` independent processes (one BLAS thread each), each running
+    ONE full evaluation of the unmodified reference, started together; throughput = n_proc / slowest process.  The
+    reference itself offers no parallelism over one evaluation (NumPy elementwise kernels in a Python loop over the
+    components), so independent evaluations -- e.g. the candidates of the sieve -- are what extra cores can take."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    start_at = time.time() + setup_s
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-worker", repr(start_at)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True) for _ in range(n_proc)]
+    outs = []
+    for p_ in procs:
+        try:
+            o, _ = p_.communicate(timeout=600)
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+        except Exception:
+            p_.kill()
+    if len(outs) < n_proc or not all(o["ok"] for o in outs) or any(o["late_s"] > 5.0 for o in outs):
+        return {"unavailable": f"{len(outs)} of {n_proc} workers finished cleanly / on time"}
+    slow = max(o["worker_s"] for o in outs)
+    return {"value": n_proc / slow, "unit": UNIT, "processes": n_proc, "slowest_s": slow,
+            "fastest_s": min(o["worker_s"] for o in outs),
+            "what": ("independent FULL evaluations of the unmodified reference, one single-threaded process per host core, "
+                     "started together; value = processes / slowest process")}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.cpu_worker is not None:
+        return _cpu_worker(float(args.cpu_worker))
     pr, _ = workload(1)  # one C3 evaluation per step at every N (see the module docstring)
     kind = CpuArm.best_kind()
     arm = CpuArm(pr, kind)
     t_eval, ts, cores, wall = arm.time(args.steps, args.warmup)
+    all_cores = cpu_all_cores(os.cpu_count() or 1) if os.environ.get("VBMC_BENCH_ALL_CORES", "1") != "0" else None
     value = 1.0 / t_eval  # C3 evaluations per second == C3-equivalent evaluations per second of the CUDA arm's unit
     wname = "C3 (D=20,N=400,K=50,S=8,N_s=400k)"
     if args.gpus > 1:
@@ -228,6 +276,8 @@ def run_reference(args):
                                           "CPU time / wall time")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if all_cores is not None:
+        line["cpu_all_cores"] = all_cores
     print(json.dumps(line))
     return 0
 
@@ -707,6 +757,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)  # internal: one process of cpu_all_cores()
     args = ap.parse_args()
     # defaults that finish within minutes: a CUDA step lasts ~0.1 ms, a full reference evaluation several seconds
     if args.steps is None:
