@@ -263,10 +263,11 @@ def _neg_elcbo(
         # side effects on vp and on the caller's theta, as the reference leaves them
         if optimize[0]:
             vp.mu = np.array(th[:DK]).reshape((D, K), order="F")
-        vp.sigma = vpo[:K].reshape(1, K).copy()
-        vp.lambd = vpo[K : K + D].reshape(D, 1).copy()
+        v = vpo.copy()  # ONE copy of the pinned block; sigma / lambda / w are views of it (three copies cost 2 us more)
+        vp.sigma = v[:K].reshape(1, K)
+        vp.lambd = v[K : K + D].reshape(D, 1)
         if optimize[3]:
-            vp.w = vpo[K + D :].reshape(1, K).copy()
+            vp.w = v[K + D :].reshape(1, K)
             if th is not theta:
                 theta[-K:] = th[-K:]
             vp.eta = theta[-K:].reshape(1, -1)  # a view of the caller's array (:1082-1085)
